@@ -1,0 +1,250 @@
+// 3x3 convolution over board rows as an implicit GEMM on the 5th-generation tensor cores.
+//
+// Replaces cudnnConvolutionBiasActivationForward as driven by
+// src/libdg_nn/layers/conv2d.rs:171-220 (`Conv2d::forward` / `forward_skip`):
+//     y = relu(alpha * conv3x3(x, w) + beta * skip + bias)
+// x / y / skip are board-row buffers (layout.h), w is KRSC fp16 re-laid out per tap.
+//
+// Design (one persistent CTA per SM, warp-specialised, 192 threads):
+//   * weights of this CTA's output-channel slice stay RESIDENT in shared memory for the whole
+//     launch (9 taps x NH k-halves x [BN x 64] fp16, 128B-swizzled, loaded once by TMA);
+//   * per 128-row tile ONE TMA box of 170 rows x 64 channels (tile + 21-row halo each side) is
+//     staged per k-half; the nine taps are nine UMMA descriptors that start at different ROW
+//     offsets inside that box -- no im2col, activations are read from L2 1.33x instead of 9x;
+//   * tcgen05.mma (M=128, N=BN, K=16) accumulates in TMEM (double-buffered accumulator) so the
+//     epilogue of tile i overlaps the MMAs of tile i+1;
+//   * epilogue: tcgen05.ld -> alpha*acc + bias (+ beta*skip) -> ReLU -> zero the halo rows ->
+//     fp16 -> global.
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_tc.h"
+#include "layout.h"
+#include "ptx.cuh"
+
+namespace dg {
+
+constexpr int kStages = 3;                       // A half-window ring
+constexpr int kWindowBytes = DG_WINDOW_ROWS * 128;   // 21,760 bytes landed per TMA box
+constexpr int kStageBytes = 22 * 1024;           // 1024-aligned slot
+constexpr int kThreads = 192;
+
+template <int NH, int BN>
+struct ConvSmem {
+    static constexpr int kSlab = BN * 128;                 // one tap, one k-half: [BN][64] fp16
+    static constexpr int kWeights = 9 * NH * kSlab;
+    static constexpr int kBars = kWeights + kStages * kStageBytes;
+    static constexpr int kTotal = kBars + 256 + BN * 4 + 1024;   // + barriers + bias + alignment slack
+};
+
+template <int NH, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvTcParams p) {
+    using L = ConvSmem<NH, BN>;
+    constexpr int kNSplit = (BN == 64) ? 2 : 1;
+    constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+    constexpr uint32_t kIdesc = umma_idesc_f16(DG_TILE_M, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_s = smem;
+    uint8_t* a_s = smem + L::kWeights;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+    uint64_t* w_full = bars;
+    uint64_t* a_full = bars + 1;
+    uint64_t* a_empty = bars + 1 + kStages;
+    uint64_t* acc_full = bars + 1 + 2 * kStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* bias_s = reinterpret_cast<float*>(bars + 32);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nslice = blockIdx.x % kNSplit;           // which BN-wide slice of the output channels
+    const int first_tile = blockIdx.x / kNSplit;
+    const int tile_step = gridDim.x / kNSplit;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_act);
+        tma_prefetch_desc(&tm_w);
+        mbar_init(w_full, 1);
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    for (int i = threadIdx.x; i < BN; i += kThreads) bias_s[i] = p.bias[nslice * BN + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(w_full, L::kWeights);
+            for (int tap = 0; tap < 9; tap++)
+                for (int h = 0; h < NH; h++)
+                    tma_load_2d(w_s + (tap * NH + h) * L::kSlab, &tm_w, w_full, h * 64, tap * (kNSplit * BN) + nslice * BN);
+            griddep_wait();   // activations of the previous launch must be complete before we read them
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = first_tile; t < p.ntiles; t += tile_step) {
+                for (int h = 0; h < NH; h++) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&a_full[stage], kWindowBytes);
+                    tma_load_2d(a_s + stage * kStageBytes, &tm_act, &a_full[stage], h * 64,
+                                DG_GUARD_ROWS + t * DG_TILE_M - DG_HALO_ROWS);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            mbar_wait(w_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            const uint32_t w_addr = smem_u32(w_s);
+            for (int t = first_tile; t < p.ntiles; t += tile_step) {
+                mbar_wait(&acc_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                uint32_t accumulate = 0;
+                for (int h = 0; h < NH; h++) {
+                    mbar_wait(&a_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(a_s + stage * kStageBytes);
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) {
+                        const int row_off = DG_HALO_ROWS + (tap / 3 - 1) * DG_LINE_STRIDE + (tap % 3 - 1);
+                        const uint32_t a_tap = a_addr + row_off * 128;
+                        const uint32_t bo = p.desc_base_offset ? ((a_tap >> 7) & 7u) : 0u;
+                        const uint32_t b_tap = w_addr + (tap * NH + h) * L::kSlab;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            umma_f16_ss(d_tmem, umma_desc_sw128(a_tap + k * 32, bo), umma_desc_sw128(b_tap + k * 32, 0), kIdesc,
+                                        accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(&a_empty[stage]);      // window slot may be refilled once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[as]);            // accumulator complete -> epilogue
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps
+        griddep_wait();
+        const int quarter = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        const float alpha = p.alpha, beta = p.beta;
+        for (int t = first_tile; t < p.ntiles; t += tile_step) {
+            const int m = t * DG_TILE_M + quarter * 32 + lane;
+            const int q = m % DG_POS_ROWS;
+            const bool halo = (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) ||
+                              (q >= DG_POS_ROWS - DG_LINE_STRIDE);
+            const size_t grow = static_cast<size_t>(DG_GUARD_ROWS + m);
+            __half* out_row = p.out + grow * p.out_stride + nslice * BN;
+            const __half* skip_row = p.skip ? p.skip + grow * p.skip_stride + nslice * BN : nullptr;
+
+            mbar_wait(&acc_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll
+            for (int c = 0; c < BN / 16; c++) {
+                uint32_t acc[16];
+                tmem_ld_32x32b_x16(taddr + c * 16, acc);
+                uint4 s0 = make_uint4(0, 0, 0, 0), s1 = make_uint4(0, 0, 0, 0);
+                if (skip_row && !halo) {
+                    s0 = *reinterpret_cast<const uint4*>(skip_row + c * 16);
+                    s1 = *reinterpret_cast<const uint4*>(skip_row + c * 16 + 8);
+                }
+                tmem_ld_wait();
+                const __half2* sh0 = reinterpret_cast<const __half2*>(&s0);
+                const __half2* sh1 = reinterpret_cast<const __half2*>(&s1);
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float2 sk = __half22float2(j < 4 ? sh0[j] : sh1[j - 4]);
+                    float v0 = fmaf(alpha, __uint_as_float(acc[2 * j]), bias_s[c * 16 + 2 * j]);
+                    float v1 = fmaf(alpha, __uint_as_float(acc[2 * j + 1]), bias_s[c * 16 + 2 * j + 1]);
+                    v0 = fmaf(beta, sk.x, v0);
+                    v1 = fmaf(beta, sk.y, v1);
+                    v0 = (v0 > 0.f && !halo) ? v0 : 0.f;     // NaN-non-propagating ReLU; halo rows stay zero
+                    v1 = (v1 > 0.f && !halo) ? v1 : 0.f;
+                    const __half2 hv = __floats2half2_rn(v0, v1);
+                    packed[j] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+                *reinterpret_cast<uint4*>(out_row + c * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4*>(out_row + c * 16 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    griddep_launch_dependents();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <int NH, int BN>
+static cudaError_t launch_one(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
+                              cudaStream_t stream, bool pdl) {
+    using L = ConvSmem<NH, BN>;
+    static bool configured = false;   // per (NH, BN) instantiation; engine creation is serialised
+    auto kernel = conv3x3_tc_kernel<NH, BN>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    constexpr int nsplit = (BN == 64) ? 2 : 1;
+    int grid = num_sms - (num_sms % nsplit);
+    const int work = p.ntiles * nsplit;
+    if (grid > work) grid = work;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, tm_act, tm_w, p);
+}
+
+cudaError_t launch_conv_tc(ConvTcShape shape, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p,
+                           int num_sms, cudaStream_t stream, bool pdl) {
+    switch (shape) {
+        case ConvTcShape::kUp:    return launch_one<1, 64>(tm_act, tm_w, p, num_sms, stream, pdl);
+        case ConvTcShape::kTower: return launch_one<2, 64>(tm_act, tm_w, p, num_sms, stream, pdl);
+        case ConvTcShape::kHeads: return launch_one<2, 16>(tm_act, tm_w, p, num_sms, stream, pdl);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace dg

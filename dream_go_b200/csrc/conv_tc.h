@@ -1,0 +1,30 @@
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace dg {
+
+struct ConvTcParams {
+    int ntiles;                 // 128-row tiles to process
+    int valid_rows;             // batch * 400; rows beyond are written as zero
+    __half* out;                // board-row buffer (row 0 = guard start)
+    int out_stride;             // elements per output row
+    const __half* skip;         // optional residual input (same rows), nullptr if none
+    int skip_stride;
+    const float* bias;          // [Cout] fp32 (already scaled and fp16-rounded where the reference does so)
+    float alpha;                // scale of the convolution result
+    float beta;                 // scale of the skip input
+    int desc_base_offset;       // debug: fill the UMMA descriptor base-offset field
+};
+
+enum class ConvTcShape {
+    kUp,      // 64 (32 real + 32 zero) -> 128 channels, two 64-channel CTAs per tile
+    kTower,   // 128 -> 128 channels
+    kHeads,   // 128 -> 16 channels (8 policy + 2 value + 6 zero)
+};
+
+cudaError_t launch_conv_tc(ConvTcShape shape, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p,
+                           int num_sms, cudaStream_t stream, bool pdl);
+
+}  // namespace dg

@@ -1,0 +1,719 @@
+// C-ABI engine: weight loading / re-layout, workspaces, forward orchestration, leaf queue.
+// Host-side counterpart of src/libdg_nn/{network,graph,loader,tensor}.rs behind include/dg_engine.h.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/dg_engine.h"
+#include "conv_tc.h"
+#include "kernels.h"
+#include "layout.h"
+#include "weights_file.h"
+
+namespace {
+
+using dg::ConvTcParams;
+using dg::ConvTcShape;
+
+constexpr int kFeatBytes = DG_FEATURE_SIZE * 2;      // 23,104 bytes of fp16 features per position
+constexpr int kChan = 128;
+constexpr int kHeadChan = 16;
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t* d_in = nullptr;          // raw NHWC features or compact positions of the current batch
+    __half *feat = nullptr, *x = nullptr, *y = nullptr, *h = nullptr;
+    __half *d_policy = nullptr, *d_value = nullptr;
+    uint8_t* h_in = nullptr;          // pinned staging
+    __half *h_policy = nullptr, *h_value = nullptr;
+    CUtensorMap tm_feat, tm_x, tm_y;
+    int resident_batch = 0;
+    int resident_kind = 0;            // 0 none, 1 raw features, 2 compact positions
+    bool busy = false;
+};
+
+struct ConvWeights {
+    __half* w = nullptr;              // [9][ntot][k] fp16
+    float* bias = nullptr;            // [ntot] fp32
+    CUtensorMap tm;
+};
+
+struct DeviceNet {
+    int num_blocks = 0;
+    ConvWeights up;
+    std::vector<ConvWeights> c1, c2;
+    std::vector<float> gate;
+    ConvWeights heads;
+    __half* w_pfc = nullptr;          // [2888][362]
+    float* b_pfc = nullptr;           // fp16(tau * b) as fp32
+    __half* w_vfc = nullptr;          // [722]
+    float b_vfc = 0.f;
+    float tau = 1.f;
+    std::vector<void*> allocations;
+    bool loaded = false;
+};
+
+struct LeafQueue {
+    int64_t capacity = 0;
+    dg_packed_position* ring = nullptr;       // pinned + mapped
+    __half* res_policy = nullptr;             // pinned [capacity][362]
+    __half* res_value = nullptr;              // pinned [capacity]
+    std::atomic<int64_t>* ready = nullptr;    // ticket+1 once the slot is filled
+    std::atomic<int64_t>* done = nullptr;     // ticket+1 once the slot is evaluated
+    std::atomic<int64_t> head{0};
+    std::atomic<int64_t> completed{0};        // all tickets below are evaluated
+    int64_t claimed = 0;                      // guarded by claim_mutex
+    std::mutex claim_mutex;
+    std::mutex wait_mutex;
+    std::condition_variable wait_cv;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct dg_engine {
+    dg_engine_config cfg;
+    int num_sms = 0;
+    EncodeTiledFn encode = nullptr;
+    std::vector<Workspace> ws;
+    std::mutex ws_mutex;
+    std::condition_variable ws_cv;
+    DeviceNet net;
+    LeafQueue queue;
+    std::mutex err_mutex;
+    std::string last_error;
+    std::vector<void*> host_allocs;
+};
+
+namespace {
+
+int32_t fail(dg_engine* e, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) {
+        std::lock_guard<std::mutex> g(e->err_mutex);
+        e->last_error = buf;
+    }
+    return code;
+}
+
+#define DG_CUDA(e, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t err__ = (call);                                                                   \
+        if (err__ != cudaSuccess)                                                                     \
+            return fail((e), DG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+bool make_tmap(dg_engine* e, CUtensorMap* m, void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------ workspaces
+
+int32_t create_workspace(dg_engine* e, Workspace& w) {
+    const int mb = e->cfg.max_batch;
+    const size_t rows = static_cast<size_t>(dg_alloc_rows(mb));
+    DG_CUDA(e, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    DG_CUDA(e, cudaEventCreate(&w.ev0));
+    DG_CUDA(e, cudaEventCreate(&w.ev1));
+    DG_CUDA(e, cudaMalloc(&w.d_in, static_cast<size_t>(mb) * kFeatBytes));
+    DG_CUDA(e, cudaMalloc(&w.feat, rows * 64 * 2));
+    DG_CUDA(e, cudaMalloc(&w.x, rows * kChan * 2));
+    DG_CUDA(e, cudaMalloc(&w.y, rows * kChan * 2));
+    DG_CUDA(e, cudaMalloc(&w.h, rows * kHeadChan * 2));
+    DG_CUDA(e, cudaMalloc(&w.d_policy, static_cast<size_t>(mb) * DG_POLICY_SIZE * 2));
+    DG_CUDA(e, cudaMalloc(&w.d_value, static_cast<size_t>(mb) * 2));
+    DG_CUDA(e, cudaMemset(w.feat, 0, rows * 64 * 2));
+    DG_CUDA(e, cudaMemset(w.x, 0, rows * kChan * 2));
+    DG_CUDA(e, cudaMemset(w.y, 0, rows * kChan * 2));
+    DG_CUDA(e, cudaMemset(w.h, 0, rows * kHeadChan * 2));
+    DG_CUDA(e, cudaHostAlloc(&w.h_in, static_cast<size_t>(mb) * kFeatBytes, cudaHostAllocDefault));
+    DG_CUDA(e, cudaHostAlloc(&w.h_policy, static_cast<size_t>(mb) * DG_POLICY_SIZE * 2, cudaHostAllocDefault));
+    DG_CUDA(e, cudaHostAlloc(&w.h_value, static_cast<size_t>(mb) * 2, cudaHostAllocDefault));
+    if (!make_tmap(e, &w.tm_feat, w.feat, 64, rows, DG_WINDOW_ROWS) || !make_tmap(e, &w.tm_x, w.x, kChan, rows, DG_WINDOW_ROWS) ||
+        !make_tmap(e, &w.tm_y, w.y, kChan, rows, DG_WINDOW_ROWS))
+        return fail(e, DG_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation buffer");
+    return DG_OK;
+}
+
+void destroy_workspace(Workspace& w) {
+    if (w.stream) cudaStreamDestroy(w.stream);
+    if (w.ev0) cudaEventDestroy(w.ev0);
+    if (w.ev1) cudaEventDestroy(w.ev1);
+    cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
+    cudaFree(w.d_policy); cudaFree(w.d_value);
+    cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value);
+}
+
+Workspace* acquire(dg_engine* e) {
+    std::unique_lock<std::mutex> lk(e->ws_mutex);
+    for (;;) {
+        for (auto& w : e->ws)
+            if (!w.busy) { w.busy = true; return &w; }
+        e->ws_cv.wait(lk);
+    }
+}
+void release(dg_engine* e, Workspace* w) {
+    { std::lock_guard<std::mutex> lk(e->ws_mutex); w->busy = false; }
+    e->ws_cv.notify_one();
+}
+// The workspace that still holds `batch` resident inputs (measurement / debug hooks only).
+Workspace* acquire_resident(dg_engine* e, int batch) {
+    std::unique_lock<std::mutex> lk(e->ws_mutex);
+    for (;;) {
+        bool any = false;
+        for (auto& w : e->ws) {
+            if (w.resident_kind == 0 || w.resident_batch != batch) continue;
+            any = true;
+            if (!w.busy) { w.busy = true; return &w; }
+        }
+        if (!any) return nullptr;
+        e->ws_cv.wait(lk);
+    }
+}
+struct WsGuard {       // mirrors WorkspaceGuard's return-to-pool-on-drop (network.rs:73-79)
+    dg_engine* e; Workspace* w;
+    WsGuard(dg_engine* e_) : e(e_), w(acquire(e_)) {}
+    WsGuard(dg_engine* e_, int resident_batch) : e(e_), w(acquire_resident(e_, resident_batch)) {}
+    ~WsGuard() { if (w) release(e, w); }
+};
+
+// ------------------------------------------------------------------------------------ weights
+
+void free_net(DeviceNet& n) {
+    for (void* p : n.allocations) cudaFree(p);
+    n = DeviceNet();
+}
+
+template <typename T>
+int32_t upload(dg_engine* e, DeviceNet& n, const std::vector<T>& host, T** dev) {
+    DG_CUDA(e, cudaMalloc(dev, host.size() * sizeof(T)));
+    n.allocations.push_back(*dev);
+    DG_CUDA(e, cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return DG_OK;
+}
+
+const dg::HostTensor* find(const dg::TensorMap& t, const std::string& name, const char* dtype, size_t min_elems) {
+    auto it = t.find(name);
+    if (it == t.end()) return nullptr;
+    const size_t esz = (it->second.dtype == "f2") ? 2 : (it->second.dtype == "i1") ? 1 : 4;
+    if (it->second.dtype != dtype || it->second.bytes.size() / esz < min_elems) return nullptr;
+    return &it->second;
+}
+
+float h2f(uint16_t bits) { __half_raw r; r.x = bits; return __half2float(__half(r)); }
+uint16_t f2h(float f) { __half h = __float2half_rn(f); return __half_raw(h).x; }
+
+// KRSC fp16 [cout][3][3][cin] -> [tap][ntot][kpad] at output-channel offset `n0` (zero elsewhere).
+void relayout_conv(const uint16_t* krsc, int cout, int cin, int ntot, int kpad, int n0, std::vector<uint16_t>& dst) {
+    for (int k = 0; k < cout; k++)
+        for (int tap = 0; tap < 9; tap++)
+            for (int c = 0; c < cin; c++)
+                dst[(static_cast<size_t>(tap) * ntot + n0 + k) * kpad + c] = krsc[(static_cast<size_t>(k) * 9 + tap) * cin + c];
+}
+
+int32_t build_conv(dg_engine* e, DeviceNet& n, ConvWeights& cw, const std::vector<uint16_t>& w, const std::vector<float>& bias,
+                   int ntot, int kpad, int box_rows) {
+    uint16_t* dw = nullptr;
+    int32_t rc = upload<uint16_t>(e, n, w, &dw);
+    if (rc) return rc;
+    cw.w = reinterpret_cast<__half*>(dw);
+    rc = upload<float>(e, n, bias, &cw.bias);
+    if (rc) return rc;
+    if (!make_tmap(e, &cw.tm, cw.w, kpad, 9ull * ntot, box_rows)) return fail(e, DG_ERR_CUDA, "cuTensorMapEncodeTiled failed for a filter");
+    return DG_OK;
+}
+
+// Restates Builder::get_workspace's tensor lookups (graph.rs:50-96) once, at load time.
+int32_t load_net(dg_engine* e, const dg::TensorMap& t) {
+    if (t.empty()) return fail(e, DG_ERR_MISSING_WEIGHTS, "no tensors");
+    auto scalar_i4 = [&](const char* name, int dflt) {
+        const dg::HostTensor* s = find(t, name, "i4", 1);
+        int v = dflt;
+        if (s) memcpy(&v, s->bytes.data(), 4);
+        return v;
+    };
+    const int channels = scalar_i4("num_channels:0", 128);   // layers/common.rs:22-50
+    const int samples = scalar_i4("num_samples:0", 8);
+    if (channels != kChan || samples != 8)
+        return fail(e, DG_ERR_KERNEL, "unsupported network shape: %d channels / %d samples (this engine is built for 128 / 8)", channels, samples);
+
+    DeviceNet n;
+    int32_t rc = DG_OK;
+    char name[96];
+    auto cleanup = [&](int32_t code) { free_net(n); return code; };
+
+    // 01_upsample (up_block.rs:42-44)
+    {
+        const dg::HostTensor* w = find(t, "01_upsample/conv_1:0", "f2", 128 * 9 * 32);
+        const dg::HostTensor* b = find(t, "01_upsample/conv_1/offset:0", "f2", 128);
+        if (!w || !b) return cleanup(fail(e, DG_ERR_MISSING_WEIGHTS, "01_upsample tensors missing or of wrong type/size"));
+        std::vector<uint16_t> wl(9 * 128 * 64, 0);
+        relayout_conv(reinterpret_cast<const uint16_t*>(w->bytes.data()), 128, 32, 128, 64, 0, wl);
+        std::vector<float> bl(128);
+        for (int i = 0; i < 128; i++) bl[i] = h2f(reinterpret_cast<const uint16_t*>(b->bytes.data())[i]);
+        if ((rc = build_conv(e, n, n.up, wl, bl, 128, 64, 64))) return cleanup(rc);
+    }
+    // NN_residual (residual_block.rs:40-78); discovery stops at the first missing block (graph.rs:76-96)
+    for (int i = 0;; i++) {
+        const dg::HostTensor *w[2], *b[2];
+        bool ok = true;
+        for (int j = 0; j < 2; j++) {
+            snprintf(name, sizeof name, "%02d_residual/conv_%d:0", i + 2, j + 1);
+            w[j] = find(t, name, "f2", 128 * 9 * 128);
+            snprintf(name, sizeof name, "%02d_residual/conv_%d/offset:0", i + 2, j + 1);
+            b[j] = find(t, name, "f2", 128);
+            ok = ok && w[j] && b[j];
+        }
+        if (!ok) break;
+        snprintf(name, sizeof name, "%02d_residual/alpha:0", i + 2);
+        float g = 0.5f;                                             // residual_block.rs:43,50
+        if (const dg::HostTensor* a = find(t, name, "f4", 1)) memcpy(&g, a->bytes.data(), 4);
+        n.gate.push_back(g);
+        n.c1.emplace_back();
+        n.c2.emplace_back();
+        for (int j = 0; j < 2; j++) {
+            std::vector<uint16_t> wl(9 * 128 * 128, 0);
+            relayout_conv(reinterpret_cast<const uint16_t*>(w[j]->bytes.data()), 128, 128, 128, 128, 0, wl);
+            std::vector<float> bl(128);
+            for (int k = 0; k < 128; k++) {
+                const float bv = h2f(reinterpret_cast<const uint16_t*>(b[j]->bytes.data())[k]);
+                // conv_2's offset is scaled by the gate in place, in fp16, once (residual_block.rs:72-74)
+                bl[k] = (j == 0) ? bv : h2f(f2h(static_cast<float>(static_cast<double>(g) * static_cast<double>(bv))));
+            }
+            if ((rc = build_conv(e, n, j == 0 ? n.c1.back() : n.c2.back(), wl, bl, 128, 128, 64))) return cleanup(rc);
+        }
+        n.num_blocks++;
+    }
+    // heads (policy_head.rs:43-103, value_head.rs:40-84); layer index = 2 + num_blocks (graph.rs:55)
+    const int hidx = 2 + n.num_blocks;
+    {
+        snprintf(name, sizeof name, "%02dp_policy/conv_1:0", hidx);
+        const dg::HostTensor* pw = find(t, name, "f2", 8 * 9 * 128);
+        snprintf(name, sizeof name, "%02dp_policy/conv_1/offset:0", hidx);
+        const dg::HostTensor* pb = find(t, name, "f2", 8);
+        snprintf(name, sizeof name, "%02dv_value/conv_1:0", hidx);
+        const dg::HostTensor* vw = find(t, name, "f2", 2 * 9 * 128);
+        snprintf(name, sizeof name, "%02dv_value/conv_1/offset:0", hidx);
+        const dg::HostTensor* vb = find(t, name, "f2", 2);
+        snprintf(name, sizeof name, "%02dp_policy/linear_1:0", hidx);
+        const dg::HostTensor* pl = find(t, name, "f2", 2888 * 362);
+        snprintf(name, sizeof name, "%02dp_policy/linear_1/offset:0", hidx);
+        const dg::HostTensor* plb = find(t, name, "f2", 362);
+        snprintf(name, sizeof name, "%02dv_value/linear_2:0", hidx);
+        const dg::HostTensor* vl = find(t, name, "f2", 722);
+        snprintf(name, sizeof name, "%02dv_value/linear_2/offset:0", hidx);
+        const dg::HostTensor* vlb = find(t, name, "f2", 1);
+        if (!pw || !pb || !vw || !vb || !pl || !plb || !vl || !vlb)
+            return cleanup(fail(e, DG_ERR_MISSING_WEIGHTS, "head tensors (%02dp_policy / %02dv_value) missing or of wrong type/size", hidx, hidx));
+        std::vector<uint16_t> wl(9 * kHeadChan * 128, 0);
+        relayout_conv(reinterpret_cast<const uint16_t*>(pw->bytes.data()), 8, 128, kHeadChan, 128, 0, wl);
+        relayout_conv(reinterpret_cast<const uint16_t*>(vw->bytes.data()), 2, 128, kHeadChan, 128, 8, wl);
+        std::vector<float> bl(kHeadChan, 0.f);
+        for (int i = 0; i < 8; i++) bl[i] = h2f(reinterpret_cast<const uint16_t*>(pb->bytes.data())[i]);
+        for (int i = 0; i < 2; i++) bl[8 + i] = h2f(reinterpret_cast<const uint16_t*>(vb->bytes.data())[i]);
+        if ((rc = build_conv(e, n, n.heads, wl, bl, kHeadChan, 128, kHeadChan))) return cleanup(rc);
+
+        const float temperature = e->cfg.softmax_temperature > 0.f ? e->cfg.softmax_temperature : 0.709888f;
+        n.tau = 1.0f / temperature;                                  // policy_head.rs:46
+        std::vector<uint16_t> pfc(reinterpret_cast<const uint16_t*>(pl->bytes.data()),
+                                  reinterpret_cast<const uint16_t*>(pl->bytes.data()) + 2888 * 362);
+        uint16_t* d = nullptr;
+        if ((rc = upload<uint16_t>(e, n, pfc, &d))) return cleanup(rc);
+        n.w_pfc = reinterpret_cast<__half*>(d);
+        std::vector<float> pfb(362);
+        for (int i = 0; i < 362; i++)   // offset scaled by tau in place, in fp16 (policy_head.rs:87-89)
+            pfb[i] = h2f(f2h(static_cast<float>(static_cast<double>(n.tau) *
+                                                 static_cast<double>(h2f(reinterpret_cast<const uint16_t*>(plb->bytes.data())[i])))));
+        if ((rc = upload<float>(e, n, pfb, &n.b_pfc))) return cleanup(rc);
+        std::vector<uint16_t> vfc(reinterpret_cast<const uint16_t*>(vl->bytes.data()),
+                                  reinterpret_cast<const uint16_t*>(vl->bytes.data()) + 722);
+        if ((rc = upload<uint16_t>(e, n, vfc, &d))) return cleanup(rc);
+        n.w_vfc = reinterpret_cast<__half*>(d);
+        n.b_vfc = h2f(reinterpret_cast<const uint16_t*>(vlb->bytes.data())[0]);
+    }
+    n.loaded = true;
+    free_net(e->net);
+    e->net = std::move(n);
+    return DG_OK;
+}
+
+// ------------------------------------------------------------------------------------ forward
+
+int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMap& tm_in, const __half* in, int cin,
+                 const ConvWeights& cw, int ntot, __half* out, int out_stride, const __half* skip, float alpha, float beta, int batch) {
+    if (e->cfg.flags & DG_FLAG_DEBUG_DIRECT_CONV) {
+        DG_CUDA(e, dg::launch_conv_direct(in, cin, cw.w, ntot, cw.bias, alpha, beta, skip, kChan, out, out_stride, batch, w.stream));
+        return DG_OK;
+    }
+    ConvTcParams p;
+    p.ntiles = dg_num_tiles(batch);
+    p.valid_rows = batch * DG_POS_ROWS;
+    p.out = out;
+    p.out_stride = out_stride;
+    p.skip = skip;
+    p.skip_stride = kChan;
+    p.bias = cw.bias;
+    p.alpha = alpha;
+    p.beta = beta;
+    p.desc_base_offset = (e->cfg.flags & DG_FLAG_DESC_BASE_OFFSET) ? 1 : 0;
+    DG_CUDA(e, dg::launch_conv_tc(shape, tm_in, cw.tm, p, e->num_sms, w.stream, false));
+    return DG_OK;
+}
+
+// Enqueues pack + tower (+ heads) of the batch resident in w.d_in.  blocks < 0 = whole network.
+// stage: 0 = everything, 1 = pack only, 2 = residual convolutions only (timing), 3 = everything but pack.
+int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int stage) {
+    const DeviceNet& n = e->net;
+    int32_t rc;
+    if (stage == 0 || stage == 1) {
+        if (w.resident_kind == 1) DG_CUDA(e, dg::launch_pack_features(w.d_in, w.feat, batch, w.stream));
+        else DG_CUDA(e, dg::launch_pack_compact(w.d_in, w.feat, batch, w.stream));
+        if (stage == 1) return DG_OK;
+    }
+    if (stage != 2)
+        if ((rc = run_conv(e, w, ConvTcShape::kUp, w.tm_feat, w.feat, 64, n.up, 128, w.x, kChan, nullptr, 1.f, 0.f, batch))) return rc;
+    const int nb = (blocks < 0 || blocks > n.num_blocks) ? n.num_blocks : blocks;
+    for (int i = 0; i < nb; i++) {
+        const float g = n.gate[i];
+        if ((rc = run_conv(e, w, ConvTcShape::kTower, w.tm_x, w.x, kChan, n.c1[i], 128, w.y, kChan, nullptr, 1.f, 0.f, batch))) return rc;
+        if ((rc = run_conv(e, w, ConvTcShape::kTower, w.tm_y, w.y, kChan, n.c2[i], 128, w.x, kChan, w.x, g, 1.0f - g, batch))) return rc;
+    }
+    if (blocks >= 0 || stage == 2) return DG_OK;
+    if ((rc = run_conv(e, w, ConvTcShape::kHeads, w.tm_x, w.x, kChan, n.heads, kHeadChan, w.h, kHeadChan, nullptr, 1.f, 0.f, batch))) return rc;
+    DG_CUDA(e, dg::launch_heads_fc(w.h, n.w_pfc, n.b_pfc, n.tau, n.w_vfc, n.b_vfc, batch, w.d_policy, w.d_value, w.stream));
+    return DG_OK;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int32_t forward_impl(dg_engine* e, const void* input, size_t bytes_per_pos, int kind, int batch, uint16_t* value_out, uint16_t* policy_out) {
+    if (!e) return DG_ERR_INVALID_ARGUMENT;
+    if (!input || !value_out || !policy_out) return fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch < 1 || batch > e->cfg.max_batch) return fail(e, DG_ERR_INVALID_ARGUMENT, "batch %d outside 1..%d", batch, e->cfg.max_batch);
+    if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    WsGuard guard(e);
+    Workspace& w = *guard.w;
+    const size_t in_bytes = bytes_per_pos * batch;
+    const void* src = input;
+    if (!is_pinned(input)) { memcpy(w.h_in, input, in_bytes); src = w.h_in; }
+    DG_CUDA(e, cudaMemcpyAsync(w.d_in, src, in_bytes, cudaMemcpyHostToDevice, w.stream));
+    w.resident_kind = kind;
+    w.resident_batch = batch;
+    int32_t rc = enqueue_network(e, w, batch, -1, 0);
+    if (rc) { cudaStreamSynchronize(w.stream); return rc; }
+    const bool pv = is_pinned(value_out), pp = is_pinned(policy_out);
+    DG_CUDA(e, cudaMemcpyAsync(pv ? static_cast<void*>(value_out) : w.h_value, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream));
+    DG_CUDA(e, cudaMemcpyAsync(pp ? static_cast<void*>(policy_out) : w.h_policy, w.d_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2, cudaMemcpyDeviceToHost, w.stream));
+    DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    if (!pv) memcpy(value_out, w.h_value, static_cast<size_t>(batch) * 2);
+    if (!pp) memcpy(policy_out, w.h_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2);
+    return DG_OK;
+}
+
+}  // namespace
+
+// ======================================================================================= C ABI
+
+extern "C" {
+
+int32_t dg_engine_abi_version(void) { return 1; }
+
+int32_t dg_engine_create(const dg_engine_config* config, dg_engine** out) {
+    if (!config || !out) return DG_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (config->max_batch < 1 || config->max_batch > 8192) return DG_ERR_INVALID_ARGUMENT;
+    dg_engine* e = new dg_engine();
+    e->cfg = *config;
+    if (e->cfg.num_workspaces <= 0) e->cfg.num_workspaces = 2;
+    *out = e;      // returned even on failure so the caller can read dg_engine_last_error, then destroy
+    DG_CUDA(e, cudaSetDevice(config->device));
+    cudaDeviceProp prop;
+    DG_CUDA(e, cudaGetDeviceProperties(&prop, config->device));
+    if (prop.major != 10)
+        return fail(e, DG_ERR_CUDA, "device %d is sm_%d%d; this engine only runs on sm_100 (B200) -- there is no fallback path",
+                    config->device, prop.major, prop.minor);
+    e->num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DG_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(e, DG_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+    e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    e->ws.resize(e->cfg.num_workspaces);
+    for (auto& w : e->ws) {
+        int32_t rc = create_workspace(e, w);
+        if (rc) return rc;
+    }
+    // leaf queue
+    LeafQueue& q = e->queue;
+    q.capacity = 4096;
+    while (q.capacity < 8ll * e->cfg.max_batch) q.capacity *= 2;
+    DG_CUDA(e, cudaHostAlloc(&q.ring, q.capacity * sizeof(dg_packed_position), cudaHostAllocMapped));
+    DG_CUDA(e, cudaHostAlloc(&q.res_policy, q.capacity * DG_POLICY_SIZE * 2, cudaHostAllocDefault));
+    DG_CUDA(e, cudaHostAlloc(&q.res_value, q.capacity * 2, cudaHostAllocDefault));
+    q.ready = new std::atomic<int64_t>[q.capacity];
+    q.done = new std::atomic<int64_t>[q.capacity];
+    for (int64_t i = 0; i < q.capacity; i++) { q.ready[i].store(0); q.done[i].store(0); }
+    return DG_OK;
+}
+
+void dg_engine_destroy(dg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& w : e->ws) destroy_workspace(w);
+    free_net(e->net);
+    if (e->queue.ring) cudaFreeHost(e->queue.ring);
+    if (e->queue.res_policy) cudaFreeHost(e->queue.res_policy);
+    if (e->queue.res_value) cudaFreeHost(e->queue.res_value);
+    delete[] e->queue.ready;
+    delete[] e->queue.done;
+    for (void* p : e->host_allocs) cudaFreeHost(p);
+    delete e;
+}
+
+const char* dg_engine_last_error(dg_engine* e) {
+    if (!e) return "null engine";
+    std::lock_guard<std::mutex> g(e->err_mutex);
+    return e->last_error.c_str();
+}
+
+int32_t dg_engine_num_blocks(dg_engine* e) { return e ? e->net.num_blocks : 0; }
+
+int32_t dg_engine_load_weights_json(dg_engine* e, const char* path) {
+    if (!e || !path) return DG_ERR_INVALID_ARGUMENT;
+    dg::TensorMap t;
+    std::string why;
+    int rc = dg::load_weights_file(path, t, why);
+    if (rc == 1) return fail(e, DG_ERR_MISSING_WEIGHTS, "%s: %s", path, why.c_str());
+    if (rc == 2) return fail(e, DG_ERR_MALFORMED_WEIGHTS, "%s: %s", path, why.c_str());
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    return load_net(e, t);
+}
+
+int32_t dg_engine_load_weights_raw(dg_engine* e, const dg_tensor_view* tensors, int32_t count) {
+    if (!e || (!tensors && count > 0)) return DG_ERR_INVALID_ARGUMENT;
+    dg::TensorMap t;
+    for (int i = 0; i < count; i++) {
+        if (!tensors[i].name || !tensors[i].dtype || (!tensors[i].data && tensors[i].nbytes)) return fail(e, DG_ERR_INVALID_ARGUMENT, "tensor %d is incomplete", i);
+        const std::string dt = tensors[i].dtype;
+        if (dt != "f2" && dt != "f4" && dt != "i4" && dt != "i1") return fail(e, DG_ERR_MALFORMED_WEIGHTS, "tensor %s has unknown type %s", tensors[i].name, dt.c_str());
+        dg::HostTensor ht;
+        ht.dtype = dt;
+        ht.bytes.assign(static_cast<const uint8_t*>(tensors[i].data), static_cast<const uint8_t*>(tensors[i].data) + tensors[i].nbytes);
+        t[tensors[i].name] = std::move(ht);
+    }
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    return load_net(e, t);
+}
+
+int32_t dg_engine_forward_f16(dg_engine* e, const uint16_t* features, int32_t batch, uint16_t* value_out, uint16_t* policy_out) {
+    return forward_impl(e, features, kFeatBytes, 1, batch, value_out, policy_out);
+}
+
+int32_t dg_engine_forward_packed(dg_engine* e, const dg_packed_position* positions, int32_t batch, uint16_t* value_out, uint16_t* policy_out) {
+    return forward_impl(e, positions, sizeof(dg_packed_position), 2, batch, value_out, policy_out);
+}
+
+int32_t dg_engine_synchronize(dg_engine* e) {
+    if (!e) return DG_ERR_INVALID_ARGUMENT;
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    DG_CUDA(e, cudaDeviceSynchronize());
+    return DG_OK;
+}
+
+void* dg_engine_alloc_host(dg_engine* e, uint64_t nbytes) {
+    if (!e || !nbytes) return nullptr;
+    void* p = nullptr;
+    cudaSetDevice(e->cfg.device);
+    if (cudaHostAlloc(&p, nbytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> g(e->err_mutex);
+    e->host_allocs.push_back(p);
+    return p;
+}
+
+void dg_engine_free_host(dg_engine* e, void* ptr) {
+    if (!e || !ptr) return;
+    {
+        std::lock_guard<std::mutex> g(e->err_mutex);
+        for (auto& p : e->host_allocs)
+            if (p == ptr) { p = e->host_allocs.back(); e->host_allocs.pop_back(); break; }
+    }
+    cudaFreeHost(ptr);
+}
+
+// ---------------------------------------------------------------------------------- leaf queue
+
+int64_t dg_engine_queue_push(dg_engine* e, const dg_packed_position* position) {
+    if (!e || !position) return DG_ERR_INVALID_ARGUMENT;
+    LeafQueue& q = e->queue;
+    int64_t t = q.head.load(std::memory_order_relaxed);
+    for (;;) {
+        if (t - q.completed.load(std::memory_order_acquire) >= q.capacity) return fail(e, DG_ERR_INVALID_ARGUMENT, "leaf queue full");
+        if (q.head.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel)) break;
+    }
+    const int64_t slot = t & (q.capacity - 1);
+    memcpy(&q.ring[slot], position, sizeof(dg_packed_position));
+    q.ready[slot].store(t + 1, std::memory_order_release);
+    return t;
+}
+
+int32_t dg_engine_queue_flush(dg_engine* e) {
+    if (!e) return DG_ERR_INVALID_ARGUMENT;
+    if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    LeafQueue& q = e->queue;
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    for (;;) {
+        int64_t start, end;
+        {   // claim a contiguous, fully written, non-wrapping range of at most max_batch leaves
+            std::lock_guard<std::mutex> g(q.claim_mutex);
+            start = q.claimed;
+            const int64_t head = q.head.load(std::memory_order_acquire);
+            end = start;
+            while (end < head && end - start < e->cfg.max_batch && ((end & (q.capacity - 1)) != 0 || end == start) &&
+                   q.ready[end & (q.capacity - 1)].load(std::memory_order_acquire) == end + 1)
+                end++;
+            q.claimed = end;
+        }
+        if (end == start) return DG_OK;
+        const int batch = static_cast<int>(end - start);
+        const int64_t slot = start & (q.capacity - 1);
+        int32_t rc;
+        {
+            WsGuard guard(e);
+            Workspace& w = *guard.w;
+            // the pack kernel gathers the leaves straight out of the mapped pinned ring
+            void* dev_ring = nullptr;
+            DG_CUDA(e, cudaHostGetDevicePointer(&dev_ring, q.ring + slot, 0));
+            w.resident_kind = 0;
+            w.resident_batch = 0;
+            DG_CUDA(e, dg::launch_pack_compact(dev_ring, w.feat, batch, w.stream));
+            rc = enqueue_network(e, w, batch, -1, 3);
+            if (rc == DG_OK) {
+                DG_CUDA(e, cudaMemcpyAsync(q.res_value + slot, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream));
+                DG_CUDA(e, cudaMemcpyAsync(q.res_policy + slot * DG_POLICY_SIZE, w.d_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2, cudaMemcpyDeviceToHost, w.stream));
+            }
+            DG_CUDA(e, cudaStreamSynchronize(w.stream));
+        }
+        for (int64_t t = start; t < end; t++) q.done[t & (q.capacity - 1)].store(rc == DG_OK ? t + 1 : -(t + 1), std::memory_order_release);
+        {   // advance the completed prefix
+            std::lock_guard<std::mutex> g(q.wait_mutex);
+            int64_t c = q.completed.load(std::memory_order_relaxed);
+            while (c < q.head.load(std::memory_order_acquire)) {
+                const int64_t d = q.done[c & (q.capacity - 1)].load(std::memory_order_acquire);
+                if (d != c + 1 && d != -(c + 1)) break;
+                c++;
+            }
+            q.completed.store(c, std::memory_order_release);
+        }
+        q.wait_cv.notify_all();
+        if (rc) return rc;
+    }
+}
+
+int32_t dg_engine_queue_wait(dg_engine* e, int64_t ticket, uint16_t* value_out, uint16_t* policy_out) {
+    if (!e || ticket < 0 || !value_out || !policy_out) return DG_ERR_INVALID_ARGUMENT;
+    LeafQueue& q = e->queue;
+    if (ticket >= q.head.load(std::memory_order_acquire)) return fail(e, DG_ERR_INVALID_ARGUMENT, "ticket %lld was never issued", static_cast<long long>(ticket));
+    const int64_t slot = ticket & (q.capacity - 1);
+    int64_t d;
+    {
+        std::unique_lock<std::mutex> lk(q.wait_mutex);
+        for (;;) {
+            d = q.done[slot].load(std::memory_order_acquire);
+            if (d == ticket + 1 || d == -(ticket + 1)) break;
+            if (d > ticket + 1 || d < -(ticket + 1)) return fail(e, DG_ERR_INVALID_ARGUMENT, "result of ticket %lld was overwritten", static_cast<long long>(ticket));
+            q.wait_cv.wait_for(lk, std::chrono::milliseconds(1));
+        }
+    }
+    if (d < 0) return fail(e, DG_ERR_KERNEL, "evaluation of ticket %lld failed", static_cast<long long>(ticket));
+    *value_out = reinterpret_cast<const uint16_t*>(q.res_value)[slot];
+    memcpy(policy_out, q.res_policy + slot * DG_POLICY_SIZE, DG_POLICY_SIZE * 2);
+    return DG_OK;
+}
+
+// ---------------------------------------------------------------------------------- measurement
+
+int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, float* ms_total, float* tower_ms, int32_t* launches) {
+    if (!e || iters < 1) return DG_ERR_INVALID_ARGUMENT;
+    if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    WsGuard guard(e, batch);
+    if (!guard.w) return fail(e, DG_ERR_INVALID_ARGUMENT, "no workspace holds a resident batch of %d positions (run a forward first)", batch);
+    Workspace& w = *guard.w;
+    int32_t rc;
+    DG_CUDA(e, cudaEventRecord(w.ev0, w.stream));
+    for (int i = 0; i < iters; i++)
+        if ((rc = enqueue_network(e, w, batch, -1, 0))) return rc;
+    DG_CUDA(e, cudaEventRecord(w.ev1, w.stream));
+    DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    float ms = 0.f;
+    DG_CUDA(e, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+    if (ms_total) *ms_total = ms;
+    if (launches) *launches = 4 + 2 * e->net.num_blocks;      // pack, up, 2 per block, head conv, head fc
+    if (tower_ms) {
+        DG_CUDA(e, cudaEventRecord(w.ev0, w.stream));
+        for (int i = 0; i < iters; i++)
+            if ((rc = enqueue_network(e, w, batch, -1, 2))) return rc;
+        DG_CUDA(e, cudaEventRecord(w.ev1, w.stream));
+        DG_CUDA(e, cudaStreamSynchronize(w.stream));
+        DG_CUDA(e, cudaEventElapsedTime(tower_ms, w.ev0, w.ev1));
+        // leave the workspace holding a complete forward again
+        if ((rc = enqueue_network(e, w, batch, -1, 0))) return rc;
+        DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    }
+    return DG_OK;
+}
+
+int32_t dg_engine_debug_read_tower(dg_engine* e, int32_t layer, int32_t batch, uint16_t* out) {
+    if (!e || !out) return DG_ERR_INVALID_ARGUMENT;
+    if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    WsGuard guard(e, batch);
+    if (!guard.w) return fail(e, DG_ERR_INVALID_ARGUMENT, "no workspace holds a resident batch of %d positions", batch);
+    Workspace& w = *guard.w;
+    const int blocks = (layer < 0) ? e->net.num_blocks : layer;
+    int32_t rc = enqueue_network(e, w, batch, blocks, 0);
+    if (rc) return rc;
+    const size_t rows = static_cast<size_t>(batch) * DG_POS_ROWS;
+    std::vector<uint16_t> host(rows * kChan);
+    DG_CUDA(e, cudaMemcpyAsync(host.data(), w.x + static_cast<size_t>(DG_GUARD_ROWS) * kChan, rows * kChan * 2, cudaMemcpyDeviceToHost, w.stream));
+    DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    for (int n = 0; n < batch; n++)
+        for (int y = 0; y < 19; y++)
+            memcpy(out + (static_cast<size_t>(n) * 361 + y * 19) * kChan,
+                   host.data() + (static_cast<size_t>(n) * DG_POS_ROWS + y * DG_LINE_STRIDE) * kChan, 19 * kChan * 2);
+    return DG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference's `dg_nn` crate surface over the C ABI.
+
+Same names, argument meaning and error behaviour as `src/libdg_nn/lib.rs:33-36`:
+
+* `Network.new()`            -- `network.rs:92-124` (searches the same five paths for `dream_go.json`)
+* `Network.get_workspace(n)` -- `network.rs:132-143` (a guard that is returned to the pool on exit)
+* `forward(workspace, feats)`-- `graph.rs:123-158`  -> `OutputMap` with `.unwrap() -> (value, policy)`
+* `Network.synchronize()`    -- `network.rs:145-159`
+* `Error`                    -- `error.rs:19-24`
+
+All arithmetic happens in `libdg_engine.so` (hand-written sm_100a CUDA, `csrc/`).  There is no
+CPU path: importing works anywhere, but creating a `Network` without the built library or without
+a B200 raises.  numpy is used only to carry host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdg_engine.so")
+
+FEATURE_SIZE = 11552
+POLICY_SIZE = 362
+
+DG_OK = 0
+FLAG_DEBUG_DIRECT_CONV = 0x1
+FLAG_DESC_BASE_OFFSET = 0x2
+
+
+class Error(Exception):
+    """`enum Error { CuDNN(Status), Cuda(Error), MalformedWeights, MissingWeights }`"""
+
+    KINDS = {-1: "Cuda", -2: "CuDNN", -3: "MalformedWeights", -4: "MissingWeights", -5: "InvalidArgument"}
+
+    def __init__(self, code: int, message: str = ""):
+        self.code = code
+        self.kind = self.KINDS.get(code, f"Unknown({code})")
+        super().__init__(f"{self.kind}: {message}" if message else self.kind)
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_batch", C.c_int32), ("softmax_temperature", C.c_float),
+                ("num_workspaces", C.c_int32), ("flags", C.c_uint32)]
+
+
+class _TensorView(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("dtype", C.c_char_p), ("data", C.c_void_p), ("nbytes", C.c_uint64)]
+
+
+PACKED_DTYPE = np.dtype([("planes", "<u4", (361,)), ("k_bits", "<u2"), ("reserved", "<u2")])   # dg_packed_position
+
+_lib = None
+
+# every symbol include/dg_engine.h declares: name -> (restype, argtypes)
+ABI = {
+    "dg_engine_abi_version": (C.c_int32, []),
+    "dg_engine_create": (C.c_int32, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
+    "dg_engine_destroy": (None, [C.c_void_p]),
+    "dg_engine_load_weights_json": (C.c_int32, [C.c_void_p, C.c_char_p]),
+    "dg_engine_load_weights_raw": (C.c_int32, [C.c_void_p, C.POINTER(_TensorView), C.c_int32]),
+    "dg_engine_forward_f16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dg_engine_forward_packed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dg_engine_queue_push": (C.c_int64, [C.c_void_p, C.c_void_p]),
+    "dg_engine_queue_flush": (C.c_int32, [C.c_void_p]),
+    "dg_engine_queue_wait": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dg_engine_synchronize": (C.c_int32, [C.c_void_p]),
+    "dg_engine_alloc_host": (C.c_void_p, [C.c_void_p, C.c_uint64]),
+    "dg_engine_free_host": (None, [C.c_void_p, C.c_void_p]),
+    "dg_engine_last_error": (C.c_char_p, [C.c_void_p]),
+    "dg_engine_num_blocks": (C.c_int32, [C.c_void_p]),
+    "dg_engine_time_resident": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "dg_engine_debug_read_tower": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Loads the engine library; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(make -C dream_go_b200/csrc); the engine has no CPU or library fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+class OutputMap:
+    """`OutputMap<f16>` (`src/libdg_nn/output_map.rs:15-33`)."""
+
+    def __init__(self, value: np.ndarray, policy: np.ndarray):
+        self.value, self.policy = value, policy
+
+    def unwrap(self) -> Tuple[np.ndarray, np.ndarray]:
+        return self.value, self.policy
+
+
+class Workspace:
+    """`WorkspaceGuard`: exclusive use of one batch size until the `with` block ends.  The engine
+    pools the actual device workspaces internally; the guard only pins the batch size, which is all
+    the reference's callers rely on (`predictors/nn.rs:93-94`)."""
+
+    def __init__(self, network: "Network", batch_size: int):
+        self.network, self.batch_size = network, batch_size
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class Network:
+    """Pool of workspaces that can be used for network evaluations (`network.rs:80-160`)."""
+
+    SEARCH_PATHS = ["dream_go.json", "models/dream_go.json", "/usr/share/dreamgo/dream_go.json",
+                    "/usr/share/dream_go/dream_go.json"]
+
+    def __init__(self, device: int = 0, max_batch: int = 256, softmax_temperature: float = 0.709888,
+                 num_workspaces: int = 2, flags: int = 0):
+        self._handle = C.c_void_p()
+        cfg = _Config(device, max_batch, softmax_temperature, num_workspaces, flags)
+        rc = lib().dg_engine_create(C.byref(cfg), C.byref(self._handle))
+        if rc != DG_OK:
+            msg = self._last_error()
+            if self._handle:
+                lib().dg_engine_destroy(self._handle)
+                self._handle = C.c_void_p()
+            raise Error(rc, msg)
+        self.max_batch = max_batch
+        self._pinned = []
+
+    # -- construction ---------------------------------------------------------------------------
+    @classmethod
+    def new(cls, **kwargs) -> Optional["Network"]:
+        """`Network::new()`: first weights file found in the reference's search order, else None.
+        A malformed file raises (the reference panics, `network.rs:111-118`)."""
+        exe_json = os.path.splitext(os.path.abspath(sys.argv[0] or "dream_go"))[0] + ".json"
+        for path in [exe_json] + cls.SEARCH_PATHS:
+            net = cls(**kwargs)
+            try:
+                net.load_json(path)
+                return net
+            except Error as err:
+                net.close()
+                if err.kind != "MissingWeights":
+                    raise
+        return None
+
+    @classmethod
+    def from_tensors(cls, tensors: Dict[str, np.ndarray], **kwargs) -> "Network":
+        net = cls(**kwargs)
+        net.load_tensors(tensors)
+        return net
+
+    def load_json(self, path: str) -> None:
+        self._check(lib().dg_engine_load_weights_json(self._handle, os.fsencode(path)))
+
+    def load_tensors(self, tensors: Dict[str, np.ndarray]) -> None:
+        codes = {np.dtype(np.float16): b"f2", np.dtype(np.float32): b"f4", np.dtype(np.int32): b"i4", np.dtype(np.int8): b"i1"}
+        keep, views = [], (_TensorView * len(tensors))()
+        for i, (name, value) in enumerate(tensors.items()):
+            arr = np.ascontiguousarray(value)
+            keep.append(arr)
+            views[i] = _TensorView(name.encode(), codes[arr.dtype], arr.ctypes.data, arr.nbytes)
+        self._check(lib().dg_engine_load_weights_raw(self._handle, views, len(tensors)))
+
+    # -- the dg_nn surface ------------------------------------------------------------------------
+    def get_workspace(self, batch_size: int) -> Workspace:
+        if batch_size < 1 or batch_size > self.max_batch:
+            raise Error(-5, f"batch {batch_size} outside 1..{self.max_batch}")
+        return Workspace(self, batch_size)
+
+    def synchronize(self) -> None:
+        self._check(lib().dg_engine_synchronize(self._handle))
+
+    @property
+    def num_blocks(self) -> int:
+        return int(lib().dg_engine_num_blocks(self._handle))
+
+    # -- extras used by the harness ---------------------------------------------------------------
+    def pinned(self, shape, dtype) -> np.ndarray:
+        """numpy view of pinned host memory from dg_engine_alloc_host (freed with the network)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        ptr = lib().dg_engine_alloc_host(self._handle, nbytes)
+        if not ptr:
+            raise Error(-1, "dg_engine_alloc_host failed")
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def forward_into(self, features: np.ndarray, value: np.ndarray, policy: np.ndarray, packed: bool = False) -> None:
+        batch = value.shape[0]
+        fn = lib().dg_engine_forward_packed if packed else lib().dg_engine_forward_f16
+        self._check(fn(self._handle, features.ctypes.data, batch, value.ctypes.data, policy.ctypes.data))
+
+    def forward_packed(self, positions: np.ndarray) -> OutputMap:
+        pos = np.ascontiguousarray(positions, dtype=PACKED_DTYPE).reshape(-1)
+        value = np.empty((pos.shape[0],), np.float16)
+        policy = np.empty((pos.shape[0], POLICY_SIZE), np.float16)
+        self.forward_into(pos, value, policy, packed=True)
+        return OutputMap(value, policy)
+
+    def queue_push(self, position: np.ndarray) -> int:
+        pos = np.ascontiguousarray(position, dtype=PACKED_DTYPE).reshape(1)
+        ticket = int(lib().dg_engine_queue_push(self._handle, pos.ctypes.data))
+        if ticket < 0:
+            raise Error(ticket, self._last_error())
+        return ticket
+
+    def queue_flush(self) -> None:
+        self._check(lib().dg_engine_queue_flush(self._handle))
+
+    def queue_wait(self, ticket: int) -> Tuple[np.float16, np.ndarray]:
+        value = np.empty((1,), np.float16)
+        policy = np.empty((POLICY_SIZE,), np.float16)
+        self._check(lib().dg_engine_queue_wait(self._handle, ticket, value.ctypes.data, policy.ctypes.data))
+        return value[0], policy
+
+    def time_resident(self, batch: int, iters: int, tower: bool = True) -> Tuple[float, float, int]:
+        """(ms for `iters` resident forwards, ms for the residual-conv launches of `iters` forwards, launches/forward)"""
+        ms, tms, launches = C.c_float(), C.c_float(), C.c_int32()
+        self._check(lib().dg_engine_time_resident(self._handle, batch, iters, C.byref(ms),
+                                                  C.byref(tms) if tower else None, C.byref(launches)))
+        return ms.value, tms.value, launches.value
+
+    def debug_read_tower(self, layer: int, batch: int) -> np.ndarray:
+        out = np.empty((batch, 361, 128), np.float16)
+        self._check(lib().dg_engine_debug_read_tower(self._handle, layer, batch, out.ctypes.data))
+        return out
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _last_error(self) -> str:
+        if not self._handle:
+            return ""
+        msg = lib().dg_engine_last_error(self._handle)
+        return msg.decode(errors="replace") if msg else ""
+
+    def _check(self, rc: int) -> None:
+        if rc != DG_OK:
+            raise Error(rc, self._last_error())
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            lib().dg_engine_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def forward(workspace: Workspace, features: np.ndarray) -> OutputMap:
+    """`dg_nn::forward(&mut Workspace, &[f16]) -> Result<OutputMap<f16>, Error>` (`graph.rs:123-158`).
+
+    `features` holds `batch * 11552` fp16 values, NHWC (`32*(19*y + x) + c`); the result carries
+    `value[batch]` (post-tanh) and `policy[batch * 362]` (post-softmax), both fp16."""
+    feats = np.ascontiguousarray(features)
+    if feats.dtype != np.float16:
+        raise Error(-5, "features must be fp16")
+    batch = workspace.batch_size
+    if feats.size != batch * FEATURE_SIZE:      # debug_assert_eq!, graph.rs:124-125
+        raise Error(-5, f"expected {batch * FEATURE_SIZE} features, got {feats.size}")
+    value = np.empty((batch,), np.float16)
+    policy = np.empty((batch * POLICY_SIZE,), np.float16)
+    workspace.network.forward_into(feats, value, policy)
+    return OutputMap(value, policy)

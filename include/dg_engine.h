@@ -1,0 +1,152 @@
+/*
+ * dg_engine.h -- C ABI of the B200 (sm_100a) self-play inference engine.
+ *
+ * This is the drop-in boundary for dream-go's neural-network hot path.  The
+ * reference boundary is a Rust crate API (`src/libdg_nn/lib.rs:33-36`:
+ * `Network`, `Workspace`, `WorkspaceGuard`, `forward`, `OutputMap`, `Error`)
+ * whose only native edge is `libdg_cuda`'s `extern "C"` bindings to
+ * cudart/cuDNN (the files under `src/libdg_cuda/cudnn/`).  A maintainer replaces the body
+ * of `libdg_nn` with ~100 lines of `extern "C"` calls into this library (the
+ * stub is shown in INTEGRATION.md); nothing above `dg_nn::forward` changes.
+ *
+ * Plain pointers and sizes only -- no torch, no C++ types.  All functions are
+ * thread-safe on one engine unless noted.  One engine owns one CUDA device.
+ *
+ * Status codes: 0 = OK, negatives map onto the reference's
+ * `enum Error { CuDNN(Status), Cuda(Error), MalformedWeights, MissingWeights }`
+ * (`src/libdg_nn/error.rs:19-24`).
+ */
+#ifndef DG_ENGINE_H
+#define DG_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DG_OK                      0
+#define DG_ERR_CUDA               -1  /* Error::Cuda(..)   -- a CUDA runtime/driver call failed */
+#define DG_ERR_KERNEL             -2  /* Error::CuDNN(..)  -- the compute path rejected the request (there is no cuDNN here) */
+#define DG_ERR_MALFORMED_WEIGHTS  -3  /* Error::MalformedWeights */
+#define DG_ERR_MISSING_WEIGHTS    -4  /* Error::MissingWeights   */
+#define DG_ERR_INVALID_ARGUMENT   -5  /* reference: debug_assert / panic (graph.rs:124-125, nn.rs:85) */
+
+/* Network geometry (src/libdg_go/utils/features.rs:88-96, layers/common.rs:22-25). */
+#define DG_NUM_FEATURES   32
+#define DG_NUM_POINTS     361
+#define DG_POLICY_SIZE    362
+#define DG_FEATURE_SIZE   (DG_NUM_POINTS * DG_NUM_FEATURES)   /* 11,552 fp16 per position */
+
+/* dg_engine_config.flags */
+#define DG_FLAG_DEBUG_DIRECT_CONV  0x1u  /* tests only: run every convolution on the slow one-thread-per-output
+                                            cross-check kernel instead of the tcgen05 kernel */
+#define DG_FLAG_DESC_BASE_OFFSET   0x2u  /* debug: encode (addr>>7)&7 in the UMMA descriptor base-offset field */
+
+typedef struct dg_engine dg_engine;
+
+/* Replaces the implicit configuration of `Network::new()` + `Builder::get_workspace`
+ * (src/libdg_nn/network.rs:92-124, graph.rs:50-74) and the `SOFTMAX_TEMPERATURE`
+ * global (src/libdg_utils/config.rs:176-177, baked in at policy_head.rs:46). */
+typedef struct dg_engine_config {
+    int32_t  device;               /* CUDA ordinal; the reference picks it with cudaSetDevice (predictors/nn.rs:87-89) */
+    int32_t  max_batch;            /* largest batch a single forward may carry (>= 1) */
+    float    softmax_temperature;  /* <= 0 -> 0.709888 */
+    int32_t  num_workspaces;       /* forwards that may be in flight concurrently; <= 0 -> 2 (nn.rs:64-67) */
+    uint32_t flags;
+} dg_engine_config;
+
+/* One named tensor of the weight file, as `loader.rs:36-100` would decode it:
+ * dtype is the file's "t" field ("f2", "f4", "i4", "i1"), data the decoded
+ * little-endian elements.  Names are the reference's JSON keys
+ * ("01_upsample/conv_1:0", ... -- SURVEY.md Appendix A). */
+typedef struct dg_tensor_view {
+    const char* name;
+    const char* dtype;
+    const void* data;
+    uint64_t    nbytes;
+} dg_tensor_view;
+
+/* Lossless compact form of one V1 feature tensor (features.rs:154-250): every
+ * plane is binary except planes 0/1 which are the constant `k`, so a position
+ * is 361 32-bit plane masks + k.  bit c of planes[p] set <=> feature (p, c) is
+ * non-zero; bits 0 and 1 mean "value k_bits", all others mean 1.0. */
+typedef struct dg_packed_position {
+    uint32_t planes[DG_NUM_POINTS];
+    uint16_t k_bits;               /* fp16 bits of k = clamp(0.5 + 0.5*komi/7.5, 0, 1) (features.rs:236) */
+    uint16_t reserved;
+} dg_packed_position;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* `Network::new()` minus the file search.  Fails with DG_ERR_CUDA when the device is missing
+ * or is not an sm_100 part -- there is no CPU or library fallback. */
+int32_t dg_engine_create(const dg_engine_config* config, dg_engine** out);
+void    dg_engine_destroy(dg_engine* engine);
+
+/* `loader::load(path)` (src/libdg_nn/loader.rs:102-116): JSON + base85 weight file.
+ * Missing/unreadable/empty file -> DG_ERR_MISSING_WEIGHTS, undecodable -> DG_ERR_MALFORMED_WEIGHTS.
+ * Weights are uploaded (and re-laid-out for the tensor cores) eagerly, replacing the lazy
+ * per-tensor upload of src/libdg_nn/tensor.rs:123-141.  Not thread-safe against forwards. */
+int32_t dg_engine_load_weights_json(dg_engine* engine, const char* path);
+/* Same, from decoded tensors (tests and embedders that already hold the tensors). */
+int32_t dg_engine_load_weights_raw(dg_engine* engine, const dg_tensor_view* tensors, int32_t count);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* `dg_nn::forward(&mut Workspace, &[f16]) -> OutputMap<f16>` (src/libdg_nn/graph.rs:123-158)
+ * fused with `Network::get_workspace(batch)` (network.rs:132-143): blocking, host buffers.
+ *   features   : batch * 11,552 fp16 bit patterns, NHWC (index 32*(19y+x)+c)
+ *   value_out  : batch fp16 (post-tanh)            policy_out : batch * 362 fp16 (post-softmax)
+ * Caller-owned buffers are not retained after return.  Buffers obtained from
+ * dg_engine_alloc_host are DMA'd directly; any other pointer is staged. */
+int32_t dg_engine_forward_f16(dg_engine* engine, const uint16_t* features, int32_t batch,
+                              uint16_t* value_out, uint16_t* policy_out);
+
+/* Same network evaluation from compact positions; the device expands them to NHWC fp16
+ * (replaces the 23,104-byte-per-leaf host copy of pool/batch.rs:87-96 with 1,448 bytes). */
+int32_t dg_engine_forward_packed(dg_engine* engine, const dg_packed_position* positions, int32_t batch,
+                                 uint16_t* value_out, uint16_t* policy_out);
+
+/* ---- leaf-batch queue (replaces pool::Batcher, src/libdg_mcts/pool/batch.rs:61-124) ---------- */
+
+/* Lock-free multi-producer enqueue of one leaf.  Returns a ticket (>= 0) or a negative status
+ * when the ring is full (caller should dg_engine_queue_flush and retry). */
+int64_t dg_engine_queue_push(dg_engine* engine, const dg_packed_position* position);
+/* Evaluates every leaf pushed so far (in batches of <= max_batch).  Any thread may call it;
+ * concurrent flushes take disjoint ticket ranges. */
+int32_t dg_engine_queue_flush(dg_engine* engine);
+/* Blocks until `ticket` has been evaluated, then copies its outputs (1 + 362 fp16). */
+int32_t dg_engine_queue_wait(dg_engine* engine, int64_t ticket, uint16_t* value_out, uint16_t* policy_out);
+
+/* ---- housekeeping -------------------------------------------------------------------------- */
+
+/* `Network::synchronize()` (network.rs:145-159): waits for all in-flight work on the device. */
+int32_t dg_engine_synchronize(dg_engine* engine);
+/* Pinned host memory the forward calls can DMA from/to directly. */
+void*   dg_engine_alloc_host(dg_engine* engine, uint64_t nbytes);
+void    dg_engine_free_host(dg_engine* engine, void* ptr);
+/* Last error text of this engine (valid until the next failing call on it). */
+const char* dg_engine_last_error(dg_engine* engine);
+/* Network shape discovered from the weights (graph.rs:76-96). */
+int32_t dg_engine_num_blocks(dg_engine* engine);
+/* Library/ABI version, for the FFI shim to assert on. */
+int32_t dg_engine_abi_version(void);
+
+/* ---- measurement hooks (bench.py, tests) ---------------------------------------------------- */
+
+/* Runs `iters` forwards of `batch` positions whose inputs are ALREADY resident in device
+ * memory (the last batch given to dg_engine_forward_*), timed with CUDA events on the
+ * engine's own stream.  ms_total = elapsed device time of all iterations.
+ * tower_ms (optional) = time of the residual-tower launches only, measured in a second pass
+ * with events around those launches. launches (optional) = kernels launched per forward. */
+int32_t dg_engine_time_resident(dg_engine* engine, int32_t batch, int32_t iters,
+                                float* ms_total, float* tower_ms, int32_t* launches);
+/* Re-evaluates the resident batch up to `layer` (0 = up-sample, i = residual block i,
+ * -1 = last block) and copies that activation into out[batch][361][128] fp16 (tests). */
+int32_t dg_engine_debug_read_tower(dg_engine* engine, int32_t layer, int32_t batch, uint16_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DG_ENGINE_H */
