@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""Benchmark of the self-play NN evaluation path (BASELINE.json configs[1]):
+9-block x 128-filter residual tower + heads, batch 256, synthetic weights and positions.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one forward of one batch (256 positions) through the whole network.  Prints ONE
+JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+
+* value      : NN evals/s with the batch already resident in HBM; every step timed with its own
+               CUDA-event pair on the engine's stream, L2 flushed (256 MiB memset) between steps.
+* e2e        : the same through the reference-facing C-ABI call `dg_engine_forward_f16`
+               (== dg_nn::forward) from pinned HOST buffers, H2D + D2H inside the timed region.
+* roofline   : dominant kernel = conv3x3_tc_kernel<2,64> (18 launches per step); tensor bound.
+* cpu_baseline / --impl reference : the CPU oracle port of dg_nn::forward on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 256
+NUM_BLOCKS = 9
+METRIC = "nn_evals_per_s"
+UNIT = "evals/s"
+FLOP_PER_EVAL = 2 * 976_681_890
+TOWER_CONV_FLOP_PER_POS = 2 * 361 * 1152 * 128    # one 3x3 128->128 convolution, algorithmic
+WORKLOAD = "residual tower 9-block x 128-filter forward, batch=256 (BASELINE.json configs[1])"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured"
+    return 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        top = sorted(sm)[len(sm) // 2:]             # upper half = samples under load
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_rate(seconds_target: float, steps: int = 1, warmup: int = 0):
+    """Times the CPU oracle port of dg_nn::forward on a bounded sample; returns (evals/s, info)."""
+    from dream_go_b200 import weights
+    from oracle import oracle
+    net = weights.synthetic_network(seed=20261017, num_blocks=NUM_BLOCKS)
+    onet = oracle.OracleNetwork(net)
+    probe = weights.bernoulli_features(2, seed=11)
+    t0 = time.perf_counter()
+    onet.forward(probe)
+    per_pos = (time.perf_counter() - t0) / 2
+    sample = int(max(2, min(BATCH, seconds_target / max(per_pos, 1e-6) / max(steps + warmup, 1))))
+    feats = weights.bernoulli_features(sample, seed=12)
+    for _ in range(warmup):
+        onet.forward(feats)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        onet.forward(feats)
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, {"cores": oracle.num_threads(), "kind": "port", "seconds": dt,
+                                 "sample": f"{sample} of the {BATCH} positions of one batch x {steps} step(s), same weights/inputs distribution"}
+
+
+def run_reference(args, rank: int):
+    """`--impl reference`: the reference's CPU-side restatement (oracle port; the Rust + cuDNN
+    reference cannot be built in this image) on the host cores."""
+    if rank != 0:
+        return
+    rate, info = oracle_rate(seconds_target=60.0, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+    per_step_ms = 1e3 * info["seconds"] / max(args.steps, 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": info["sample"]},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    from dream_go_b200 import nn, weights
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tensors = weights.synthetic_network(seed=20261017, num_blocks=NUM_BLOCKS)
+    net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=BATCH, num_workspaces=1)
+    feats = net.pinned((BATCH, 361, 32), np.float16)
+    feats[...] = weights.bernoulli_features(BATCH, seed=1000 + rank)       # each rank (shard) has its own positions
+    value = net.pinned((BATCH,), np.float16)
+    policy = net.pinned((BATCH, 362), np.float16)
+
+    # ---- warm-up (also makes the batch resident) -------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        net.forward_into(feats, value, policy)
+    assert np.isfinite(policy.astype(np.float32)).all() and abs(float(policy[0].astype(np.float32).sum()) - 1.0) < 2e-2
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    barrier()
+    net.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        ms_total, tower_ms, launches = net.time_resident(BATCH, args.steps, tower=True, flush_l2=True)
+        net.synchronize()
+    barrier()
+    ms_total = max_over_ranks(ms_total)
+    ms_per_step = ms_total / args.steps
+    value_evals = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI from pinned host buffers --------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net.forward_into(feats, value, policy)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_evals = world * BATCH * args.steps / e2e_s
+    packed = net.pinned((BATCH,), nn.PACKED_DTYPE)
+    packed[...] = nn.pack_positions(feats)
+    net.forward_into(packed, value, policy, packed=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net.forward_into(packed, value, policy, packed=True)
+    e2e_packed_s = max_over_ranks(time.perf_counter() - t0)
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak_tf, _peak_gbs, peak_kind = measured_peaks()
+    conv_launch_s = tower_ms * 1e-3 / (args.steps * 2 * NUM_BLOCKS)
+    achieved_tf = BATCH * TOWER_CONV_FLOP_PER_POS / conv_launch_s / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("conv3x3_tc_kernel<2,64>_dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value_evals, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "blocks": NUM_BLOCKS, "filters": 128,
+                   "inputs": "iid Bernoulli(0.2) fp16 features (dg_tests/benches/batch_sizes.rs:44-49), seeded He-init weights",
+                   "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)",
+                   "parallelism": f"{world} independent engine shard(s), no collective"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_evals, "unit": UNIT, "h2d_bytes_per_step": BATCH * 11552 * 2, "d2h_bytes_per_step": BATCH * 363 * 2,
+                "call": "dg_engine_forward_f16 (pinned host buffers, blocking)"},
+        "e2e_packed": {"value": world * BATCH * args.steps / e2e_packed_s, "unit": UNIT,
+                       "h2d_bytes_per_step": BATCH * nn.PACKED_DTYPE.itemsize, "d2h_bytes_per_step": BATCH * 363 * 2,
+                       "call": "dg_engine_forward_packed"},
+        "gpu_launches": launches * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel<2,64> (3x3 128->128, 18 launches/step)",
+                     "achieved": achieved_tf, "peak": peak_tf, "peak_kind": f"{peak_kind} burst bf16 (MEASURED_PEAKS.json)",
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                     "us_per_launch": conv_launch_s * 1e6,
+                     "whole_net_frac": (value_evals / world) * FLOP_PER_EVAL / (peak_tf * 1e12)},
+    }
+    if world == 1 and not os.environ.get("DG_BENCH_SKIP_CPU"):      # skipped only under the profiler
+        rate, info = oracle_rate(seconds_target=15.0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

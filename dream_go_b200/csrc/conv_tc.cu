@@ -10,7 +10,9 @@
 //     launch (9 taps x NH k-halves x [BN x 64] fp16, 128B-swizzled, loaded once by TMA);
 //   * per 128-row tile ONE TMA box of 170 rows x 64 channels (tile + 21-row halo each side) is
 //     staged per k-half; the nine taps are nine UMMA descriptors that start at different ROW
-//     offsets inside that box -- no im2col, activations are read from L2 1.33x instead of 9x;
+//     offsets inside that box -- no im2col, activations are read from L2 1.33x instead of 9x.
+//     (The 128B swizzle is a function of the absolute shared-memory address, so a descriptor may
+//     start at any 128-byte row of a TMA-written box with base_offset = 0; verified on B200.)
 //   * tcgen05.mma (M=128, N=BN, K=16) accumulates in TMEM (double-buffered accumulator) so the
 //     epilogue of tile i overlaps the MMAs of tile i+1;
 //   * epilogue: tcgen05.ld -> alpha*acc + bias (+ beta*skip) -> ReLU -> zero the halo rows ->
@@ -130,11 +132,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
                     for (int tap = 0; tap < 9; tap++) {
                         const int row_off = DG_HALO_ROWS + (tap / 3 - 1) * DG_LINE_STRIDE + (tap % 3 - 1);
                         const uint32_t a_tap = a_addr + row_off * 128;
-                        const uint32_t bo = p.desc_base_offset ? ((a_tap >> 7) & 7u) : 0u;
                         const uint32_t b_tap = w_addr + (tap * NH + h) * L::kSlab;
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            umma_f16_ss(d_tmem, umma_desc_sw128(a_tap + k * 32, bo), umma_desc_sw128(b_tap + k * 32, 0), kIdesc,
+                            umma_f16_ss(d_tmem, umma_desc_sw128(a_tap + k * 32), umma_desc_sw128(b_tap + k * 32), kIdesc,
                                         accumulate);
                             accumulate = 1;
                         }

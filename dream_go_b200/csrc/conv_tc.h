@@ -15,7 +15,6 @@ struct ConvTcParams {
     const float* bias;          // [Cout] fp32 (already scaled and fp16-rounded where the reference does so)
     float alpha;                // scale of the convolution result
     float beta;                 // scale of the skip input
-    int desc_base_offset;       // debug: fill the UMMA descriptor base-offset field
 };
 
 enum class ConvTcShape {

@@ -99,6 +99,7 @@ struct dg_engine {
     std::mutex err_mutex;
     std::string last_error;
     std::vector<void*> host_allocs;
+    void* flush_buf = nullptr;
 };
 
 namespace {
@@ -381,7 +382,6 @@ int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMa
     p.bias = cw.bias;
     p.alpha = alpha;
     p.beta = beta;
-    p.desc_base_offset = (e->cfg.flags & DG_FLAG_DESC_BASE_OFFSET) ? 1 : 0;
     DG_CUDA(e, dg::launch_conv_tc(shape, tm_in, cw.tm, p, e->num_sms, w.stream, false));
     return DG_OK;
 }
@@ -499,6 +499,7 @@ void dg_engine_destroy(dg_engine* e) {
     delete[] e->queue.ready;
     delete[] e->queue.done;
     for (void* p : e->host_allocs) cudaFreeHost(p);
+    cudaFree(e->flush_buf);
     delete e;
 }
 
@@ -519,6 +520,26 @@ int32_t dg_engine_load_weights_json(dg_engine* e, const char* path) {
     if (rc == 2) return fail(e, DG_ERR_MALFORMED_WEIGHTS, "%s: %s", path, why.c_str());
     DG_CUDA(e, cudaSetDevice(e->cfg.device));
     return load_net(e, t);
+}
+
+int32_t dg_weights_file_probe(const char* path, const char* name, int32_t* num_tensors, float* scale, uint64_t* nbytes) {
+    if (!path) return DG_ERR_INVALID_ARGUMENT;
+    dg::TensorMap t;
+    std::string why;
+    const int rc = dg::load_weights_file(path, t, why);
+    if (num_tensors) *num_tensors = static_cast<int32_t>(t.size());
+    if (scale) *scale = 0.f;
+    if (nbytes) *nbytes = 0;
+    if (rc == 1) return DG_ERR_MISSING_WEIGHTS;
+    if (rc == 2) return DG_ERR_MALFORMED_WEIGHTS;
+    if (name) {
+        auto it = t.find(name);
+        if (it != t.end()) {
+            if (scale) *scale = it->second.scale;
+            if (nbytes) *nbytes = it->second.bytes.size();
+        }
+    }
+    return DG_OK;
 }
 
 int32_t dg_engine_load_weights_raw(dg_engine* e, const dg_tensor_view* tensors, int32_t count) {
@@ -664,7 +685,8 @@ int32_t dg_engine_queue_wait(dg_engine* e, int64_t ticket, uint16_t* value_out, 
 
 // ---------------------------------------------------------------------------------- measurement
 
-int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, float* ms_total, float* tower_ms, int32_t* launches) {
+int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, int32_t flush_l2, float* ms_total, float* tower_ms,
+                                int32_t* launches) {
     if (!e || iters < 1) return DG_ERR_INVALID_ARGUMENT;
     if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
     DG_CUDA(e, cudaSetDevice(e->cfg.device));
@@ -672,27 +694,40 @@ int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, floa
     if (!guard.w) return fail(e, DG_ERR_INVALID_ARGUMENT, "no workspace holds a resident batch of %d positions (run a forward first)", batch);
     Workspace& w = *guard.w;
     int32_t rc;
-    DG_CUDA(e, cudaEventRecord(w.ev0, w.stream));
-    for (int i = 0; i < iters; i++)
-        if ((rc = enqueue_network(e, w, batch, -1, 0))) return rc;
-    DG_CUDA(e, cudaEventRecord(w.ev1, w.stream));
-    DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    constexpr size_t kFlushBytes = 256u << 20;       // > 126 MB of L2
+    if (flush_l2 && !e->flush_buf) DG_CUDA(e, cudaMalloc(&e->flush_buf, kFlushBytes));
+    // one event pair per step so that the L2 flush between steps stays outside the timed region
+    std::vector<cudaEvent_t> ev(2 * static_cast<size_t>(iters));
+    for (auto& x : ev) DG_CUDA(e, cudaEventCreate(&x));
+    auto timed_pass = [&](int stage, float* total) -> int32_t {
+        for (int i = 0; i < iters; i++) {
+            if (flush_l2) DG_CUDA(e, cudaMemsetAsync(e->flush_buf, i & 0xff, kFlushBytes, w.stream));
+            DG_CUDA(e, cudaEventRecord(ev[2 * i], w.stream));
+            if ((rc = enqueue_network(e, w, batch, -1, stage))) return rc;
+            DG_CUDA(e, cudaEventRecord(ev[2 * i + 1], w.stream));
+        }
+        DG_CUDA(e, cudaStreamSynchronize(w.stream));
+        double sum = 0.0;
+        for (int i = 0; i < iters; i++) {
+            float ms = 0.f;
+            DG_CUDA(e, cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+            sum += ms;
+        }
+        *total = static_cast<float>(sum);
+        return DG_OK;
+    };
     float ms = 0.f;
-    DG_CUDA(e, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
-    if (ms_total) *ms_total = ms;
+    rc = timed_pass(0, &ms);
+    if (rc == DG_OK && ms_total) *ms_total = ms;
     if (launches) *launches = 4 + 2 * e->net.num_blocks;      // pack, up, 2 per block, head conv, head fc
-    if (tower_ms) {
-        DG_CUDA(e, cudaEventRecord(w.ev0, w.stream));
-        for (int i = 0; i < iters; i++)
-            if ((rc = enqueue_network(e, w, batch, -1, 2))) return rc;
-        DG_CUDA(e, cudaEventRecord(w.ev1, w.stream));
-        DG_CUDA(e, cudaStreamSynchronize(w.stream));
-        DG_CUDA(e, cudaEventElapsedTime(tower_ms, w.ev0, w.ev1));
+    if (rc == DG_OK && tower_ms) {
+        rc = timed_pass(2, tower_ms);
         // leave the workspace holding a complete forward again
-        if ((rc = enqueue_network(e, w, batch, -1, 0))) return rc;
-        DG_CUDA(e, cudaStreamSynchronize(w.stream));
+        if (rc == DG_OK) rc = enqueue_network(e, w, batch, -1, 0);
+        cudaStreamSynchronize(w.stream);
     }
-    return DG_OK;
+    for (auto& x : ev) cudaEventDestroy(x);
+    return rc;
 }
 
 int32_t dg_engine_debug_read_tower(dg_engine* e, int32_t layer, int32_t batch, uint16_t* out) {

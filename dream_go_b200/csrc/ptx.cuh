@@ -96,13 +96,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart.
 // Fields (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), base_offset [49,52), layout_type [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t base_offset) {
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>(1) << 16;                     // LBO (unused for swizzled K-major)
     d |= static_cast<uint64_t>(1024 >> 4) << 32;             // SBO
     d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (Blackwell)
-    d |= static_cast<uint64_t>(base_offset & 7u) << 49;
     d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
     return d;
 }

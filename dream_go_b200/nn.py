@@ -29,7 +29,6 @@ POLICY_SIZE = 362
 
 DG_OK = 0
 FLAG_DEBUG_DIRECT_CONV = 0x1
-FLAG_DESC_BASE_OFFSET = 0x2
 
 
 class Error(Exception):
@@ -68,12 +67,14 @@ ABI = {
     "dg_engine_queue_push": (C.c_int64, [C.c_void_p, C.c_void_p]),
     "dg_engine_queue_flush": (C.c_int32, [C.c_void_p]),
     "dg_engine_queue_wait": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dg_weights_file_probe": (C.c_int32, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                          C.POINTER(C.c_uint64)]),
     "dg_engine_synchronize": (C.c_int32, [C.c_void_p]),
     "dg_engine_alloc_host": (C.c_void_p, [C.c_void_p, C.c_uint64]),
     "dg_engine_free_host": (None, [C.c_void_p, C.c_void_p]),
     "dg_engine_last_error": (C.c_char_p, [C.c_void_p]),
     "dg_engine_num_blocks": (C.c_int32, [C.c_void_p]),
-    "dg_engine_time_resident": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+    "dg_engine_time_resident": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "dg_engine_debug_read_tower": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -227,10 +228,10 @@ class Network:
         self._check(lib().dg_engine_queue_wait(self._handle, ticket, value.ctypes.data, policy.ctypes.data))
         return value[0], policy
 
-    def time_resident(self, batch: int, iters: int, tower: bool = True) -> Tuple[float, float, int]:
+    def time_resident(self, batch: int, iters: int, tower: bool = True, flush_l2: bool = True) -> Tuple[float, float, int]:
         """(ms for `iters` resident forwards, ms for the residual-conv launches of `iters` forwards, launches/forward)"""
         ms, tms, launches = C.c_float(), C.c_float(), C.c_int32()
-        self._check(lib().dg_engine_time_resident(self._handle, batch, iters, C.byref(ms),
+        self._check(lib().dg_engine_time_resident(self._handle, batch, iters, int(flush_l2), C.byref(ms),
                                                   C.byref(tms) if tower else None, C.byref(launches)))
         return ms.value, tms.value, launches.value
 
@@ -260,6 +261,28 @@ class Network:
             self.close()
         except Exception:
             pass
+
+
+def probe_weights_file(path: str, name: Optional[str] = None) -> Tuple[int, float, int]:
+    """`loader::load` without a device: (number of tensors, scale of `name`, decoded bytes of `name`)."""
+    n, scale, nbytes = C.c_int32(), C.c_float(), C.c_uint64()
+    rc = lib().dg_weights_file_probe(os.fsencode(path), name.encode() if name else None, C.byref(n), C.byref(scale),
+                                     C.byref(nbytes))
+    if rc != DG_OK:
+        raise Error(rc, path)
+    return n.value, scale.value, nbytes.value
+
+
+def pack_positions(features: np.ndarray) -> np.ndarray:
+    """Compact form (`dg_packed_position`) of V1 feature tensors [B, 361, 32] whose planes 2..31 are
+    binary and whose planes 0/1 are 0 or the constant k (`features.rs:154-250`)."""
+    f = np.ascontiguousarray(features, dtype=np.float16).reshape(-1, 361, 32)
+    out = np.zeros((f.shape[0],), dtype=PACKED_DTYPE)
+    bits = (f != 0).astype(np.uint32) << np.arange(32, dtype=np.uint32)
+    out["planes"] = bits.sum(axis=2, dtype=np.uint32)
+    k = f[:, :, :2].reshape(f.shape[0], -1).max(axis=1)
+    out["k_bits"] = k.view(np.uint16)
+    return out
 
 
 def forward(workspace: Workspace, features: np.ndarray) -> OutputMap:

@@ -41,7 +41,6 @@ extern "C" {
 /* dg_engine_config.flags */
 #define DG_FLAG_DEBUG_DIRECT_CONV  0x1u  /* tests only: run every convolution on the slow one-thread-per-output
                                             cross-check kernel instead of the tcgen05 kernel */
-#define DG_FLAG_DESC_BASE_OFFSET   0x2u  /* debug: encode (addr>>7)&7 in the UMMA descriptor base-offset field */
 
 typedef struct dg_engine dg_engine;
 
@@ -119,6 +118,14 @@ int32_t dg_engine_queue_flush(dg_engine* engine);
 /* Blocks until `ticket` has been evaluated, then copies its outputs (1 + 362 fp16). */
 int32_t dg_engine_queue_wait(dg_engine* engine, int64_t ticket, uint16_t* value_out, uint16_t* policy_out);
 
+/* ---- weight file (device-independent; usable without an engine) ------------------------------ */
+
+/* Parses `path` exactly like dg_engine_load_weights_json would and reports one tensor:
+ * its "s" scale and decoded size in bytes (0 / 0 when `name` is absent or NULL).  Returns DG_OK,
+ * DG_ERR_MISSING_WEIGHTS or DG_ERR_MALFORMED_WEIGHTS; num_tensors (optional) = entries found.
+ * (The reference's loader test, src/libdg_nn/loader.rs:124-142, asserts on exactly these.) */
+int32_t dg_weights_file_probe(const char* path, const char* name, int32_t* num_tensors, float* scale, uint64_t* nbytes);
+
 /* ---- housekeeping -------------------------------------------------------------------------- */
 
 /* `Network::synchronize()` (network.rs:145-159): waits for all in-flight work on the device. */
@@ -136,11 +143,12 @@ int32_t dg_engine_abi_version(void);
 /* ---- measurement hooks (bench.py, tests) ---------------------------------------------------- */
 
 /* Runs `iters` forwards of `batch` positions whose inputs are ALREADY resident in device
- * memory (the last batch given to dg_engine_forward_*), timed with CUDA events on the
- * engine's own stream.  ms_total = elapsed device time of all iterations.
- * tower_ms (optional) = time of the residual-tower launches only, measured in a second pass
- * with events around those launches. launches (optional) = kernels launched per forward. */
-int32_t dg_engine_time_resident(dg_engine* engine, int32_t batch, int32_t iters,
+ * memory (the last batch given to dg_engine_forward_*), each step timed with its own CUDA event
+ * pair on the engine's stream; with flush_l2 != 0 a 256 MiB memset evicts L2 between steps
+ * (outside the timed pairs).  ms_total = summed device time of all steps.
+ * tower_ms (optional) = same for the residual-block convolution launches only (2 per block),
+ * measured in a second pass.  launches (optional) = kernels launched per forward. */
+int32_t dg_engine_time_resident(dg_engine* engine, int32_t batch, int32_t iters, int32_t flush_l2,
                                 float* ms_total, float* tower_ms, int32_t* launches);
 /* Re-evaluates the resident batch up to `layer` (0 = up-sample, i = residual block i,
  * -1 = last block) and copies that activation into out[batch][361][128] fp16 (tests). */

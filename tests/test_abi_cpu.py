@@ -1,0 +1,110 @@
+"""CPU-side checks of the boundary: the library loads, exports every symbol the header declares,
+and the device-independent weight-file reader follows the reference loader (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dream_go_b200 import nn, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "dg_engine.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    handle = ctypes.CDLL(nn.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/dg_engine.h but not exported"
+    assert set(names) == set(nn.ABI), "python binding table and header disagree"
+
+
+def test_abi_version():
+    assert nn.lib().dg_engine_abi_version() == 1
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(nn.Error) as err:
+        nn.Network(max_batch=4)
+    assert err.value.kind == "Cuda"
+
+
+def test_loader_kat(tmp_path):
+    # src/libdg_nn/loader.rs:131-141
+    path = tmp_path / "net.json"
+    path.write_text('{"11v_value/linear_2/offset:0": {"s": "(^d>V", "t": "f2", "v": "(^d>V"}}')
+    count, scale, nbytes = nn.probe_weights_file(str(path), "11v_value/linear_2/offset:0")
+    assert count == 1
+    assert np.float32(scale) == np.float32(0.13704996)
+    assert nbytes == 4
+
+
+def test_loader_errors(tmp_path):
+    # empty input is an error (loader.rs:124-129); a missing file is MissingWeights (loader.rs:110-116)
+    empty = tmp_path / "empty.json"
+    empty.write_text("")
+    with pytest.raises(nn.Error) as err:
+        nn.probe_weights_file(str(empty))
+    assert err.value.kind == "MissingWeights"
+    with pytest.raises(nn.Error) as err:
+        nn.probe_weights_file(str(tmp_path / "nope.json"))
+    assert err.value.kind == "MissingWeights"
+    for bad in ['{"a": {"t": "f8", "v": "(^d>V"}}',        # unknown type
+                '{"a": {"t": "f2", "v": "(^d> "}}',        # invalid base85 character
+                '{"a": {"t": "f2", "q": "(^d>V"}}',        # unknown attribute
+                '{"a": [1, 2]}', '[]']:
+        p = tmp_path / "bad.json"
+        p.write_text(bad)
+        with pytest.raises(nn.Error) as err:
+            nn.probe_weights_file(str(p))
+        assert err.value.kind == "MalformedWeights", bad
+    only_strings = tmp_path / "s.json"
+    only_strings.write_text('{"model_name:0": "x"}')
+    with pytest.raises(nn.Error) as err:
+        nn.probe_weights_file(str(only_strings))
+    assert err.value.kind == "MissingWeights"
+
+
+def test_dumped_network_is_readable(tmp_path, small_net):
+    path = tmp_path / "dream_go.json"
+    weights.dump_json(small_net, str(path))
+    count, scale, nbytes = nn.probe_weights_file(str(path), "01_upsample/conv_1:0")
+    assert count == len(small_net)                       # model_name:0 is a plain string and is skipped
+    assert nbytes == 128 * 9 * 32 * 2
+    assert np.float32(scale) == np.float32(np.abs(small_net["01_upsample/conv_1:0"].astype(np.float64)).max())
+    _, _, nb = nn.probe_weights_file(str(path), "04p_policy/linear_1/offset:0")
+    assert nb == 362 * 2                                 # 724 bytes: already a multiple of 4
+    _, _, nb = nn.probe_weights_file(str(path), "04v_value/linear_2/offset:0")
+    assert nb == 4                                       # one fp16 + base85 padding
+
+
+def test_pack_positions_roundtrip():
+    rng = np.random.default_rng(3)
+    f = (rng.random((5, 361, 32)) < 0.3).astype(np.float16)
+    k = np.float16(0.9667)
+    f[:, :, 0] = np.where(np.arange(5)[:, None] % 2 == 0, k, 0)
+    f[:, :, 1] = np.where(np.arange(5)[:, None] % 2 == 1, k, 0)
+    p = nn.pack_positions(f)
+    assert p.dtype.itemsize == 1448
+    back = ((p["planes"][:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.float16)
+    back[:, :, :2] *= p["k_bits"].view(np.float16)[:, None, None]
+    assert np.array_equal(back, f)
+
+
+def test_forward_argument_checks_need_no_device():
+    ws = nn.Workspace(network=None, batch_size=2)
+    with pytest.raises(nn.Error):
+        nn.forward(ws, np.zeros((2 * 11552 - 1,), np.float16))
+    with pytest.raises(nn.Error):
+        nn.forward(ws, np.zeros((2 * 11552,), np.float32))

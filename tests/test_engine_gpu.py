@@ -1,0 +1,229 @@
+"""Parity of the sm_100a engine (through the C ABI) against the CPU oracle of dg_nn::forward.
+
+Tolerances: value |d| <= 4e-3; policy |d| <= 1e-3 + 1e-2 * p; tower
+activations: relative L2 error <= 2e-3 (fp32 tensor-core accumulation vs the oracle's double
+accumulation, both rounded to fp16 after every layer)."""
+import threading
+
+import numpy as np
+import pytest
+
+from dream_go_b200 import nn, weights
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+VALUE_TOL = 4e-3
+
+
+def check_outputs(value, policy, want_v, want_p):
+    v, wv = value.astype(np.float32), want_v.astype(np.float32)
+    p, wp = policy.reshape(-1, 362).astype(np.float32), want_p.astype(np.float32)
+    assert np.isfinite(v).all() and np.isfinite(p).all()
+    assert np.abs(v - wv).max() <= VALUE_TOL
+    assert (np.abs(p - wp) <= 1e-3 + 1e-2 * wp).all()
+    assert np.abs(p.sum(axis=1) - 1.0).max() < 1e-2
+
+
+def rel_l2(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def small_engine(small_net):
+    net = nn.Network.from_tensors(small_net, max_batch=64, num_workspaces=2)
+    yield net
+    net.close()
+
+
+@pytest.fixture(scope="module")
+def full_engine(full_net):
+    net = nn.Network.from_tensors(full_net, max_batch=256, num_workspaces=2)
+    yield net
+    net.close()
+
+
+@pytest.mark.parametrize("batch", [1, 2, 7, 33, 64])
+def test_small_network_matches_oracle(small_engine, small_net, batch):
+    feats = weights.bernoulli_features(batch, seed=100 + batch)
+    with small_engine.get_workspace(batch) as ws:
+        value, policy = nn.forward(ws, feats).unwrap()
+    want_v, want_p, blocks = oracle.OracleNetwork(small_net).forward(feats, want_blocks=True)
+    check_outputs(value, policy, want_v, want_p)
+    for layer in range(small_engine.num_blocks + 1):
+        got = small_engine.debug_read_tower(layer, batch)
+        assert rel_l2(got, blocks[layer]) <= 2e-3, layer
+        assert np.abs(got.astype(np.float32) - blocks[layer].astype(np.float32)).max() <= 2e-2
+
+
+def test_full_network_matches_oracle(full_engine, full_net):
+    batch = 12
+    feats = weights.bernoulli_features(batch, seed=9)
+    with full_engine.get_workspace(batch) as ws:
+        value, policy = nn.forward(ws, feats).unwrap()
+    want_v, want_p, tower = oracle.OracleNetwork(full_net).forward(feats, want_tower=True)
+    check_outputs(value, policy, want_v, want_p)
+    assert rel_l2(full_engine.debug_read_tower(-1, batch), tower) <= 2e-3
+    assert full_engine.num_blocks == 9
+
+
+def test_random_gates_full_depth():
+    tensors = weights.synthetic_network(seed=5, num_blocks=9, gate="random")
+    feats = weights.bernoulli_features(4, seed=10)
+    net = nn.Network.from_tensors(tensors, max_batch=4)
+    with net.get_workspace(4) as ws:
+        value, policy = nn.forward(ws, feats).unwrap()
+    want_v, want_p = oracle.OracleNetwork(tensors).forward(feats)
+    check_outputs(value, policy, want_v, want_p)
+    net.close()
+
+
+def test_edge_inputs(small_engine, small_net):
+    """All-zero planes, all-one planes and a lone stone in each corner (padding / halo handling)."""
+    feats = np.zeros((6, 361, 32), np.float16)
+    feats[1] = 1.0
+    for i, point in enumerate([0, 18, 342, 360]):
+        feats[2 + i, point, :] = 1.0
+    with small_engine.get_workspace(6) as ws:
+        value, policy = nn.forward(ws, feats).unwrap()
+    want_v, want_p, blocks = oracle.OracleNetwork(small_net).forward(feats, want_blocks=True)
+    check_outputs(value, policy, want_v, want_p)
+    got = small_engine.debug_read_tower(0, 6)
+    assert np.abs(got.astype(np.float32) - blocks[0].astype(np.float32)).max() <= 4e-3
+
+
+def test_tensor_core_kernel_matches_direct_kernel_at_full_size(full_net):
+    """BASELINE size (batch 256, 9 blocks): tcgen05 path vs the one-thread-per-output cross-check
+    kernel on the device (the CPU oracle takes minutes at this size)."""
+    feats = weights.bernoulli_features(256, seed=2)
+    outs = []
+    for flags in (0, nn.FLAG_DEBUG_DIRECT_CONV):
+        net = nn.Network.from_tensors(full_net, max_batch=256, num_workspaces=1, flags=flags)
+        with net.get_workspace(256) as ws:
+            value, policy = nn.forward(ws, feats).unwrap()
+        outs.append((value.copy(), policy.copy(), net.debug_read_tower(-1, 256)))
+        net.close()
+    (v0, p0, t0), (v1, p1, t1) = outs
+    assert rel_l2(t0, t1) <= 1e-3
+    assert np.abs(v0.astype(np.float32) - v1.astype(np.float32)).max() <= VALUE_TOL
+    assert np.abs(p0.astype(np.float32) - p1.astype(np.float32)).max() <= 1e-3
+    # size-independent property: every position of the batch is evaluated independently
+    net = nn.Network.from_tensors(full_net, max_batch=256, num_workspaces=1)
+    sel = [0, 100, 255]
+    with net.get_workspace(3) as ws:
+        v3, p3 = nn.forward(ws, feats[sel]).unwrap()
+    assert np.array_equal(v3, v0[sel])
+    assert np.array_equal(p3.reshape(3, 362), p0.reshape(256, 362)[sel])
+    net.close()
+
+
+def test_batch_shrink_leaves_no_stale_rows(small_engine, small_net):
+    big = weights.bernoulli_features(64, seed=1)
+    small = weights.bernoulli_features(3, seed=2)
+    with small_engine.get_workspace(64) as ws:
+        nn.forward(ws, big)
+    with small_engine.get_workspace(64) as ws:
+        nn.forward(ws, big)            # touch both pooled workspaces
+    with small_engine.get_workspace(3) as ws:
+        value, policy = nn.forward(ws, small).unwrap()
+    want_v, want_p = oracle.OracleNetwork(small_net).forward(small)
+    check_outputs(value, policy, want_v, want_p)
+
+
+def test_deterministic_and_packed_path_bit_exact(small_engine):
+    feats = weights.bernoulli_features(17, seed=4)
+    feats[:, :, 0] = np.float16(0.9667)         # k plane (to move = black)
+    feats[:, :, 1] = 0
+    with small_engine.get_workspace(17) as ws:
+        v1, p1 = nn.forward(ws, feats).unwrap()
+        v2, p2 = nn.forward(ws, feats).unwrap()
+    assert np.array_equal(v1, v2) and np.array_equal(p1, p2)
+    out = small_engine.forward_packed(nn.pack_positions(feats))
+    assert np.array_equal(out.value, v1)
+    assert np.array_equal(out.policy.reshape(-1), p1)
+
+
+def test_leaf_queue_matches_forward(small_engine):
+    feats = weights.bernoulli_features(150, seed=6)       # > max_batch: several flush batches
+    feats[:, :, 0] = 0
+    feats[:, :, 1] = np.float16(0.5)
+    packed = nn.pack_positions(feats)
+    tickets = [None] * 150
+
+    def producer(lo, hi):
+        for i in range(lo, hi):
+            tickets[i] = small_engine.queue_push(packed[i])
+
+    threads = [threading.Thread(target=producer, args=(i * 50, (i + 1) * 50)) for i in range(3)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert sorted(tickets) == list(range(min(tickets), min(tickets) + 150))
+    small_engine.queue_flush()
+    want_v, want_p = [], []
+    for lo in range(0, 150, 50):
+        o = small_engine.forward_packed(packed[lo:lo + 50])
+        want_v.append(o.value)
+        want_p.append(o.policy)
+    want_v, want_p = np.concatenate(want_v), np.concatenate(want_p)
+    for i in range(150):
+        v, p = small_engine.queue_wait(tickets[i])
+        assert v == want_v[i] and np.array_equal(p, want_p[i])
+
+
+def test_concurrent_forwards(small_engine, small_net):
+    """The reference allows 2 forwards in flight per device (predictors/nn.rs:64-67)."""
+    onet = oracle.OracleNetwork(small_net)
+    errors = []
+
+    def worker(seed):
+        try:
+            feats = weights.bernoulli_features(5 + seed, seed=seed)
+            for _ in range(5):
+                with small_engine.get_workspace(5 + seed) as ws:
+                    value, policy = nn.forward(ws, feats).unwrap()
+            want_v, want_p = onet.forward(feats)
+            check_outputs(value, policy, want_v, want_p)
+        except Exception as exc:   # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+
+
+def test_errors(tmp_path, small_net):
+    net = nn.Network(max_batch=4)
+    with pytest.raises(nn.Error) as err:      # forward before load
+        net.forward_into(np.zeros((1, 361, 32), np.float16), np.zeros(1, np.float16), np.zeros((1, 362), np.float16))
+    assert err.value.kind == "MissingWeights"
+    with pytest.raises(nn.Error) as err:
+        net.load_json(str(tmp_path / "missing.json"))
+    assert err.value.kind == "MissingWeights"
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"01_upsample/conv_1:0": {"t": "zz", "v": "00000"}}')
+    with pytest.raises(nn.Error) as err:
+        net.load_json(str(bad))
+    assert err.value.kind == "MalformedWeights"
+    incomplete = dict(small_net)
+    del incomplete["01_upsample/conv_1/offset:0"]
+    with pytest.raises(nn.Error) as err:
+        net.load_tensors(incomplete)
+    assert err.value.kind == "MissingWeights"
+    with pytest.raises(nn.Error):
+        net.get_workspace(5)
+    path = tmp_path / "dream_go.json"
+    weights.dump_json(small_net, str(path))
+    net.load_json(str(path))                  # the JSON route gives the same network as raw tensors
+    feats = weights.bernoulli_features(2, seed=8)
+    with net.get_workspace(2) as ws:
+        value, policy = nn.forward(ws, feats).unwrap()
+    want_v, want_p = oracle.OracleNetwork(oracle.load_json(str(path))).forward(feats)
+    check_outputs(value, policy, want_v, want_p)
+    net.close()
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()
