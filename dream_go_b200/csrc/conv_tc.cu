@@ -51,7 +51,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
     constexpr uint32_t kIdesc = umma_idesc_f16(DG_TILE_M, BN);
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 128B swizzle needs 1024-byte alignment
     uint8_t* w_s = smem;
     uint8_t* a_s = smem + L::kWeights;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
@@ -89,6 +89,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    int tr = 0;      // trace cursor of this role
+#define DG_TRACE(role)                                                                          \
+    do {                                                                                        \
+        if (p.trace && tr < 64) p.trace[(blockIdx.x * 3 + (role)) * 64 + tr++] = clock64();     \
+    } while (0)
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -98,11 +103,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
                 for (int h = 0; h < NH; h++)
                     tma_load_2d(w_s + (tap * NH + h) * L::kSlab, &tm_w, w_full, h * 64, tap * (kNSplit * BN) + nslice * BN);
             griddep_wait();   // activations of the previous launch must be complete before we read them
+            DG_TRACE(0);
             int stage = 0;
             uint32_t phase = 0;
             for (int t = first_tile; t < p.ntiles; t += tile_step) {
                 for (int h = 0; h < NH; h++) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
+                    DG_TRACE(0);
                     mbar_expect_tx(&a_full[stage], kWindowBytes);
                     tma_load_2d(a_s + stage * kStageBytes, &tm_act, &a_full[stage], h * 64,
                                 DG_GUARD_ROWS + t * DG_TILE_M - DG_HALO_ROWS);
@@ -111,41 +118,45 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            mbar_wait(w_full, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int as = 0;
-            uint32_t aphase = 0;
-            const uint32_t w_addr = smem_u32(w_s);
-            for (int t = first_tile; t < p.ntiles; t += tile_step) {
-                mbar_wait(&acc_empty[as], aphase ^ 1);
+        // ------------------------------------------------------------ MMA issuer
+        // The whole warp walks the loop (so every address stays in uniform registers); one elected
+        // lane issues the MMAs and the commits.  Per MMA only the low descriptor words change, by
+        // compile-time constants.
+        mbar_wait(w_full, 0);
+        if (lane == 0) DG_TRACE(1);
+        int stage = 0;
+        uint32_t phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        const uint32_t w_lo = umma_desc_lo(smem_u32(w_s));
+        for (int t = first_tile; t < p.ntiles; t += tile_step) {
+            mbar_wait(&acc_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+#pragma unroll
+            for (int h = 0; h < NH; h++) {
+                mbar_wait(&a_full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                uint32_t accumulate = 0;
-                for (int h = 0; h < NH; h++) {
-                    mbar_wait(&a_full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_s + stage * kStageBytes);
+                if (lane == 0) DG_TRACE(1);
+                const uint32_t a_lo = umma_desc_lo(smem_u32(a_s + stage * kStageBytes));
+                if (elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
                         const int row_off = DG_HALO_ROWS + (tap / 3 - 1) * DG_LINE_STRIDE + (tap % 3 - 1);
-                        const uint32_t a_tap = a_addr + row_off * 128;
-                        const uint32_t b_tap = w_addr + (tap * NH + h) * L::kSlab;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            umma_f16_ss(d_tmem, umma_desc_sw128(a_tap + k * 32), umma_desc_sw128(b_tap + k * 32), kIdesc,
-                                        accumulate);
-                            accumulate = 1;
-                        }
+                        for (int k = 0; k < 4; k++)
+                            umma_f16_ss_lo(d_tmem, a_lo + ((row_off * 128 + k * 32) >> 4),
+                                           w_lo + (((tap * NH + h) * L::kSlab + k * 32) >> 4), kUmmaDescHiSw128, kIdesc,
+                                           (h | tap | k) != 0);
                     }
                     umma_commit(&a_empty[stage]);      // window slot may be refilled once these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (h == NH - 1) umma_commit(&acc_full[as]);   // accumulator complete -> epilogue
                 }
-                umma_commit(&acc_full[as]);            // accumulator complete -> epilogue
-                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (lane == 0) DG_TRACE(1);
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else {
         // ------------------------------------------------------------ epilogue warps
@@ -163,8 +174,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
             __half* out_row = p.out + grow * p.out_stride + nslice * BN;
             const __half* skip_row = p.skip ? p.skip + grow * p.skip_stride + nslice * BN : nullptr;
 
+            if (warp == 2 && lane == 0) DG_TRACE(2);
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
+            if (warp == 2 && lane == 0) DG_TRACE(2);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll
             for (int c = 0; c < BN / 16; c++) {
@@ -201,6 +214,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
         }
     }
 
+    if (lane == 0 && (warp <= 2)) DG_TRACE(warp);
     tc_fence_before();
     __syncthreads();
     griddep_launch_dependents();

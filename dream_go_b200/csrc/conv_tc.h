@@ -15,6 +15,7 @@ struct ConvTcParams {
     const float* bias;          // [Cout] fp32 (already scaled and fp16-rounded where the reference does so)
     float alpha;                // scale of the convolution result
     float beta;                 // scale of the skip input
+    long long* trace;           // optional [grid][3 roles][64] clock64() samples (debug), nullptr normally
 };
 
 enum class ConvTcShape {
@@ -25,5 +26,9 @@ enum class ConvTcShape {
 
 cudaError_t launch_conv_tc(ConvTcShape shape, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p,
                            int num_sms, cudaStream_t stream, bool pdl);
+
+// Tower (k_halves = 2) / up-sampling (k_halves = 1) convolution on CTA pairs (conv_tc2.cu).
+cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
+                             cudaStream_t stream, bool pdl);
 
 }  // namespace dg

@@ -1,0 +1,289 @@
+// Residual-tower 3x3 convolution (128 -> 128 channels) on CTA PAIRS: tcgen05.mma.cta_group::2.
+//
+// Replaces cudnnConvolutionBiasActivationForward as driven by `ResidualLayer::forward`
+// (src/libdg_nn/layers/residual_block.rs:64-78, conv2d.rs:171-220):
+//     y   = relu(conv1(x) + b1)
+//     out = relu(g * conv2(y) + (1 - g) * x + fp16(g * b2))
+//
+// One persistent cluster of two CTAs per SM pair.  Each unit of work is 256 consecutive board rows
+// (two 128-row tiles, one per CTA) x all 128 output channels:
+//   * each CTA keeps HALF of the filter bank resident in shared memory for the whole launch
+//     (its 64 output channels x 9 taps x 128 input channels = 144 KiB, TMA-loaded once); the pair's
+//     UMMA (M=256, N=128, K=16) reads both halves, so weights are never re-fetched per tile and each
+//     SM reads only 96 B/cycle of operands from shared memory (a single CTA needs 128-192 B/cycle);
+//   * activations: per tile and 64-channel k-half ONE TMA box of 170 rows (tile + 21 halo rows
+//     each side); the nine taps are UMMA descriptors starting at nine row offsets in that box;
+//   * accumulators: 2 x 128 TMEM columns per CTA (double buffered) so the epilogue of unit i
+//     overlaps the MMAs of unit i+1;
+//   * epilogue (8 warps, one thread per row and 64-channel half): the skip row is prefetched with
+//     256-bit loads before the accumulator is ready; tcgen05.ld -> g*acc + b (+ (1-g)*skip) ->
+//     ReLU -> halo rows := 0 -> fp16 -> 256-bit stores (every access is one full 32-byte sector).
+// warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader CTA only), warps 2..9 = epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <utility>
+
+#include "conv_tc.h"
+#include "layout.h"
+#include "ptx.cuh"
+
+namespace dg {
+
+namespace t2 {
+constexpr int kStages = 3;
+constexpr int kThreads = 320;
+constexpr int kWindowBytes = DG_WINDOW_ROWS * 128;      // 21,760
+constexpr int kStageBytes = 22 * 1024;
+constexpr int kSlab = 64 * 128;                          // [64 out][64 in] fp16
+template <int NH>
+struct Smem {
+    static constexpr int kWeights = 9 * NH * kSlab;      // 147,456 for the tower (NH = 2)
+    static constexpr int kAOff = kWeights;
+    static constexpr int kBarOff = kAOff + kStages * kStageBytes;
+    static constexpr int kTotal = kBarOff + 1024 + 1024; // + barriers/bias + alignment slack
+};
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kIdesc = umma_idesc_f16(256, 128);
+}  // namespace t2
+
+template <int NH, int H, int I>
+__device__ __forceinline__ void issue_one(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
+    constexpr int tap = I / 4, k = I % 4;
+    constexpr int row_off = DG_HALO_ROWS + (tap / 3 - 1) * DG_LINE_STRIDE + (tap % 3 - 1);
+    umma_f16_ss_pair<((row_off * 128 + k * 32) >> 4), (((tap * NH + H) * t2::kSlab + k * 32) >> 4)>(
+        d_tmem, a_lo, w_lo, kUmmaDescHiSw128, t2::kIdesc, (H | I) != 0);
+}
+template <int NH, int H, int... I>
+__device__ __forceinline__ void issue_half(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo, std::integer_sequence<int, I...>) {
+    (issue_one<NH, H, I>(d_tmem, a_lo, w_lo), ...);
+}
+
+// NH = number of 64-channel k-halves of the input: 2 for the tower (128 channels), 1 for the
+// up-sampling layer (32 feature planes zero-padded to 64).
+template <int NH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2::kThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvTcParams p) {
+    using namespace t2;
+    constexpr int kWeights = Smem<NH>::kWeights, kAOff = Smem<NH>::kAOff, kBarOff = Smem<NH>::kBarOff;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_s = smem;
+    uint8_t* a_s = smem + kAOff;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+    uint64_t* w_full = bars;
+    uint64_t* a_full = bars + 1;
+    uint64_t* a_empty = bars + 1 + kStages;
+    uint64_t* acc_full = bars + 1 + 2 * kStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* bias_s = reinterpret_cast<float*>(bars + 32);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int first_unit = blockIdx.x >> 1;
+    const int unit_step = gridDim.x >> 1;
+    const int nunits = (p.ntiles + 1) >> 1;
+    const bool has_skip = p.skip != nullptr;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_act);
+        tma_prefetch_desc(&tm_w);
+        mbar_init(w_full, 1);
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 16);      // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+    for (int i = threadIdx.x; i < 128; i += kThreads) bias_s[i] = p.bias[i];
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    griddep_launch_dependents();   // the next layer may start its prologue / weight loads (it waits for us before touching activations)
+    const uint32_t tmem_base = *tmem_slot;
+    int tr = 0;
+#define DG_TRACE(role)                                                                          \
+    do {                                                                                        \
+        if (p.trace && tr < 64) p.trace[(blockIdx.x * 3 + (role)) * 64 + tr++] = clock64();     \
+    } while (0)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            // completion bytes of BOTH CTAs are credited to the leader's barriers
+            const uint32_t w_full0 = mapa_shared(smem_u32(w_full), 0);
+            if (rank == 0) mbar_expect_tx(w_full, 2 * kWeights);
+            for (int tap = 0; tap < 9; tap++)
+                for (int h = 0; h < NH; h++)
+                    tma_load_2d_pair(w_s + (tap * NH + h) * kSlab, &tm_w, w_full0, h * 64, tap * 128 + rank * 64);
+            griddep_wait();
+            DG_TRACE(0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = first_unit; u < nunits; u += unit_step) {
+                const int tile = 2 * u + rank;
+                for (int h = 0; h < NH; h++) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    DG_TRACE(0);
+                    if (rank == 0) mbar_expect_tx(&a_full[stage], 2 * kWindowBytes);
+                    tma_load_2d_pair(a_s + stage * kStageBytes, &tm_act, mapa_shared(smem_u32(&a_full[stage]), 0), h * 64,
+                                     DG_GUARD_ROWS + tile * DG_TILE_M - DG_HALO_ROWS);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA, one elected lane)
+        if (rank == 0) {
+            mbar_wait(w_full, 0);
+            if (lane == 0) DG_TRACE(1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            const uint32_t w_lo = umma_desc_lo(smem_u32(w_s));
+            for (int u = first_unit; u < nunits; u += unit_step) {
+                mbar_wait_cluster(&acc_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 128;
+                // k-half 0
+                mbar_wait(&a_full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) DG_TRACE(1);
+                if (elect_one()) {
+                    issue_half<NH, 0>(d_tmem, umma_desc_lo(smem_u32(a_s + stage * kStageBytes)), w_lo, std::make_integer_sequence<int, 36>{});
+                    umma_commit_pair(&a_empty[stage], 3);
+                    if (NH == 1) umma_commit_pair(&acc_full[as], 3);
+                }
+                __syncwarp();
+                if (lane == 0) DG_TRACE(1);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (NH == 2) {   // k-half 1
+                    mbar_wait(&a_full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) DG_TRACE(1);
+                    if (elect_one()) {
+                        issue_half<NH, NH - 1>(d_tmem, umma_desc_lo(smem_u32(a_s + stage * kStageBytes)), w_lo, std::make_integer_sequence<int, 36>{});
+                        umma_commit_pair(&a_empty[stage], 3);
+                        umma_commit_pair(&acc_full[as], 3);
+                    }
+                    __syncwarp();
+                    if (lane == 0) DG_TRACE(1);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (both CTAs)
+        griddep_wait();
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+        const int colhalf = (warp - 2) >> 2;             // which 64 output channels
+        const int row = quarter * 32 + lane;
+        const bool tracer = (threadIdx.x == 64);
+        const uint32_t acc_empty0[2] = {mapa_shared(smem_u32(&acc_empty[0]), 0), mapa_shared(smem_u32(&acc_empty[1]), 0)};
+        const float* bias_h = bias_s + colhalf * 64;
+        int as = 0;
+        uint32_t aphase = 0;
+        const float alpha = p.alpha, beta = p.beta;
+        for (int u = first_unit; u < nunits; u += unit_step) {
+            const int tile = 2 * u + rank;
+            const int m = tile * DG_TILE_M + row;
+            const int q = m % DG_POS_ROWS;
+            const bool halo = (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) ||
+                              (q >= DG_POS_ROWS - DG_LINE_STRIDE);
+            const size_t off = static_cast<size_t>(DG_GUARD_ROWS + m) * 128 + colhalf * 64;
+            uint32_t sk[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) sk[i] = 0;
+            if (has_skip && !halo) {                     // prefetch the residual input while the MMAs run
+#pragma unroll
+                for (int i = 0; i < 4; i++) ld_global_256(p.skip + off + i * 16, &sk[i * 8]);
+            }
+            if (tracer) DG_TRACE(2);
+            mbar_wait(&acc_full[as], aphase);
+            tc_fence_after();
+            if (tracer) DG_TRACE(2);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 128 + colhalf * 64;
+#pragma unroll
+            for (int part = 0; part < 2; part++) {          // 32 output channels per part
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(taddr + part * 32, acc);
+                tmem_ld_wait();
+                if (part == 1) {                             // accumulator fully read: hand it back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc_empty0[as]);
+                }
+                uint32_t packed[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&sk[part * 16 + e]));
+                    float v0 = fmaf(alpha, __uint_as_float(acc[2 * e]), bias_h[part * 32 + 2 * e]);
+                    float v1 = fmaf(alpha, __uint_as_float(acc[2 * e + 1]), bias_h[part * 32 + 2 * e + 1]);
+                    v0 = fmaf(beta, s2.x, v0);
+                    v1 = fmaf(beta, s2.y, v1);
+                    v0 = (v0 > 0.f && !halo) ? v0 : 0.f;     // NaN-non-propagating ReLU; halo rows stay zero
+                    v1 = (v1 > 0.f && !halo) ? v1 : 0.f;
+                    const __half2 hv = __floats2half2_rn(v0, v1);
+                    packed[e] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+                st_global_256(p.out + off + part * 32, &packed[0]);
+                st_global_256(p.out + off + part * 32 + 16, &packed[8]);
+            }
+            if (tracer) DG_TRACE(2);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    if (lane == 0 && warp <= 1) DG_TRACE(warp);
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, t2::kTmemCols);
+    }
+#undef DG_TRACE
+}
+
+template <int NH>
+static cudaError_t launch_pair(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
+                               cudaStream_t stream, bool pdl) {
+    static bool configured = false;
+    auto kernel = conv3x3_pair_kernel<NH>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::Smem<NH>::kTotal);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int nunits = (p.ntiles + 1) / 2;
+    int pairs = num_sms / 2;
+    if (pairs > nunits) pairs = nunits;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(t2::kThreads);
+    cfg.dynamicSmemBytes = t2::Smem<NH>::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, tm_act, tm_w, p);
+}
+
+cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
+                             cudaStream_t stream, bool pdl) {
+    return k_halves == 1 ? launch_pair<1>(tm_act, tm_w, p, num_sms, stream, pdl) : launch_pair<2>(tm_act, tm_w, p, num_sms, stream, pdl);
+}
+
+}  // namespace dg

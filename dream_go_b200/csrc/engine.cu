@@ -39,7 +39,7 @@ struct Workspace {
     __half *d_policy = nullptr, *d_value = nullptr;
     uint8_t* h_in = nullptr;          // pinned staging
     __half *h_policy = nullptr, *h_value = nullptr;
-    CUtensorMap tm_feat, tm_x, tm_y;
+    CUtensorMap tm_feat, tm_x, tm_y;           // 170-row load windows
     int resident_batch = 0;
     int resident_kind = 0;            // 0 none, 1 raw features, 2 compact positions
     bool busy = false;
@@ -100,6 +100,7 @@ struct dg_engine {
     std::string last_error;
     std::vector<void*> host_allocs;
     void* flush_buf = nullptr;
+    long long* trace_buf = nullptr;   // set only inside dg_engine_debug_conv_trace
 };
 
 namespace {
@@ -382,7 +383,12 @@ int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMa
     p.bias = cw.bias;
     p.alpha = alpha;
     p.beta = beta;
-    DG_CUDA(e, dg::launch_conv_tc(shape, tm_in, cw.tm, p, e->num_sms, w.stream, false));
+    p.trace = e->trace_buf;
+    const bool pdl = !(e->cfg.flags & DG_FLAG_NO_PDL);
+    if (shape == ConvTcShape::kHeads)
+        DG_CUDA(e, dg::launch_conv_tc(shape, tm_in, cw.tm, p, e->num_sms, w.stream, pdl));
+    else   // tower and up-sampling layers run on CTA pairs
+        DG_CUDA(e, dg::launch_conv_pair(shape == ConvTcShape::kUp ? 1 : 2, tm_in, cw.tm, p, e->num_sms, w.stream, pdl));
     return DG_OK;
 }
 
@@ -727,6 +733,27 @@ int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, int3
         cudaStreamSynchronize(w.stream);
     }
     for (auto& x : ev) cudaEventDestroy(x);
+    return rc;
+}
+
+int32_t dg_engine_debug_conv_trace(dg_engine* e, int32_t batch, int64_t* out, int32_t out_len) {
+    if (!e || !out) return DG_ERR_INVALID_ARGUMENT;
+    if (!e->net.loaded || e->net.num_blocks < 1) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    WsGuard guard(e, batch);
+    if (!guard.w) return fail(e, DG_ERR_INVALID_ARGUMENT, "no workspace holds a resident batch of %d positions", batch);
+    Workspace& w = *guard.w;
+    const size_t n = static_cast<size_t>(e->num_sms) * 3 * 64;
+    long long* buf = nullptr;
+    DG_CUDA(e, cudaMalloc(&buf, n * 8));
+    DG_CUDA(e, cudaMemset(buf, 0, n * 8));
+    e->trace_buf = buf;
+    const float g = e->net.gate[0];
+    int32_t rc = run_conv(e, w, ConvTcShape::kTower, w.tm_y, w.y, kChan, e->net.c2[0], 128, w.x, kChan, w.x, g, 1.0f - g, batch);
+    e->trace_buf = nullptr;
+    cudaStreamSynchronize(w.stream);
+    if (rc == DG_OK) cudaMemcpy(out, buf, (n < static_cast<size_t>(out_len) ? n : static_cast<size_t>(out_len)) * 8, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
     return rc;
 }
 

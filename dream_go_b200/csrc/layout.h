@@ -23,4 +23,5 @@
 #define DG_WINDOW_ROWS (DG_TILE_M + 2 * DG_HALO_ROWS)   /* 170 rows staged per tile */
 
 static inline int dg_num_tiles(int batch) { return (batch * DG_POS_ROWS + DG_TILE_M - 1) / DG_TILE_M; }
-static inline long dg_alloc_rows(int batch) { return (long)DG_GUARD_ROWS + (long)dg_num_tiles(batch) * DG_TILE_M + DG_TAIL_ROWS; }
+/* tiles are processed in pairs (one per CTA of a cluster), so buffers cover an even number of tiles */
+static inline long dg_alloc_rows(int batch) { return (long)DG_GUARD_ROWS + (long)((dg_num_tiles(batch) + 1) & ~1) * DG_TILE_M + DG_TAIL_ROWS; }

@@ -29,6 +29,7 @@ POLICY_SIZE = 362
 
 DG_OK = 0
 FLAG_DEBUG_DIRECT_CONV = 0x1
+FLAG_NO_PDL = 0x2
 
 
 class Error(Exception):
@@ -77,6 +78,7 @@ ABI = {
     "dg_engine_time_resident": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "dg_engine_debug_read_tower": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "dg_engine_debug_conv_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
 }
 
 
@@ -238,6 +240,11 @@ class Network:
     def debug_read_tower(self, layer: int, batch: int) -> np.ndarray:
         out = np.empty((batch, 361, 128), np.float16)
         self._check(lib().dg_engine_debug_read_tower(self._handle, layer, batch, out.ctypes.data))
+        return out
+
+    def debug_conv_trace(self, batch: int, ctas: int = 148) -> np.ndarray:
+        out = np.zeros((ctas, 3, 64), np.int64)
+        self._check(lib().dg_engine_debug_conv_trace(self._handle, batch, out.ctypes.data, out.size))
         return out
 
     # -- plumbing -------------------------------------------------------------------------------

@@ -42,6 +42,8 @@ extern "C" {
 #define DG_FLAG_DEBUG_DIRECT_CONV  0x1u  /* tests only: run every convolution on the slow one-thread-per-output
                                             cross-check kernel instead of the tcgen05 kernel */
 
+#define DG_FLAG_NO_PDL             0x2u  /* debug: launch the layers without programmatic dependent launch */
+
 typedef struct dg_engine dg_engine;
 
 /* Replaces the implicit configuration of `Network::new()` + `Builder::get_workspace`
@@ -153,6 +155,11 @@ int32_t dg_engine_time_resident(dg_engine* engine, int32_t batch, int32_t iters,
 /* Re-evaluates the resident batch up to `layer` (0 = up-sample, i = residual block i,
  * -1 = last block) and copies that activation into out[batch][361][128] fp16 (tests). */
 int32_t dg_engine_debug_read_tower(dg_engine* engine, int32_t layer, int32_t batch, uint16_t* out);
+
+/* Runs ONE residual-block convolution (block 0, conv_2 with skip) on the resident batch with
+ * in-kernel clock64() tracing and copies min(out_len, SMs*3*64) samples to out, laid out
+ * [cta][role: 0 TMA producer, 1 MMA issuer, 2 epilogue][64] (perf debugging). */
+int32_t dg_engine_debug_conv_trace(dg_engine* engine, int32_t batch, int64_t* out, int32_t out_len);
 
 #ifdef __cplusplus
 }

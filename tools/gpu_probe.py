@@ -20,7 +20,7 @@ def report(tag, got, want):
 
 
 def main():
-    variants = sys.argv[1:] or ["direct", "tc0", "tc1"]
+    variants = sys.argv[1:] or ["direct", "tc", "nopdl"]
     nb, batch = 2, 3
     net = weights.synthetic_network(seed=7, num_blocks=nb, gate="random")
     feats = weights.bernoulli_features(batch, seed=3)
@@ -28,7 +28,7 @@ def main():
     t0 = time.time()
     ov, op, oblocks = onet.forward(feats, want_blocks=True)
     print(f"oracle: {time.time() - t0:.2f}s", flush=True)
-    flags = {"direct": nn.FLAG_DEBUG_DIRECT_CONV, "tc0": 0, "tc1": nn.FLAG_DESC_BASE_OFFSET}
+    flags = {"direct": nn.FLAG_DEBUG_DIRECT_CONV, "tc": 0, "nopdl": nn.FLAG_NO_PDL}
     for v in variants:
         print(f"== {v}", flush=True)
         try:
