@@ -195,20 +195,29 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
         int as = 0;
         uint32_t aphase = 0;
         const float alpha = p.alpha, beta = p.beta;
-        for (int u = first_unit; u < nunits; u += unit_step) {
-            const int tile = 2 * u + rank;
-            const int m = tile * DG_TILE_M + row;
+        // the residual input of unit i+1 is prefetched (256-bit loads) before the epilogue math of unit i
+        auto row_info = [&](int u, size_t& off) -> bool {
+            const int m = (2 * u + static_cast<int>(rank)) * DG_TILE_M + row;
             const int q = m % DG_POS_ROWS;
-            const bool halo = (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) ||
-                              (q >= DG_POS_ROWS - DG_LINE_STRIDE);
-            const size_t off = static_cast<size_t>(DG_GUARD_ROWS + m) * 128 + colhalf * 64;
-            uint32_t sk[32];
+            off = static_cast<size_t>(DG_GUARD_ROWS + m) * 128 + colhalf * 64;
+            return (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) || (q >= DG_POS_ROWS - DG_LINE_STRIDE);
+        };
+        auto prefetch_skip = [&](int u, uint32_t (&dst)[32]) {
+            size_t o;
+            const bool h = (u >= nunits) || row_info(u, o);
 #pragma unroll
-            for (int i = 0; i < 32; i++) sk[i] = 0;
-            if (has_skip && !halo) {                     // prefetch the residual input while the MMAs run
+            for (int i = 0; i < 32; i++) dst[i] = 0;
+            if (has_skip && !h) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) ld_global_256(p.skip + off + i * 16, &sk[i * 8]);
+                for (int i = 0; i < 4; i++) ld_global_256(p.skip + o + i * 16, &dst[i * 8]);
             }
+        };
+        uint32_t sk[32], sk_next[32];
+        prefetch_skip(first_unit, sk);
+        for (int u = first_unit; u < nunits; u += unit_step) {
+            size_t off;
+            const bool halo = row_info(u, off);
+            prefetch_skip(u + unit_step, sk_next);
             if (tracer) DG_TRACE(2);
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
@@ -241,6 +250,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
                 st_global_256(p.out + off + part * 32 + 16, &packed[8]);
             }
             if (tracer) DG_TRACE(2);
+#pragma unroll
+            for (int i = 0; i < 32; i++) sk[i] = sk_next[i];
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }

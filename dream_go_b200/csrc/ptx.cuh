@@ -170,7 +170,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default (.release.cta) semantics: no generic-memory data is handed over through these barriers (only
+    // TMEM state, ordered by tcgen05.fence), and a cluster-scope release costs a MEMBAR.ALL + ERRBAR per arrive
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
