@@ -31,4 +31,33 @@ cudaError_t launch_conv_tc(ConvTcShape shape, const CUtensorMap& tm_act, const C
 cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
                              cudaStream_t stream, bool pdl);
 
+// ---------------------------------------------------------------------------------------------
+// Whole residual tower in ONE persistent launch (conv_tc2.cu: tower_kernel).
+constexpr int kTowerMaxLayers = 41;          // up-sampling layer + 2 convolutions x 20 blocks
+
+struct TowerLayer {
+    int in_map;                 // activation tensor map this layer reads: 0 = features, 1 = x, 2 = y
+    int nh;                     // 64-channel k-halves of the input (1 for the up-sampling layer, else 2)
+    int has_skip;               // add beta * skip (the residual input) in the epilogue
+    float alpha, beta;
+    const float* bias;          // [128] fp32
+    __half* out;                // output board-row buffer (row 0 = guard start)
+    const __half* skip;         // residual input buffer or nullptr
+};
+
+struct TowerParams {
+    CUtensorMap act[3];                     // 170-row x 64-channel load windows over features / x / y
+    CUtensorMap w[kTowerMaxLayers];         // per-layer filter banks, [64 out x 64 in] boxes
+    TowerLayer layer[kTowerMaxLayers];
+    int nlayers;
+    int ntiles;
+    int valid_rows;
+    int rot;                                // per-layer rotation of the unit -> CTA-pair assignment
+    uint32_t gen;                           // flag base of this launch: done[tile] = gen + layers completed
+    uint32_t* done;                         // [ntiles rounded up to even] progress flags
+    long long* trace;
+};
+
+cudaError_t launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream);
+
 }  // namespace dg

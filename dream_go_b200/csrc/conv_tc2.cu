@@ -63,7 +63,7 @@ __device__ __forceinline__ void issue_half(uint32_t d_tmem, uint32_t a_lo, uint3
 
 // NH = number of 64-channel k-halves of the input: 2 for the tower (128 channels), 1 for the
 // up-sampling layer (32 feature planes zero-padded to 64).
-template <int NH>
+template <int NH, bool SKIP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2::kThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w, ConvTcParams p) {
     using namespace t2;
@@ -87,7 +87,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
     const int first_unit = blockIdx.x >> 1;
     const int unit_step = gridDim.x >> 1;
     const int nunits = (p.ntiles + 1) >> 1;
-    const bool has_skip = p.skip != nullptr;
+    constexpr bool has_skip = SKIP;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_act);
@@ -223,32 +223,38 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
             tc_fence_after();
             if (tracer) DG_TRACE(2);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 128 + colhalf * 64;
-#pragma unroll
-            for (int part = 0; part < 2; part++) {          // 32 output channels per part
-                uint32_t acc[32];
-                tmem_ld_32x32b_x32(taddr + part * 32, acc);
-                tmem_ld_wait();
-                if (part == 1) {                             // accumulator fully read: hand it back to the MMA issuer
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(acc_empty0[as]);
-                }
+            uint32_t acc0[32], acc1[32];
+            tmem_ld_32x32b_x32(taddr, acc0);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 32, acc1);           // in flight while the first 32 channels are finished
+            auto finish = [&](const uint32_t (&acc)[32], int part) {
                 uint32_t packed[16];
+                if (halo) {                                  // halo rows stay zero
 #pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&sk[part * 16 + e]));
-                    float v0 = fmaf(alpha, __uint_as_float(acc[2 * e]), bias_h[part * 32 + 2 * e]);
-                    float v1 = fmaf(alpha, __uint_as_float(acc[2 * e + 1]), bias_h[part * 32 + 2 * e + 1]);
-                    v0 = fmaf(beta, s2.x, v0);
-                    v1 = fmaf(beta, s2.y, v1);
-                    v0 = (v0 > 0.f && !halo) ? v0 : 0.f;     // NaN-non-propagating ReLU; halo rows stay zero
-                    v1 = (v1 > 0.f && !halo) ? v1 : 0.f;
-                    const __half2 hv = __floats2half2_rn(v0, v1);
-                    packed[e] = *reinterpret_cast<const uint32_t*>(&hv);
+                    for (int e = 0; e < 16; e++) packed[e] = 0;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        float v0 = fmaf(alpha, __uint_as_float(acc[2 * e]), bias_h[part * 32 + 2 * e]);
+                        float v1 = fmaf(alpha, __uint_as_float(acc[2 * e + 1]), bias_h[part * 32 + 2 * e + 1]);
+                        if (has_skip) {
+                            const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&sk[part * 16 + e]));
+                            v0 = fmaf(beta, s2.x, v0);
+                            v1 = fmaf(beta, s2.y, v1);
+                        }
+                        const __half2 hv = __floats2half2_rn(fmaxf(v0, 0.f), fmaxf(v1, 0.f));   // NaN-non-propagating ReLU
+                        packed[e] = *reinterpret_cast<const uint32_t*>(&hv);
+                    }
                 }
                 st_global_256(p.out + off + part * 32, &packed[0]);
                 st_global_256(p.out + off + part * 32 + 16, &packed[8]);
-            }
+            };
+            finish(acc0, 0);
+            tmem_ld_wait();
+            tc_fence_before();                               // accumulator fully read: hand it back to the MMA issuer
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty0[as]);
+            finish(acc1, 1);
             if (tracer) DG_TRACE(2);
 #pragma unroll
             for (int i = 0; i < 32; i++) sk[i] = sk_next[i];
@@ -266,11 +272,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
 #undef DG_TRACE
 }
 
-template <int NH>
+template <int NH, bool SKIP>
 static cudaError_t launch_pair(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
                                cudaStream_t stream, bool pdl) {
     static bool configured = false;
-    auto kernel = conv3x3_pair_kernel<NH>;
+    auto kernel = conv3x3_pair_kernel<NH, SKIP>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::Smem<NH>::kTotal);
         if (e != cudaSuccess) return e;
@@ -294,7 +300,306 @@ static cudaError_t launch_pair(const CUtensorMap& tm_act, const CUtensorMap& tm_
 
 cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
                              cudaStream_t stream, bool pdl) {
-    return k_halves == 1 ? launch_pair<1>(tm_act, tm_w, p, num_sms, stream, pdl) : launch_pair<2>(tm_act, tm_w, p, num_sms, stream, pdl);
+    if (k_halves == 1) return launch_pair<1, false>(tm_act, tm_w, p, num_sms, stream, pdl);
+    return p.skip ? launch_pair<2, true>(tm_act, tm_w, p, num_sms, stream, pdl) : launch_pair<2, false>(tm_act, tm_w, p, num_sms, stream, pdl);
+}
+
+// =============================================================================================
+// The whole tower (up-sampling layer + every residual-block convolution) as ONE persistent launch.
+//
+// Same CTA-pair machinery as conv3x3_pair_kernel, plus:
+//   * no global barrier between layers: a 256-row unit of layer l only needs units u-1, u, u+1 of
+//     layer l-1, published through per-tile progress flags (st.release by the epilogue, ld.acquire
+//     + fence.proxy.async by the TMA producer).  The same RAW chain also covers every WAR hazard of
+//     the x/y ping-pong buffers;
+//   * the filter bank of layer l+1 replaces layer l's in shared memory half by half: the k-half-0
+//     slabs are reloaded while the last unit of layer l still runs its k-half-1 MMAs, the
+//     k-half-1 slabs while the first unit of layer l+1 runs its k-half-0 MMAs -- no weight bubble;
+//   * the unit -> pair assignment rotates by `rot` pairs per layer so that the pairs that get the
+//     extra (6th) unit differ from layer to layer.
+// The grid must be fully co-resident (<= one CTA per SM, cooperative launch).
+constexpr int kTowerSmem = t2::Smem<2>::kBarOff + 256 + 2 * 512 + 1024;   // + barriers + bias[2][128] + alignment slack
+
+template <int UNUSED = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2::kThreads, 1)
+tower_kernel(const __grid_constant__ TowerParams p) {
+    using namespace t2;
+    constexpr int kWeights = Smem<2>::kWeights, kAOff = Smem<2>::kAOff, kBarOff = Smem<2>::kBarOff;
+    constexpr uint32_t kHalfBytes = 9 * kSlab;           // one k-half of this CTA's filter slice
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_s = smem;
+    uint8_t* a_s = smem + kAOff;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+    uint64_t* a_full = bars;                 // [kStages]
+    uint64_t* a_empty = bars + kStages;      // [kStages]
+    uint64_t* acc_full = bars + 2 * kStages; // [2]
+    uint64_t* acc_empty = acc_full + 2;      // [2]
+    uint64_t* w_full = acc_empty + 2;        // [2] per k-half
+    uint64_t* w_free = w_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* bias_s = reinterpret_cast<float*>(bars + 32);      // [2][128]
+    // barriers (256 B) + two bias buffers (1 KiB) follow the activation ring; see kTowerSmem
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int npairs = gridDim.x >> 1;
+    const int nunits = (p.ntiles + 1) >> 1;
+    auto first_unit = [&](int l) { return (pair + npairs - (l * p.rot) % npairs) % npairs; };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3; i++) tma_prefetch_desc(&p.act[i]);
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 16);
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_free[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    griddep_launch_dependents();
+    const uint32_t tmem_base = *tmem_slot;
+    int tr = 0;
+#define DG_TRACE(role)                                                                          \
+    do {                                                                                        \
+        if (p.trace && tr < 64) p.trace[(blockIdx.x * 3 + (role)) * 64 + tr++] = clock64();     \
+    } while (0)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            const uint32_t w_full0[2] = {mapa_shared(smem_u32(&w_full[0]), 0), mapa_shared(smem_u32(&w_full[1]), 0)};
+            uint32_t a_full0[kStages];
+            for (int i = 0; i < kStages; i++) a_full0[i] = mapa_shared(smem_u32(&a_full[i]), 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            const int ntiles_even = 2 * nunits;
+            for (int l = 0; l < p.nlayers; l++) {
+                const int nh = p.layer[l].nh;
+                const CUtensorMap* tm_w = &p.w[l];
+                const CUtensorMap* tm_a = &p.act[p.layer[l].in_map];
+                auto load_weights = [&](int h) {
+                    if (l > 0) mbar_wait(&w_free[h], (l - 1) & 1);      // layer l-1 no longer reads these slabs
+                    if (rank == 0) mbar_expect_tx(&w_full[h], 2 * kHalfBytes);
+                    for (int tap = 0; tap < 9; tap++)
+                        tma_load_2d_pair(w_s + (tap * 2 + h) * kSlab, tm_w, w_full0[h], h * 64, tap * 128 + rank * 64);
+                };
+                load_weights(0);
+                if (l == 0) { griddep_wait(); DG_TRACE(0); }
+                const int u0 = first_unit(l);
+                for (int u = u0; u < nunits; u += npairs) {
+                    const int tile = 2 * u + rank;
+                    if (l > 0) {        // rows tile*128-21 .. +149 of layer l-1 must be complete and visible
+                        const uint32_t want = p.gen + l;
+                        for (int t = tile - 1; t <= tile + 1; t++) {
+                            if (t < 0 || t >= ntiles_even) continue;
+                            while (static_cast<int32_t>(ld_acquire_gpu(p.done + t) - want) < 0) {
+                            }
+                        }
+                        fence_proxy_async_global();
+                    }
+                    for (int h = 0; h < nh; h++) {
+                        if (u == u0 && h == 1) load_weights(1);
+                        mbar_wait(&a_empty[stage], phase ^ 1);
+                        DG_TRACE(0);
+                        if (rank == 0) mbar_expect_tx(&a_full[stage], 2 * kWindowBytes);
+                        tma_load_2d_pair(a_s + stage * kStageBytes, tm_a, a_full0[stage], h * 64,
+                                         DG_GUARD_ROWS + tile * DG_TILE_M - DG_HALO_ROWS);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA)
+        if (rank == 0) {
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0, wfull_phase[2] = {0, 0};
+            const uint32_t w_lo = umma_desc_lo(smem_u32(w_s));
+            for (int l = 0; l < p.nlayers; l++) {
+                const int nh = p.layer[l].nh;
+                const int u0 = first_unit(l);
+                for (int u = u0; u < nunits; u += npairs) {
+                    const bool last = (u + npairs >= nunits);
+                    mbar_wait_cluster(&acc_empty[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * 128;
+                    // k-half 0
+                    if (u == u0) { mbar_wait(&w_full[0], wfull_phase[0]); wfull_phase[0] ^= 1; }
+                    mbar_wait(&a_full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) DG_TRACE(1);
+                    if (elect_one()) {
+                        issue_half<2, 0>(d_tmem, umma_desc_lo(smem_u32(a_s + stage * kStageBytes)), w_lo, std::make_integer_sequence<int, 36>{});
+                        umma_commit_pair(&a_empty[stage], 3);
+                        if (last) umma_commit_pair(&w_free[0], 3);
+                        if (nh == 1) {
+                            if (last) umma_commit_pair(&w_free[1], 3);
+                            umma_commit_pair(&acc_full[as], 3);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (nh == 2) {   // k-half 1
+                        if (u == u0) { mbar_wait(&w_full[1], wfull_phase[1]); wfull_phase[1] ^= 1; }
+                        mbar_wait(&a_full[stage], phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            issue_half<2, 1>(d_tmem, umma_desc_lo(smem_u32(a_s + stage * kStageBytes)), w_lo, std::make_integer_sequence<int, 36>{});
+                            umma_commit_pair(&a_empty[stage], 3);
+                            if (last) umma_commit_pair(&w_free[1], 3);
+                            umma_commit_pair(&acc_full[as], 3);
+                        }
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    if (lane == 0) DG_TRACE(1);
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (both CTAs)
+        griddep_wait();
+        const int quarter = warp & 3;
+        const int colhalf = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const bool tracer = (threadIdx.x == 64);
+        const uint32_t acc_empty0[2] = {mapa_shared(smem_u32(&acc_empty[0]), 0), mapa_shared(smem_u32(&acc_empty[1]), 0)};
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int l = 0; l < p.nlayers; l++) {
+            const TowerLayer& L = p.layer[l];
+            const bool has_skip = L.has_skip != 0;
+            const float alpha = L.alpha, beta = L.beta;
+            float* bias_l = bias_s + (l & 1) * 128;
+            if (threadIdx.x - 64 < 128) bias_l[threadIdx.x - 64] = L.bias[threadIdx.x - 64];
+            named_bar_sync(2, 256);
+            const float* bias_h = bias_l + colhalf * 64;
+            __half* out = L.out;
+            const __half* skip = L.skip;
+            auto row_info = [&](int u, size_t& off) -> bool {
+                const int m = (2 * u + static_cast<int>(rank)) * DG_TILE_M + row;
+                const int q = m % DG_POS_ROWS;
+                off = static_cast<size_t>(DG_GUARD_ROWS + m) * 128 + colhalf * 64;
+                return (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) || (q >= DG_POS_ROWS - DG_LINE_STRIDE);
+            };
+            // residual input of unit u: written two layers ago, possibly by another pair -> check its flag,
+            // then read it with L2-coherent 256-bit loads, one unit ahead of its use
+            auto prefetch_skip = [&](int u, uint32_t (&dst)[32]) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) dst[i] = 0;
+                if (!has_skip || u >= nunits) return;
+                size_t o;
+                const bool h = row_info(u, o);
+                if (lane == 0) {
+                    const uint32_t want = p.gen + l - 1;
+                    while (static_cast<int32_t>(ld_acquire_gpu(p.done + 2 * u + rank) - want) < 0) {
+                    }
+                }
+                __syncwarp();
+                if (!h) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) ld_global_cg_256(skip + o + i * 16, &dst[i * 8]);
+                }
+            };
+            uint32_t sk[32], sk_next[32];
+            const int u0 = first_unit(l);
+            prefetch_skip(u0, sk);
+            for (int u = u0; u < nunits; u += npairs) {
+                size_t off;
+                const bool halo = row_info(u, off);
+                prefetch_skip(u + npairs, sk_next);
+                if (tracer) DG_TRACE(2);
+                mbar_wait(&acc_full[as], aphase);
+                tc_fence_after();
+                if (tracer) DG_TRACE(2);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 128 + colhalf * 64;
+                uint32_t acc0[32], acc1[32];
+                tmem_ld_32x32b_x32(taddr, acc0);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(taddr + 32, acc1);
+                auto finish = [&](const uint32_t (&acc)[32], int part) {
+                    uint32_t packed[16];
+                    if (halo) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) packed[e] = 0;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) {
+                            float v0 = fmaf(alpha, __uint_as_float(acc[2 * e]), bias_h[part * 32 + 2 * e]);
+                            float v1 = fmaf(alpha, __uint_as_float(acc[2 * e + 1]), bias_h[part * 32 + 2 * e + 1]);
+                            const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&sk[part * 16 + e]));
+                            v0 = fmaf(beta, s2.x, v0);
+                            v1 = fmaf(beta, s2.y, v1);
+                            const __half2 hv = __floats2half2_rn(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+                            packed[e] = *reinterpret_cast<const uint32_t*>(&hv);
+                        }
+                    }
+                    st_global_256(out + off + part * 32, &packed[0]);
+                    st_global_256(out + off + part * 32 + 16, &packed[8]);
+                };
+                finish(acc0, 0);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty0[as]);
+                finish(acc1, 1);
+                // publish: this CTA's tile of layer l is complete once all 8 warps have stored their part
+                named_bar_sync(1, 256);
+                if (threadIdx.x == 64) {
+                    __threadfence();
+                    st_release_gpu(p.done + 2 * u + rank, p.gen + l + 1);
+                }
+                if (tracer) DG_TRACE(2);
+#pragma unroll
+                for (int i = 0; i < 32; i++) sk[i] = sk_next[i];
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, t2::kTmemCols);
+    }
+#undef DG_TRACE
+}
+
+cudaError_t launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream) {
+    static bool configured = false;
+    auto kernel = tower_kernel<0>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTowerSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int nunits = (p.ntiles + 1) / 2;
+    int pairs = num_sms / 2;
+    if (pairs > nunits) pairs = nunits;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(t2::kThreads);
+    cfg.dynamicSmemBytes = kTowerSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;     // every CTA must be resident: CTAs wait on each other's flags
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 }  // namespace dg

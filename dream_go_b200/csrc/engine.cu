@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -40,6 +41,8 @@ struct Workspace {
     uint8_t* h_in = nullptr;          // pinned staging
     __half *h_policy = nullptr, *h_value = nullptr;
     CUtensorMap tm_feat, tm_x, tm_y;           // 170-row load windows
+    uint32_t* done = nullptr;          // per-tile progress flags of the persistent tower kernel
+    uint32_t flag_gen = 0;
     int resident_batch = 0;
     int resident_kind = 0;            // 0 none, 1 raw features, 2 compact positions
     bool busy = false;
@@ -154,6 +157,8 @@ int32_t create_workspace(dg_engine* e, Workspace& w) {
     DG_CUDA(e, cudaMemset(w.x, 0, rows * kChan * 2));
     DG_CUDA(e, cudaMemset(w.y, 0, rows * kChan * 2));
     DG_CUDA(e, cudaMemset(w.h, 0, rows * kHeadChan * 2));
+    DG_CUDA(e, cudaMalloc(&w.done, (static_cast<size_t>(dg_num_tiles(mb)) + 2) * 4));
+    DG_CUDA(e, cudaMemset(w.done, 0, (static_cast<size_t>(dg_num_tiles(mb)) + 2) * 4));
     DG_CUDA(e, cudaHostAlloc(&w.h_in, static_cast<size_t>(mb) * kFeatBytes, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_policy, static_cast<size_t>(mb) * DG_POLICY_SIZE * 2, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_value, static_cast<size_t>(mb) * 2, cudaHostAllocDefault));
@@ -168,7 +173,7 @@ void destroy_workspace(Workspace& w) {
     if (w.ev0) cudaEventDestroy(w.ev0);
     if (w.ev1) cudaEventDestroy(w.ev1);
     cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
-    cudaFree(w.d_policy); cudaFree(w.d_value);
+    cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done);
     cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value);
 }
 
@@ -402,13 +407,45 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
         else DG_CUDA(e, dg::launch_pack_compact(w.d_in, w.feat, batch, w.stream));
         if (stage == 1) return DG_OK;
     }
-    if (stage != 2)
-        if ((rc = run_conv(e, w, ConvTcShape::kUp, w.tm_feat, w.feat, 64, n.up, 128, w.x, kChan, nullptr, 1.f, 0.f, batch))) return rc;
     const int nb = (blocks < 0 || blocks > n.num_blocks) ? n.num_blocks : blocks;
-    for (int i = 0; i < nb; i++) {
-        const float g = n.gate[i];
-        if ((rc = run_conv(e, w, ConvTcShape::kTower, w.tm_x, w.x, kChan, n.c1[i], 128, w.y, kChan, nullptr, 1.f, 0.f, batch))) return rc;
-        if ((rc = run_conv(e, w, ConvTcShape::kTower, w.tm_y, w.y, kChan, n.c2[i], 128, w.x, kChan, w.x, g, 1.0f - g, batch))) return rc;
+    const bool layerwise = (e->cfg.flags & (DG_FLAG_DEBUG_DIRECT_CONV | DG_FLAG_LAYERWISE)) != 0;
+    if (!layerwise) {
+        // the whole tower in one persistent launch (tower_kernel)
+        dg::TowerParams tp;
+        tp.act[0] = w.tm_feat; tp.act[1] = w.tm_x; tp.act[2] = w.tm_y;
+        int nl = 0;
+        auto add = [&](int in_map, int nh, const ConvWeights& cw, __half* out, const __half* skip, float alpha, float beta) {
+            tp.w[nl] = cw.tm;
+            tp.layer[nl] = dg::TowerLayer{in_map, nh, skip != nullptr, alpha, beta, cw.bias, out, skip};
+            nl++;
+        };
+        if (stage != 2) add(0, 1, n.up, w.x, nullptr, 1.f, 0.f);
+        for (int i = 0; i < nb; i++) {
+            const float g = n.gate[i];
+            add(1, 2, n.c1[i], w.y, nullptr, 1.f, 0.f);
+            add(2, 2, n.c2[i], w.x, w.x, g, 1.0f - g);
+        }
+        if (nl > 0) {
+            tp.nlayers = nl;
+            tp.ntiles = dg_num_tiles(batch);
+            tp.valid_rows = batch * DG_POS_ROWS;
+            const int nunits = (tp.ntiles + 1) / 2;
+            const int pairs = std::min(e->num_sms / 2, nunits);
+            tp.rot = (e->cfg.flags & DG_FLAG_NO_ROTATE) ? 0 : nunits % pairs;
+            w.flag_gen += 64;                         // > layers per launch; flags compare modulo 2^32
+            tp.gen = w.flag_gen;
+            tp.done = w.done;
+            tp.trace = e->trace_buf;
+            DG_CUDA(e, dg::launch_tower(tp, e->num_sms, w.stream));
+        }
+    } else {
+        if (stage != 2)
+            if ((rc = run_conv(e, w, ConvTcShape::kUp, w.tm_feat, w.feat, 64, n.up, 128, w.x, kChan, nullptr, 1.f, 0.f, batch))) return rc;
+        for (int i = 0; i < nb; i++) {
+            const float g = n.gate[i];
+            if ((rc = run_conv(e, w, ConvTcShape::kTower, w.tm_x, w.x, kChan, n.c1[i], 128, w.y, kChan, nullptr, 1.f, 0.f, batch))) return rc;
+            if ((rc = run_conv(e, w, ConvTcShape::kTower, w.tm_y, w.y, kChan, n.c2[i], 128, w.x, kChan, w.x, g, 1.0f - g, batch))) return rc;
+        }
     }
     if (blocks >= 0 || stage == 2) return DG_OK;
     if ((rc = run_conv(e, w, ConvTcShape::kHeads, w.tm_x, w.x, kChan, n.heads, kHeadChan, w.h, kHeadChan, nullptr, 1.f, 0.f, batch))) return rc;
@@ -725,7 +762,7 @@ int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, int3
     float ms = 0.f;
     rc = timed_pass(0, &ms);
     if (rc == DG_OK && ms_total) *ms_total = ms;
-    if (launches) *launches = 4 + 2 * e->net.num_blocks;      // pack, up, 2 per block, head conv, head fc
+    if (launches) *launches = (e->cfg.flags & (DG_FLAG_DEBUG_DIRECT_CONV | DG_FLAG_LAYERWISE)) ? 4 + 2 * e->net.num_blocks : 4;   // pack, tower, head conv, head fc
     if (rc == DG_OK && tower_ms) {
         rc = timed_pass(2, tower_ms);
         // leave the workspace holding a complete forward again

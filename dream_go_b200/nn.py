@@ -30,6 +30,8 @@ POLICY_SIZE = 362
 DG_OK = 0
 FLAG_DEBUG_DIRECT_CONV = 0x1
 FLAG_NO_PDL = 0x2
+FLAG_LAYERWISE = 0x4
+FLAG_NO_ROTATE = 0x8
 
 
 class Error(Exception):

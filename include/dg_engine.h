@@ -43,6 +43,8 @@ extern "C" {
                                             cross-check kernel instead of the tcgen05 kernel */
 
 #define DG_FLAG_NO_PDL             0x2u  /* debug: launch the layers without programmatic dependent launch */
+#define DG_FLAG_LAYERWISE          0x4u  /* debug: one launch per convolution instead of the persistent tower kernel */
+#define DG_FLAG_NO_ROTATE          0x8u  /* debug: do not rotate the unit -> CTA-pair assignment between layers */
 
 typedef struct dg_engine dg_engine;
 

@@ -28,7 +28,7 @@ def main():
     t0 = time.time()
     ov, op, oblocks = onet.forward(feats, want_blocks=True)
     print(f"oracle: {time.time() - t0:.2f}s", flush=True)
-    flags = {"direct": nn.FLAG_DEBUG_DIRECT_CONV, "tc": 0, "nopdl": nn.FLAG_NO_PDL}
+    flags = {"direct": nn.FLAG_DEBUG_DIRECT_CONV, "tc": 0, "nopdl": nn.FLAG_NO_PDL, "layerwise": nn.FLAG_LAYERWISE, "norot": nn.FLAG_NO_ROTATE}
     for v in variants:
         print(f"== {v}", flush=True)
         try:
