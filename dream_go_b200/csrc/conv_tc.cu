@@ -1,9 +1,9 @@
-// 3x3 convolution over board rows as an implicit GEMM on the 5th-generation tensor cores.
+// Head 3x3 convolutions (128 -> 8 policy samples + 2 value samples, one N=16 implicit GEMM) on the
+// 5th-generation tensor cores.
 //
-// Replaces cudnnConvolutionBiasActivationForward as driven by
-// src/libdg_nn/layers/conv2d.rs:171-220 (`Conv2d::forward` / `forward_skip`):
-//     y = relu(alpha * conv3x3(x, w) + beta * skip + bias)
-// x / y / skip are board-row buffers (layout.h), w is KRSC fp16 re-laid out per tap.
+// Replaces the two cudnnConvolutionBiasActivationForward calls of policy_head.rs:49-52 and
+// value_head.rs:45-49:  p1 = relu(conv3x3(x, Wp) + bp),  v1 = relu(conv3x3(x, Wv) + bv).
+// x is a board-row buffer (layout.h), the filters are KRSC fp16 re-laid out per tap.
 //
 // Design (one persistent CTA per SM, warp-specialised, 192 threads):
 //   * weights of this CTA's output-channel slice stay RESIDENT in shared memory for the whole
@@ -164,49 +164,36 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_const
         const int quarter = warp & 3;
         int as = 0;
         uint32_t aphase = 0;
-        const float alpha = p.alpha, beta = p.beta;
+        const float alpha = p.alpha;
         for (int t = first_tile; t < p.ntiles; t += tile_step) {
             const int m = t * DG_TILE_M + quarter * 32 + lane;
             const int q = m % DG_POS_ROWS;
             const bool halo = (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) ||
                               (q >= DG_POS_ROWS - DG_LINE_STRIDE);
             const size_t grow = static_cast<size_t>(DG_GUARD_ROWS + m);
-            __half* out_row = p.out + grow * p.out_stride + nslice * BN;
-            const __half* skip_row = p.skip ? p.skip + grow * p.skip_stride + nslice * BN : nullptr;
 
             if (warp == 2 && lane == 0) DG_TRACE(2);
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
             if (warp == 2 && lane == 0) DG_TRACE(2);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+            static_assert(BN == 16, "this kernel is instantiated for the 16-channel head convolution only");
+            uint32_t acc[16];
+            tmem_ld_32x32b_x16(taddr, acc);
+            tmem_ld_wait();
+            uint32_t packed[8];
 #pragma unroll
-            for (int c = 0; c < BN / 16; c++) {
-                uint32_t acc[16];
-                tmem_ld_32x32b_x16(taddr + c * 16, acc);
-                uint4 s0 = make_uint4(0, 0, 0, 0), s1 = make_uint4(0, 0, 0, 0);
-                if (skip_row && !halo) {
-                    s0 = *reinterpret_cast<const uint4*>(skip_row + c * 16);
-                    s1 = *reinterpret_cast<const uint4*>(skip_row + c * 16 + 8);
-                }
-                tmem_ld_wait();
-                const __half2* sh0 = reinterpret_cast<const __half2*>(&s0);
-                const __half2* sh1 = reinterpret_cast<const __half2*>(&s1);
-                uint32_t packed[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float2 sk = __half22float2(j < 4 ? sh0[j] : sh1[j - 4]);
-                    float v0 = fmaf(alpha, __uint_as_float(acc[2 * j]), bias_s[c * 16 + 2 * j]);
-                    float v1 = fmaf(alpha, __uint_as_float(acc[2 * j + 1]), bias_s[c * 16 + 2 * j + 1]);
-                    v0 = fmaf(beta, sk.x, v0);
-                    v1 = fmaf(beta, sk.y, v1);
-                    v0 = (v0 > 0.f && !halo) ? v0 : 0.f;     // NaN-non-propagating ReLU; halo rows stay zero
-                    v1 = (v1 > 0.f && !halo) ? v1 : 0.f;
-                    const __half2 hv = __floats2half2_rn(v0, v1);
-                    packed[j] = *reinterpret_cast<const uint32_t*>(&hv);
-                }
-                *reinterpret_cast<uint4*>(out_row + c * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4*>(out_row + c * 16 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            for (int j = 0; j < 8; j++) {
+                float v0 = fmaf(alpha, __uint_as_float(acc[2 * j]), bias_s[2 * j]);
+                float v1 = fmaf(alpha, __uint_as_float(acc[2 * j + 1]), bias_s[2 * j + 1]);
+                v0 = (v0 > 0.f && !halo) ? v0 : 0.f;     // NaN-non-propagating ReLU; halo rows stay zero
+                v1 = (v1 > 0.f && !halo) ? v1 : 0.f;
+                const __half2 hv = __floats2half2_rn(v0, v1);
+                packed[j] = *reinterpret_cast<const uint32_t*>(&hv);
             }
+            // channels 0..7 = policy samples -> out[row][8]; channels 8..9 = value samples -> out2[row][2]
+            *reinterpret_cast<uint4*>(p.out + grow * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint32_t*>(p.out2 + grow * 2) = packed[4];
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -254,12 +241,8 @@ static cudaError_t launch_one(const CUtensorMap& tm_act, const CUtensorMap& tm_w
 
 cudaError_t launch_conv_tc(ConvTcShape shape, const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p,
                            int num_sms, cudaStream_t stream, bool pdl) {
-    switch (shape) {
-        case ConvTcShape::kUp:    return launch_one<1, 64>(tm_act, tm_w, p, num_sms, stream, pdl);
-        case ConvTcShape::kTower: return launch_one<2, 64>(tm_act, tm_w, p, num_sms, stream, pdl);
-        case ConvTcShape::kHeads: return launch_one<2, 16>(tm_act, tm_w, p, num_sms, stream, pdl);
-    }
-    return cudaErrorInvalidValue;
+    if (shape != ConvTcShape::kHeads) return cudaErrorInvalidValue;   // tower / up-sampling run in conv_tc2.cu
+    return launch_one<2, 16>(tm_act, tm_w, p, num_sms, stream, pdl);
 }
 
 }  // namespace dg

@@ -10,6 +10,7 @@ struct ConvTcParams {
     int valid_rows;             // batch * 400; rows beyond are written as zero
     __half* out;                // board-row buffer (row 0 = guard start)
     int out_stride;             // elements per output row
+    __half* out2;               // head convolution only: value samples [row][2]
     const __half* skip;         // optional residual input (same rows), nullptr if none
     int skip_stride;
     const float* bias;          // [Cout] fp32 (already scaled and fp16-rounded where the reference does so)

@@ -36,7 +36,12 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint8_t* d_in = nullptr;          // raw NHWC features or compact positions of the current batch
-    __half *feat = nullptr, *x = nullptr, *y = nullptr, *h = nullptr;
+    __half *feat = nullptr, *x = nullptr, *y = nullptr;
+    __half *h = nullptr;               // [row][16] head-conv output of the debug direct path only
+    __half *pbuf = nullptr;            // [row][8] policy samples = A operand of the policy FC GEMM
+    __half *vbuf = nullptr;            // [row][2] value samples
+    float* part = nullptr;             // [K split][batch rounded to 128][384] fp32 partial sums
+    CUtensorMap tm_pa;                 // [batch][3200] view of pbuf
     __half *d_policy = nullptr, *d_value = nullptr;
     uint8_t* h_in = nullptr;          // pinned staging
     __half *h_policy = nullptr, *h_value = nullptr;
@@ -60,9 +65,10 @@ struct DeviceNet {
     std::vector<ConvWeights> c1, c2;
     std::vector<float> gate;
     ConvWeights heads;
-    __half* w_pfc = nullptr;          // [2888][362]
+    __half* w_pfc = nullptr;          // [384 out][3200 = 400 board rows x 8 samples] (zero for halo rows / padding)
+    CUtensorMap tm_pfc;
     float* b_pfc = nullptr;           // fp16(tau * b) as fp32
-    __half* w_vfc = nullptr;          // [722]
+    __half* w_vfc = nullptr;          // [400 board rows][2 samples] (zero for halo rows)
     float b_vfc = 0.f;
     float tau = 1.f;
     std::vector<void*> allocations;
@@ -157,13 +163,19 @@ int32_t create_workspace(dg_engine* e, Workspace& w) {
     DG_CUDA(e, cudaMemset(w.x, 0, rows * kChan * 2));
     DG_CUDA(e, cudaMemset(w.y, 0, rows * kChan * 2));
     DG_CUDA(e, cudaMemset(w.h, 0, rows * kHeadChan * 2));
+    DG_CUDA(e, cudaMalloc(&w.pbuf, rows * 8 * 2));
+    DG_CUDA(e, cudaMalloc(&w.vbuf, rows * 2 * 2));
+    DG_CUDA(e, cudaMemset(w.pbuf, 0, rows * 8 * 2));
+    DG_CUDA(e, cudaMemset(w.vbuf, 0, rows * 2 * 2));
+    DG_CUDA(e, cudaMalloc(&w.part, static_cast<size_t>(dg::kPolicyFcSplit) * ((mb + 127) / 128 * 128) * dg::kPolicyFcN * 4));
     DG_CUDA(e, cudaMalloc(&w.done, (static_cast<size_t>(dg_num_tiles(mb)) + 2) * 4));
     DG_CUDA(e, cudaMemset(w.done, 0, (static_cast<size_t>(dg_num_tiles(mb)) + 2) * 4));
     DG_CUDA(e, cudaHostAlloc(&w.h_in, static_cast<size_t>(mb) * kFeatBytes, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_policy, static_cast<size_t>(mb) * DG_POLICY_SIZE * 2, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_value, static_cast<size_t>(mb) * 2, cudaHostAllocDefault));
     if (!make_tmap(e, &w.tm_feat, w.feat, 64, rows, DG_WINDOW_ROWS) || !make_tmap(e, &w.tm_x, w.x, kChan, rows, DG_WINDOW_ROWS) ||
-        !make_tmap(e, &w.tm_y, w.y, kChan, rows, DG_WINDOW_ROWS))
+        !make_tmap(e, &w.tm_y, w.y, kChan, rows, DG_WINDOW_ROWS) ||
+        !make_tmap(e, &w.tm_pa, w.pbuf + static_cast<size_t>(DG_GUARD_ROWS) * 8, dg::kPolicyFcK, mb, 128))
         return fail(e, DG_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation buffer");
     return DG_OK;
 }
@@ -173,7 +185,7 @@ void destroy_workspace(Workspace& w) {
     if (w.ev0) cudaEventDestroy(w.ev0);
     if (w.ev1) cudaEventDestroy(w.ev1);
     cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
-    cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done);
+    cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done); cudaFree(w.pbuf); cudaFree(w.vbuf); cudaFree(w.part);
     cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value);
 }
 
@@ -348,18 +360,30 @@ int32_t load_net(dg_engine* e, const dg::TensorMap& t) {
 
         const float temperature = e->cfg.softmax_temperature > 0.f ? e->cfg.softmax_temperature : 0.709888f;
         n.tau = 1.0f / temperature;                                  // policy_head.rs:46
-        std::vector<uint16_t> pfc(reinterpret_cast<const uint16_t*>(pl->bytes.data()),
-                                  reinterpret_cast<const uint16_t*>(pl->bytes.data()) + 2888 * 362);
+        // policy FC weight, file order [2888 in = 8*point + sample][362 out] (dense.py:32-39), re-laid out K-major
+        // over board ROWS: w'[out][8*row + sample], zero where the row is a halo row
+        const uint16_t* plw = reinterpret_cast<const uint16_t*>(pl->bytes.data());
+        std::vector<uint16_t> pfc(static_cast<size_t>(dg::kPolicyFcN) * dg::kPolicyFcK, 0);
+        for (int y = 0; y < 19; y++)
+            for (int x = 0; x < 19; x++)
+                for (int sm = 0; sm < 8; sm++) {
+                    const int in = 8 * (19 * y + x) + sm, kk = 8 * (DG_LINE_STRIDE * y + x) + sm;
+                    for (int o = 0; o < 362; o++) pfc[static_cast<size_t>(o) * dg::kPolicyFcK + kk] = plw[static_cast<size_t>(in) * 362 + o];
+                }
         uint16_t* d = nullptr;
         if ((rc = upload<uint16_t>(e, n, pfc, &d))) return cleanup(rc);
         n.w_pfc = reinterpret_cast<__half*>(d);
+        if (!make_tmap(e, &n.tm_pfc, n.w_pfc, dg::kPolicyFcK, dg::kPolicyFcN, 128)) return cleanup(fail(e, DG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the policy FC weight"));
         std::vector<float> pfb(362);
         for (int i = 0; i < 362; i++)   // offset scaled by tau in place, in fp16 (policy_head.rs:87-89)
             pfb[i] = h2f(f2h(static_cast<float>(static_cast<double>(n.tau) *
                                                  static_cast<double>(h2f(reinterpret_cast<const uint16_t*>(plb->bytes.data())[i])))));
         if ((rc = upload<float>(e, n, pfb, &n.b_pfc))) return cleanup(rc);
-        std::vector<uint16_t> vfc(reinterpret_cast<const uint16_t*>(vl->bytes.data()),
-                                  reinterpret_cast<const uint16_t*>(vl->bytes.data()) + 722);
+        const uint16_t* vlw = reinterpret_cast<const uint16_t*>(vl->bytes.data());
+        std::vector<uint16_t> vfc(DG_POS_ROWS * 2, 0);
+        for (int y = 0; y < 19; y++)
+            for (int x = 0; x < 19; x++)
+                for (int sm = 0; sm < 2; sm++) vfc[2 * (DG_LINE_STRIDE * y + x) + sm] = vlw[2 * (19 * y + x) + sm];
         if ((rc = upload<uint16_t>(e, n, vfc, &d))) return cleanup(rc);
         n.w_vfc = reinterpret_cast<__half*>(d);
         n.b_vfc = h2f(reinterpret_cast<const uint16_t*>(vlb->bytes.data())[0]);
@@ -373,7 +397,8 @@ int32_t load_net(dg_engine* e, const dg::TensorMap& t) {
 // ------------------------------------------------------------------------------------ forward
 
 int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMap& tm_in, const __half* in, int cin,
-                 const ConvWeights& cw, int ntot, __half* out, int out_stride, const __half* skip, float alpha, float beta, int batch) {
+                 const ConvWeights& cw, int ntot, __half* out, int out_stride, const __half* skip, float alpha, float beta, int batch,
+                 __half* out2 = nullptr) {
     if (e->cfg.flags & DG_FLAG_DEBUG_DIRECT_CONV) {
         DG_CUDA(e, dg::launch_conv_direct(in, cin, cw.w, ntot, cw.bias, alpha, beta, skip, kChan, out, out_stride, batch, w.stream));
         return DG_OK;
@@ -383,6 +408,7 @@ int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMa
     p.valid_rows = batch * DG_POS_ROWS;
     p.out = out;
     p.out_stride = out_stride;
+    p.out2 = out2;
     p.skip = skip;
     p.skip_stride = kChan;
     p.bias = cw.bias;
@@ -448,8 +474,14 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
         }
     }
     if (blocks >= 0 || stage == 2) return DG_OK;
-    if ((rc = run_conv(e, w, ConvTcShape::kHeads, w.tm_x, w.x, kChan, n.heads, kHeadChan, w.h, kHeadChan, nullptr, 1.f, 0.f, batch))) return rc;
-    DG_CUDA(e, dg::launch_heads_fc(w.h, n.w_pfc, n.b_pfc, n.tau, n.w_vfc, n.b_vfc, batch, w.d_policy, w.d_value, w.stream));
+    if (e->cfg.flags & DG_FLAG_DEBUG_DIRECT_CONV) {
+        if ((rc = run_conv(e, w, ConvTcShape::kHeads, w.tm_x, w.x, kChan, n.heads, kHeadChan, w.h, kHeadChan, nullptr, 1.f, 0.f, batch))) return rc;
+        DG_CUDA(e, dg::launch_split_heads(w.h, w.pbuf, w.vbuf, batch, w.stream));
+    } else {
+        if ((rc = run_conv(e, w, ConvTcShape::kHeads, w.tm_x, w.x, kChan, n.heads, kHeadChan, w.pbuf, 8, nullptr, 1.f, 0.f, batch, w.vbuf))) return rc;
+    }
+    DG_CUDA(e, dg::launch_policy_fc(w.tm_pa, n.tm_pfc, w.part, batch, w.stream));
+    DG_CUDA(e, dg::launch_heads_finish(w.part, batch, n.b_pfc, n.tau, w.vbuf, n.w_vfc, n.b_vfc, w.d_policy, w.d_value, w.stream));
     return DG_OK;
 }
 
@@ -762,7 +794,7 @@ int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, int3
     float ms = 0.f;
     rc = timed_pass(0, &ms);
     if (rc == DG_OK && ms_total) *ms_total = ms;
-    if (launches) *launches = (e->cfg.flags & (DG_FLAG_DEBUG_DIRECT_CONV | DG_FLAG_LAYERWISE)) ? 4 + 2 * e->net.num_blocks : 4;   // pack, tower, head conv, head fc
+    if (launches) *launches = (e->cfg.flags & (DG_FLAG_DEBUG_DIRECT_CONV | DG_FLAG_LAYERWISE)) ? 5 + 2 * e->net.num_blocks : 5;   // pack, tower, head conv, policy FC, finish
     if (rc == DG_OK && tower_ms) {
         rc = timed_pass(2, tower_ms);
         // leave the workspace holding a complete forward again
