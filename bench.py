@@ -11,7 +11,9 @@ JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
                CUDA-event pair on the engine's stream, L2 flushed (256 MiB memset) between steps.
 * e2e        : the same through the reference-facing C-ABI call `dg_engine_forward_f16`
                (== dg_nn::forward) from pinned HOST buffers, H2D + D2H inside the timed region.
-* roofline   : dominant kernel = conv3x3_tc_kernel<2,64> (18 launches per step); tensor bound.
+* roofline   : dominant kernel = tower_kernel (ONE persistent launch per step that runs the up-sampling
+               layer and all 18 residual 3x3 128->128 convolutions); tensor bound.  `achieved` is timed
+               live on the 18 residual convolutions alone (a second pass of tower-only launches).
 * cpu_baseline / --impl reference : the CPU oracle port of dg_nn::forward on the host cores.
 """
 from __future__ import annotations
@@ -58,7 +60,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -117,6 +119,28 @@ def oracle_rate(seconds_target: float, steps: int = 1, warmup: int = 0):
                                  "sample": f"{sample} of the {BATCH} positions of one batch x {steps} step(s), same weights/inputs distribution"}
 
 
+def cudnn_baseline(tensors, feats, steps: int):
+    """The reference's own GPU path restated call for call on the image's cuDNN (baseline/cudnn_ref.cu),
+    same weights, same positions, same box: device-resident and end-to-end (blocking H2D/D2H) rates."""
+    try:
+        from baseline import cudnn_ref
+        ref = cudnn_ref.CudnnNetwork(tensors, BATCH)
+        host = np.array(feats)                      # the reference passes a plain (pageable) slice
+        ref.forward(host)
+        ref.time_resident(5)
+        ms = ref.time_resident(steps) / steps
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ref.forward(host)
+        e2e = (time.perf_counter() - t0) / steps
+        info = ref.info
+        ref.close()
+        return {"value": BATCH / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "e2e": BATCH / e2e, "kind": "cuDNN 9.10.2 legacy API, 25 launches/forward (graph.rs:123-158)",
+                "algos": info[:160]}
+    except Exception as exc:   # noqa: BLE001
+        return {"unavailable": repr(exc)[:200]}
+
+
 def run_reference(args, rank: int):
     """`--impl reference`: the reference's CPU-side restatement (oracle port; the Rust + cuDNN
     reference cannot be built in this image) on the host cores."""
@@ -173,9 +197,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- device-resident timing -------------------------------------------------------------------
     barrier()
     net.synchronize()
-    with ClockSampler(local_rank) as clocks:
-        ms_total, tower_ms, launches = net.time_resident(BATCH, args.steps, tower=True, flush_l2=True)
-        net.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    ms_total, tower_ms, launches = net.time_resident(BATCH, args.steps, tower=True, flush_l2=True)
+    net.synchronize()
     barrier()
     ms_total = max_over_ranks(ms_total)
     ms_per_step = ms_total / args.steps
@@ -195,6 +220,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     for _ in range(args.steps):
         net.forward_into(packed, value, policy, packed=True)
     e2e_packed_s = max_over_ranks(time.perf_counter() - t0)
+    clocks.__exit__()
 
     if dist is not None:
         dist.barrier()
@@ -202,13 +228,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if rank != 0:
         return
     peak_tf, _peak_gbs, peak_kind = measured_peaks()
-    conv_launch_s = tower_ms * 1e-3 / (args.steps * 2 * NUM_BLOCKS)
-    achieved_tf = BATCH * TOWER_CONV_FLOP_PER_POS / conv_launch_s / 1e12
+    tower_launch_s = tower_ms * 1e-3 / args.steps                      # one tower-only launch = 18 convolutions
+    achieved_tf = 2 * NUM_BLOCKS * BATCH * TOWER_CONV_FLOP_PER_POS / tower_launch_s / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("conv3x3_tc_kernel<2,64>_dram_bytes_per_launch")
+            traffic = json.load(fh).get("tower_kernel_dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": value_evals, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -224,13 +250,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "h2d_bytes_per_step": BATCH * nn.PACKED_DTYPE.itemsize, "d2h_bytes_per_step": BATCH * 363 * 2,
                        "call": "dg_engine_forward_packed"},
         "gpu_launches": launches * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel<2,64> (3x3 128->128, 18 launches/step)",
+        "roofline": {"bound": "tensor", "kernel": "tower_kernel (persistent; 18 residual 3x3 128->128 convolutions per launch)",
                      "achieved": achieved_tf, "peak": peak_tf, "peak_kind": f"{peak_kind} burst bf16 (MEASURED_PEAKS.json)",
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
-                     "us_per_launch": conv_launch_s * 1e6,
+                     "us_per_launch": tower_launch_s * 1e6, "us_per_conv_layer": tower_launch_s * 1e6 / (2 * NUM_BLOCKS),
                      "whole_net_frac": (value_evals / world) * FLOP_PER_EVAL / (peak_tf * 1e12)},
     }
     if world == 1 and not os.environ.get("DG_BENCH_SKIP_CPU"):      # skipped only under the profiler
+        line["cudnn_baseline"] = cudnn_baseline(tensors, feats, args.steps)
         rate, info = oracle_rate(seconds_target=15.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
     print(json.dumps(line), flush=True)
@@ -239,7 +266,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

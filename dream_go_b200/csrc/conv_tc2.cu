@@ -318,7 +318,7 @@ cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUte
 //   * the unit -> pair assignment rotates by `rot` pairs per layer so that the pairs that get the
 //     extra (6th) unit differ from layer to layer.
 // The grid must be fully co-resident (<= one CTA per SM, cooperative launch).
-constexpr int kTowerSmem = t2::Smem<2>::kBarOff + 256 + 2 * 512 + 1024;   // + barriers + bias[2][128] + alignment slack
+constexpr int kTowerSmem = t2::Smem<2>::kBarOff + 256 + 4 * 512 + 1024;   // + barriers + bias[2][2][128] + alignment slack
 
 template <int UNUSED = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2::kThreads, 1)
@@ -338,7 +338,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
     uint64_t* w_full = acc_empty + 2;        // [2] per k-half
     uint64_t* w_free = w_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    float* bias_s = reinterpret_cast<float*>(bars + 32);      // [2][128]
+    float* bias_s = reinterpret_cast<float*>(bars + 32);      // [2 groups][2][128]
     // barriers (256 B) + two bias buffers (1 KiB) follow the activation ring; see kTowerSmem
 
     const int warp = threadIdx.x >> 5;
@@ -357,7 +357,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 16);
+            mbar_init(&acc_empty[i], 8);           // 4 warps of one epilogue group x 2 CTAs
             mbar_init(&w_full[i], 1);
             mbar_init(&w_free[i], 1);
         }
@@ -372,7 +372,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
     int tr = 0;
 #define DG_TRACE(role)                                                                          \
     do {                                                                                        \
-        if (p.trace && tr < 64) p.trace[(blockIdx.x * 3 + (role)) * 64 + tr++] = clock64();     \
+        if (p.trace && tr < 1024) p.trace[(blockIdx.x * 3 + (role)) * 1024 + tr++] = clock64(); \
     } while (0)
 
     if (warp == 0) {
@@ -399,6 +399,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                 const int u0 = first_unit(l);
                 for (int u = u0; u < nunits; u += npairs) {
                     const int tile = 2 * u + rank;
+                    DG_TRACE(0);
                     if (l > 0) {        // rows tile*128-21 .. +149 of layer l-1 must be complete and visible
                         const uint32_t want = p.gen + l;
                         for (int t = tile - 1; t <= tile + 1; t++) {
@@ -410,8 +411,8 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                     }
                     for (int h = 0; h < nh; h++) {
                         if (u == u0 && h == 1) load_weights(1);
+                        if (h == 0) DG_TRACE(0);
                         mbar_wait(&a_empty[stage], phase ^ 1);
-                        DG_TRACE(0);
                         if (rank == 0) mbar_expect_tx(&a_full[stage], 2 * kWindowBytes);
                         tma_load_2d_pair(a_s + stage * kStageBytes, tm_a, a_full0[stage], h * 64,
                                          DG_GUARD_ROWS + tile * DG_TILE_M - DG_HALO_ROWS);
@@ -431,8 +432,10 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                 const int u0 = first_unit(l);
                 for (int u = u0; u < nunits; u += npairs) {
                     const bool last = (u + npairs >= nunits);
+                    if (lane == 0) DG_TRACE(1);
                     mbar_wait_cluster(&acc_empty[as], aphase ^ 1);
                     tc_fence_after();
+                    if (lane == 0) DG_TRACE(1);
                     const uint32_t d_tmem = tmem_base + as * 128;
                     // k-half 0
                     if (u == u0) { mbar_wait(&w_full[0], wfull_phase[0]); wfull_phase[0] ^= 1; }
@@ -470,102 +473,127 @@ tower_kernel(const __grid_constant__ TowerParams p) {
         }
     } else {
         // ------------------------------------------------------------ epilogue warps (both CTAs)
+        // Two independent groups of four warps: group g drains accumulator stage g, i.e. every second unit
+        // of this pair, one thread per row and all 128 output channels.  The groups run out of phase (one
+        // reads TMEM / does the math while the other one's stores drain), and each has two unit-times per unit.
         griddep_wait();
         const int quarter = warp & 3;
-        const int colhalf = (warp - 2) >> 2;
+        const int g = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const bool tracer = (threadIdx.x == 64);
-        const uint32_t acc_empty0[2] = {mapa_shared(smem_u32(&acc_empty[0]), 0), mapa_shared(smem_u32(&acc_empty[1]), 0)};
-        int as = 0;
+        const bool leader = ((threadIdx.x - 64) & 127) == 0;
+        const uint32_t acc_empty0 = mapa_shared(smem_u32(&acc_empty[g]), 0);
+        float* bias_g = bias_s + g * 256;                  // [2][128] per group
         uint32_t aphase = 0;
-        for (int l = 0; l < p.nlayers; l++) {
+        auto next_item = [&](int& l, int& u) {
+            u += npairs;
+            if (u >= nunits) {
+                l++;
+                if (l < p.nlayers) u = first_unit(l);
+            }
+        };
+        auto row_info = [&](int u, size_t& off) -> bool {
+            const int m = (2 * u + static_cast<int>(rank)) * DG_TILE_M + row;
+            const int q = m % DG_POS_ROWS;
+            off = static_cast<size_t>(DG_GUARD_ROWS + m) * 128;
+            return (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) || (q >= DG_POS_ROWS - DG_LINE_STRIDE);
+        };
+        uint32_t sk[64];
+        // residual input of unit (l, u): written two layers ago, possibly by another pair -> check its flag, then
+        // read it with L2-coherent 256-bit loads; issued as soon as the previous unit of this group is done
+        auto prefetch_skip = [&](int l, int u) {
+            if (!p.layer[l].has_skip) return;
+            size_t o;
+            const bool h = row_info(u, o);
+            if (lane == 0) {
+                const uint32_t want = p.gen + l - 1;
+                while (static_cast<int32_t>(ld_acquire_gpu(p.done + 2 * u + rank) - want) < 0) {
+                }
+            }
+            __syncwarp();
+            if (!h) {
+                const __half* src = p.layer[l].skip + o;
+#pragma unroll
+                for (int i = 0; i < 8; i++) ld_global_cg_256(src + i * 16, &sk[i * 8]);
+            }
+        };
+        int l = 0, u = first_unit(0);
+        if (g == 1) next_item(l, u);
+        int bias_layer = -1;
+        if (l < p.nlayers) prefetch_skip(l, u);
+        while (l < p.nlayers) {
             const TowerLayer& L = p.layer[l];
+            float* bias_l = bias_g + (l & 1) * 128;
+            if (bias_layer != l) {
+                bias_l[(threadIdx.x - 64) & 127] = L.bias[(threadIdx.x - 64) & 127];
+                named_bar_sync(3 + g, 128);
+                bias_layer = l;
+            }
             const bool has_skip = L.has_skip != 0;
             const float alpha = L.alpha, beta = L.beta;
-            float* bias_l = bias_s + (l & 1) * 128;
-            if (threadIdx.x - 64 < 128) bias_l[threadIdx.x - 64] = L.bias[threadIdx.x - 64];
-            named_bar_sync(2, 256);
-            const float* bias_h = bias_l + colhalf * 64;
             __half* out = L.out;
-            const __half* skip = L.skip;
-            auto row_info = [&](int u, size_t& off) -> bool {
-                const int m = (2 * u + static_cast<int>(rank)) * DG_TILE_M + row;
-                const int q = m % DG_POS_ROWS;
-                off = static_cast<size_t>(DG_GUARD_ROWS + m) * 128 + colhalf * 64;
-                return (m >= p.valid_rows) || (q % DG_LINE_STRIDE == DG_LINE_STRIDE - 1) || (q >= DG_POS_ROWS - DG_LINE_STRIDE);
-            };
-            // residual input of unit u: written two layers ago, possibly by another pair -> check its flag,
-            // then read it with L2-coherent 256-bit loads, one unit ahead of its use
-            auto prefetch_skip = [&](int u, uint32_t (&dst)[32]) {
+            size_t off;
+            const bool halo = row_info(u, off);
+            if (tracer) DG_TRACE(2);
+            mbar_wait(&acc_full[g], aphase);
+            aphase ^= 1;
+            tc_fence_after();
+            if (tracer) DG_TRACE(2);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * 128;
+            auto finish = [&](const uint32_t (&acc)[32], int part) {
+                uint32_t packed[16];
+                if (halo) {
 #pragma unroll
-                for (int i = 0; i < 32; i++) dst[i] = 0;
-                if (!has_skip || u >= nunits) return;
-                size_t o;
-                const bool h = row_info(u, o);
-                if (lane == 0) {
-                    const uint32_t want = p.gen + l - 1;
-                    while (static_cast<int32_t>(ld_acquire_gpu(p.done + 2 * u + rank) - want) < 0) {
+                    for (int e = 0; e < 16; e++) packed[e] = 0;
+                } else if (has_skip) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        float v0 = fmaf(alpha, __uint_as_float(acc[2 * e]), bias_l[part * 32 + 2 * e]);
+                        float v1 = fmaf(alpha, __uint_as_float(acc[2 * e + 1]), bias_l[part * 32 + 2 * e + 1]);
+                        const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&sk[part * 16 + e]));
+                        v0 = fmaf(beta, s2.x, v0);
+                        v1 = fmaf(beta, s2.y, v1);
+                        const __half2 hv = __floats2half2_rn(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+                        packed[e] = *reinterpret_cast<const uint32_t*>(&hv);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const float v0 = fmaf(alpha, __uint_as_float(acc[2 * e]), bias_l[part * 32 + 2 * e]);
+                        const float v1 = fmaf(alpha, __uint_as_float(acc[2 * e + 1]), bias_l[part * 32 + 2 * e + 1]);
+                        const __half2 hv = __floats2half2_rn(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+                        packed[e] = *reinterpret_cast<const uint32_t*>(&hv);
                     }
                 }
-                __syncwarp();
-                if (!h) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) ld_global_cg_256(skip + o + i * 16, &dst[i * 8]);
-                }
+                st_global_256(out + off + part * 32, &packed[0]);
+                st_global_256(out + off + part * 32 + 16, &packed[8]);
             };
-            uint32_t sk[32], sk_next[32];
-            const int u0 = first_unit(l);
-            prefetch_skip(u0, sk);
-            for (int u = u0; u < nunits; u += npairs) {
-                size_t off;
-                const bool halo = row_info(u, off);
-                prefetch_skip(u + npairs, sk_next);
-                if (tracer) DG_TRACE(2);
-                mbar_wait(&acc_full[as], aphase);
-                tc_fence_after();
-                if (tracer) DG_TRACE(2);
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 128 + colhalf * 64;
-                uint32_t acc0[32], acc1[32];
-                tmem_ld_32x32b_x32(taddr, acc0);
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(taddr + 32, acc1);
-                auto finish = [&](const uint32_t (&acc)[32], int part) {
-                    uint32_t packed[16];
-                    if (halo) {
-#pragma unroll
-                        for (int e = 0; e < 16; e++) packed[e] = 0;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; e++) {
-                            float v0 = fmaf(alpha, __uint_as_float(acc[2 * e]), bias_h[part * 32 + 2 * e]);
-                            float v1 = fmaf(alpha, __uint_as_float(acc[2 * e + 1]), bias_h[part * 32 + 2 * e + 1]);
-                            const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&sk[part * 16 + e]));
-                            v0 = fmaf(beta, s2.x, v0);
-                            v1 = fmaf(beta, s2.y, v1);
-                            const __half2 hv = __floats2half2_rn(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
-                            packed[e] = *reinterpret_cast<const uint32_t*>(&hv);
-                        }
-                    }
-                    st_global_256(out + off + part * 32, &packed[0]);
-                    st_global_256(out + off + part * 32 + 16, &packed[8]);
-                };
-                finish(acc0, 0);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty0[as]);
-                finish(acc1, 1);
-                // publish: this CTA's tile of layer l is complete once all 8 warps have stored their part
-                named_bar_sync(1, 256);
-                if (threadIdx.x == 64) {
-                    __threadfence();
-                    st_release_gpu(p.done + 2 * u + rank, p.gen + l + 1);
-                }
-                if (tracer) DG_TRACE(2);
-#pragma unroll
-                for (int i = 0; i < 32; i++) sk[i] = sk_next[i];
-                if (++as == 2) { as = 0; aphase ^= 1; }
+            uint32_t acc0[32], acc1[32];
+            tmem_ld_32x32b_x32(taddr, acc0);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 32, acc1);
+            finish(acc0, 0);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 64, acc0);
+            finish(acc1, 1);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 96, acc1);
+            finish(acc0, 2);
+            tmem_ld_wait();
+            tc_fence_before();                          // accumulator stage fully read: hand it back to the MMA issuer
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty0);
+            finish(acc1, 3);
+            // publish: this CTA's tile of layer l is complete once the four warps of the group have stored their rows
+            named_bar_sync(1 + g, 128);
+            if (leader) {
+                __threadfence();
+                st_release_gpu(p.done + 2 * u + rank, p.gen + l + 1);
             }
+            if (tracer) DG_TRACE(2);
+            next_item(l, u);
+            if (l < p.nlayers) next_item(l, u);
+            if (l < p.nlayers) prefetch_skip(l, u);
         }
     }
 

@@ -826,6 +826,26 @@ int32_t dg_engine_debug_conv_trace(dg_engine* e, int32_t batch, int64_t* out, in
     return rc;
 }
 
+int32_t dg_engine_debug_tower_trace(dg_engine* e, int32_t batch, int64_t* out, int32_t out_len) {
+    if (!e || !out) return DG_ERR_INVALID_ARGUMENT;
+    if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    WsGuard guard(e, batch);
+    if (!guard.w) return fail(e, DG_ERR_INVALID_ARGUMENT, "no workspace holds a resident batch of %d positions", batch);
+    Workspace& w = *guard.w;
+    const size_t n = static_cast<size_t>(e->num_sms) * 3 * 1024;
+    long long* buf = nullptr;
+    DG_CUDA(e, cudaMalloc(&buf, n * 8));
+    DG_CUDA(e, cudaMemset(buf, 0, n * 8));
+    e->trace_buf = buf;
+    int32_t rc = enqueue_network(e, w, batch, e->net.num_blocks, 3);
+    e->trace_buf = nullptr;
+    cudaStreamSynchronize(w.stream);
+    if (rc == DG_OK) cudaMemcpy(out, buf, (n < static_cast<size_t>(out_len) ? n : static_cast<size_t>(out_len)) * 8, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    return rc;
+}
+
 int32_t dg_engine_debug_read_tower(dg_engine* e, int32_t layer, int32_t batch, uint16_t* out) {
     if (!e || !out) return DG_ERR_INVALID_ARGUMENT;
     if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");

@@ -81,6 +81,7 @@ ABI = {
                                             C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "dg_engine_debug_read_tower": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_engine_debug_conv_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
+    "dg_engine_debug_tower_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
 }
 
 
@@ -247,6 +248,11 @@ class Network:
     def debug_conv_trace(self, batch: int, ctas: int = 148) -> np.ndarray:
         out = np.zeros((ctas, 3, 64), np.int64)
         self._check(lib().dg_engine_debug_conv_trace(self._handle, batch, out.ctypes.data, out.size))
+        return out
+
+    def debug_tower_trace(self, batch: int, ctas: int = 148) -> np.ndarray:
+        out = np.zeros((ctas, 3, 1024), np.int64)
+        self._check(lib().dg_engine_debug_tower_trace(self._handle, batch, out.ctypes.data, out.size))
         return out
 
     # -- plumbing -------------------------------------------------------------------------------

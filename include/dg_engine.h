@@ -162,6 +162,10 @@ int32_t dg_engine_debug_read_tower(dg_engine* engine, int32_t layer, int32_t bat
  * in-kernel clock64() tracing and copies min(out_len, SMs*3*64) samples to out, laid out
  * [cta][role: 0 TMA producer, 1 MMA issuer, 2 epilogue][64] (perf debugging). */
 int32_t dg_engine_debug_conv_trace(dg_engine* engine, int32_t batch, int64_t* out, int32_t out_len);
+/* Same for one launch of the persistent tower kernel: [cta][role][1024] samples.  Producer: (before flag wait,
+ * after flag wait) per unit; MMA issuer: (unit start, accumulator free, operands of k-half 0 landed, unit issued)
+ * per unit; epilogue (first warp): (before accumulator wait, after, unit stored) per unit. */
+int32_t dg_engine_debug_tower_trace(dg_engine* engine, int32_t batch, int64_t* out, int32_t out_len);
 
 #ifdef __cplusplus
 }

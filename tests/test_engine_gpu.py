@@ -227,3 +227,23 @@ def test_errors(tmp_path, small_net):
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_no_further_from_oracle_than_cudnn(full_engine, full_net):
+    """"the new engine must be no further from oracle 2 than cuDNN is" -- the cuDNN
+    restatement of the reference forward (baseline/cudnn_ref.cu) is the second oracle."""
+    from baseline import cudnn_ref
+    batch = 8
+    feats = weights.bernoulli_features(batch, seed=77)
+    want_v, want_p, want_t = oracle.OracleNetwork(full_net).forward(feats, want_tower=True)
+    ref = cudnn_ref.CudnnNetwork(full_net, batch)
+    cv, cp = ref.forward(feats)
+    ct = ref.read_tower()
+    ref.close()
+    with full_engine.get_workspace(batch) as ws:
+        ev, ep = nn.forward(ws, feats).unwrap()
+    et = full_engine.debug_read_tower(-1, batch)
+    check_outputs(cv, cp, want_v, want_p)                      # the baseline itself agrees with the CPU oracle
+    assert rel_l2(et, want_t) <= max(rel_l2(ct, want_t), 5e-4)
+    assert np.abs(ev.astype(np.float32) - cv.astype(np.float32)).max() <= VALUE_TOL
+    assert np.abs(ep.reshape(batch, 362).astype(np.float32) - cp.astype(np.float32)).max() <= 1e-3
