@@ -1,0 +1,492 @@
+// go_board.h -- host-side Go rules, ladder reader and V1 feature extraction of the self-play engine.
+//
+// Product code (the host half of the hot path).  It computes what
+// `dg_go::Board` / `features::V1` compute (reference: src/libdg_go/board.rs, board_fast.rs,
+// utils/features.rs, utils/ladder.rs, utils/symmetry.rs) but is organised for the engine, not after the
+// reference:
+//
+//   * points are the packed indices 19*y + x the network uses (no padded border; neighbour tables instead);
+//   * every chain keeps its liberties as a 361-bit set, so "liberties if played" (24 of the 32 feature
+//     planes) is an OR + popcount instead of a walk over the chain with a 420-entry seen-array;
+//   * ladders are only read for the points that can start one (an adjacent enemy chain with exactly two
+//     liberties / an adjacent own chain in atari) -- the reference clones the board and places a stone for
+//     every legal point before finding that out;
+//   * features are produced directly in the engine's compact H2D format (`dg_packed_position`: one
+//     32-bit plane mask per point), 16x smaller than the fp16 NHWC tensor, with the symmetry applied on
+//     the fly; the fp16 tensor is expanded on the GPU (kernels.cu: pack_compact_kernel).
+//
+// tests/test_go_parity.py checks all of it bit-exactly against the oracle restatement of the reference.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace dg {
+
+constexpr int N_POINTS = 361;
+constexpr int PASS = 361;
+constexpr int BLACK = 1, WHITE = 2;
+inline int opposite(int c) { return 3 - c; }
+
+struct Bits {                       // 361-bit set over packed indices
+    uint64_t w[6];
+    void clear() { w[0] = w[1] = w[2] = w[3] = w[4] = w[5] = 0; }
+    void set(int i) { w[i >> 6] |= 1ull << (i & 63); }
+    void reset(int i) { w[i >> 6] &= ~(1ull << (i & 63)); }
+    bool test(int i) const { return (w[i >> 6] >> (i & 63)) & 1; }
+    int count() const {
+        return __builtin_popcountll(w[0]) + __builtin_popcountll(w[1]) + __builtin_popcountll(w[2]) +
+               __builtin_popcountll(w[3]) + __builtin_popcountll(w[4]) + __builtin_popcountll(w[5]);
+    }
+    bool any() const { return (w[0] | w[1] | w[2] | w[3] | w[4] | w[5]) != 0; }
+    void or_with(const Bits& o) { for (int i = 0; i < 6; ++i) w[i] |= o.w[i]; }
+    int first() const {             // lowest set bit, -1 when empty
+        for (int i = 0; i < 6; ++i) if (w[i]) return 64 * i + __builtin_ctzll(w[i]);
+        return -1;
+    }
+};
+
+// Static geometry: neighbours in the reference's reading order East, South(-y), West, North(+y)
+// (iter/adjacent_iter.rs:42-43), the 8 dihedral maps in the order of symmetry::ALL
+// (utils/symmetry.rs:121-130) and the zobrist constants.
+struct Tables {
+    int16_t nbr[N_POINTS][4];       // -1 = off board
+    uint8_t n_nbr[N_POINTS];
+    int16_t nbr_list[N_POINTS][4];  // on-board neighbours only, same order
+    Bits nbr_mask[N_POINTS];
+    uint16_t sym[8][N_POINTS + 1];  // sym[t][i] = where point i goes under transform t; 361 -> 361
+    uint8_t sym_inverse[8];
+    uint64_t zobrist[3][N_POINTS];
+
+    Tables() {
+        static const int dx[4] = {1, 0, -1, 0}, dy[4] = {0, -1, 0, 1};
+        for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+            int p = 19 * y + x, n = 0;
+            nbr_mask[p].clear();
+            for (int d = 0; d < 4; ++d) {
+                int xx = x + dx[d], yy = y + dy[d];
+                bool on = xx >= 0 && xx < 19 && yy >= 0 && yy < 19;
+                nbr[p][d] = on ? (int16_t)(19 * yy + xx) : (int16_t)-1;
+                if (on) { nbr_list[p][n++] = (int16_t)(19 * yy + xx); nbr_mask[p].set(19 * yy + xx); }
+            }
+            n_nbr[p] = (uint8_t)n;
+            for (int k = n; k < 4; ++k) nbr_list[p][k] = -1;
+        }
+        for (int t = 0; t < 8; ++t) {
+            for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+                int cx = x - 9, cy = y - 9, tx, ty;
+                switch (t) {
+                    case 0: tx = cx; ty = cy; break;       // Identity
+                    case 1: tx = -cx; ty = cy; break;      // FlipLR
+                    case 2: tx = cx; ty = -cy; break;      // FlipUD
+                    case 3: tx = cy; ty = cx; break;       // Transpose
+                    case 4: tx = -cy; ty = -cx; break;     // TransposeAnti
+                    case 5: tx = cy; ty = -cx; break;      // Rot90
+                    case 6: tx = -cx; ty = -cy; break;     // Rot180
+                    default: tx = -cy; ty = cx; break;     // Rot270
+                }
+                sym[t][19 * y + x] = (uint16_t)(19 * (ty + 9) + (tx + 9));
+            }
+            sym[t][PASS] = PASS;
+        }
+        static const uint8_t inv[8] = {0, 1, 2, 3, 4, 7, 6, 5};     // symmetry.rs:78-89
+        memcpy(sym_inverse, inv, 8);
+        // The reference's constants are arbitrary random numbers (zobrist.rs:16-17); any table gives the
+        // same rules.  splitmix64 stream, laid out over the reference's padded indices so that the
+        // oracle (which uses the same generator by default) produces identical hashes.
+        uint64_t s = 0x6472656d2d676f21ull;
+        for (int c = 0; c < 3; ++c)
+            for (int i = 0; i < 420; ++i) {
+                uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+                z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+                z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+                z ^= z >> 31;
+                int col = i % 20, row = i / 20;
+                if (col >= 1 && row >= 1 && row <= 19) zobrist[c][19 * (row - 1) + (col - 1)] = z;
+            }
+    }
+};
+
+inline const Tables& tables() {
+    static const Tables t;
+    return t;
+}
+
+// One board = stones + chains + the history the features and the super-ko rule need
+// (board.rs:27-49: last 8 moves, last 16 whole-board hashes, komi, move count, last colour).
+// Chains live in slots handed out from a free list, so copying a board (one copy per tree probe, one per
+// ladder step) moves only the slots in use: ~5 KB mid-game instead of 19 KB.
+struct Board {
+    uint8_t color[N_POINTS + 3];
+    uint16_t slot[N_POINTS];        // chain slot of the stone at a point
+    uint16_t next[N_POINTS];        // circular list of the stones of a chain
+    uint16_t free_list[N_POINTS];
+    Bits stones[3];                 // [1] black, [2] white
+    Bits visited;                   // point has held a stone at some time (board_fast.rs:446, board.rs:135)
+    uint64_t hash;
+    uint64_t hash_history[16];
+    int16_t moves[8];               // most recent moves (ring)
+    uint8_t moves_pos, hash_pos, last_played, pad_;
+    uint16_t count;
+    uint16_t n_slots, n_free;       // slots ever handed out / currently on the free list
+    float komi;
+    Bits libs[N_POINTS];            // liberties of the chain in a slot; only [0, n_slots) is meaningful
+
+    Board() {}
+    Board(const Board& o) { copy_from(o); }
+    Board& operator=(const Board& o) { if (this != &o) copy_from(o); return *this; }
+    void copy_from(const Board& o) {
+        memcpy(static_cast<void*>(this), static_cast<const void*>(&o), offsetof(Board, libs) + o.n_slots * sizeof(Bits));
+    }
+
+    void init(float komi_) {
+        memset(static_cast<void*>(this), 0, sizeof(*this));
+        komi = komi_;
+        for (int i = 0; i < 8; ++i) moves[i] = PASS;
+    }
+    int to_move() const { return last_played ? opposite(last_played) : BLACK; }        // board.rs:102-107
+    int n_liberty(int p) const { return libs[slot[p]].count(); }
+    int recent_move(int i) const { return moves[(moves_pos + 7 - i) & 7]; }
+    int alloc_slot() { return n_free ? free_list[--n_free] : n_slots++; }
+    void free_slot(int s) { free_list[n_free++] = (uint16_t)s; }
+
+    Bits empty_neighbours(int p) const {
+        const Bits& m = tables().nbr_mask[p];
+        Bits e;
+        for (int i = 0; i < 6; ++i) e.w[i] = m.w[i] & ~(stones[1].w[i] | stones[2].w[i]);
+        return e;
+    }
+
+    // Tromp-Taylor legality without super-ko (board_fast.rs:216-243).
+    bool is_valid_fast(int c, int p) const {
+        if (color[p]) return false;
+        const Tables& T = tables();
+        for (int k = 0; k < T.n_nbr[p]; ++k) {
+            int q = T.nbr_list[p][k];
+            if (!color[q]) return true;
+            int nl = libs[slot[q]].count();
+            if ((color[q] == c) == (nl >= 2)) return true;
+        }
+        return false;
+    }
+
+    // Hash change if `c` played `p` (board_fast.rs:406-424): the stone plus every captured chain.
+    uint64_t place_hash(int c, int p) const {
+        const Tables& T = tables();
+        int opp = opposite(c);
+        uint64_t h = T.zobrist[c][p];
+        int seen[4], ns = 0;
+        for (int k = 0; k < T.n_nbr[p]; ++k) {
+            int q = T.nbr_list[p][k];
+            if (color[q] != opp) continue;
+            int sl = slot[q];
+            if (libs[sl].count() >= 2) continue;
+            bool dup = false;
+            for (int j = 0; j < ns; ++j) dup |= seen[j] == sl;
+            if (dup) continue;
+            seen[ns++] = sl;
+            int s = q;
+            do { h ^= T.zobrist[opp][s]; s = next[s]; } while (s != q);
+        }
+        return h;
+    }
+
+    // Positional super-ko over the last 16 positions (board.rs:132-141).
+    bool is_ko(int c, int p) const {
+        if (!visited.test(p)) return false;
+        uint64_t h = hash ^ place_hash(c, p);
+        for (int i = 0; i < 16; ++i) if (hash_history[i] == h) return true;
+        return false;
+    }
+    bool is_valid(int c, int p) const { return is_valid_fast(c, p) && !is_ko(c, p); }     // board.rs:151-153
+
+    void remove_chain(int at) {
+        const Tables& T = tables();
+        int own = color[at];
+        free_slot(slot[at]);
+        int s = at;
+        do {
+            int nx = next[s];
+            color[s] = 0;
+            stones[own].reset(s);
+            hash ^= T.zobrist[own][s];
+            for (int k = 0; k < T.n_nbr[s]; ++k) {
+                int q = T.nbr_list[s][k];
+                if (color[q] && color[q] != own) libs[slot[q]].set(s);
+            }
+            s = nx;
+        } while (s != at);
+    }
+
+    // Plays without any legality check (board_fast.rs:434-475, board.rs:164-188).
+    void place(int c, int p) {
+        const Tables& T = tables();
+        int opp = opposite(c);
+        int mine = alloc_slot();
+        color[p] = (uint8_t)c;
+        stones[c].set(p);
+        visited.set(p);
+        slot[p] = (uint16_t)mine;
+        next[p] = (uint16_t)p;
+        libs[mine].clear();
+        hash ^= T.zobrist[c][p];
+        for (int k = 0; k < T.n_nbr[p]; ++k) {               // enemies lose a liberty; captures first so that
+            int q = T.nbr_list[p][k];                        // the freed points count as liberties below
+            if (color[q] != opp) continue;
+            int sl = slot[q];
+            libs[sl].reset(p);
+            if (!libs[sl].any()) remove_chain(q);
+        }
+        libs[mine] = empty_neighbours(p);
+        for (int k = 0; k < T.n_nbr[p]; ++k) {               // merge with friends
+            int q = T.nbr_list[p][k];
+            if (color[q] != c) continue;
+            int a = slot[p], b = slot[q];
+            if (a == b) continue;
+            libs[b].or_with(libs[a]);
+            int s = p;
+            do { slot[s] = (uint16_t)b; s = next[s]; } while (s != p);
+            uint16_t t = next[p]; next[p] = next[q]; next[q] = t;
+            free_slot(a);
+        }
+        libs[slot[p]].reset(p);
+        last_played = (uint8_t)c;
+        count += 1;
+        moves[moves_pos] = (int16_t)p;
+        moves_pos = (moves_pos + 1) & 7;
+        hash_history[hash_pos] = hash;
+        hash_pos = (hash_pos + 1) & 15;
+    }
+
+    // Liberties the stone's chain would have after `c` plays the legal move `p` (board_fast.rs:484-539),
+    // and whether the move is legal at all (fused: the feature loop needs both).  Returns -1 if illegal.
+    // `nl` (optional) = liberty count per slot, precomputed by the caller.
+    int liberties_if(int c, int p, const uint16_t* nl = nullptr) const {
+        const Tables& T = tables();
+        int n_empty = 0, nf = 0, nc = 0;
+        int friends[4], captured[4], captured_at[4];
+        bool ok = false;
+        for (int k = 0; k < T.n_nbr[p]; ++k) {
+            int q = T.nbr_list[p][k];
+            if (!color[q]) { ++n_empty; continue; }
+            int sl = slot[q];
+            int n = nl ? nl[sl] : libs[sl].count();
+            if (color[q] == c) {
+                ok |= n >= 2;
+                bool dup = false;
+                for (int j = 0; j < nf; ++j) dup |= friends[j] == sl;
+                if (!dup) friends[nf++] = sl;
+            } else if (n == 1) {
+                bool dup = false;
+                for (int j = 0; j < nc; ++j) dup |= captured[j] == sl;
+                if (!dup) { captured[nc] = sl; captured_at[nc++] = q; }
+            }
+        }
+        if (!(ok || n_empty || nc)) return -1;
+        if (!nf && !nc) return n_empty;                     // a lone stone: its empty neighbours
+        Bits L = empty_neighbours(p);
+        for (int j = 0; j < nf; ++j) L.or_with(libs[friends[j]]);
+        L.reset(p);
+        for (int j = 0; j < nc; ++j) {                      // rare: freed points next to the new chain
+            int at = captured_at[j], s = at;
+            do {
+                bool touches = false;
+                for (int k = 0; k < T.n_nbr[s] && !touches; ++k) {
+                    int t = T.nbr_list[s][k];
+                    if (t == p) touches = true;
+                    else if (color[t] == c)
+                        for (int f = 0; f < nf; ++f) touches |= friends[f] == slot[t];
+                }
+                if (touches) L.set(s);
+                s = next[s];
+            } while (s != at);
+        }
+        return L.count();
+    }
+};
+
+// ---- ladder reader (utils/ladder.rs) ---------------------------------------------------------------------------
+// The reference recurses with a cloned board per step; here the boards of one reading live in a per-thread
+// arena indexed by depth (a ladder can run 100+ steps and a Board is too large for that many stack frames).
+
+inline bool chain_can_capture(const Board& b, int at) {      // ladder.rs:33-41
+    const Tables& T = tables();
+    int own = b.color[at], s = at;
+    do {
+        for (int k = 0; k < T.n_nbr[s]; ++k) {
+            int q = T.nbr_list[s][k];
+            if (b.color[q] && b.color[q] != own && b.libs[b.slot[q]].count() < 2) return true;
+        }
+        s = b.next[s];
+    } while (s != at);
+    return false;
+}
+
+struct LadderArena {
+    static constexpr int MAX_DEPTH = 400;   // > 361 / 2 alternating placements; deeper readings answer "no ladder"
+    Board* boards;
+    LadderArena() : boards(static_cast<Board*>(::operator new(sizeof(Board) * (MAX_DEPTH + 2)))) {}
+    ~LadderArena() { ::operator delete(boards); }
+    LadderArena(const LadderArena&) = delete;
+    LadderArena& operator=(const LadderArena&) = delete;
+};
+inline LadderArena& ladder_arena() {
+    static thread_local LadderArena arena;
+    return arena;
+}
+
+// arena.boards[depth] already holds the attacker's stone at `p`.  ladder.rs:53-119.
+inline bool ladder_capture_after_place(LadderArena& arena, int depth, int c, int p) {
+    const Tables& T = tables();
+    Board& board = arena.boards[depth];
+    int opp = opposite(c);
+    int run = -1;
+    for (int k = 0; k < T.n_nbr[p] && run < 0; ++k) {
+        int q = T.nbr_list[p][k];
+        if (board.color[q] != opp) continue;
+        int sl = board.slot[q];
+        if (board.libs[sl].count() >= 2 || chain_can_capture(board, q)) continue;
+        int lib = board.libs[sl].first();                    // in atari: its only liberty
+        if (lib >= 0 && board.is_valid_fast(opp, lib)) run = lib;
+    }
+    if (run < 0) return false;
+    board.place(opp, run);
+    int nl = board.n_liberty(run);
+    if (nl < 2) return true;
+    if (nl >= 3) return false;
+    for (int k = 0; k < T.n_nbr[run]; ++k) {
+        int q = T.nbr_list[run][k];
+        if (board.color[q] == c && board.n_liberty(q) < 2) return false;
+    }
+    if (depth + 1 >= LadderArena::MAX_DEPTH) return false;
+    for (int k = 0; k < T.n_nbr[run]; ++k) {
+        int q = T.nbr_list[run][k];
+        if (!board.is_valid_fast(c, q)) continue;
+        Board& child = arena.boards[depth + 1];
+        child.copy_from(board);
+        child.place(c, q);
+        if (ladder_capture_after_place(arena, depth + 1, c, q)) return true;
+    }
+    return false;
+}
+
+inline bool is_ladder_capture(const Board& b, int c, int p, const uint16_t* nl = nullptr) {       // ladder.rs:131-135
+    // a ladder starts by putting an adjacent enemy chain in atari: it needs exactly two liberties now
+    const Tables& T = tables();
+    int opp = opposite(c);
+    bool candidate = false;
+    for (int k = 0; k < T.n_nbr[p]; ++k) {
+        int q = T.nbr_list[p][k];
+        if (b.color[q] == opp && (nl ? nl[b.slot[q]] : b.libs[b.slot[q]].count()) == 2) candidate = true;
+    }
+    if (!candidate) return false;
+    LadderArena& arena = ladder_arena();
+    arena.boards[0].copy_from(b);
+    arena.boards[0].place(c, p);
+    return ladder_capture_after_place(arena, 0, c, p);
+}
+
+inline bool is_ladder_escape(const Board& b, int c, int p, const uint16_t* nl = nullptr) {        // ladder.rs:144-178
+    const Tables& T = tables();
+    bool in_atari = false;
+    for (int k = 0; k < T.n_nbr[p]; ++k) {
+        int q = T.nbr_list[p][k];
+        if (b.color[q] == c && (nl ? nl[b.slot[q]] : b.libs[b.slot[q]].count()) < 2) in_atari = true;
+    }
+    if (!in_atari) return false;
+    LadderArena& arena = ladder_arena();
+    Board& board = arena.boards[0];
+    board.copy_from(b);
+    board.place(c, p);
+    if (board.n_liberty(p) != 2) return false;
+    int opp = opposite(c);
+    for (int k = 0; k < T.n_nbr[p]; ++k) {
+        int q = T.nbr_list[p][k];
+        if (!board.is_valid_fast(opp, q)) continue;
+        Board& child = arena.boards[1];
+        child.copy_from(board);
+        child.place(opp, q);
+        if (ladder_capture_after_place(arena, 1, opp, q)) return false;
+    }
+    return true;
+}
+
+// ---- V1 features in the compact format (utils/features.rs:154-250) ---------------------------------------------
+
+inline uint16_t f32_to_f16_bits(float f) {                  // round to nearest even (fp16.rs:64-68)
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16) & 0x8000u, e8 = (x >> 23) & 0xff, man = x & 0x7fffffu;
+    if (e8 == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));
+    int e = (int)e8 - 112;
+    if (e >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        int shift = 14 - e;
+        uint32_t h = man >> shift, rem = man & ((1u << shift) - 1), mid = 1u << (shift - 1);
+        if (rem > mid || (rem == mid && (h & 1))) h++;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)e << 10) | (man >> 13), rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++;
+    return (uint16_t)(sign | h);
+}
+
+inline uint16_t komi_plane_bits(float komi) {               // features.rs:236
+    float k = 0.5f + (0.5f * komi) / 7.5f;
+    k = k > 1.0f ? 1.0f : k;
+    k = k < 0.0f ? 0.0f : k;
+    return f32_to_f16_bits(k);
+}
+
+// planes[sym(p)] bit c <=> feature (p, c) non-zero.  Also returns the legal-move mask (Board::is_valid,
+// i.e. with super-ko) of `to_move` in `legal` when it is not null -- the prior construction
+// (pool/policy_helper.rs:39-43) needs exactly the valid/ko bits this pass computes anyway.
+inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t planes[N_POINTS], uint16_t* k_bits,
+                        uint8_t* legal /* [361] or null, identity orientation */) {
+    const Tables& T = tables();
+    const uint16_t* sym = T.sym[symmetry];
+    int opp = opposite(to_move);
+    uint32_t global = to_move == BLACK ? 1u : 2u;
+    uint16_t nl[N_POINTS];                                  // liberties per chain slot, counted once
+    for (int i = 0; i < b.n_slots; ++i) nl[i] = 0;
+    for (int p = 0; p < N_POINTS; ++p)
+        if (b.color[p] && !nl[b.slot[p]]) nl[b.slot[p]] = (uint16_t)b.libs[b.slot[p]].count();
+    uint32_t local[N_POINTS];
+    bool any_ko = false;
+    static const uint32_t ge_mask[7] = {0, 1, 3, 7, 15, 31, 63};   // ">= 1 .. >= n" thermometer code
+    for (int p = 0; p < N_POINTS; ++p) {
+        uint32_t m = 0;
+        int col = b.color[p];
+        if (col) {
+            int n = nl[b.slot[p]];
+            m = ge_mask[n > 6 ? 6 : n] << (col == to_move ? 5 : 17);
+            if (legal) legal[p] = 0;
+        } else {
+            int mine = b.liberties_if(to_move, p, nl);
+            int theirs = b.liberties_if(opp, p, nl);
+            if (mine >= 0) m |= ge_mask[mine > 6 ? 6 : mine] << 11;
+            if (theirs >= 0) m |= ge_mask[theirs > 6 ? 6 : theirs] << 23;
+            bool ko = false;
+            if (mine >= 0) {
+                ko = b.is_ko(to_move, p);
+                if (ko) { m |= 1u << 29; any_ko = true; }
+                if (is_ladder_capture(b, to_move, p, nl)) m |= 1u << 30;
+                if (is_ladder_escape(b, to_move, p, nl)) m |= 1u << 31;
+            }
+            if (legal) legal[p] = mine >= 0 && !ko;
+        }
+        local[p] = m;
+    }
+    int m0 = b.recent_move(0), m1 = b.recent_move(1);
+    if (m0 != PASS) local[m0] |= 1u << 3;
+    if (m1 != PASS) local[m1] |= 1u << 4;
+    if (any_ko) global |= 4u;
+    for (int p = 0; p < N_POINTS; ++p) planes[sym[p]] = local[p] | global;
+    *k_bits = komi_plane_bits(b.komi);
+}
+
+}  // namespace dg

@@ -1,0 +1,222 @@
+"""Parity of the product's host Go code (csrc/go_board.h through include/dg_go.h) with the oracle restatement of
+the reference's libdg_go: bit-exact stones, hashes, legal moves, liberties, ladders, feature planes and (to fp32
+rounding) priors.  CPU only -- this half of the hot path runs on the host in the reference too."""
+import numpy as np
+import pytest
+
+from dream_go_b200 import go as pgo
+from oracle import go as ogo
+
+BLACK, WHITE = 1, 2
+
+
+def random_playout(seed: int, plies: int, komi: float = 7.5, pass_rate: float = 0.02):
+    """Uniform-random legal playout (legality decided by the ORACLE), returns (colors, moves)."""
+    rng = np.random.default_rng(seed)
+    board = ogo.Board(komi)
+    colors, moves = [], []
+    color = BLACK
+    for _ in range(plies):
+        legal = np.flatnonzero(board.legal_mask(color))
+        if len(legal) == 0 or rng.random() < pass_rate:
+            colors.append(color)
+            moves.append(361)
+        else:
+            m = int(rng.choice(legal))
+            board.place_index(color, m)
+            colors.append(color)
+            moves.append(m)
+        color = 3 - color
+    return np.array(colors, np.uint8), np.array(moves, np.uint16)
+
+
+def assert_same_replay(colors, moves, komi):
+    want = ogo.replay(colors, moves, komi, features=True, legal=True, hashes=True)
+    got = pgo.replay(colors, moves, komi, features=True, legal=True, hashes=True)
+    assert (got["hash"] == want["hash"]).all()
+    assert (got["legal"] == want["legal"]).all()
+    feats = pgo.unpack_features(got["features"])
+    bad = np.argwhere(feats.view(np.uint16) != want["features"].view(np.uint16))
+    assert len(bad) == 0, f"first mismatch (ply, point, plane) = {bad[0]}"
+
+
+# ---- the reference's unit KATs, run against the PRODUCT (same assertions as tests/test_oracle_go.py) -----------
+
+def test_reference_unit_kats_on_product():
+    b = pgo.Board()
+    b.place(BLACK, 9, 9)
+    for x, y in [(8, 9), (10, 9), (9, 8), (9, 10)]:
+        b.place(WHITE, x, y)
+    assert b.at(9, 9) == 0 and not b.is_valid(BLACK, 9, 9) and b.is_valid(WHITE, 9, 9)      # board.rs:281-337
+    b = pgo.Board()
+    for c, x, y in [(1, 0, 0), (1, 0, 2), (1, 1, 1), (2, 1, 0), (2, 0, 1)]:
+        b.place(c, x, y)
+    assert not b.is_valid(BLACK, 0, 0)                                                       # board.rs:341-351 (ko)
+    b = pgo.Board()
+    b.place(BLACK, 0, 1); b.place(BLACK, 1, 0); b.place(WHITE, 1, 1); b.place(WHITE, 2, 0)   # board_fast.rs:548-562
+    assert [b.get_n_liberty_if(WHITE, *p) for p in [(0, 0), (2, 1), (0, 2), (9, 9)]] == [1, 4, 2, 4]
+    b.place(WHITE, 0, 2)
+    assert b.get_n_liberty_if(WHITE, 0, 0) == 2
+
+
+def test_ladder_kats_on_product():   # utils/ladder.rs:187-351
+    b = pgo.Board()
+    for x, y in [(0, 0), (0, 18), (18, 0), (18, 18)]:
+        b.place(BLACK, x, y)
+    want = {(1, 0), (0, 1), (18, 17), (17, 18), (1, 18), (18, 1), (0, 17), (17, 0)}
+    for y in range(19):
+        for x in range(19):
+            if b.is_valid(WHITE, x, y):
+                assert b.is_ladder_capture(WHITE, x, y) == ((x, y) in want)
+    b = pgo.Board()
+    b.place(WHITE, 3, 3); b.place(WHITE, 15, 15)
+    for x, y in [(2, 3), (3, 2), (4, 2), (3, 4)]:
+        b.place(BLACK, x, y)
+    for y in range(19):
+        for x in range(19):
+            if b.is_valid(WHITE, x, y):
+                assert not b.is_ladder_capture(BLACK, x, y)
+                assert b.is_ladder_escape(WHITE, x, y) == ((x, y) == (4, 3))
+    from test_oracle_go import NOT_LADDER
+    b = pgo.Board()
+    for c, x, y in NOT_LADDER:
+        b.place(c, x, y)
+    assert b.is_ladder_escape(WHITE, 4, 13)
+
+
+@pytest.mark.parametrize("t", range(8))
+def test_symmetry_tables(t):
+    assert [pgo.symmetry_apply(t, i) for i in range(362)] == [ogo.symmetry_apply(t, i) for i in range(362)]
+    assert pgo.lib().dg_symmetry_inverse(t) == ogo.lib().dgo_symmetry_inverse(t)
+
+
+# ---- bit-exact replay parity on the reference's corpus and on capture-heavy random games -------------------------
+
+def test_example_games_bit_exact():
+    """All 18,649 positions of dg_tests/fixtures/example_games.sgf: hash, legal mask and all 32 planes."""
+    for colors, moves, komi in ogo.load_games():
+        assert_same_replay(colors, moves, komi)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_playouts_bit_exact(seed):
+    """Random play fills the board and produces the captures, kos and snapbacks that real games rarely have."""
+    colors, moves = random_playout(20261017 + seed, 420, komi=[7.5, 6.5, 0.5, -3.5, 0.0, 20.0][seed])
+    assert_same_replay(colors, moves, [7.5, 6.5, 0.5, -3.5, 0.0, 20.0][seed])
+
+
+def test_features_every_symmetry_and_fp16_form():
+    colors, moves, komi = ogo.load_games()[7]
+    po, oo = pgo.Board(komi), ogo.Board(komi)
+    for i, (c, m) in enumerate(zip(colors[:150], moves[:150])):
+        if m < 361:
+            po.place_index(int(c), int(m))
+            oo.place_index(int(c), int(m))
+    for t in range(8):
+        for to_move in (BLACK, WHITE):
+            want = oo.features(to_move, t)
+            assert (po.features(to_move, t).view(np.uint16) == want.view(np.uint16)).all()
+            packed, legal = po.features_packed(to_move, t, legal=True)
+            assert (pgo.unpack_features(packed)[0].view(np.uint16) == want.view(np.uint16)).all()
+            assert (legal == oo.legal_mask(to_move)).all()
+            assert (po.legal_moves(to_move) == legal).all()
+    assert (po.stones() == oo.stones()).all()
+    for t in range(8):
+        assert po.is_symmetric(t) == oo.is_symmetric(t)
+
+
+def test_extract_batch_matches_single_calls():
+    games = ogo.load_games()
+    boards, tm = [], []
+    for g in range(32):
+        colors, moves, komi = games[g]
+        b = pgo.Board(komi)
+        n = 20 + 5 * g
+        for c, m in zip(colors[:n], moves[:n]):
+            if m < 361:
+                b.place_index(int(c), int(m))
+        boards.append(b)
+        tm.append(b.to_move())
+    sym = np.arange(32) % 8
+    out, legal = pgo.extract_batch(boards, tm, sym, legal=True, threads=4)
+    for i, b in enumerate(boards):
+        one, lg = b.features_packed(tm[i], int(sym[i]), legal=True)
+        assert out[i].tobytes() == one[0].tobytes()
+        assert (legal[i] == lg).all()
+
+
+# ---- prior construction (pool/policy_helper.rs) -------------------------------------------------------------------
+
+def oracle_prior(board: "ogo.Board", to_move: int, policy_f16: np.ndarray, symmetry: int, sum_to: float) -> np.ndarray:
+    """Restatement of create_initial_policy (policy_helper.rs:28-75, StandardSearch options.rs:53-57),
+    add_valid_candidates (:87-104) and normalize_policy (:113-134; lane order of asm/sum_finite.rs:23-57)."""
+    prior = np.full(368, -np.inf, np.float32)
+    legal = board.legal_mask(to_move)
+    prior[:361][legal != 0] = 0.0
+    prior[361] = 0.0
+    syms = [t for t in range(8) if board.is_symmetric(t)]
+    indices = np.zeros(362, np.int64)
+    indices[361] = 361
+    for i in range(361):
+        target = min(ogo.symmetry_apply(t, i) for t in syms)
+        indices[i] = target
+        if i != target:
+            prior[i] = -np.inf
+    src = policy_f16.astype(np.float32)
+    prior[361] += src[361]
+    inv = ogo.lib().dgo_symmetry_inverse(symmetry)
+    for i in range(361):
+        j = indices[ogo.symmetry_apply(inv, i)]
+        prior[j] = np.float32(prior[j] + src[i])
+    lanes = np.zeros(8, np.float32)
+    for i in range(368):
+        if np.isfinite(prior[i]):
+            lanes[i & 7] = np.float32(lanes[i & 7] + prior[i])
+    total = np.float32(np.float32(np.float32(lanes[0] + lanes[1]) + np.float32(lanes[2] + lanes[3])) +
+                       np.float32(np.float32(lanes[4] + lanes[5]) + np.float32(lanes[6] + lanes[7])))
+    finite = np.isfinite(prior)
+    if total < 1e-6:
+        prior[finite] = np.float32(sum_to) / np.float32(finite.sum())
+    else:
+        recip = np.float32(1.0) / np.float32(total / np.float32(sum_to))
+        prior = (prior * recip).astype(np.float32)
+    return prior
+
+
+@pytest.mark.parametrize("case", ["empty", "opening", "midgame", "ko"])
+def test_prior_matches_policy_helper(case):
+    rng = np.random.default_rng(5)
+    po, oo = pgo.Board(7.5), ogo.Board(7.5)
+    plays = {"empty": [], "opening": [(1, 9, 9)], "ko": [(1, 0, 0), (1, 0, 2), (1, 1, 1), (2, 1, 0), (2, 0, 1)]}.get(case)
+    if plays is None:
+        colors, moves, _ = ogo.load_games()[11]
+        plays = [(int(c), int(m) % 19, int(m) // 19) for c, m in zip(colors[:140], moves[:140]) if m < 361]
+    for c, x, y in plays:
+        po.place(c, x, y)
+        oo.place(c, x, y)
+    to_move = po.to_move()
+    for symmetry in range(8):
+        logits = rng.normal(size=362).astype(np.float32)
+        policy = (np.exp(logits) / np.exp(logits).sum()).astype(np.float16)
+        for sum_to in (1.0, 0.125):
+            want = oracle_prior(oo, to_move, policy, symmetry, sum_to)
+            got = po.prior(to_move, policy, symmetry, sum_to)
+            assert (np.isfinite(got) == np.isfinite(want)).all()
+            f = np.isfinite(want)
+            assert (got[f].view(np.uint32) == want[f].view(np.uint32)).all()        # same operation order: bit-exact
+            assert abs(float(got[f].sum()) - sum_to) < 1e-4
+    if case == "empty":      # symmetric board: only one representative per orbit survives (policy_helper.rs:54-72)
+        assert np.isfinite(po.prior(BLACK, np.full(362, 1 / 362, np.float16))[:361]).sum() == 55
+    # all-zero policy -> uniform over the candidates (policy_helper.rs:119-124)
+    z = po.prior(to_move, np.zeros(362, np.float16))
+    f = np.isfinite(z)
+    assert np.allclose(z[f], 1.0 / f.sum())
+
+
+def test_prediction_with_transform_kat():
+    """predictor.rs:99-107: un-rotating a Rot180 policy moves entry 0 to 360 and keeps the pass entry."""
+    b = pgo.Board(7.5)
+    b.place(BLACK, 3, 2)            # break every symmetry so no folding happens
+    policy = (np.arange(362) / 1000.0).astype(np.float16)
+    raw = b.prior(WHITE, policy, pgo.ROT180, sum_to=float(policy.astype(np.float32).sum() - policy[360 - pgo.idx(3, 2)]))
+    assert abs(raw[360] - float(policy[0])) < 1e-3 and abs(raw[361] - float(policy[361])) < 1e-3
