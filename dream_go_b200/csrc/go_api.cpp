@@ -125,20 +125,33 @@ int32_t dg_go_replay(float komi, const uint8_t* colors, const uint16_t* moves, i
     return n;
 }
 
-void dg_board_prior(const dg_board* board, int32_t to_move, const uint8_t* legal, const uint16_t* policy, int32_t symmetry,
-                    float sum_to, float* prior) {
+int32_t dg_board_is_scorable(const dg_board* board) { return dg::is_scorable(*B(board)); }
+
+void dg_board_benson(const dg_board* board, int32_t color, uint8_t* out) {
+    dg::Bits alive, eyes;
+    dg::benson(*B(board), color, alive, eyes);
+    for (int p = 0; p < dg::N_POINTS; ++p) out[p] = alive.test(p) ? 1 : eyes.test(p) ? 2 : 0;
+}
+
+void dg_board_policy_candidates(const dg_board* board, int32_t to_move, int32_t search, const uint8_t* legal, uint8_t* out) {
     const Board* b = B(board);
-    const dg::Tables& T = dg::tables();
-    const float NEG_INF = -std::numeric_limits<float>::infinity();
     uint8_t local_legal[dg::N_POINTS];
     if (!legal) {
         for (int p = 0; p < dg::N_POINTS; ++p) local_legal[p] = (uint8_t)b->is_valid(to_move, p);
         legal = local_legal;
     }
-    // policy_helper.rs:36-47: candidates start at 0, everything else (and the padding) at -inf; pass is a candidate
+    dg::policy_candidates(*b, to_move, search, legal, out);
+}
+
+void dg_board_prior(const dg_board* board, int32_t to_move, int32_t search, const uint8_t* legal, const uint16_t* policy,
+                    int32_t symmetry, float sum_to, float* prior) {
+    const dg::Tables& T = dg::tables();
+    const float NEG_INF = -std::numeric_limits<float>::infinity();
+    uint8_t candidates[dg::N_POINTS + 1];
+    dg_board_policy_candidates(board, to_move, search, legal, candidates);
+    // policy_helper.rs:36-47: candidates start at 0, everything else (and the padding) at -inf
     for (int i = 0; i < 368; ++i) prior[i] = NEG_INF;
-    for (int p = 0; p < dg::N_POINTS; ++p) if (legal[p]) prior[p] = 0.0f;
-    prior[361] = 0.0f;
+    for (int p = 0; p <= dg::N_POINTS; ++p) if (candidates[p]) prior[p] = 0.0f;
     // :54-72: on a symmetric board keep the smallest index of each orbit
     int syms[8], ns = 0;
     for (int t = 0; t < 8; ++t) if (dg_board_is_symmetric(board, t)) syms[ns++] = t;

@@ -413,6 +413,139 @@ inline bool is_ladder_escape(const Board& b, int c, int p, const uint16_t* nl = 
     return true;
 }
 
+// ---- unconditional life (utils/benson.rs, utils/flood_fill.rs) and what self-play builds on it --------------------
+// Benson's algorithm on bitsets: a region is an empty-seeded connected component of the points not occupied by
+// `color` (benson.rs:293-320), it is vital to a chain when every one of its points touches the chain
+// (:188-208), a chain stays alive with two vital regions (:95-111) and a region stays while all the stones
+// around it are alive (:115-131).
+inline void benson(const Board& b, int color, Bits& alive, Bits& eyes) {
+    const Tables& T = tables();
+    struct Region { Bits points, around; };
+    struct Chain { Bits stones, touch; };
+    Region regions[N_POINTS / 2 + 1];
+    Chain chains[N_POINTS / 2 + 1];
+    int nr = 0, nc = 0;
+    {
+        uint8_t seen[N_POINTS];
+        memset(seen, 0, sizeof(seen));
+        int16_t queue[N_POINTS];
+        for (int start = 0; start < N_POINTS; ++start) {
+            if (seen[start] || b.color[start]) continue;
+            Region& r = regions[nr];
+            r.points.clear();
+            r.around.clear();
+            int qh = 0, qt = 0;
+            queue[qt++] = (int16_t)start;
+            seen[start] = 1;
+            while (qh < qt) {
+                int p = queue[qh++];
+                r.points.set(p);
+                for (int k = 0; k < T.n_nbr[p]; ++k) {
+                    int q = T.nbr_list[p][k];
+                    if (b.color[q] == color) r.around.set(q);
+                    else if (!seen[q]) { seen[q] = 1; queue[qt++] = (int16_t)q; }
+                }
+            }
+            if (r.around.any()) ++nr;
+        }
+        uint8_t slot_seen[N_POINTS];
+        memset(slot_seen, 0, b.n_slots);
+        for (int p = 0; p < N_POINTS; ++p) {
+            if (b.color[p] != color || slot_seen[b.slot[p]]) continue;
+            slot_seen[b.slot[p]] = 1;
+            Chain& c = chains[nc++];
+            c.stones.clear();
+            c.touch.clear();
+            int s = p;
+            do { c.stones.set(s); c.touch.or_with(T.nbr_mask[s]); s = b.next[s]; } while (s != p);
+        }
+    }
+    auto vital = [](const Region& r, const Chain& c) {
+        uint64_t miss = 0;
+        for (int i = 0; i < 6; ++i) miss |= r.points.w[i] & ~c.touch.w[i];
+        return miss == 0;
+    };
+    {   // regions that are vital to nobody go first (benson.rs:128-143)
+        int keep = 0;
+        for (int i = 0; i < nr; ++i) {
+            bool v = false;
+            for (int j = 0; j < nc && !v; ++j) v = vital(regions[i], chains[j]);
+            if (v) { if (keep != i) regions[keep] = regions[i]; ++keep; }
+        }
+        nr = keep;
+    }
+    for (;;) {
+        bool changed = false;
+        int keep = 0;
+        for (int j = 0; j < nc; ++j) {
+            int n = 0;
+            for (int i = 0; i < nr; ++i) n += vital(regions[i], chains[j]);
+            if (n >= 2) { if (keep != j) chains[keep] = chains[j]; ++keep; } else changed = true;
+        }
+        nc = keep;
+        alive.clear();
+        for (int j = 0; j < nc; ++j) alive.or_with(chains[j].stones);
+        keep = 0;
+        for (int i = 0; i < nr; ++i) {
+            uint64_t miss = 0;
+            for (int k = 0; k < 6; ++k) miss |= regions[i].around.w[k] & ~alive.w[k];
+            if (!miss) { if (keep != i) regions[keep] = regions[i]; ++keep; } else changed = true;
+        }
+        nr = keep;
+        if (!changed) break;
+    }
+    alive.clear();
+    for (int j = 0; j < nc; ++j) alive.or_with(chains[j].stones);
+    eyes.clear();
+    for (int i = 0; i < nr; ++i) eyes.or_with(regions[i].points);
+}
+
+// Score::is_scorable (utils/score.rs:97-110): every point is settled by unconditional life.
+inline bool is_scorable(const Board& b) {
+    Bits alive[3], eyes[3];
+    benson(b, BLACK, alive[BLACK], eyes[BLACK]);
+    benson(b, WHITE, alive[WHITE], eyes[WHITE]);
+    for (int p = 0; p < N_POINTS; ++p) {
+        int c = b.color[p];
+        bool ok = c == 0 ? (eyes[BLACK].test(p) || eyes[WHITE].test(p)) : (alive[c].test(p) || eyes[opposite(c)].test(p));
+        if (!ok) return false;
+    }
+    return true;
+}
+
+// The own-eye heuristic of ScoringSearch (libdg_mcts/options.rs:180-214).
+inline bool is_simple_eye(const Board& b, int color, int p) {
+    int x = p % 19, y = p / 19, cross = 0, diag = 0;
+    for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+        if (!dx && !dy) continue;
+        int xx = x + dx, yy = y + dy;
+        if (xx < 0 || xx > 18 || yy < 0 || yy > 18 || b.color[19 * yy + xx] != color) continue;
+        if (dx && dy) ++diag; else ++cross;
+    }
+    bool ex = x == 0 || x == 18, ey = y == 0 || y == 18;
+    if (ex && ey) return cross >= 2 && diag >= 1;
+    if (ex || ey) return cross >= 3 && diag >= 2;
+    return cross >= 4 && diag >= 3;
+}
+
+enum SearchKind { STANDARD_SEARCH = 0, SCORING_SEARCH = 1 };
+
+// PolicyChecker::is_policy_candidate for all 362 moves (options.rs:53-57 and :109-138).  `legal` = Board::is_valid
+// of `to_move` for the 361 points (as features_v1 returns it).
+inline void policy_candidates(const Board& b, int to_move, int kind, const uint8_t* legal, uint8_t out[N_POINTS + 1]) {
+    if (kind == STANDARD_SEARCH) {
+        memcpy(out, legal, N_POINTS);
+        out[PASS] = 1;
+        return;
+    }
+    Bits alive, eyes_b, eyes_w;
+    benson(b, BLACK, alive, eyes_b);
+    benson(b, WHITE, alive, eyes_w);
+    for (int p = 0; p < N_POINTS; ++p)
+        out[p] = legal[p] && !eyes_b.test(p) && !eyes_w.test(p) && !is_simple_eye(b, to_move, p);
+    out[PASS] = 0;
+}
+
 // ---- V1 features in the compact format (utils/features.rs:154-250) ---------------------------------------------
 
 inline uint16_t f32_to_f16_bits(float f) {                  // round to nearest even (fp16.rs:64-68)

@@ -15,6 +15,7 @@ import numpy as np
 from . import nn
 
 BLACK, WHITE, PASS = 1, 2, 361
+STANDARD_SEARCH, SCORING_SEARCH = 0, 1
 IDENTITY, FLIP_LR, FLIP_UD, TRANSPOSE, TRANSPOSE_ANTI, ROT90, ROT180, ROT270 = range(8)   # symmetry::ALL
 
 _P, _I, _F = C.c_void_p, C.c_int32, C.c_float
@@ -31,7 +32,9 @@ ABI = {
     "dg_board_features_packed": (None, [_P, _I, _I, _P, _P]), "dg_board_features_f16": (None, [_P, _I, _I, _P]),
     "dg_go_extract_batch": (None, [_P, _P, _P, _I, _P, _P, _I]),
     "dg_go_replay": (_I, [_F, _P, _P, _I, _P, _P, _P]),
-    "dg_board_prior": (None, [_P, _I, _P, _P, _I, _F, _P]),
+    "dg_board_prior": (None, [_P, _I, _I, _P, _P, _I, _F, _P]),
+    "dg_board_is_scorable": (_I, [_P]), "dg_board_benson": (None, [_P, _I, _P]),
+    "dg_board_policy_candidates": (None, [_P, _I, _I, _P, _P]),
 }
 _ready = False
 
@@ -125,14 +128,29 @@ class Board:
         lib().dg_board_features_f16(self._h, to_move, symmetry, out.ctypes.data)
         return out
 
-    def prior(self, to_move: int, policy: np.ndarray, symmetry: int = IDENTITY, sum_to: float = 1.0, legal=None) -> np.ndarray:
+    def is_scorable(self) -> bool:
+        """`Score::is_scorable` (utils/score.rs:97-110)."""
+        return bool(lib().dg_board_is_scorable(self._h))
+
+    def benson(self, color: int) -> np.ndarray:
+        out = np.empty(361, np.uint8)
+        lib().dg_board_benson(self._h, color, out.ctypes.data)
+        return out
+
+    def policy_candidates(self, to_move: int, search: int = STANDARD_SEARCH) -> np.ndarray:
+        out = np.empty(362, np.uint8)
+        lib().dg_board_policy_candidates(self._h, to_move, search, None, out.ctypes.data)
+        return out
+
+    def prior(self, to_move: int, policy: np.ndarray, symmetry: int = IDENTITY, sum_to: float = 1.0, legal=None,
+              search: int = STANDARD_SEARCH) -> np.ndarray:
         """create_initial_policy + add_valid_candidates + normalize_policy (pool/worker_thread.rs:88-93)."""
         policy = np.ascontiguousarray(policy, np.float16)
         assert policy.shape == (362,)
         out = np.empty(368, np.float32)
         lg = None if legal is None else np.ascontiguousarray(legal, np.uint8)
-        lib().dg_board_prior(self._h, to_move, None if lg is None else lg.ctypes.data, policy.ctypes.data, symmetry, sum_to,
-                             out.ctypes.data)
+        lib().dg_board_prior(self._h, to_move, search, None if lg is None else lg.ctypes.data, policy.ctypes.data, symmetry,
+                             sum_to, out.ctypes.data)
         return out
 
 

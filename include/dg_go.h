@@ -77,12 +77,23 @@ int32_t   dg_go_replay(float komi, const uint8_t* colors, const uint16_t* moves,
                        dg_packed_position* features, uint8_t* legal, uint64_t* hashes);
 
 /* ---- prior construction (src/libdg_mcts/pool/policy_helper.rs, predictor.rs:30-44) --------------------------- */
-/* create_initial_policy (StandardSearch) + add_valid_candidates + normalize_policy(sum_to), as the Insert event of
+/* create_initial_policy (for the given `search` options) + add_valid_candidates + normalize_policy(sum_to), as the Insert event of
  * pool/worker_thread.rs:88-93 runs them: `policy` is the network output (362 fp16, in the orientation `symmetry`
  * the features were extracted with); `prior` receives 368 floats (-inf = not a candidate, 362..367 padding = -inf).
  * `legal` may be NULL (recomputed) or the mask dg_board_features_packed returned. */
-void      dg_board_prior(const dg_board* board, int32_t to_move, const uint8_t* legal, const uint16_t* policy,
+void      dg_board_prior(const dg_board* board, int32_t to_move, int32_t search, const uint8_t* legal, const uint16_t* policy,
                          int32_t symmetry, float sum_to, float* prior /* [368] */);
+
+/* ---- what self-play needs on top (utils/benson.rs, utils/score.rs, libdg_mcts/options.rs) --------------------- */
+#define DG_STANDARD_SEARCH 0   /* StandardSearch: pass or Board::is_valid                      options.rs:53-57   */
+#define DG_SCORING_SEARCH  1   /* ScoringSearch: no pass, no Benson eye of either colour, no simple own eye  :109-138 */
+/* Score::is_scorable (utils/score.rs:97-110) */
+int32_t   dg_board_is_scorable(const dg_board* board);
+/* Benson status per point for `color`: 0 none, 1 unconditionally alive stone, 2 vital region (benson.rs:152-165) */
+void      dg_board_benson(const dg_board* board, int32_t color, uint8_t* out /* [361] */);
+/* PolicyChecker::is_policy_candidate for moves 0..361 under `search`; `legal` optional as above. */
+void      dg_board_policy_candidates(const dg_board* board, int32_t to_move, int32_t search, const uint8_t* legal,
+                                     uint8_t* out /* [362] */);
 
 #ifdef __cplusplus
 }

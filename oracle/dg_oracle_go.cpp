@@ -519,6 +519,144 @@ void features_v1(const Board& b, int to_move, int symmetry, uint16_t* out /* [36
     }
 }
 
+// ---- utils/flood_fill.rs + utils/benson.rs (unconditional life) ------------------------------------------------
+// PointStatus (benson.rs:48-53)
+enum { ST_NONE = 0, ST_BLOCK = 1, ST_REGION = 2 };
+
+struct Benson {
+    uint8_t points[MAXP];
+
+    struct Region { std::vector<int> points, neighbours; };
+    struct Block { int at; std::vector<int> stones; std::vector<uint8_t> adjacent; };   // adjacent[p] = p in adjacencies_of(at)
+
+    static bool is_vital(const Region& r, const Block& b) {          // benson.rs:188-190, 197-208
+        for (int p : r.points) if (!b.adjacent[p]) return false;
+        return true;
+    }
+
+    Benson(const BoardFast& board, int to_move) {                    // benson.rs:62-78
+        memset(points, ST_NONE, sizeof(points));
+        // AllRegionsImpl::all (benson.rs:293-320): flood from every empty point through everything that is not
+        // `to_move` coloured (flood_fill.rs:47-88); regions without a `to_move` neighbour are dropped
+        std::vector<Region> regions;
+        {
+            int head[MAXP];
+            for (int i = 0; i < MAXP; ++i) head[i] = -1;
+            for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+                int start = point_new(x, y);
+                if (head[start] != -1 || v_color(board.vertices[start]) != 0) continue;
+                Region r;
+                std::vector<int> queue{start};
+                head[start] = start;
+                for (size_t qi = 0; qi < queue.size(); ++qi) {
+                    int point = queue[qi];
+                    r.points.push_back(point);
+                    int adj[4];
+                    int n = board.adjacent_to(point, adj);
+                    for (int i = 0; i < n; ++i) {
+                        if (v_color(board.vertices[adj[i]]) == to_move) r.neighbours.push_back(adj[i]);
+                        else if (head[adj[i]] == -1) { head[adj[i]] = start; queue.push_back(adj[i]); }
+                    }
+                }
+                if (!r.neighbours.empty()) regions.push_back(std::move(r));
+            }
+        }
+        // AllBlocksImpl::all (benson.rs:214-232)
+        std::vector<Block> blocks;
+        {
+            bool visited[MAXP];
+            memset(visited, 0, sizeof(visited));
+            for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+                int p = point_new(x, y);
+                if (v_color(board.vertices[p]) != to_move) continue;
+                int hd = v_head(board.vertices[p]);
+                if (visited[hd]) continue;
+                visited[hd] = true;
+                Block b;
+                b.at = p;
+                b.adjacent.assign(MAXP, 0);
+                board.for_block(p, [&](int cur) {
+                    b.stones.push_back(cur);
+                    int adj[4];
+                    int n = board.adjacent_to(cur, adj);
+                    for (int i = 0; i < n; ++i) b.adjacent[adj[i]] = 1;
+                    return true;
+                });
+                blocks.push_back(std::move(b));
+            }
+        }
+        for (auto& b : blocks) for (int p : b.stones) points[p] = ST_BLOCK;          // mark_all_blocks
+        for (auto& r : regions) for (int p : r.points) points[p] = ST_REGION;        // mark_all_regions
+        {   // remove_non_vital_regions (benson.rs:128-143)
+            std::vector<Region> keep;
+            for (auto& r : regions) {
+                bool vital = false;
+                for (auto& b : blocks) if (is_vital(r, b)) { vital = true; break; }
+                if (vital) keep.push_back(std::move(r));
+                else for (int p : r.points) points[p] = ST_NONE;
+            }
+            regions.swap(keep);
+        }
+        for (;;) {                                                                   // benson.rs:73-75 (non-short-circuit |)
+            bool changed = false;
+            {   // remove_non_alive_blocks (:95-111)
+                std::vector<Block> keep;
+                for (auto& b : blocks) {
+                    int vital = 0;
+                    for (auto& r : regions) vital += is_vital(r, b);
+                    if (vital >= 2) keep.push_back(std::move(b));
+                    else { for (int p : b.stones) points[p] = ST_NONE; changed = true; }
+                }
+                blocks.swap(keep);
+            }
+            {   // remove_non_surrounded_regions (:115-131); `points` is updated while the list is filtered
+                std::vector<Region> keep;
+                for (auto& r : regions) {
+                    bool healthy = true;
+                    for (int p : r.neighbours) if (points[p] != ST_BLOCK) { healthy = false; break; }
+                    if (healthy) keep.push_back(std::move(r));
+                    else { for (int p : r.points) points[p] = ST_NONE; changed = true; }
+                }
+                regions.swap(keep);
+            }
+            if (!changed) break;
+        }
+    }
+    bool is_alive(int p) const { return points[p] == ST_BLOCK; }     // :152-154
+    bool is_eye(int p) const { return points[p] == ST_REGION; }      // :163-165
+};
+
+// utils/score.rs:97-110
+bool is_scorable(const Board& b) {
+    Benson black(b.inner, BLACK), white(b.inner, WHITE);
+    for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+        int p = point_new(x, y);
+        int c = v_color(b.inner.vertices[p]);
+        bool ok = c == 0 ? (black.is_eye(p) || white.is_eye(p))
+                : c == BLACK ? (black.is_alive(p) || white.is_eye(p))
+                             : (white.is_alive(p) || black.is_eye(p));
+        if (!ok) return false;
+    }
+    return true;
+}
+
+// libdg_mcts/options.rs:180-214 (the "7 of 8 neighbours" own-eye heuristic of ScoringSearch)
+bool is_vertex_filled(const Board& b, int color, int p, int dx, int dy) {
+    int other = point_offset(p, dx, dy);
+    return b.inner.is_part_of(other) && v_color(b.inner.vertices[other]) == color;
+}
+bool is_simple_eye(const Board& b, int color, int p) {
+    static const int CROSS[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+    static const int DIAG[4][2] = {{1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+    int nc = 0, nd = 0;
+    for (auto& d : CROSS) nc += is_vertex_filled(b, color, p, d[0], d[1]);
+    for (auto& d : DIAG) nd += is_vertex_filled(b, color, p, d[0], d[1]);
+    int x = point_x(p), y = point_y(p);
+    if ((x == 0 || x == 18) && (y == 0 || y == 18)) return nc >= 2 && nd >= 1;
+    if (x == 0 || x == 18 || y == 0 || y == 18) return nc >= 3 && nd >= 2;
+    return nc >= 4 && nd >= 3;
+}
+
 void ensure_init() {
     if (!g_zobrist_ready) zobrist_default();
     if (!g_sym_ready) symmetry_init();
@@ -540,6 +678,7 @@ void dgo_set_zobrist_table(const uint64_t* table /* [3][420] */) {
     memcpy(g_zobrist, table, sizeof(g_zobrist));
     g_zobrist_ready = true;
 }
+void dgo_reset_zobrist_table(void) { zobrist_default(); }
 dgo_board* dgo_board_new(float komi) { ensure_init(); return reinterpret_cast<dgo_board*>(new Board(komi)); }
 dgo_board* dgo_board_clone(dgo_board* b) { return reinterpret_cast<dgo_board*>(new Board(*B(b))); }
 void dgo_board_free(dgo_board* b) { delete B(b); }
@@ -576,6 +715,30 @@ int dgo_board_is_symmetric(dgo_board* b, int transform) {
 }
 int dgo_symmetry_apply(int transform, int index) { ensure_init(); return index == 361 ? 361 : to_packed_index(g_sym[transform][from_packed(index)]); }
 int dgo_symmetry_inverse(int transform) { return SYM_INVERSE[transform]; }
+/* Benson status of every point for `color`: 0 none, 1 unconditionally alive block, 2 vital region (eye). */
+void dgo_board_benson(dgo_board* b, int color, uint8_t* out /* [361] */) {
+    Benson bn(B(b)->inner, color);
+    for (int i = 0; i < 361; ++i) out[i] = bn.points[from_packed(i)];
+}
+int dgo_board_is_scorable(dgo_board* b) { return is_scorable(*B(b)); }
+/* PolicyChecker::is_policy_candidate over 0..361.  kind 0 = StandardSearch (options.rs:53-57),
+ * kind 1 = ScoringSearch (options.rs:109-138). */
+void dgo_board_policy_candidates(dgo_board* b, int to_move, int kind, uint8_t* out /* [362] */) {
+    const Board& board = *B(b);
+    if (kind == 0) {
+        for (int i = 0; i < 361; ++i) out[i] = (uint8_t)board.is_valid(to_move, from_packed(i));
+        out[361] = 1;
+        return;
+    }
+    Benson black(board.inner, BLACK), white(board.inner, WHITE);
+    for (int i = 0; i < 361; ++i) {
+        int p = from_packed(i);
+        bool ok = !black.is_eye(p) && !white.is_eye(p);
+        out[i] = (uint8_t)(ok && board.is_valid(to_move, p) && !is_simple_eye(board, to_move, p));
+    }
+    out[361] = 0;
+}
+int dgo_board_is_simple_eye(dgo_board* b, int color, int index) { return is_simple_eye(*B(b), color, from_packed(index)); }
 long dgo_ladder_nodes(void) { return g_ladder_nodes; }
 uint16_t dgo_f32_to_f16(float f) { return f32_to_f16(f); }
 

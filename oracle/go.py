@@ -25,7 +25,7 @@ def lib() -> C.CDLL:
     if not _ready:
         P, I, F, U64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
         sig = {
-            "dgo_set_zobrist_table": (None, [P]),
+            "dgo_set_zobrist_table": (None, [P]), "dgo_reset_zobrist_table": (None, []),
             "dgo_board_new": (P, [F]), "dgo_board_clone": (P, [P]), "dgo_board_free": (None, [P]),
             "dgo_board_set_komi": (None, [P, F]),
             "dgo_board_place": (None, [P, I, I]), "dgo_board_is_valid": (I, [P, I, I]),
@@ -38,6 +38,8 @@ def lib() -> C.CDLL:
             "dgo_board_is_symmetric": (I, [P, I]), "dgo_symmetry_apply": (I, [I, I]), "dgo_symmetry_inverse": (I, [I]),
             "dgo_ladder_nodes": (C.c_long, []), "dgo_f32_to_f16": (C.c_uint16, [F]),
             "dgo_replay": (I, [F, P, P, I, P, P, P]),
+            "dgo_board_benson": (None, [P, I, P]), "dgo_board_is_scorable": (I, [P]),
+            "dgo_board_policy_candidates": (None, [P, I, I, P]), "dgo_board_is_simple_eye": (I, [P, I, I]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -50,6 +52,11 @@ def use_reference_zobrist() -> None:
     """Loads the reference's zobrist constants (data fixture) so hashes compare with real_games.rs."""
     table = np.ascontiguousarray(np.load(_GOLDEN)["zobrist"], np.uint64)
     lib().dgo_set_zobrist_table(table.ctypes.data)
+
+
+def use_default_zobrist() -> None:
+    """Back to the splitmix64 constants the product also uses (hashes then compare product vs oracle)."""
+    lib().dgo_reset_zobrist_table()
 
 
 def idx(x: int, y: int) -> int:
@@ -124,6 +131,23 @@ class Board:
 
     def is_symmetric(self, transform: int) -> bool:
         return bool(lib().dgo_board_is_symmetric(self._h, transform))
+
+    def benson(self, color: int) -> np.ndarray:
+        """0 none / 1 unconditionally alive / 2 vital region per point (utils/benson.rs:152-175)."""
+        out = np.empty(361, np.uint8)
+        lib().dgo_board_benson(self._h, color, out.ctypes.data)
+        return out
+
+    def is_scorable(self) -> bool:
+        return bool(lib().dgo_board_is_scorable(self._h))
+
+    def policy_candidates(self, to_move: int, kind: int = 0) -> np.ndarray:
+        out = np.empty(362, np.uint8)
+        lib().dgo_board_policy_candidates(self._h, to_move, kind, out.ctypes.data)
+        return out
+
+    def is_simple_eye(self, color: int, x: int, y: int) -> bool:
+        return bool(lib().dgo_board_is_simple_eye(self._h, color, idx(x, y)))
 
 
 def symmetry_apply(transform: int, index: int) -> int:

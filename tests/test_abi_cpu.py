@@ -12,8 +12,8 @@ from dream_go_b200 import nn, weights
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    text = open(os.path.join(ROOT, "include", "dg_engine.h")).read()
+def header_functions(header="dg_engine.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(dg_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,6 +25,16 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(handle, name), f"{name} declared in include/dg_engine.h but not exported"
     assert set(names) == set(nn.ABI), "python binding table and header disagree"
+
+
+def test_library_exports_every_go_symbol():
+    from dream_go_b200 import go
+    handle = ctypes.CDLL(nn.LIB_PATH)
+    names = header_functions("dg_go.h")
+    assert len(names) >= 24
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/dg_go.h but not exported"
+    assert set(names) == set(go.ABI), "python binding table and header disagree"
 
 
 def test_abi_version():

@@ -10,6 +10,11 @@ from oracle import go as ogo
 BLACK, WHITE = 1, 2
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _zobrist():
+    ogo.use_default_zobrist()
+
+
 def random_playout(seed: int, plies: int, komi: float = 7.5, pass_rate: float = 0.02):
     """Uniform-random legal playout (legality decided by the ORACLE), returns (colors, moves)."""
     rng = np.random.default_rng(seed)
@@ -220,3 +225,70 @@ def test_prediction_with_transform_kat():
     policy = (np.arange(362) / 1000.0).astype(np.float16)
     raw = b.prior(WHITE, policy, pgo.ROT180, sum_to=float(policy.astype(np.float32).sum() - policy[360 - pgo.idx(3, 2)]))
     assert abs(raw[360] - float(policy[0])) < 1e-3 and abs(raw[361] - float(policy[361])) < 1e-3
+
+
+# ---- unconditional life / scoring candidates (utils/benson.rs, utils/score.rs, libdg_mcts/options.rs) ---------------
+
+def settled_position(seed: int):
+    """Walled-off territories with two-eyed groups plus random filler: exercises alive blocks, vital regions,
+    dead stones inside eyes and regions that fail to be vital."""
+    rng = np.random.default_rng(seed)
+    stones = []
+    for x in range(19):
+        stones.append((BLACK, x, 1))
+        stones.append((WHITE, x, 17))
+        if x not in (3, 9):
+            stones.append((BLACK, x, 0))
+        if x not in (5, 6, 14):                       # a two-point region (not vital) and a one-point eye
+            stones.append((WHITE, x, 18))
+    stones += [(WHITE, 9, 0)] if seed % 2 else []     # a dead stone inside an eye
+    for _ in range(int(rng.integers(0, 60))):
+        stones.append((int(rng.integers(1, 3)), int(rng.integers(0, 19)), int(rng.integers(2, 16))))
+    return stones
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_benson_scorable_candidates_parity(seed):
+    po, oo = pgo.Board(6.5), ogo.Board(6.5)
+    for c, x, y in settled_position(seed):
+        if oo.at(x, y) == 0 and oo.is_valid(c, x, y):
+            po.place(c, x, y)
+            oo.place(c, x, y)
+    assert (po.stones() == oo.stones()).all()
+    for color in (BLACK, WHITE):
+        assert (po.benson(color) == oo.benson(color)).all()
+        for kind in (0, 1):
+            assert (po.policy_candidates(color, kind) == oo.policy_candidates(color, kind)).all()
+    assert po.is_scorable() == oo.is_scorable()
+    assert (oo.benson(BLACK) != 0).any() and (oo.benson(WHITE) != 0).any()
+
+
+def test_benson_parity_on_corpus_endgames():
+    """Final and late positions of the fixture games (nothing is pinned by the reference here beyond its KATs)."""
+    n_settled = 0
+    for colors, moves, komi in ogo.load_games()[::3]:
+        po, oo = pgo.Board(komi), ogo.Board(komi)
+        for i, (c, m) in enumerate(zip(colors, moves)):
+            if m < 361:
+                po.place_index(int(c), int(m))
+                oo.place_index(int(c), int(m))
+            if i % 40 == 39 or i == len(moves) - 1:
+                for color in (BLACK, WHITE):
+                    want = oo.benson(color)
+                    n_settled += int((want != 0).sum())
+                    assert (po.benson(color) == want).all()
+                    assert (po.policy_candidates(color, 1) == oo.policy_candidates(color, 1)).all()
+                assert po.is_scorable() == oo.is_scorable()
+    assert n_settled > 0
+
+
+def test_scorable_kats_on_product():   # utils/score.rs:289-349
+    for color in (BLACK, WHITE):
+        b = pgo.Board(0.5)
+        for y in range(19):
+            for x in range(1, 19, 2):
+                b.place(color, x, y)
+        assert b.is_scorable()
+    b = pgo.Board(7.5)
+    b.place(BLACK, 0, 0)
+    assert not b.is_scorable()

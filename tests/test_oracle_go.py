@@ -277,3 +277,83 @@ def test_features_symmetry_is_a_permutation(t):
     sym = b.features(BLACK, t)
     perm = np.array([go.symmetry_apply(t, i) for i in range(361)])
     assert (sym[perm] == base).all()
+
+
+# ---- utils/benson.rs:616-677, utils/score.rs:289-349, libdg_mcts/options.rs:217-262 -------------------------------
+
+def test_benson_empty_is_all_valid():
+    b = Board(0.5)
+    assert (b.benson(BLACK) == 0).all() and (b.benson(WHITE) == 0).all()
+
+
+def test_benson_eyes():
+    b = Board(0.5)
+    for x, y in [(0, 1), (1, 1), (2, 0), (2, 1), (3, 1), (4, 0), (4, 1)]:
+        b.place(WHITE, x, y)
+    b.place(BLACK, 0, 0)
+    st = b.benson(WHITE)
+    for y in range(19):
+        for x in range(19):
+            if b.at(x, y) == WHITE:
+                assert st[go.idx(x, y)] == 1, (x, y)
+    for x, y in [(0, 0), (1, 0), (3, 0)]:
+        assert st[go.idx(x, y)] == 2, (x, y)
+
+
+BENSON_BENCH = [
+    (1, 15, 16), (2, 16, 3), (1, 3, 2), (2, 3, 15), (1, 14, 3), (2, 14, 2), (1, 13, 2), (2, 15, 2),
+    (1, 12, 3), (2, 16, 5), (1, 9, 2), (2, 2, 5), (1, 3, 4), (2, 1, 3), (1, 3, 5), (2, 2, 6),
+    (1, 3, 6), (2, 2, 7), (1, 4, 8), (2, 2, 2), (1, 2, 1), (2, 3, 9), (1, 4, 9), (2, 3, 10),
+    (1, 4, 10), (2, 3, 11), (1, 2, 16), (2, 2, 15), (1, 3, 16), (2, 5, 16), (1, 5, 17), (2, 9, 6),
+    (1, 16, 13), (2, 8, 3), (1, 8, 2), (2, 7, 3), (1, 6, 16), (2, 5, 15), (1, 7, 17), (2, 9, 3),
+    (1, 10, 2), (2, 13, 16), (1, 11, 16), (2, 15, 14), (1, 16, 14), (2, 15, 17), (1, 16, 16), (2, 13, 14),
+    (1, 11, 14), (2, 16, 17), (1, 17, 17), (2, 14, 16), (1, 16, 18), (2, 14, 18), (1, 14, 12), (2, 15, 15),
+    (1, 16, 15), (2, 16, 8), (1, 12, 17), (2, 13, 17), (1, 17, 18), (2, 12, 16), (1, 11, 17), (2, 11, 13),
+    (1, 10, 13), (2, 11, 12), (1, 10, 12), (2, 12, 14), (1, 10, 14), (2, 11, 11), (1, 11, 9), (2, 11, 6),
+    (1, 9, 9), (2, 13, 4), (1, 12, 4), (2, 13, 5), (1, 10, 5), (2, 10, 6), (1, 9, 5), (2, 8, 5),
+    (1, 8, 6), (2, 7, 5), (1, 8, 7), (2, 7, 2), (1, 11, 5), (2, 12, 5), (1, 10, 3), (2, 4, 1),
+    (1, 4, 2), (2, 5, 2), (1, 5, 3), (2, 6, 1), (1, 3, 1), (2, 6, 3), (1, 5, 4), (2, 13, 1),
+    (1, 12, 1), (2, 13, 3), (1, 12, 2), (2, 8, 1),
+]
+
+
+def test_benson_midgame_position_has_nothing_settled():   # benson.rs:585-613 (bench body asserts is_valid everywhere)
+    b = Board(0.5)
+    for c, x, y in BENSON_BENCH:
+        b.place(c, x, y)
+    assert (b.benson(WHITE) == 0).all()
+
+
+def test_is_scorable_kats():
+    b = Board(7.5)
+    b.place(BLACK, 0, 0)
+    assert not b.is_scorable()
+    b = Board(7.5)
+    for x, y in [(1, 0), (0, 1), (1, 1), (1, 2), (0, 3), (1, 3)]:
+        b.place(WHITE, x, y)
+    for x, y in [(2, 0), (2, 1), (2, 2), (2, 3), (0, 4), (1, 4), (2, 4)]:
+        b.place(BLACK, x, y)
+    assert not b.is_scorable()
+    for color in (BLACK, WHITE):
+        b = Board(0.5)
+        for y in range(19):
+            for x in range(1, 19, 2):
+                b.place(color, x, y)
+        assert b.is_scorable()
+
+
+def test_simple_eye_kats():   # libdg_mcts/options.rs:217-262
+    b = Board(0.5)
+    for x, y in [(1, 0), (0, 1), (1, 1)]:
+        b.place(BLACK, x, y)
+    assert b.is_simple_eye(BLACK, 0, 0) and not b.is_simple_eye(WHITE, 0, 0)
+    b = Board(0.5)
+    for x, y in [(0, 0), (0, 1), (1, 1), (2, 1), (2, 0)]:
+        b.place(BLACK, x, y)
+    assert b.is_simple_eye(BLACK, 1, 0) and not b.is_simple_eye(WHITE, 1, 0)
+    b = Board(0.5)
+    for x, y in [(0, 1), (0, 2), (1, 0), (2, 0), (2, 2), (2, 1), (1, 2)]:
+        b.place(BLACK, x, y)
+    assert b.is_simple_eye(BLACK, 1, 1) and not b.is_simple_eye(WHITE, 1, 1)
+    b.place(BLACK, 0, 0)
+    assert b.is_simple_eye(BLACK, 1, 1) and not b.is_simple_eye(WHITE, 1, 1)
