@@ -1,0 +1,418 @@
+// search.h -- Monte-Carlo tree search of the self-play engine (host side, product code).
+//
+// Computes what `dg_mcts::tree` / `dg_mcts::predict` compute (reference: src/libdg_mcts/tree.rs:1027-1510,
+// lib.rs:83-200, time_control/mod.rs:47-97, choose.rs, dirichlet.rs, libdg_utils/config.rs:181-336, lcb.rs), with
+// the data organised for the batched engine instead of a pool of racing worker threads:
+//
+//   * a node stores only its candidate moves (finite prior) as sorted (move, prior) pairs plus one small edge
+//     record per VISITED child -- the reference keeps a dense prior[368] and an 8-slot / 362-slot child table
+//     (tree.rs:540-700);
+//   * a search advances in rounds: up to P probes are collected (virtual loss keeps them apart), their leaves are
+//     evaluated as ONE batch together with the leaves of every other game on the device, then inserted in probe
+//     order.  No locks, no atomics, and the result is a pure function of (position, weights, seed) -- the
+//     reference's result depends on thread timing.  With P = 1 this is exactly the sequential algorithm.
+//
+// Arithmetic is fp32 in the reference's operation order (compiled with -ffp-contract=off) so that visit counts
+// are bit-identical to the oracle restatement (tests/test_mcts_parity.py).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "go_board.h"
+
+namespace dg {
+
+constexpr int VLOSS_CNT = 32;                 // config.rs:187
+constexpr int MIN_LCB_VISITS = 80;            // tree.rs:34
+constexpr float NEG_INF = -std::numeric_limits<float>::infinity();
+
+// Piecewise-linear schedules over the visit count of the CURRENT node (config.rs:181-192, 297-336).
+struct Knot { int x; float y; };
+inline float interpolate(const Knot* pts, int n, int x) {
+    int i = 0;
+    while (i < n && pts[i].x < x) ++i;
+    if (i == n) return pts[n - 1].y;
+    const Knot& x0 = pts[i == 0 ? 0 : i - 1];
+    const Knot& x1 = pts[i];
+    float a = x0.x >= x1.x ? 0.5f : (float)(x - x0.x) / (float)(x1.x - x0.x);
+    return (1.0f - a) * x0.y + a * x1.y;
+}
+inline float uct_exp(int visits) {
+    static const Knot k[5] = {{0, 0.77392f}, {800, 1.05439f}, {1600, 1.22798f}, {3200, 0.813532f}, {6400, 0.764326f}};
+    return interpolate(k, 5, visits);
+}
+inline float fpu_reduce(int visits) {
+    static const Knot k[5] = {{0, 0.631571f}, {800, 0.431547f}, {1600, 0.656083f}, {3200, 0.429231f}, {6400, 0.514494f}};
+    return interpolate(k, 5, visits);
+}
+inline float lcb_critical_value(int visits) {
+    static const Knot k[5] = {{0, 1.91753f}, {800, 1.86478f}, {1600, 1.86943f}, {3200, 2.20033f}, {6400, 1.78053f}};
+    return interpolate(k, 5, visits);
+}
+
+struct Node;
+
+struct Edge {                                  // one visited (or disqualified) child
+    uint16_t move;
+    bool expanding;
+    int32_t count;
+    int32_t vcount;
+    float value;
+    float value_s;
+    Node* child;
+};
+
+struct Node {
+    uint8_t to_move;
+    int16_t pass_count;
+    float initial_value;
+    int32_t total_count, vtotal_count;
+    std::vector<uint16_t> cand_move;           // ascending
+    std::vector<float> cand_prior;             // finite
+    std::vector<Edge> edges;                   // unordered, few
+
+    Node(int to_move_, float value, const float* prior /* [362] */)
+        : to_move((uint8_t)to_move_), pass_count(0), initial_value(value), total_count(0), vtotal_count(0) {
+        set_prior(prior);
+    }
+    ~Node() { for (Edge& e : edges) delete e.child; }
+    Node(const Node&) = delete;
+    Node& operator=(const Node&) = delete;
+
+    void set_prior(const float* prior) {       // lib.rs:170-182 replaces the prior of a re-used root
+        cand_move.clear();
+        cand_prior.clear();
+        for (int i = 0; i < 362; ++i)
+            if (std::isfinite(prior[i])) { cand_move.push_back((uint16_t)i); cand_prior.push_back(prior[i]); }
+    }
+    Edge* find(int move) {
+        for (Edge& e : edges) if (e.move == move) return &e;
+        return nullptr;
+    }
+    const Edge* find(int move) const { return const_cast<Node*>(this)->find(move); }
+    Edge& edge(int move) {                     // tree.rs:276-285: an absent child reads as (count 0, value = initial)
+        if (Edge* e = find(move)) return *e;
+        edges.push_back(Edge{(uint16_t)move, false, 0, 0, initial_value, 0.0f, nullptr});
+        return edges.back();
+    }
+    float prior_of(int move) const {
+        auto it = std::lower_bound(cand_move.begin(), cand_move.end(), (uint16_t)move);
+        return it != cand_move.end() && *it == move ? cand_prior[it - cand_move.begin()] : NEG_INF;
+    }
+    int count_of(int move) const { const Edge* e = find(move); return e ? e->count : 0; }
+    float value_of(int move) const { const Edge* e = find(move); return e ? e->value : initial_value; }
+
+    void disqualify(int move) {                // tree.rs:1296-1301
+        Edge& e = edge(move);
+        e.value = NEG_INF;
+        e.count = 0;
+    }
+};
+
+enum ProbeStatus { PROBE_FOUND = 0, PROBE_CONFLICT = 1, PROBE_NO_RESULT = 2 };
+struct TraceEntry { Node* node; int move; };
+typedef std::vector<TraceEntry> Trace;
+
+// Node::select (tree.rs:1311-1385) and asm/argmax.rs:23-76: the reference scans 368 scores in blocks of 8; among
+// equal maxima the LAST block wins and inside a block the FIRST lane.
+inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move) {
+    const int n = node.total_count + node.vtotal_count;
+    const float sqrt_n = std::sqrt((float)(1 + n));
+    const float u = uct_exp(n) * sqrt_n;
+    float unvisited = node.initial_value;
+    float reduce = 0.0f;
+    if (apply_fpu) {
+        reduce = fpu_reduce(n);
+        float v = unvisited - reduce;
+        unvisited = v > 0.0f ? v : 0.0f;       // _mm256_max_ps(v, 0): also maps -inf / NaN to 0
+    }
+    float best = NEG_INF;
+    int best_move = -1;
+    auto consider = [&](int move, float score) {
+        if (score > best || (score == best && best_move >= 0 && (move >> 3) > (best_move >> 3)) || (best_move < 0 && score == best)) {
+            best = score;
+            best_move = move;
+        }
+    };
+    const size_t nc = node.cand_move.size();
+    if (node.edges.empty()) {
+        for (size_t i = 0; i < nc; ++i) consider(node.cand_move[i], unvisited + node.cand_prior[i] * u);
+    } else {
+        // edges of moves that are not (or no longer) candidates have prior -inf and never win
+        for (size_t i = 0; i < nc; ++i) {
+            int move = node.cand_move[i];
+            float value = unvisited, bonus = u;
+            if (const Edge* e = node.find(move)) {
+                int total = e->count + e->vcount;
+                if (total != 0) {
+                    value = e->value;
+                    bonus = u / (float)(1 + total);
+                } else if (apply_fpu) {
+                    float v = e->value - reduce;
+                    value = v > 0.0f ? v : 0.0f;
+                } else {
+                    value = e->value;
+                }
+            }
+            consider(move, value + node.cand_prior[i] * bonus);
+        }
+    }
+    if (best_move < 0 || !std::isfinite(best)) return PROBE_NO_RESULT;
+    Edge& e = node.edge(best_move);
+    bool was_expanding = e.expanding;
+    e.expanding = true;
+    if (was_expanding && !e.child) return PROBE_CONFLICT;
+    e.vcount += VLOSS_CNT;
+    node.vtotal_count += VLOSS_CNT;
+    *out_move = best_move;
+    return PROBE_FOUND;
+}
+
+inline void undo(const Trace& trace, bool undo_expanding) {    // tree.rs:1397-1409
+    for (const TraceEntry& t : trace) {
+        t.node->vtotal_count -= VLOSS_CNT;
+        Edge& e = t.node->edge(t.move);
+        e.vcount -= VLOSS_CNT;
+        if (undo_expanding && !e.child) e.expanding = false;
+    }
+}
+
+// tree::probe (tree.rs:1421-1471): walks down, playing the moves on `board`.
+inline ProbeStatus probe(Node& root, Board& board, Trace& trace) {
+    trace.clear();
+    Node* current = &root;
+    for (;;) {
+        int move;
+        ProbeStatus st = select(*current, !trace.empty(), &move);
+        if (st == PROBE_CONFLICT) { undo(trace, false); trace.clear(); return st; }
+        if (st == PROBE_NO_RESULT) return st;
+        trace.push_back(TraceEntry{current, move});
+        if (move != PASS) board.place(current->to_move, move);
+        else if (current->pass_count >= 1) break;
+        Node* child = current->edge(move).child;
+        if (!child) break;
+        current = child;
+    }
+    return PROBE_FOUND;
+}
+
+// tree::insert + UCT::update (tree.rs:1482-1510, 125-159)
+inline void insert(const Trace& trace, int color, float value, const float* prior /* [362] */) {
+    if (!trace.empty()) {
+        const TraceEntry& last = trace.back();
+        Edge& e = last.node->edge(last.move);
+        if (!e.child) {
+            Node* next = new Node(color, value, prior);
+            if (last.move == PASS) next->pass_count = (int16_t)(last.node->pass_count + 1);
+            e.child = next;
+        }
+    }
+    for (const TraceEntry& t : trace) {
+        float v = color == t.node->to_move ? value : 1.0f - value;
+        t.node->total_count += 1;
+        t.node->vtotal_count -= VLOSS_CNT;
+        Edge& e = t.node->edge(t.move);
+        float prev = e.value, prev_s = e.value_s;
+        int prev_count = e.count;
+        e.count = prev_count + 1;
+        float next = prev + (v - prev) / (float)(prev_count + 1);
+        e.value = next;
+        e.value_s = prev_s + (v - prev) * (v - next);
+        e.vcount -= VLOSS_CNT;
+    }
+}
+
+// time_control::is_done with RolloutLimit (time_control/mod.rs:47-97, rollout_limit.rs:35-45)
+inline bool is_done(const Node& root, int limit) {
+    if (root.total_count == 0) return false;
+    if (root.total_count >= limit) return true;
+    int remaining = limit - root.total_count;
+    // argmax_count: the first maximum over 0..362 in index order; top_2: first strict maximum among the rest
+    int top1 = 0, c1 = root.count_of(0);
+    {
+        int bc = std::numeric_limits<int>::min();
+        top1 = -1;
+        for (int i = 0; i < 362; ++i) { int c = root.count_of(i); if (c > bc) { bc = c; top1 = i; } }
+        c1 = bc;
+    }
+    int top2 = top1 == 0 ? 1 : 0;
+    // children.nonzero() iterates the visited children; only a strictly larger count replaces top_2
+    std::vector<int> visited;
+    for (const Edge& e : root.edges) if (e.count != 0) visited.push_back(e.move);
+    std::sort(visited.begin(), visited.end());
+    for (int i : visited) if (i != top1 && root.count_of(i) > root.count_of(top2)) top2 = i;
+    int c2 = root.count_of(top2);
+    int min_promote = c1 > c2 ? c1 - c2 : 0;
+    return min_promote > remaining;
+}
+
+// ---- choosing the move ------------------------------------------------------------------------------------------
+
+inline float normal_lcb(float p_hat, float p_std, int n, int m) {      // libdg_utils/lcb.rs:28-36
+    if (n <= 0) return 0.0f;
+    float z = lcb_critical_value(m);
+    return p_hat - z * p_std / std::sqrt((float)n);
+}
+
+// tree.rs:1524-1560; returns <0, 0, >0 like Ordering
+inline int compare_children(const Node& node, int a, int b) {
+    const Edge* ea = node.find(a);
+    const Edge* eb = node.find(b);
+    int ac = ea ? ea->count : 0, bc = eb ? eb->count : 0;
+    auto cmp = [](float x, float y) { return x < y ? -1 : x > y ? 1 : 0; };
+    if (ac >= MIN_LCB_VISITS && bc >= MIN_LCB_VISITS) {
+        float as = std::sqrt(ea->value_s / ((float)ac + 1e-5f)), bs = std::sqrt(eb->value_s / ((float)bc + 1e-5f));
+        float al = normal_lcb(ea->value, as, ac, node.total_count), bl = normal_lcb(eb->value, bs, bc, node.total_count);
+        if (al != bl) return cmp(al, bl);
+    }
+    if (ac != bc) return ac < bc ? -1 : 1;
+    float ap = node.prior_of(a), bp = node.prior_of(b);
+    if (ap != bp) return cmp(ap, bp);
+    return cmp(node.value_of(a), node.value_of(b));
+}
+
+// choose.rs:62-99 (+ percentile :25-48).  items are visit counts (or a policy); returns the index or -1.
+inline int choose(const std::vector<double>& items, double cutoff_percentile, double temperature, double at) {
+    double total = 0.0;
+    for (double x : items) if (std::isfinite(x)) total += x;
+    std::vector<int> order(items.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return items[a] < items[b]; });   // only values matter below
+    double max_value = total * (1.0 - cutoff_percentile), so_far = 0.0, threshold = 0.0;
+    bool found = false;
+    for (size_t k = order.size(); k-- > 0;) {
+        so_far += items[order[k]];
+        if (so_far >= max_value) { threshold = items[order[k]]; found = true; break; }
+    }
+    if (!found) return -1;
+    double cum_total = 0.0;
+    std::vector<double> cum(items.size(), std::numeric_limits<double>::quiet_NaN());
+    for (size_t i = 0; i < items.size(); ++i)
+        if (items[i] >= threshold) { cum_total += std::pow(items[i] / so_far, temperature); cum[i] = cum_total; }
+    double target = at * cum_total;
+    for (size_t i = 0; i < items.size(); ++i) if (cum[i] >= target) return (int)i;
+    return -1;
+}
+
+// Node::best (tree.rs:1232-1283).  `at` = the uniform random number the stochastic branch draws.
+inline int best(const Node& node, float temperature, double at, float* value_out) {
+    int pick;
+    if (temperature <= 9e-2f) {
+        std::vector<int> visited;
+        for (const Edge& e : node.edges) if (e.count != 0) visited.push_back(e.move);
+        std::sort(visited.begin(), visited.end());
+        pick = PASS;
+        bool first = true;
+        for (int i : visited) {                // Iterator::max_by keeps the LAST of equal maxima
+            if (first || compare_children(node, pick, i) <= 0) { pick = i; first = false; }
+        }
+        *value_out = node.value_of(pick);
+        return pick;
+    }
+    std::vector<double> visits(362);
+    for (int i = 0; i < 362; ++i) visits[i] = (double)node.count_of(i);
+    pick = choose(visits, 0.5, 1.0 / (double)temperature, at);
+    if (pick < 0) { *value_out = node.initial_value; return PASS; }
+    *value_out = node.value_of(pick);
+    return pick;
+}
+
+// Node::forward (tree.rs:1198-1225): detaches and returns the sub-tree of `move` (nullptr if there is none);
+// the rest of `node` is destroyed.
+inline Node* forward(Node* node, int move) {
+    Node* next = nullptr;
+    if (Edge* e = node->find(move)) { next = e->child; e->child = nullptr; }
+    if (!next && move == PASS) {
+        float prior[362];
+        for (int i = 0; i < 362; ++i) prior[i] = 0.0f;
+        next = new Node(opposite(node->to_move), 0.5f, prior);
+        next->pass_count = (int16_t)(node->pass_count + 1);
+    }
+    delete node;
+    return next;
+}
+
+// Node::softmax (tree.rs:1275-1289): visit distribution of the root.
+inline void visit_distribution(const Node& node, float out[362]) {
+    float total = 0.0f;
+    for (int i = 0; i < 362; ++i) out[i] = 0.0f;
+    std::vector<int> visited;
+    for (const Edge& e : node.edges) if (e.count != 0) visited.push_back(e.move);
+    std::sort(visited.begin(), visited.end());
+    for (int i : visited) total += (float)node.count_of(i);
+    for (int i : visited) out[i] = (float)node.count_of(i) / total;
+}
+
+// ---- root prior: average over the 8 symmetries (lib.rs:83-133) and Dirichlet noise (dirichlet.rs:40-76) ----------
+
+// dirichlet::add_ex with the normalised sample `eta` supplied by the caller (eta[i] = g_i / sum g over the finite entries)
+inline void mix_noise(float* x /* [362] */, const float* eta, float beta) {
+    for (int i = 0; i < 362; ++i)
+        if (std::isfinite(x[i])) x[i] = (1.0f - beta) * x[i] + beta * eta[i];
+}
+
+// ---- randomness (injected everywhere; the reference uses thread_rng) ------------------------------------------------
+struct Rng {
+    uint64_t s[4];
+    explicit Rng(uint64_t seed = 1) { reseed(seed); }
+    void reseed(uint64_t seed) {
+        for (int i = 0; i < 4; ++i) {
+            uint64_t z = (seed += 0x9e3779b97f4a7c15ull);
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            s[i] = z ^ (z >> 31);
+        }
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() {                          // xoshiro256**
+        uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+        return r;
+    }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }       // [0, 1)
+    int below(int n) { return (int)(uniform() * n); }
+    double normal() {
+        for (;;) {                             // Marsaglia polar method
+            double u = 2.0 * uniform() - 1.0, v = 2.0 * uniform() - 1.0, q = u * u + v * v;
+            if (q > 0.0 && q < 1.0) return u * std::sqrt(-2.0 * std::log(q) / q);
+        }
+    }
+    double gamma(double shape) {               // Marsaglia & Tsang; shape < 1 boosted by U^(1/shape) (as rand_distr does)
+        if (shape < 1.0) {
+            double u = uniform();
+            while (u <= 0.0) u = uniform();
+            return gamma(shape + 1.0) * std::pow(u, 1.0 / shape);
+        }
+        double d = shape - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+        for (;;) {
+            double x = normal(), v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            double u = uniform();
+            if (u < 1.0 - 0.0331 * x * x * x * x) return d * v;
+            if (std::log(u) < 0.5 * x * x + d * (1.0 - v + std::log(v))) return d * v;
+        }
+    }
+    // eta for mix_noise: Gamma(shape) samples over the finite entries of x, normalised (dirichlet.rs:48-70)
+    void dirichlet(const float* x, double shape, float* eta) {
+        double g[362], sum;
+        int count;
+        do {
+            sum = 0.0;
+            count = 0;
+            for (int i = 0; i < 362; ++i) {
+                g[i] = 0.0;
+                if (std::isfinite(x[i])) { g[i] = gamma(shape); sum += g[i]; ++count; }
+            }
+        } while (count != 0 && !(sum > std::numeric_limits<double>::min()));
+        for (int i = 0; i < 362; ++i) eta[i] = count ? (float)(g[i] / sum) : 0.0f;
+    }
+};
+
+}  // namespace dg
