@@ -135,7 +135,7 @@ inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move) {
     float best = NEG_INF;
     int best_move = -1;
     auto consider = [&](int move, float score) {
-        if (score > best || (score == best && best_move >= 0 && (move >> 3) > (best_move >> 3)) || (best_move < 0 && score == best)) {
+        if (best_move < 0 || score > best || (score == best && (move >> 3) > (best_move >> 3))) {
             best = score;
             best_move = move;
         }
@@ -144,24 +144,33 @@ inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move) {
     if (node.edges.empty()) {
         for (size_t i = 0; i < nc; ++i) consider(node.cand_move[i], unvisited + node.cand_prior[i] * u);
     } else {
-        // edges of moves that are not (or no longer) candidates have prior -inf and never win
+        // move -> edge lookup through a per-thread scratch table (edges of moves that are not candidates any
+        // more have prior -inf in the reference and never win)
+        static thread_local int16_t slot_of[362];
+        static thread_local bool slot_init = false;
+        if (!slot_init) { for (int i = 0; i < 362; ++i) slot_of[i] = -1; slot_init = true; }
+        const size_t ne = node.edges.size();
+        for (size_t k = 0; k < ne; ++k) slot_of[node.edges[k].move] = (int16_t)k;
         for (size_t i = 0; i < nc; ++i) {
             int move = node.cand_move[i];
             float value = unvisited, bonus = u;
-            if (const Edge* e = node.find(move)) {
-                int total = e->count + e->vcount;
+            int k = slot_of[move];
+            if (k >= 0) {
+                const Edge& e = node.edges[k];
+                int total = e.count + e.vcount;
                 if (total != 0) {
-                    value = e->value;
+                    value = e.value;
                     bonus = u / (float)(1 + total);
                 } else if (apply_fpu) {
-                    float v = e->value - reduce;
+                    float v = e.value - reduce;
                     value = v > 0.0f ? v : 0.0f;
                 } else {
-                    value = e->value;
+                    value = e.value;
                 }
             }
             consider(move, value + node.cand_prior[i] * bonus);
         }
+        for (size_t k = 0; k < ne; ++k) slot_of[node.edges[k].move] = -1;
     }
     if (best_move < 0 || !std::isfinite(best)) return PROBE_NO_RESULT;
     Edge& e = node.edge(best_move);
@@ -233,21 +242,13 @@ inline bool is_done(const Node& root, int limit) {
     if (root.total_count == 0) return false;
     if (root.total_count >= limit) return true;
     int remaining = limit - root.total_count;
-    // argmax_count: the first maximum over 0..362 in index order; top_2: first strict maximum among the rest
-    int top1 = 0, c1 = root.count_of(0);
-    {
-        int bc = std::numeric_limits<int>::min();
-        top1 = -1;
-        for (int i = 0; i < 362; ++i) { int c = root.count_of(i); if (c > bc) { bc = c; top1 = i; } }
-        c1 = bc;
+    // min_promote_rollouts (:47-74): visits the runner-up needs to catch up = largest count - second largest
+    // (whichever of two tied leaders the reference's argmax picks, the difference is the same)
+    int c1 = 0, c2 = 0;
+    for (const Edge& e : root.edges) {
+        if (e.count > c1) { c2 = c1; c1 = e.count; }
+        else if (e.count > c2) c2 = e.count;
     }
-    int top2 = top1 == 0 ? 1 : 0;
-    // children.nonzero() iterates the visited children; only a strictly larger count replaces top_2
-    std::vector<int> visited;
-    for (const Edge& e : root.edges) if (e.count != 0) visited.push_back(e.move);
-    std::sort(visited.begin(), visited.end());
-    for (int i : visited) if (i != top1 && root.count_of(i) > root.count_of(top2)) top2 = i;
-    int c2 = root.count_of(top2);
     int min_promote = c1 > c2 ? c1 - c2 : 0;
     return min_promote > remaining;
 }
@@ -304,9 +305,11 @@ inline int choose(const std::vector<double>& items, double cutoff_percentile, do
 inline int best(const Node& node, float temperature, double at, float* value_out) {
     int pick;
     if (temperature <= 9e-2f) {
+        // children.nonzero() (tree.rs:871-890) walks the 8-slot table in insertion order while the node is
+        // sparse and the dense table in index order once a 9th child exists; it only matters for exact ties
         std::vector<int> visited;
         for (const Edge& e : node.edges) if (e.count != 0) visited.push_back(e.move);
-        std::sort(visited.begin(), visited.end());
+        if (node.edges.size() > 8) std::sort(visited.begin(), visited.end());
         pick = PASS;
         bool first = true;
         for (int i : visited) {                // Iterator::max_by keeps the LAST of equal maxima

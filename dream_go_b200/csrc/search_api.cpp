@@ -1,0 +1,489 @@
+// search_api.cpp -- C ABI of include/dg_mcts.h: blocking single search (dg_mcts_predict) and the self-play driver.
+//
+// The driver is the engine-side replacement of `self_play` + `Pool` + `Batcher` (src/libdg_mcts/self_play.rs:423-500,
+// pool/pool.rs, pool/batch.rs): the games in flight are split into two groups that alternate -- while the device
+// evaluates the leaves of one group, the host threads insert the previous results of the other group, probe its
+// trees and extract the next features.  Every game owns its random stream, so the games played are a function of
+// the seed alone, whatever the thread count.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <future>
+#include <string>
+#include <thread>
+
+#include "../../include/dg_mcts.h"
+#include "search_task.h"
+
+using namespace dg;
+
+static inline Node* N(dg_tree* t) { return reinterpret_cast<Node*>(t); }
+static inline const Node* N(const dg_tree* t) { return reinterpret_cast<const Node*>(t); }
+
+static SearchOptions convert(const dg_search_options* o) {
+    SearchOptions s;
+    s.search_kind = o->search;
+    s.deterministic = o->deterministic != 0;
+    s.num_rollout = o->num_rollout;
+    s.probes_per_round = o->probes_per_round > 0 ? o->probes_per_round : 1;
+    s.dirichlet_beta = o->dirichlet_noise;
+    s.temperature = o->temperature;
+    s.noise = o->noise;
+    s.leaf_symmetries = o->leaf_symmetries;
+    s.n_leaf_symmetries = o->n_leaf_symmetries;
+    s.choose_at = o->choose_at;
+    return s;
+}
+
+static int64_t count_nodes(const Node* n) {
+    int64_t c = 1;
+    for (const Edge& e : n->edges) if (e.child) c += count_nodes(e.child);
+    return c;
+}
+
+// ---- SGF record (self_play.rs:187-214, game_result.rs:23-43) ---------------------------------------------------------
+static const char B85[] = "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz!#$%&()*+-;<=>?@^_`{|}~";
+
+static void b85_encode_f16(const float* x, int n, std::string& out) {      // libdg_utils/b85.rs:141-165
+    for (int i = 0; i + 1 < n; i += 2) {
+        uint16_t a = f32_to_f16_bits(x[i]), b = f32_to_f16_bits(x[i + 1]);
+        a = (uint16_t)((a << 8) | (a >> 8));
+        b = (uint16_t)((b << 8) | (b >> 8));
+        uint64_t acc = ((uint64_t)a << 16) | b;
+        out.push_back(B85[acc / 52200625]);
+        out.push_back(B85[(acc / 614125) % 85]);
+        out.push_back(B85[(acc / 7225) % 85]);
+        out.push_back(B85[(acc / 85) % 85]);
+        out.push_back(B85[acc % 85]);
+    }
+}
+
+static void sgf_point(int index, std::string& out) {                        // utils/sgf.rs:36-43 (CGoban)
+    if (index >= N_POINTS) return;
+    out.push_back((char)('a' + index % 19));
+    out.push_back((char)('a' + index / 19));
+}
+
+// Tromp-Taylor area score without komi (utils/score.rs:230-282): stones + empty regions that reach one colour only.
+static void tromp_taylor(const Board& b, int* black, int* white) {
+    const Tables& T = tables();
+    uint8_t reach[N_POINTS];
+    memset(reach, 0, sizeof(reach));
+    for (int c = BLACK; c <= WHITE; ++c) {
+        std::vector<int> stack;
+        for (int p = 0; p < N_POINTS; ++p) if (b.color[p] == c) stack.push_back(p);
+        while (!stack.empty()) {
+            int p = stack.back();
+            stack.pop_back();
+            for (int k = 0; k < T.n_nbr[p]; ++k) {
+                int q = T.nbr_list[p][k];
+                if (!b.color[q] && !(reach[q] & c)) { reach[q] |= (uint8_t)c; stack.push_back(q); }
+            }
+        }
+    }
+    *black = *white = 0;
+    for (int p = 0; p < N_POINTS; ++p) {
+        if (b.color[p] == BLACK || (!b.color[p] && reach[p] == BLACK)) ++*black;
+        else if (b.color[p] == WHITE || (!b.color[p] && reach[p] == WHITE)) ++*white;
+    }
+}
+
+namespace {
+
+struct Player {                                                  // self_play.rs:217-241
+    float winrate = 0.5f;
+    Node* root = nullptr;
+    int color = BLACK;
+    int num_rollout(int max_rollout) const {
+        float m = 4.0f * winrate * (1.0f - winrate);
+        m = m < 0.1f ? 0.1f : m;
+        return (int)(m * (float)max_rollout);
+    }
+    void update(float value) { winrate -= 0.2f * (winrate - value); }        // MovingAverage, MOMENTUM = 0.2
+};
+
+struct Game {
+    enum Mode { IDLE, SEARCH, EX_IT };
+    int64_t id = -1;
+    Board board;
+    Player players[2];                                           // players[0] is to move (self_play.rs:433-457)
+    int pass_count = 0;
+    bool active = false;
+    Mode mode = IDLE;
+    bool allow_pass = false;
+    Rng rng;
+    SearchTask task;
+    std::string sgf;
+    std::vector<uint16_t> moves;
+    std::vector<dg_packed_position> batch;                       // this round's leaves
+    int n_emitted = 0;
+    size_t batch_offset = 0;
+    // result of the main search, kept while an ex-it search replaces the recorded statistics
+    float value = 0.5f;
+    int index = PASS;
+    Node* tree = nullptr;
+    int64_t evals = 0, searches = 0, n_moves = 0;
+
+    ~Game() { clear_trees(); }
+    void clear_trees() {
+        delete players[0].root; players[0].root = nullptr;
+        delete players[1].root; players[1].root = nullptr;
+        delete tree; tree = nullptr;
+    }
+};
+
+float random_komi(Rng& rng) {                                    // lib.rs:210-224
+    float v = (float)rng.uniform();
+    if (v < 0.4f) return 7.5f;
+    if (v < 0.8f) return 6.5f;
+    if (v < 0.9f) return 0.5f;
+    return (float)(rng.below(16) - 8) + 0.5f;
+}
+
+struct Driver {
+    dg_selfplay_config cfg;
+    std::vector<Game> games;
+    int64_t started = 0, finished = 0;
+    std::string sgf_all;
+    uint64_t digest = 0;
+    int64_t total_moves = 0, total_evals = 0, total_searches = 0;
+
+    void start_game(Game& g) {
+        g.clear_trees();
+        g.id = started++;
+        g.rng.reseed(cfg.seed * 0x9e3779b97f4a7c15ull + (uint64_t)g.id * 0xd1342543de82ef95ull + 1);
+        g.board.init(random_komi(g.rng));
+        g.players[0] = Player();
+        g.players[1] = Player();
+        g.players[0].color = BLACK;
+        g.players[1].color = WHITE;
+        g.pass_count = 0;
+        g.active = true;
+        g.mode = Game::IDLE;
+        g.sgf.clear();
+        g.moves.clear();
+    }
+
+    void finish_game(Game& g) {                                  // game_result.rs:23-43 (Ended)
+        int black, white;
+        tromp_taylor(g.board, &black, &white);
+        float w = (float)white + g.board.komi, b = (float)black;
+        char head[160], res[32];
+        if (b > w) snprintf(res, sizeof(res), "B+%.1f", b - w);
+        else if (w > b) snprintf(res, sizeof(res), "W+%.1f", w - b);
+        else snprintf(res, sizeof(res), "0");
+        snprintf(head, sizeof(head), "(;GM[1]FF[4]SZ[19]RU[Chinese]KM[%.1f]RE[%s]", g.board.komi, res);
+        sgf_all += head;
+        sgf_all += g.sgf;
+        sgf_all += ")\n";
+        uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)g.id;
+        for (uint16_t m : g.moves) { h ^= m; h *= 0x100000001b3ull; }
+        digest += h * 0x9e3779b97f4a7c15ull;
+        total_moves += g.n_moves;
+        total_evals += g.evals;
+        total_searches += g.searches;
+        g.n_moves = g.evals = g.searches = 0;
+        g.active = false;
+        g.clear_trees();
+        ++finished;
+    }
+
+    void begin_search(Game& g, bool ex_it) {                     // Player::predict / predict_aux (self_play.rs:243-276, 321-358)
+        Player& p = g.players[0];
+        SearchOptions opt;
+        opt.search_kind = g.allow_pass ? STANDARD_SEARCH : SCORING_SEARCH;
+        opt.deterministic = !g.allow_pass;                       // ScoringSearch::deterministic() (options.rs:160-162)
+        opt.probes_per_round = cfg.probes_per_round > 0 ? cfg.probes_per_round : 1;
+        opt.dirichlet_beta = cfg.dirichlet_noise;
+        opt.temperature = cfg.temperature;
+        opt.num_rollout = ex_it ? cfg.num_ex_it_rollout : p.num_rollout(cfg.num_rollout);
+        opt.policy_only = !ex_it && opt.num_rollout <= 1;
+        Node* tree = p.root;
+        p.root = nullptr;
+        if (tree && !g.allow_pass) tree->disqualify(PASS);
+        g.task.start(g.board, p.color, opt, tree, g.rng.next());
+        g.mode = ex_it ? Game::EX_IT : Game::SEARCH;
+        ++g.searches;
+    }
+
+    void record(Game& g, int color, int index, bool with_value, float value, const Node* tree, int rollouts, const float* softmax) {
+        std::string& s = g.sgf;                                  // Display for Played (self_play.rs:187-214), without C[]
+        s += color == BLACK ? ";B[" : ";W[";
+        sgf_point(index, s);
+        s += "]";
+        if (tree) {
+            int arg = PASS;
+            float bestp = NEG_INF;
+            for (size_t i = 0; i < tree->cand_move.size(); ++i)
+                if (tree->cand_prior[i] > bestp) { bestp = tree->cand_prior[i]; arg = tree->cand_move[i]; }
+            if (arg != PASS) { s += "TR["; sgf_point(arg, s); s += "]"; }
+        }
+        if (rollouts > 1 && softmax) {
+            char tv[32];
+            snprintf(tv, sizeof(tv), "TV[%d]P[", rollouts);
+            s += tv;
+            b85_encode_f16(softmax, 362, s);
+            s += "]";
+        }
+        if (with_value) {
+            char v[32];
+            snprintf(v, sizeof(v), "V[%.4f]", color == BLACK ? 2.0f * value - 1.0f : -2.0f * value + 1.0f);
+            s += v;
+        }
+    }
+
+};
+
+}  // namespace
+
+extern "C" {
+
+int32_t dg_engine_predict(void* engine, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy) {
+    return dg_engine_forward_packed(static_cast<dg_engine*>(engine), positions, n, value, policy);
+}
+
+int32_t dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
+                        const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
+                        int64_t* evals_out) {
+    if (!predictor || !options || !board) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
+    SearchTask task;
+    task.start(*reinterpret_cast<const Board*>(board), color, convert(options), N(starting_tree), options->seed);
+    std::vector<dg_packed_position> batch;
+    std::vector<uint16_t> value, policy;
+    for (;;) {
+        batch.clear();
+        int n = task.emit(batch);
+        if (n == 0) break;
+        value.resize(n);
+        policy.resize((size_t)n * 362);
+        int32_t rc = predictor(ctx, batch.data(), n, value.data(), policy.data());
+        if (rc) return rc;
+        task.absorb(value.data(), policy.data());
+    }
+    if (value_out) *value_out = task.value();
+    if (index_out) *index_out = task.index();
+    if (evals_out) *evals_out = task.evals();
+    Node* root = task.take_root();
+    if (tree_out) *tree_out = reinterpret_cast<dg_tree*>(root);
+    else delete root;
+    return DG_OK;
+}
+
+void dg_tree_free(dg_tree* tree) { delete N(tree); }
+dg_tree* dg_tree_forward(dg_tree* tree, int32_t index) { return reinterpret_cast<dg_tree*>(forward(N(tree), index)); }
+void dg_tree_disqualify(dg_tree* tree, int32_t index) { N(tree)->disqualify(index); }
+int32_t dg_tree_total_count(const dg_tree* tree) { return N(tree)->total_count; }
+int32_t dg_tree_to_move(const dg_tree* tree) { return N(tree)->to_move; }
+float dg_tree_initial_value(const dg_tree* tree) { return N(tree)->initial_value; }
+void dg_tree_children(const dg_tree* tree, int32_t* count, float* value, float* prior) {
+    const Node* n = N(tree);
+    for (int i = 0; i < 362; ++i) {
+        if (count) count[i] = 0;
+        if (value) value[i] = n->initial_value;
+        if (prior) prior[i] = NEG_INF;
+    }
+    for (const Edge& e : n->edges) {
+        if (count) count[e.move] = e.count;
+        if (value) value[e.move] = e.value;
+    }
+    if (prior) for (size_t i = 0; i < n->cand_move.size(); ++i) prior[n->cand_move[i]] = n->cand_prior[i];
+}
+int64_t dg_tree_num_nodes(const dg_tree* tree) { return tree ? count_nodes(N(tree)) : 0; }
+
+int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
+                        char* sgf_out, int64_t sgf_capacity) {
+    if (!predictor || !config || config->num_games <= 0 || config->num_parallel <= 0) return DG_ERR_INVALID_ARGUMENT;
+    Driver d;
+    d.cfg = *config;
+    if (d.cfg.max_plies <= 0 || d.cfg.max_plies > 722) d.cfg.max_plies = 722;
+    int hw = (int)std::thread::hardware_concurrency();
+    int n_threads = d.cfg.num_threads > 0 ? d.cfg.num_threads : (hw > 0 ? hw : 1);
+    int n_slots = std::min(config->num_parallel, config->num_games);
+    d.games = std::vector<Game>(n_slots);
+    for (Game& g : d.games) d.start_game(g);
+
+    const int n_groups = n_slots >= 2 ? 2 : 1;
+    struct Group {
+        std::vector<int> slots;
+        std::vector<dg_packed_position> batch;
+        std::vector<uint16_t> value, policy;
+        std::future<int32_t> pending;
+        bool in_flight = false;
+    } groups[2];
+    for (int i = 0; i < n_slots; ++i) groups[i % n_groups].slots.push_back(i);
+
+    auto t_start = std::chrono::steady_clock::now();
+    auto seconds = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    std::atomic<int64_t> eval_ns{0};
+    int64_t rounds = 0, positions = 0;
+    int32_t rc = DG_OK;
+
+    // self_play_one's loop body after `predict` returned (self_play.rs:439-457); true when the game has ended.
+    auto after_move = [&](Game& g) {
+        Player& me = g.players[0];
+        int index = g.index;
+        g.moves.push_back((uint16_t)index);
+        ++g.n_moves;
+        g.mode = Game::IDLE;
+        if (index == PASS) {
+            g.pass_count += 1;
+            if (g.pass_count >= 2 && is_scorable(g.board)) { g.active = false; g.n_emitted = -1; return true; }
+        } else {
+            g.pass_count = 0;
+            g.board.place(me.color, index);
+        }
+        Player& other = g.players[1];
+        if (other.root) other.root = forward(other.root, index);
+        std::swap(g.players[0], g.players[1]);
+        return false;
+    };
+
+    // Advances one game until it has leaves for the device (returns with g.batch filled) or has nothing to do.
+    auto advance = [&](Game& g, const uint16_t* value, const uint16_t* policy) {
+        if (!g.active) return;
+        if (g.n_emitted > 0) {
+            g.task.absorb(value + g.batch_offset, policy + g.batch_offset * 362);
+            g.evals += g.n_emitted;
+            g.n_emitted = 0;
+        }
+        g.batch.clear();
+        for (;;) {
+            if (g.mode == Game::IDLE) {
+                if ((int)g.board.count >= d.cfg.max_plies) { g.mode = Game::IDLE; g.active = false; g.n_emitted = -1; return; }   // ended: 722 plies
+                g.allow_pass = is_scorable(g.board);
+                d.begin_search(g, false);
+            }
+            int n = g.task.emit(g.batch);
+            if (n > 0) { g.n_emitted = n; return; }
+            // the search is done
+            Player& me = g.players[0];
+            if (g.mode == Game::SEARCH) {
+                g.value = g.task.value();
+                g.index = g.task.index();
+                delete g.tree;
+                g.tree = g.task.take_root();
+                bool policy_only = g.task.policy_only();
+                if (!policy_only && !std::isfinite(g.value)) {  // self_play.rs:333-336: pass, forget the tree
+                    delete g.tree;
+                    g.tree = nullptr;
+                    g.index = PASS;
+                    d.record(g, me.color, PASS, false, 0.0f, nullptr, 0, nullptr);
+                    if (after_move(g)) return;
+                    continue;
+                }
+                if (d.cfg.ex_it && g.rng.uniform() < 0.05) {     // is_good_candidate (self_play.rs:287-291); value is a winrate
+                    d.begin_search(g, true);
+                    continue;
+                }
+                if (policy_only) {
+                    d.record(g, me.color, g.index, true, g.value, nullptr, 1, nullptr);
+                } else {
+                    float softmax[362];
+                    visit_distribution(*g.tree, softmax);
+                    d.record(g, me.color, g.index, true, g.value, g.tree, g.tree->total_count, softmax);
+                }
+            } else {                                             // EX_IT: statistics from the second search, move from the first
+                Node* deep = g.task.take_root();
+                float softmax[362];
+                visit_distribution(*deep, softmax);
+                d.record(g, me.color, g.index, true, g.task.value(), deep, deep->total_count, softmax);
+                delete deep;
+            }
+            me.update(g.value);
+            if (g.tree) { me.root = forward(g.tree, g.index); g.tree = nullptr; }
+            if (after_move(g)) return;
+        }
+    };
+
+    auto run_group = [&](Group& grp, bool absorb_results) {
+        std::atomic<size_t> next{0};
+        auto worker = [&] {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= grp.slots.size()) break;
+                advance(d.games[grp.slots[i]], absorb_results ? grp.value.data() : nullptr, absorb_results ? grp.policy.data() : nullptr);
+            }
+        };
+        int nt = std::min<int>(n_threads, (int)grp.slots.size());
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto& th : pool) th.join();
+        // serial part: finished games are replaced, leaves are gathered in slot order
+        grp.batch.clear();
+        for (int s : grp.slots) {
+            Game& g = d.games[s];
+            if (g.n_emitted == -1) {
+                g.n_emitted = 0;
+                g.active = true;
+                d.finish_game(g);
+                bool time_left = d.cfg.max_seconds <= 0 || seconds() < d.cfg.max_seconds;
+                if (d.started < d.cfg.num_games && time_left) {
+                    d.start_game(g);
+                    advance(g, nullptr, nullptr);
+                    if (g.n_emitted == -1) { g.n_emitted = 0; g.active = false; }
+                }
+            }
+            if (g.active && g.n_emitted > 0) {
+                g.batch_offset = grp.batch.size();
+                grp.batch.insert(grp.batch.end(), g.batch.begin(), g.batch.end());
+            }
+        }
+    };
+
+    auto launch = [&](Group& grp) {
+        if (grp.batch.empty()) { grp.in_flight = false; return; }
+        grp.value.resize(grp.batch.size());
+        grp.policy.resize(grp.batch.size() * 362);
+        ++rounds;
+        positions += (int64_t)grp.batch.size();
+        grp.in_flight = true;
+        grp.pending = std::async(std::launch::async, [&grp, predictor, ctx, &eval_ns] {
+            auto t0 = std::chrono::steady_clock::now();
+            int32_t r = predictor(ctx, grp.batch.data(), (int32_t)grp.batch.size(), grp.value.data(), grp.policy.data());
+            eval_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+            return r;
+        });
+    };
+
+    for (int gi = 0; gi < n_groups; ++gi) { run_group(groups[gi], false); launch(groups[gi]); }
+    for (;;) {
+        bool any = false;
+        for (int gi = 0; gi < n_groups && rc == DG_OK; ++gi) {
+            Group& grp = groups[gi];
+            if (!grp.in_flight) continue;
+            any = true;
+            rc = grp.pending.get();
+            grp.in_flight = false;
+            if (rc != DG_OK) break;
+            bool out_of_time = d.cfg.max_seconds > 0 && seconds() >= d.cfg.max_seconds;
+            if (out_of_time) continue;                            // drop the in-flight work, stop
+            run_group(grp, true);
+            launch(grp);
+        }
+        if (!any || rc != DG_OK) break;
+    }
+    for (int gi = 0; gi < n_groups; ++gi) if (groups[gi].in_flight) groups[gi].pending.wait();
+
+    // account for the games that were cut off by max_seconds
+    for (Game& g : d.games) { d.total_moves += g.n_moves; d.total_evals += g.evals; d.total_searches += g.searches; }
+    if (stats) {
+        stats->games_finished = d.finished;
+        stats->moves = d.total_moves;
+        stats->evals = positions;
+        stats->rounds = rounds;
+        stats->searches = d.total_searches;
+        stats->seconds = seconds();
+        stats->eval_seconds = (double)eval_ns.load() * 1e-9;
+        stats->mean_batch = rounds ? (double)positions / (double)rounds : 0.0;
+        stats->digest = d.digest;
+    }
+    if (sgf_out && sgf_capacity > 0) {
+        size_t n = std::min<size_t>(d.sgf_all.size(), (size_t)sgf_capacity - 1);
+        memcpy(sgf_out, d.sgf_all.data(), n);
+        sgf_out[n] = 0;
+    }
+    return rc;
+}
+
+}  // extern "C"

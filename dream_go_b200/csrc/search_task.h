@@ -1,0 +1,255 @@
+// search_task.h -- one tree search as a resumable task that EMITS leaf positions and ABSORBS their evaluations.
+//
+// `dg_mcts::predict` (src/libdg_mcts/lib.rs:145-200) blocks a game thread while a pool of workers probes its tree
+// (pool/worker_thread.rs:60-177).  Here a search never blocks: the self-play driver asks every game for its next
+// leaves, evaluates all of them as one device batch, and hands the results back.  Phases:
+//
+//   ROOT     8 positions = the root under all 8 symmetries (full_forward, lib.rs:83-133)
+//   PROBING  up to `probes_per_round` leaves per round (tree::probe -> Event::predict, pool/event.rs:46-59)
+//   DONE     move chosen (Node::best, lib.rs:190-194)
+#pragma once
+
+#include <vector>
+
+#include "../../include/dg_engine.h"
+#include "search.h"
+
+namespace dg {
+
+inline float f16_to_f32(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1f, m = h & 0x3ffu, x;
+    if (e == 0) {
+        if (m == 0) x = sign;
+        else {
+            int s = 0;
+            while (!(m & 0x400u)) { m <<= 1; ++s; }
+            x = sign | ((uint32_t)(113 - s) << 23) | ((m & 0x3ffu) << 13);
+        }
+    } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
+    else x = sign | ((e + 112) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &x, 4);
+    return f;
+}
+
+// What create_initial_policy (pool/policy_helper.rs:28-75) derives from the board alone; computed when the leaf is
+// emitted (the feature pass already produced the legal mask), applied when its evaluation arrives.
+struct PriorPlan {
+    uint8_t candidate[N_POINTS + 1];           // after symmetry elimination
+    uint16_t rep[N_POINTS + 1];                // orbit representative of each point (`indices`, :54-72)
+
+    void build(const Board& b, int to_move, int search_kind, const uint8_t* legal) {
+        const Tables& T = tables();
+        policy_candidates(b, to_move, search_kind, legal, candidate);
+        int syms[8], ns = 0;
+        for (int t = 0; t < 8; ++t) {
+            bool same = true;
+            const uint16_t* m = T.sym[t];
+            for (int p = 0; p < N_POINTS && same; ++p) same = b.color[p] == b.color[m[p]];
+            if (same) syms[ns++] = t;
+        }
+        for (int p = 0; p < N_POINTS; ++p) {
+            int best = p;
+            for (int k = 0; k < ns; ++k) { int q = T.sym[syms[k]][p]; if (q < best) best = q; }
+            rep[p] = (uint16_t)best;
+            if (best != p) candidate[p] = 0;
+        }
+        rep[PASS] = PASS;
+    }
+
+    // add_valid_candidates + normalize_policy (policy_helper.rs:87-134; lane order of asm/sum_finite.rs:23-57)
+    void apply(const uint16_t* policy /* [362] fp16, orientation `symmetry` */, int symmetry, float sum_to, float* prior /* [368] */) const {
+        const Tables& T = tables();
+        for (int i = 0; i < 368; ++i) prior[i] = NEG_INF;
+        for (int p = 0; p <= N_POINTS; ++p) if (candidate[p]) prior[p] = 0.0f;
+        prior[PASS] += f16_to_f32(policy[PASS]);
+        const uint16_t* inv = T.sym[T.sym_inverse[symmetry]];
+        for (int i = 0; i < N_POINTS; ++i) prior[rep[inv[i]]] += f16_to_f32(policy[i]);
+        float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int finite = 0;
+        for (int i = 0; i < 368; ++i) if (std::isfinite(prior[i])) { lane[i & 7] += prior[i]; ++finite; }
+        float sum = ((lane[0] + lane[1]) + (lane[2] + lane[3])) + ((lane[4] + lane[5]) + (lane[6] + lane[7]));
+        if (sum < 1e-6f) {
+            for (int i = 0; i < 368; ++i) if (std::isfinite(prior[i])) prior[i] = sum_to / (float)finite;
+        } else {
+            float recip = 1.0f / (sum / sum_to);
+            for (int i = 0; i < 368; ++i) prior[i] *= recip;
+        }
+    }
+};
+
+struct SearchOptions {
+    int search_kind = STANDARD_SEARCH;         // which PolicyChecker (options.rs)
+    bool deterministic = false;                // SearchOptions::deterministic()
+    int num_rollout = 800;                     // RolloutLimit
+    int probes_per_round = 1;
+    float dirichlet_beta = 0.25f;              // config.rs:165-166 (self-play)
+    float dirichlet_shape = 0.03f;             // lib.rs:164
+    float temperature = 0.8f;                  // config.rs:171-172 (self-play)
+    const float* noise = nullptr;              // injected eta[362] (tests); else drawn from the task's Rng
+    const uint8_t* leaf_symmetries = nullptr;  // injected sequence (tests); else drawn from the task's Rng
+    int n_leaf_symmetries = 0;
+    double choose_at = -1.0;                   // injected uniform number for the stochastic move choice
+    bool policy_only = false;                  // no tree: play from the averaged policy (self_play.rs:360-396)
+};
+
+class SearchTask {
+  public:
+    enum Phase { ROOT, PROBING, DONE };
+
+    SearchTask() {}
+    ~SearchTask() { delete root_; }
+    SearchTask(const SearchTask&) = delete;
+    SearchTask& operator=(const SearchTask&) = delete;
+
+    // `starting_tree` (may be null) is consumed, as in lib.rs:150.
+    void start(const Board& board, int color, const SearchOptions& opt, Node* starting_tree, uint64_t seed) {
+        delete root_;
+        root_ = starting_tree;
+        board_ = board;
+        color_ = color;
+        opt_ = opt;
+        rng_.reseed(seed);
+        phase_ = ROOT;
+        pending_.clear();
+        n_pending_ = 0;
+        leaf_counter_ = 0;
+        evals_ = 0;
+        value_ = 0.5f;
+        index_ = PASS;
+    }
+
+    Phase phase() const { return phase_; }
+    bool done() const { return phase_ == DONE; }
+    float value() const { return value_; }
+    int index() const { return index_; }
+    long evals() const { return evals_; }
+    const Node* root() const { return root_; }
+    Node* take_root() { Node* r = root_; root_ = nullptr; return r; }
+    bool policy_only() const { return opt_.policy_only; }
+    const float* root_policy() const { return root_policy_; }
+
+    // Appends this round's leaf positions to `out` and returns how many; 0 with done() == true ends the search.
+    int emit(std::vector<dg_packed_position>& out) {
+        if (phase_ == DONE) return 0;
+        if (phase_ == ROOT) {
+            uint8_t legal[N_POINTS];
+            size_t at = out.size();
+            out.resize(at + 8);
+            for (int t = 0; t < 8; ++t) {
+                features_v1(board_, color_, t, out[at + t].planes, &out[at + t].k_bits, t == 0 ? legal : nullptr);
+                out[at + t].reserved = 0;
+            }
+            root_plan_.build(board_, color_, opt_.search_kind, legal);
+            n_pending_ = 8;
+            return 8;
+        }
+        int emitted = 0;
+        if (pending_.size() < (size_t)opt_.probes_per_round) pending_.resize(opt_.probes_per_round);
+        while (emitted < opt_.probes_per_round) {
+            if (is_done(*root_, opt_.num_rollout)) break;
+            Pending& p = pending_[emitted];
+            p.board.copy_from(board_);
+            ProbeStatus st = probe(*root_, p.board, p.trace);
+            if (st == PROBE_CONFLICT) break;                 // somebody (an earlier probe of this round) is expanding it
+            if (st == PROBE_NO_RESULT) break;
+            p.to_move = opposite(p.trace.back().node->to_move);
+            p.symmetry = next_leaf_symmetry();
+            uint8_t legal[N_POINTS];
+            out.emplace_back();
+            dg_packed_position& pos = out.back();
+            features_v1(p.board, p.to_move, p.symmetry, pos.planes, &pos.k_bits, legal);
+            pos.reserved = 0;
+            p.plan.build(p.board, p.to_move, opt_.search_kind, legal);
+            ++emitted;
+        }
+        n_pending_ = emitted;
+        if (emitted == 0) finish();
+        return emitted;
+    }
+
+    // Evaluations of the leaves of the last emit(), in the same order.
+    void absorb(const uint16_t* value, const uint16_t* policy /* [n][362] */) {
+        evals_ += n_pending_;
+        if (phase_ == ROOT) {
+            float prior[368], acc[368];
+            for (int i = 0; i < 368; ++i) acc[i] = NEG_INF;
+            for (int p = 0; p <= N_POINTS; ++p) if (root_plan_.candidate[p]) acc[p] = 0.0f;
+            float v = 0.0f;
+            for (int t = 0; t < 8; ++t) {                     // lib.rs:112-127
+                root_plan_.apply(policy + (size_t)t * 362, t, 0.125f, prior);
+                v += (0.5f * f16_to_f32(value[t]) + 0.5f) * 0.125f;
+                for (int i = 0; i < 362; ++i) acc[i] += prior[i];
+            }
+            memcpy(root_policy_, acc, sizeof(root_policy_));
+            if (opt_.policy_only) {                          // self_play.rs:360-377
+                std::vector<double> items(362);
+                for (int i = 0; i < 362; ++i) items[i] = (double)acc[i];
+                double at = opt_.choose_at >= 0.0 ? opt_.choose_at : rng_.uniform();
+                int pick = choose(items, 0.5, 1.0 / (double)opt_.temperature, at);
+                index_ = pick < 0 ? PASS : pick;
+                value_ = v;
+                phase_ = DONE;
+                n_pending_ = 0;
+                return;
+            }
+            if (!opt_.deterministic) {                       // lib.rs:163-165
+                float eta[362];
+                const float* noise = opt_.noise;
+                if (!noise) { rng_.dirichlet(acc, opt_.dirichlet_shape, eta); noise = eta; }
+                mix_noise(acc, noise, opt_.dirichlet_beta);
+            }
+            if (root_) root_->set_prior(acc);                // lib.rs:170-182
+            else root_ = new Node(color_, v, acc);
+            root_value_ = v;
+            phase_ = PROBING;
+            n_pending_ = 0;
+            return;
+        }
+        float prior[368];
+        for (int k = 0; k < n_pending_; ++k) {               // pool/worker_thread.rs:88-98
+            Pending& p = pending_[k];
+            p.plan.apply(policy + (size_t)k * 362, p.symmetry, 1.0f, prior);
+            float winrate = 0.5f * f16_to_f32(value[k]) + 0.5f;
+            insert(p.trace, p.to_move, winrate, prior);
+        }
+        n_pending_ = 0;
+    }
+
+  private:
+    struct Pending {
+        Trace trace;
+        Board board;
+        PriorPlan plan;
+        int to_move, symmetry;
+    };
+
+    int next_leaf_symmetry() {                               // pool/event.rs:47: one random symmetry per leaf
+        if (opt_.leaf_symmetries && opt_.n_leaf_symmetries > 0) return opt_.leaf_symmetries[leaf_counter_++ % opt_.n_leaf_symmetries];
+        ++leaf_counter_;
+        return rng_.below(8);
+    }
+
+    void finish() {                                          // lib.rs:190-194
+        float t = (!opt_.deterministic && board_.count < 8) ? opt_.temperature : 0.0f;
+        double at = opt_.choose_at >= 0.0 ? opt_.choose_at : (t > 9e-2f ? rng_.uniform() : 0.0);
+        index_ = best(*root_, t, at, &value_);
+        phase_ = DONE;
+    }
+
+    Node* root_ = nullptr;
+    Board board_;
+    int color_ = BLACK;
+    SearchOptions opt_;
+    Rng rng_;
+    Phase phase_ = DONE;
+    PriorPlan root_plan_;
+    std::vector<Pending> pending_;
+    int n_pending_ = 0;
+    long leaf_counter_ = 0, evals_ = 0;
+    float value_ = 0.5f, root_value_ = 0.5f;
+    float root_policy_[362];
+    int index_ = PASS;
+};
+
+}  // namespace dg

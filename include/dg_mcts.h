@@ -1,0 +1,92 @@
+/*
+ * dg_mcts.h -- C ABI of the tree search and the self-play driver (host side of the self-play hot path).
+ *
+ * Replaces, for this path, the Rust crate API of `dg_mcts`:
+ *   `predict(pool, options, time_strategy, starting_tree, board, color)`     src/libdg_mcts/lib.rs:145-200
+ *   `tree::Node::{forward, disqualify, best, softmax}`                        src/libdg_mcts/tree.rs:1198-1301
+ *   `trait Predictor::predict(features, batch)`                               src/libdg_mcts/predictor.rs:59-92
+ *   `self_play(network, num_games, ex_it)`                                    src/libdg_mcts/self_play.rs:423-591
+ * Exported by the same `libdg_engine.so` as dg_engine.h / dg_go.h.
+ */
+#ifndef DG_MCTS_H
+#define DG_MCTS_H
+
+#include <stdint.h>
+#include "dg_engine.h"
+#include "dg_go.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* `Predictor::predict` (predictor.rs:91) over the compact position format: evaluates `n` positions, writes n fp16
+ * values (post-tanh) and n*362 fp16 policies (post-softmax).  Returns 0 on success.  Called from one thread at a
+ * time per search / per self-play driver. */
+typedef int32_t (*dg_predict_fn)(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
+
+/* The predictor that is the product: ctx = dg_engine*, evaluation through dg_engine_forward_packed. */
+int32_t dg_engine_predict(void* engine, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
+
+typedef struct dg_search_options {
+    int32_t  search;              /* DG_STANDARD_SEARCH / DG_SCORING_SEARCH (options.rs:66-81, 141-162)                 */
+    int32_t  deterministic;       /* SearchOptions::deterministic(): no Dirichlet noise, greedy move choice             */
+    int32_t  num_rollout;         /* RolloutLimit::new(n) (time_control/rollout_limit.rs)                               */
+    int32_t  probes_per_round;    /* leaves of ONE tree evaluated together (1 = the sequential algorithm)               */
+    float    dirichlet_noise;     /* DIRICHLET_NOISE, 0.25 in self-play (config.rs:165-166)                             */
+    float    temperature;         /* TEMPERATURE, 0.8 in self-play, used for the first 8 plies (lib.rs:190-194)         */
+    uint64_t seed;                /* all randomness of the search derives from it (the reference uses thread_rng)       */
+    const float*   noise;         /* optional: the normalised Dirichlet sample eta[362] to mix in (tests)              */
+    const uint8_t* leaf_symmetries; /* optional: symmetry of the k-th leaf = leaf_symmetries[k % n] (tests)            */
+    int32_t  n_leaf_symmetries;
+    double   choose_at;           /* optional: the uniform number of the stochastic move choice; < 0 = draw it          */
+} dg_search_options;
+
+typedef struct dg_tree dg_tree;   /* `tree::Node` */
+
+/* `dg_mcts::predict`: searches `board` for `color`.  `starting_tree` (may be NULL) is consumed.  Outputs: the value
+ * and index (0..361, 361 = pass) of the chosen move, and the searched tree (caller frees or forwards it).
+ * evals_out (optional) = positions evaluated.  Returns 0, or the predictor's error. */
+int32_t  dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
+                         const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
+                         int64_t* evals_out);
+void     dg_tree_free(dg_tree* tree);
+dg_tree* dg_tree_forward(dg_tree* tree, int32_t index);            /* Node::forward (tree.rs:1198-1225); consumes `tree` */
+void     dg_tree_disqualify(dg_tree* tree, int32_t index);         /* Node::disqualify (tree.rs:1296-1301) */
+int32_t  dg_tree_total_count(const dg_tree* tree);
+int32_t  dg_tree_to_move(const dg_tree* tree);
+float    dg_tree_initial_value(const dg_tree* tree);
+/* per child 0..361: visit count, mean value (initial value if unvisited), prior (-inf = not a candidate) */
+void     dg_tree_children(const dg_tree* tree, int32_t* count, float* value, float* prior);
+int64_t  dg_tree_num_nodes(const dg_tree* tree);
+
+/* ---- self-play (self_play.rs:423-591) ------------------------------------------------------------------------------ */
+typedef struct dg_selfplay_config {
+    int32_t  num_games;           /* games to play in total (`--self-play N`)                                           */
+    int32_t  num_parallel;        /* games in flight (`--num-games`, config.rs NUM_GAMES)                               */
+    int32_t  num_rollout;         /* `--num-rollout` (config.rs NUM_ROLLOUT); per move 800*max(0.1, 4w(1-w)), :234-241   */
+    int32_t  probes_per_round;    /* leaves per tree per device batch                                                   */
+    int32_t  max_plies;           /* 722 in the reference (self_play.rs:437); smaller values bound benchmark runs       */
+    int32_t  num_threads;         /* host threads for probing / feature extraction (<= 0: all cores)                    */
+    int32_t  ex_it;               /* `--ex-it`: 5 % of the eligible positions get a full search (self_play.rs:287-319)  */
+    int32_t  num_ex_it_rollout;   /* `--num-ex-it-rollout`                                                              */
+    float    dirichlet_noise, temperature;
+    uint64_t seed;
+    double   max_seconds;         /* stop starting new rounds after this much wall time (<= 0: no limit)                */
+} dg_selfplay_config;
+
+typedef struct dg_selfplay_stats {
+    int64_t games_finished, moves, evals, rounds, searches;
+    double  seconds, eval_seconds;        /* wall time total / spent inside the predictor                              */
+    double  mean_batch;                   /* positions per predictor call                                              */
+    uint64_t digest;                      /* order-independent hash of every finished game's move list (determinism)   */
+} dg_selfplay_stats;
+
+/* Plays `num_games` games, `num_parallel` at a time, all sharing one predictor; one SGF record per finished game is
+ * appended to `sgf_out` (NUL-terminated, truncated at sgf_capacity; may be NULL).  Returns 0 or the predictor's error. */
+int32_t  dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
+                         char* sgf_out, int64_t sgf_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DG_MCTS_H */

@@ -37,6 +37,16 @@ def test_library_exports_every_go_symbol():
     assert set(names) == set(go.ABI), "python binding table and header disagree"
 
 
+def test_library_exports_every_mcts_symbol():
+    from dream_go_b200 import mcts
+    handle = ctypes.CDLL(nn.LIB_PATH)
+    names = [n for n in header_functions("dg_mcts.h") if n != "dg_predict_fn"]
+    assert len(names) >= 11
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/dg_mcts.h but not exported"
+    assert set(names) == set(mcts.ABI), "python binding table and header disagree"
+
+
 def test_abi_version():
     assert nn.lib().dg_engine_abi_version() == 1
 

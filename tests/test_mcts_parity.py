@@ -1,0 +1,166 @@
+"""Parity of the product's tree search (csrc/search*.h through include/dg_mcts.h) with the oracle restatement of
+the reference's `dg_mcts`: under the same deterministic stub predictor, injected noise / leaf symmetries / random
+numbers, the visit count of EVERY root child, the value estimates, the chosen move and the number of evaluated
+positions are bit-identical -- with one probe in flight and with several.  CPU only (the predictor is a stub)."""
+import numpy as np
+import pytest
+
+from dream_go_b200 import go as pgo, mcts as pm
+from oracle import go as ogo, mcts as om
+from mcts_common import dirichlet_sample, fake_predictor, hash_predictor, nan_predictor, uniform_predictor
+
+BLACK, WHITE = 1, 2
+
+
+def boards(plays, komi=7.5):
+    po, oo = pgo.Board(komi), ogo.Board(komi)
+    for c, m in plays:
+        po.place_index(int(c), int(m))
+        oo.place_index(int(c), int(m))
+    return po, oo
+
+
+def corpus_position(game: int, plies: int):
+    colors, moves, komi = ogo.load_games()[game]
+    return [(c, m) for c, m in zip(colors[:plies], moves[:plies]) if m < 361], komi
+
+
+def assert_same_search(stub, po, oo, color, **kw):
+    want_v, want_i, want_root, want_evals = om.predict(stub, oo, color, **kw)
+    got_v, got_i, tree, got_evals = pm.predict(pm.python_predictor(stub), po, color, **kw)
+    count, value, prior = tree.children()
+    assert (count == want_root.count[:362]).all(), np.flatnonzero(count != want_root.count[:362])
+    assert tree.total_count == want_root.total_count
+    assert (prior.view(np.uint32) == want_root.prior[:362].view(np.uint32)).all()
+    visited = count > 0
+    assert (value[visited].view(np.uint32) == want_root.value[:362][visited].view(np.uint32)).all()
+    assert got_i == want_i
+    assert np.float32(got_v).view(np.uint32) == np.float32(want_v).view(np.uint32)
+    assert got_evals == want_evals
+    return tree, want_root
+
+
+@pytest.mark.parametrize("probes", [1, 4])
+def test_empty_board_deterministic(probes):
+    po, oo = boards([])
+    assert_same_search(hash_predictor(), po, oo, BLACK, deterministic=True, num_rollout=120, probes_per_round=probes,
+                       leaf_symmetries=[0, 5, 3, 6, 1, 7, 2, 4])
+
+
+@pytest.mark.parametrize("probes", [1, 3])
+def test_midgame_with_noise_and_temperature(probes):
+    plays, komi = corpus_position(5, 6)          # count < 8: the stochastic move choice is active
+    po, oo = boards(plays, komi)
+    color = po.to_move()
+    _, policy = om.full_forward(hash_predictor(), 0, oo, color)
+    noise = dirichlet_sample(3, policy[:362])
+    assert_same_search(hash_predictor(), po, oo, color, deterministic=False, num_rollout=100, probes_per_round=probes,
+                       noise=noise, leaf_symmetries=[2, 2, 7, 0, 4], choose_at=0.37)
+
+
+def test_late_game_scoring_search_and_tree_reuse():
+    plays, komi = corpus_position(11, 150)
+    po, oo = boards(plays, komi)
+    color = po.to_move()
+    kw = dict(search=1, deterministic=True, num_rollout=90, probes_per_round=2, leaf_symmetries=[1, 6, 3])
+    tree, want_root = assert_same_search(hash_predictor(1.0), po, oo, color, **kw)
+    # play the move, hand the sub-tree to the next search (self_play.rs:339-341, lib.rs:170-182)
+    count, _, _ = tree.children()
+    move = int(np.argmax(count))
+    po.place_index(color, move)
+    oo.place_index(color, move)
+    sub, want_sub = tree.forward(move), om.forward(want_root, move)
+    assert (sub is None) == (want_sub is None)
+    if sub is not None:
+        assert sub.total_count == want_sub.total_count
+        sub.disqualify(361)                        # Player::predict_aux without allow_pass (self_play.rs:252-256)
+        want_sub.disqualify(361)
+        stub = hash_predictor(1.0)
+        gv, gi, tree2, ge = pm.predict(pm.python_predictor(stub), po, 3 - color, starting_tree=sub, **kw)
+        wv, wi, root2, we = om.predict(stub, oo, 3 - color, starting_tree=want_sub, **kw)
+        count2, _, _ = tree2.children()
+        assert (count2 == root2.count[:362]).all() and gi == wi and ge == we and count2[361] == 0
+
+
+def test_tree_reuse_bit_exact():
+    plays, komi = corpus_position(20, 60)
+    po, oo = boards(plays, komi)
+    color = po.to_move()
+    stub = hash_predictor(1.5)
+    kw = dict(deterministic=True, num_rollout=80, probes_per_round=2, leaf_symmetries=[4, 0, 1])
+    gv, gi, tree, _ = pm.predict(pm.python_predictor(stub), po, color, **kw)
+    wv, wi, root, _ = om.predict(stub, oo, color, **kw)
+    assert gi == wi
+    po.place_index(color, gi)
+    oo.place_index(color, wi)
+    sub, want_sub = tree.forward(gi), om.forward(root, wi)
+    assert sub is not None and want_sub is not None and sub.total_count == want_sub.total_count
+    gv, gi, tree2, ge = pm.predict(pm.python_predictor(stub), po, 3 - color, starting_tree=sub, **kw)
+    wv, wi, root2, we = om.predict(stub, oo, 3 - color, starting_tree=want_sub, **kw)
+    count, value, prior = tree2.children()
+    assert (count == root2.count[:362]).all() and gi == wi and ge == we
+    assert tree2.total_count == root2.total_count >= want_sub.total_count
+
+
+def test_symmetric_position_folds_candidates():
+    po, oo = boards([(BLACK, 9 * 19 + 9)])        # tengen: the full symmetry group survives
+    tree, _ = assert_same_search(uniform_predictor(0.1), po, oo, WHITE, deterministic=True, num_rollout=60,
+                                 leaf_symmetries=[0])
+    _, _, prior = tree.children()
+    assert np.isfinite(prior[:361]).sum() == 54   # 55 orbits minus the occupied centre
+
+
+def test_degenerate_predictors():                 # lib.rs:245-281
+    po, oo = boards([])
+    v, i, tree, _ = pm.predict(pm.python_predictor(nan_predictor()), po, BLACK, deterministic=True, num_rollout=1600)
+    assert v == 0.5 and i == 361 and tree.total_count == 0
+    v, i, tree, _ = pm.predict(pm.python_predictor(fake_predictor(1, 0.6)), pgo.Board(0.5), BLACK, deterministic=True, num_rollout=40)
+    assert i == 1
+
+
+def test_visit_order_is_descending_prior_on_product():   # tree.rs:1773-1823 through the public search call
+    """First round with many probes in flight: the leaves arrive in order of decreasing root prior."""
+    seen = []
+
+    def stub(feats):
+        for f in feats:
+            last = np.flatnonzero(f[:, 3].astype(np.float32))
+            seen.append(int(last[0]) if len(last) else -1)
+        return hash_predictor()(feats)
+
+    po = pgo.Board(7.5)
+    po.place(BLACK, 2, 3)                          # no symmetry
+    _, _, tree, _ = pm.predict(pm.python_predictor(stub), po, WHITE, deterministic=True, num_rollout=2, probes_per_round=400,
+                               leaf_symmetries=[0])
+    _, _, prior = tree.children()
+    first_round = [m for m in seen[8:] if m >= 0]
+    assert len(first_round) > 100
+    p = prior[first_round]
+    assert (np.diff(p) <= 0).all()
+
+
+def test_run_to_run_and_thread_count_determinism_of_self_play():
+    stub = pm.python_predictor(hash_predictor())
+    a, sgf_a = pm.self_play(stub, num_games=3, num_parallel=3, num_rollout=12, probes_per_round=2, max_plies=12, seed=7, num_threads=1)
+    b, sgf_b = pm.self_play(stub, num_games=3, num_parallel=3, num_rollout=12, probes_per_round=2, max_plies=12, seed=7, num_threads=4)
+    c, _ = pm.self_play(stub, num_games=3, num_parallel=3, num_rollout=12, probes_per_round=2, max_plies=12, seed=8, num_threads=4)
+    assert a["digest"] == b["digest"] and sorted(sgf_a) == sorted(sgf_b)
+    assert a["digest"] != c["digest"]
+    assert a["games_finished"] == 3 and a["moves"] == 36
+    assert all(g.startswith("(;GM[1]FF[4]SZ[19]RU[Chinese]KM[") and g.endswith(")") for g in sgf_a)
+
+
+def test_gamma_sampler_statistics():
+    """The product's own Dirichlet(0.03) sample (used when no noise is injected): normalised, sparse, seeded."""
+    po = pgo.Board(7.5)
+    po.place(WHITE, 2, 3)                          # no symmetry: the prior before the noise is uniform
+    stub = pm.python_predictor(uniform_predictor())
+    _, _, t1, _ = pm.predict(stub, po, BLACK, deterministic=False, num_rollout=1, seed=11, leaf_symmetries=[0])
+    _, _, t2, _ = pm.predict(stub, po, BLACK, deterministic=False, num_rollout=1, seed=11, leaf_symmetries=[0])
+    _, _, t3, _ = pm.predict(stub, po, BLACK, deterministic=False, num_rollout=1, seed=12, leaf_symmetries=[0])
+    p1, p2, p3 = t1.children()[2], t2.children()[2], t3.children()[2]
+    assert (p1 == p2).all() and (p1 != p3).any()
+    f = np.isfinite(p1)
+    assert abs(float(p1[f].sum()) - 1.0) < 1e-3
+    base = 0.75 / f.sum()
+    assert (p1[f] >= base * 0.999).all() and p1[f].max() > 0.05      # 25 % of the mass on a few points
