@@ -46,6 +46,21 @@ struct Bits {                       // 361-bit set over packed indices
         for (int i = 0; i < 6; ++i) if (w[i]) return 64 * i + __builtin_ctzll(w[i]);
         return -1;
     }
+    Bits operator&(const Bits& o) const { Bits r; for (int i = 0; i < 6; ++i) r.w[i] = w[i] & o.w[i]; return r; }
+    Bits operator|(const Bits& o) const { Bits r; for (int i = 0; i < 6; ++i) r.w[i] = w[i] | o.w[i]; return r; }
+    Bits andnot(const Bits& o) const { Bits r; for (int i = 0; i < 6; ++i) r.w[i] = w[i] & ~o.w[i]; return r; }   // this & ~o
+    Bits shl(int k) const {         // k in 1..63
+        Bits r;
+        r.w[0] = w[0] << k;
+        for (int i = 1; i < 6; ++i) r.w[i] = (w[i] << k) | (w[i - 1] >> (64 - k));
+        return r;
+    }
+    Bits shr(int k) const {
+        Bits r;
+        for (int i = 0; i < 5; ++i) r.w[i] = (w[i] >> k) | (w[i + 1] << (64 - k));
+        r.w[5] = w[5] >> k;
+        return r;
+    }
 };
 
 // Static geometry: neighbours in the reference's reading order East, South(-y), West, North(+y)
@@ -59,8 +74,15 @@ struct Tables {
     uint16_t sym[8][N_POINTS + 1];  // sym[t][i] = where point i goes under transform t; 361 -> 361
     uint8_t sym_inverse[8];
     uint64_t zobrist[3][N_POINTS];
+    Bits board, not_col0, not_col18;   // all 361 points / without column x = 0 / without column x = 18
 
     Tables() {
+        board.clear(); not_col0.clear(); not_col18.clear();
+        for (int p = 0; p < N_POINTS; ++p) {
+            board.set(p);
+            if (p % 19 != 0) not_col0.set(p);
+            if (p % 19 != 18) not_col18.set(p);
+        }
         static const int dx[4] = {1, 0, -1, 0}, dy[4] = {0, -1, 0, 1};
         for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
             int p = 19 * y + x, n = 0;
@@ -418,49 +440,73 @@ inline bool is_ladder_escape(const Board& b, int c, int p, const uint16_t* nl = 
 // `color` (benson.rs:293-320), it is vital to a chain when every one of its points touches the chain
 // (:188-208), a chain stays alive with two vital regions (:95-111) and a region stays while all the stones
 // around it are alive (:115-131).
+// All points adjacent to a point of `x` (the set itself is not included unless it is adjacent to itself).
+inline Bits dilate(const Bits& x) {
+    const Tables& T = tables();
+    Bits r = x.shl(19) | x.shr(19) | (x.shl(1) & T.not_col0) | (x.shr(1) & T.not_col18);
+    return r & T.board;
+}
+
 inline void benson(const Board& b, int color, Bits& alive, Bits& eyes) {
     const Tables& T = tables();
+    alive.clear();
+    eyes.clear();
+    const Bits& own = b.stones[color];
+    if (!own.any()) return;
+    // A region with a point that touches no stone of `color` is vital to nobody and is dropped before anything
+    // else happens (benson.rs:128-143): flood those regions away with whole-board bit operations first.  What is
+    // left -- usually nothing before the endgame -- are the small enclosed regions the algorithm is about.
+    const Bits other = T.board.andnot(own);                  // empty or enemy
+    Bits dead = other.andnot(dilate(own));
+    if (dead.any())
+        for (;;) {
+            Bits grow = (dilate(dead) & other).andnot(dead);
+            if (!grow.any()) break;
+            dead.or_with(grow);
+        }
+    const Bits rest = other.andnot(dead);
+    Bits seeds = rest.andnot(b.stones[opposite(color)]);     // regions start from empty points (benson.rs:297-301)
+    if (!seeds.any()) return;
     struct Region { Bits points, around; };
     struct Chain { Bits stones, touch; };
     Region regions[N_POINTS / 2 + 1];
-    Chain chains[N_POINTS / 2 + 1];
-    int nr = 0, nc = 0;
-    {
-        uint8_t seen[N_POINTS];
-        memset(seen, 0, sizeof(seen));
-        int16_t queue[N_POINTS];
-        for (int start = 0; start < N_POINTS; ++start) {
-            if (seen[start] || b.color[start]) continue;
-            Region& r = regions[nr];
-            r.points.clear();
-            r.around.clear();
-            int qh = 0, qt = 0;
-            queue[qt++] = (int16_t)start;
-            seen[start] = 1;
-            while (qh < qt) {
-                int p = queue[qh++];
-                r.points.set(p);
-                for (int k = 0; k < T.n_nbr[p]; ++k) {
-                    int q = T.nbr_list[p][k];
-                    if (b.color[q] == color) r.around.set(q);
-                    else if (!seen[q]) { seen[q] = 1; queue[qt++] = (int16_t)q; }
-                }
-            }
-            if (r.around.any()) ++nr;
+    int nr = 0;
+    Bits around_all;
+    around_all.clear();
+    while (seeds.any()) {
+        Region& r = regions[nr];
+        r.points.clear();
+        r.points.set(seeds.first());
+        for (;;) {
+            Bits grow = (dilate(r.points) & rest).andnot(r.points);
+            if (!grow.any()) break;
+            r.points.or_with(grow);
         }
+        r.around = dilate(r.points) & own;                   // never empty: every point of `rest` touches `own`
+        around_all.or_with(r.around);
+        seeds = seeds.andnot(r.points);
+        ++nr;
+    }
+    if (nr < 2) return;                                      // a chain needs two vital regions (benson.rs:95-111)
+    Chain chains[N_POINTS / 2 + 1];                          // only chains next to a region can ever qualify
+    int nc = 0;
+    {
         uint8_t slot_seen[N_POINTS];
         memset(slot_seen, 0, b.n_slots);
-        for (int p = 0; p < N_POINTS; ++p) {
-            if (b.color[p] != color || slot_seen[b.slot[p]]) continue;
+        Bits todo = around_all;
+        while (todo.any()) {
+            int p = todo.first();
+            todo.reset(p);
+            if (slot_seen[b.slot[p]]) continue;
             slot_seen[b.slot[p]] = 1;
             Chain& c = chains[nc++];
             c.stones.clear();
-            c.touch.clear();
             int s = p;
-            do { c.stones.set(s); c.touch.or_with(T.nbr_mask[s]); s = b.next[s]; } while (s != p);
+            do { c.stones.set(s); s = b.next[s]; } while (s != p);
+            c.touch = dilate(c.stones);
         }
     }
-    auto vital = [](const Region& r, const Chain& c) {
+    auto vital = [](const Region& r, const Chain& c) {       // every point of the region touches the chain (:188-208)
         uint64_t miss = 0;
         for (int i = 0; i < 6; ++i) miss |= r.points.w[i] & ~c.touch.w[i];
         return miss == 0;
@@ -496,7 +542,6 @@ inline void benson(const Board& b, int color, Bits& alive, Bits& eyes) {
     }
     alive.clear();
     for (int j = 0; j < nc; ++j) alive.or_with(chains[j].stones);
-    eyes.clear();
     for (int i = 0; i < nr; ++i) eyes.or_with(regions[i].points);
 }
 
@@ -515,17 +560,15 @@ inline bool is_scorable(const Board& b) {
 
 // The own-eye heuristic of ScoringSearch (libdg_mcts/options.rs:180-214).
 inline bool is_simple_eye(const Board& b, int color, int p) {
-    int x = p % 19, y = p / 19, cross = 0, diag = 0;
-    for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
-        if (!dx && !dy) continue;
+    const Tables& T = tables();
+    // corner needs 2 of 2, edge 3 of 3, middle 4 of 4 orthogonal neighbours: all that exist
+    for (int k = 0; k < T.n_nbr[p]; ++k) if (b.color[T.nbr_list[p][k]] != color) return false;
+    int x = p % 19, y = p / 19, diag = 0;
+    for (int dy = -1; dy <= 1; dy += 2) for (int dx = -1; dx <= 1; dx += 2) {
         int xx = x + dx, yy = y + dy;
-        if (xx < 0 || xx > 18 || yy < 0 || yy > 18 || b.color[19 * yy + xx] != color) continue;
-        if (dx && dy) ++diag; else ++cross;
+        if (xx >= 0 && xx <= 18 && yy >= 0 && yy <= 18 && b.color[19 * yy + xx] == color) ++diag;
     }
-    bool ex = x == 0 || x == 18, ey = y == 0 || y == 18;
-    if (ex && ey) return cross >= 2 && diag >= 1;
-    if (ex || ey) return cross >= 3 && diag >= 2;
-    return cross >= 4 && diag >= 3;
+    return diag >= (T.n_nbr[p] == 2 ? 1 : T.n_nbr[p] == 3 ? 2 : 3);
 }
 
 enum SearchKind { STANDARD_SEARCH = 0, SCORING_SEARCH = 1 };

@@ -61,6 +61,7 @@ struct Node;
 struct Edge {                                  // one visited (or disqualified) child
     uint16_t move;
     bool expanding;
+    float prior;                               // -inf = not (or no longer) a candidate
     int32_t count;
     int32_t vcount;
     float value;
@@ -73,9 +74,14 @@ struct Node {
     int16_t pass_count;
     float initial_value;
     int32_t total_count, vtotal_count;
-    std::vector<uint16_t> cand_move;           // ascending
-    std::vector<float> cand_prior;             // finite
-    std::vector<Edge> edges;                   // unordered, few
+    // Candidates (finite prior).  The first `sorted_n` are in DECREASING prior order (ties: increasing move); the
+    // rest is unordered and gets selection-sorted only as far as a select() actually walks -- most nodes are
+    // visited once or twice, so a full sort per node would cost more than the rest of the search.
+    std::vector<uint16_t> cand_move;
+    std::vector<float> cand_prior;
+    std::vector<uint8_t> cand_edge;            // 1 = the candidate has an edge record
+    int sorted_n = 0;
+    std::vector<Edge> edges;                   // in creation order, few
 
     Node(int to_move_, float value, const float* prior /* [362] */)
         : to_move((uint8_t)to_move_), pass_count(0), initial_value(value), total_count(0), vtotal_count(0) {
@@ -90,6 +96,29 @@ struct Node {
         cand_prior.clear();
         for (int i = 0; i < 362; ++i)
             if (std::isfinite(prior[i])) { cand_move.push_back((uint16_t)i); cand_prior.push_back(prior[i]); }
+        cand_edge.assign(cand_move.size(), 0);
+        sorted_n = 0;
+        for (Edge& e : edges) {
+            e.prior = std::isfinite(prior[e.move]) ? prior[e.move] : NEG_INF;
+            int c = cand_index(e.move);
+            if (c >= 0) cand_edge[c] = 1;
+        }
+    }
+    void sort_up_to(int k) {                   // makes positions [0, k] final
+        const int n = (int)cand_move.size();
+        while (sorted_n <= k && sorted_n < n) {
+            int best = sorted_n;
+            for (int i = sorted_n + 1; i < n; ++i)
+                if (cand_prior[i] > cand_prior[best] || (cand_prior[i] == cand_prior[best] && cand_move[i] < cand_move[best])) best = i;
+            std::swap(cand_move[sorted_n], cand_move[best]);
+            std::swap(cand_prior[sorted_n], cand_prior[best]);
+            std::swap(cand_edge[sorted_n], cand_edge[best]);
+            ++sorted_n;
+        }
+    }
+    int cand_index(int move) const {
+        for (size_t k = 0; k < cand_move.size(); ++k) if (cand_move[k] == move) return (int)k;
+        return -1;
     }
     Edge* find(int move) {
         for (Edge& e : edges) if (e.move == move) return &e;
@@ -98,13 +127,12 @@ struct Node {
     const Edge* find(int move) const { return const_cast<Node*>(this)->find(move); }
     Edge& edge(int move) {                     // tree.rs:276-285: an absent child reads as (count 0, value = initial)
         if (Edge* e = find(move)) return *e;
-        edges.push_back(Edge{(uint16_t)move, false, 0, 0, initial_value, 0.0f, nullptr});
+        int c = cand_index(move);
+        if (c >= 0) cand_edge[c] = 1;
+        edges.push_back(Edge{(uint16_t)move, false, c >= 0 ? cand_prior[c] : NEG_INF, 0, 0, initial_value, 0.0f, nullptr});
         return edges.back();
     }
-    float prior_of(int move) const {
-        auto it = std::lower_bound(cand_move.begin(), cand_move.end(), (uint16_t)move);
-        return it != cand_move.end() && *it == move ? cand_prior[it - cand_move.begin()] : NEG_INF;
-    }
+    float prior_of(int move) const { int c = cand_index(move); return c >= 0 ? cand_prior[c] : NEG_INF; }
     int count_of(int move) const { const Edge* e = find(move); return e ? e->count : 0; }
     float value_of(int move) const { const Edge* e = find(move); return e ? e->value : initial_value; }
 
@@ -134,43 +162,39 @@ inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move) {
     }
     float best = NEG_INF;
     int best_move = -1;
-    auto consider = [&](int move, float score) {
-        if (best_move < 0 || score > best || (score == best && (move >> 3) > (best_move >> 3))) {
+    auto consider = [&](int move, float score) {   // equal scores: highest block of 8, then lowest index
+        if (best_move < 0 || score > best ||
+            (score == best && ((move >> 3) > (best_move >> 3) || ((move >> 3) == (best_move >> 3) && move < best_move)))) {
             best = score;
             best_move = move;
         }
     };
-    const size_t nc = node.cand_move.size();
-    if (node.edges.empty()) {
-        for (size_t i = 0; i < nc; ++i) consider(node.cand_move[i], unvisited + node.cand_prior[i] * u);
-    } else {
-        // move -> edge lookup through a per-thread scratch table (edges of moves that are not candidates any
-        // more have prior -inf in the reference and never win)
-        static thread_local int16_t slot_of[362];
-        static thread_local bool slot_init = false;
-        if (!slot_init) { for (int i = 0; i < 362; ++i) slot_of[i] = -1; slot_init = true; }
-        const size_t ne = node.edges.size();
-        for (size_t k = 0; k < ne; ++k) slot_of[node.edges[k].move] = (int16_t)k;
-        for (size_t i = 0; i < nc; ++i) {
-            int move = node.cand_move[i];
-            float value = unvisited, bonus = u;
-            int k = slot_of[move];
-            if (k >= 0) {
-                const Edge& e = node.edges[k];
-                int total = e.count + e.vcount;
-                if (total != 0) {
-                    value = e.value;
-                    bonus = u / (float)(1 + total);
-                } else if (apply_fpu) {
-                    float v = e.value - reduce;
-                    value = v > 0.0f ? v : 0.0f;
-                } else {
-                    value = e.value;
-                }
-            }
-            consider(move, value + node.cand_prior[i] * bonus);
+    // children with an edge record: their own value / visit count (an edge whose move is not a candidate any more
+    // has prior -inf in the reference and never wins)
+    for (const Edge& e : node.edges) {
+        if (!(e.prior > NEG_INF)) continue;
+        float value, bonus = u;
+        int total = e.count + e.vcount;
+        if (total != 0) {
+            value = e.value;
+            bonus = u / (float)(1 + total);
+        } else if (apply_fpu) {
+            float v = e.value - reduce;
+            value = v > 0.0f ? v : 0.0f;
+        } else {
+            value = e.value;
         }
-        for (size_t k = 0; k < ne; ++k) slot_of[node.edges[k].move] = -1;
+        consider(e.move, value + e.prior * bonus);
+    }
+    // untouched children all score `unvisited + prior * u`, which never increases along the prior-sorted list:
+    // stop at the first one that falls strictly below the best score seen
+    const size_t nc = node.cand_move.size();
+    for (size_t i = 0; i < nc; ++i) {
+        node.sort_up_to((int)i);
+        if (node.cand_edge[i]) continue;
+        float score = unvisited + node.cand_prior[i] * u;
+        if (best_move >= 0 && score < best) break;
+        consider(node.cand_move[i], score);
     }
     if (best_move < 0 || !std::isfinite(best)) return PROBE_NO_RESULT;
     Edge& e = node.edge(best_move);

@@ -7,8 +7,11 @@
 // the seed alone, whatever the thread count.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
 #include <future>
+#include <mutex>
 #include <string>
 #include <thread>
 
@@ -89,6 +92,53 @@ static void tromp_taylor(const Board& b, int* black, int* white) {
 }
 
 namespace {
+
+// Persistent helper threads: every round hands the same job to all of them (each pulls game indices from an atomic
+// counter); creating threads per round would cost more than the round itself.
+class Helpers {
+  public:
+    explicit Helpers(int n) {
+        for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); });
+    }
+    ~Helpers() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++generation_; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void run(const std::function<void()>& job) {          // the caller works too; returns when everybody is done
+        if (threads_.empty()) { job(); return; }
+        { std::lock_guard<std::mutex> g(m_); job_ = &job; remaining_ = (int)threads_.size(); ++generation_; }
+        cv_.notify_all();
+        job();
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [this] { return remaining_ == 0; });
+        job_ = nullptr;
+    }
+
+  private:
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void()>* job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_) return;
+                job = job_;
+            }
+            (*job)();
+            { std::lock_guard<std::mutex> g(m_); if (--remaining_ == 0) done_cv_.notify_one(); }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void()>* job_ = nullptr;
+    uint64_t generation_ = 0;
+    int remaining_ = 0;
+    bool stop_ = false;
+};
 
 struct Player {                                                  // self_play.rs:217-241
     float winrate = 0.5f;
@@ -212,10 +262,14 @@ struct Driver {
         sgf_point(index, s);
         s += "]";
         if (tree) {
+            // Node::prior() = argmax_f32 over the dense prior (tree.rs:1266-1270, asm/argmax.rs tie rule)
             int arg = PASS;
             float bestp = NEG_INF;
-            for (size_t i = 0; i < tree->cand_move.size(); ++i)
-                if (tree->cand_prior[i] > bestp) { bestp = tree->cand_prior[i]; arg = tree->cand_move[i]; }
+            for (size_t i = 0; i < tree->cand_move.size(); ++i) {
+                int m = tree->cand_move[i];
+                float p = tree->cand_prior[i];
+                if (p > bestp || (p == bestp && ((m >> 3) > (arg >> 3) || ((m >> 3) == (arg >> 3) && m < arg)))) { bestp = p; arg = m; }
+            }
             if (arg != PASS) { s += "TR["; sgf_point(arg, s); s += "]"; }
         }
         if (rollouts > 1 && softmax) {
@@ -240,6 +294,23 @@ extern "C" {
 
 int32_t dg_engine_predict(void* engine, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy) {
     return dg_engine_forward_packed(static_cast<dg_engine*>(engine), positions, n, value, policy);
+}
+
+// `RandomPredictor` (predictors/random.rs:30-59) made a function of the position: value uniform in (-1, 1), policy
+// 362 uniform numbers normalised to 1.  Host-only: measures the search / feature path without a device.
+int32_t dg_random_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy) {
+    uint64_t salt = ctx ? *static_cast<const uint64_t*>(ctx) : 0;
+    for (int i = 0; i < n; ++i) {
+        uint64_t h = 0xcbf29ce484222325ull ^ salt;
+        for (int p = 0; p < N_POINTS; ++p) { h ^= positions[i].planes[p]; h *= 0x100000001b3ull; }
+        Rng rng(h ^ positions[i].k_bits);
+        value[i] = f32_to_f16_bits((float)(2.0 * rng.uniform() - 1.0));
+        float x[362], total = 0.0f;
+        for (int k = 0; k < 362; ++k) { x[k] = (float)rng.uniform(); total += x[k]; }
+        float recip = 1.0f / total;
+        for (int k = 0; k < 362; ++k) policy[(size_t)i * 362 + k] = f32_to_f16_bits(x[k] * recip);
+    }
+    return DG_OK;
 }
 
 int32_t dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
@@ -395,20 +466,17 @@ int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_co
         }
     };
 
+    Helpers helpers(std::max(0, std::min(n_threads, (n_slots + n_groups - 1) / n_groups) - 1));
     auto run_group = [&](Group& grp, bool absorb_results) {
         std::atomic<size_t> next{0};
-        auto worker = [&] {
+        std::function<void()> worker = [&] {
             for (;;) {
                 size_t i = next.fetch_add(1);
                 if (i >= grp.slots.size()) break;
                 advance(d.games[grp.slots[i]], absorb_results ? grp.value.data() : nullptr, absorb_results ? grp.policy.data() : nullptr);
             }
         };
-        int nt = std::min<int>(n_threads, (int)grp.slots.size());
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
-        worker();
-        for (auto& th : pool) th.join();
+        helpers.run(worker);
         // serial part: finished games are replaced, leaves are gathered in slot order
         grp.batch.clear();
         for (int s : grp.slots) {

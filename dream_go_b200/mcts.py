@@ -42,6 +42,7 @@ _P, _I = C.c_void_p, C.c_int32
 # every symbol include/dg_mcts.h declares
 ABI = {
     "dg_engine_predict": (_I, [_P, _P, _I, _P, _P]),
+    "dg_random_predict": (_I, [_P, _P, _I, _P, _P]),
     "dg_mcts_predict": (_I, [PREDICT_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
                              C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "dg_tree_free": (None, [_P]), "dg_tree_forward": (_P, [_P, _I]), "dg_tree_disqualify": (None, [_P, _I]),
@@ -87,6 +88,14 @@ class EnginePredictor:
         self.network = network
         self.fn = C.cast(lib().dg_engine_predict, PREDICT_FN)
         self.ctx = network._handle
+
+
+class RandomPredictor:
+    """`predictors::RandomPredictor` as a deterministic function of the position (host only, no device)."""
+
+    def __init__(self):
+        self.fn = C.cast(lib().dg_random_predict, PREDICT_FN)
+        self.ctx = None
 
 
 class Tree:
@@ -136,7 +145,7 @@ class Tree:
 
 
 def _fn_ctx(predictor):
-    if isinstance(predictor, EnginePredictor):
+    if isinstance(predictor, (EnginePredictor, RandomPredictor)):
         return predictor.fn, predictor.ctx
     return predictor, None
 

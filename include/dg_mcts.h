@@ -27,6 +27,10 @@ typedef int32_t (*dg_predict_fn)(void* ctx, const dg_packed_position* positions,
 /* The predictor that is the product: ctx = dg_engine*, evaluation through dg_engine_forward_packed. */
 int32_t dg_engine_predict(void* engine, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
 
+/* `RandomPredictor` (predictors/random.rs:30-59) as a deterministic function of the position; ctx = NULL or a
+ * uint64_t* salt.  No device involved: it measures the host half of self-play alone. */
+int32_t dg_random_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
+
 typedef struct dg_search_options {
     int32_t  search;              /* DG_STANDARD_SEARCH / DG_SCORING_SEARCH (options.rs:66-81, 141-162)                 */
     int32_t  deterministic;       /* SearchOptions::deterministic(): no Dirichlet noise, greedy move choice             */

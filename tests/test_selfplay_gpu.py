@@ -1,0 +1,66 @@
+"""The whole hot path on the device: real feature planes -> engine -> priors -> tree search.
+
+* a search driven by the B200 engine gives the SAME visit counts as the oracle search fed by the same engine
+  ("MCTS visit counts bit-exact under a fixed seed");
+* self-play on the engine is reproducible run to run and independent of the host thread count (no float atomics
+  anywhere on the device, every game owns its random stream)."""
+import numpy as np
+import pytest
+
+from dream_go_b200 import go as pgo, mcts as pm, nn, weights
+from oracle import go as ogo, mcts as om, oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(small_net):
+    net = nn.Network.from_tensors(small_net, max_batch=256, num_workspaces=2)
+    yield net
+    net.close()
+
+
+def test_real_feature_planes_match_oracle_network(engine, small_net):
+    """Real positions (not Bernoulli noise) through pack_compact_kernel + tower + heads vs the CPU oracle network."""
+    colors, moves, komi = ogo.load_games()[2]
+    out = pgo.replay(colors[:64], moves[:64], komi, features=True)
+    want_feats = ogo.replay(colors[:64], moves[:64], komi, features=True)["features"]
+    got = engine.forward_packed(out["features"])
+    want_v, want_p = oracle.OracleNetwork(small_net).forward(want_feats)
+    v, p = got.value.astype(np.float32), got.policy.reshape(-1, 362).astype(np.float32)
+    assert np.abs(v - want_v.astype(np.float32)).max() <= 4e-3
+    assert (np.abs(p - want_p.astype(np.float32)) <= 1e-3 + 1e-2 * want_p.astype(np.float32)).all()
+
+
+@pytest.mark.parametrize("probes", [1, 4])
+def test_search_on_engine_matches_oracle_search(engine, probes):
+    ogo.use_default_zobrist()
+    colors, moves, komi = ogo.load_games()[9]
+    po, oo = pgo.Board(komi), ogo.Board(komi)
+    for c, m in zip(colors[:40], moves[:40]):
+        if m < 361:
+            po.place_index(int(c), int(m))
+            oo.place_index(int(c), int(m))
+    color = po.to_move()
+
+    def engine_on_features(feats):          # the oracle search evaluates fp16 feature tensors on the same engine
+        with engine.get_workspace(len(feats)) as ws:
+            value, policy = nn.forward(ws, np.ascontiguousarray(feats)).unwrap()
+        return value, policy.reshape(-1, 362)
+
+    kw = dict(deterministic=True, num_rollout=150, probes_per_round=probes, leaf_symmetries=[0, 3, 6, 1, 5])
+    want_v, want_i, want_root, want_evals = om.predict(engine_on_features, oo, color, **kw)
+    got_v, got_i, tree, got_evals = pm.predict(pm.EnginePredictor(engine), po, color, **kw)
+    count, value, prior = tree.children()
+    assert (count == want_root.count[:362]).all()
+    assert got_i == want_i and got_evals == want_evals
+    assert np.float32(got_v).view(np.uint32) == np.float32(want_v).view(np.uint32)
+    assert (prior.view(np.uint32) == want_root.prior[:362].view(np.uint32)).all()
+
+
+def test_self_play_on_engine_is_reproducible(engine):
+    kw = dict(num_games=4, num_parallel=4, num_rollout=40, probes_per_round=4, max_plies=16, seed=5)
+    a, sgf_a = pm.self_play(pm.EnginePredictor(engine), num_threads=1, **kw)
+    b, sgf_b = pm.self_play(pm.EnginePredictor(engine), num_threads=4, **kw)
+    assert a["digest"] == b["digest"] and sorted(sgf_a) == sorted(sgf_b)
+    assert a["games_finished"] == 4 and a["moves"] == 64 and a["evals"] == b["evals"] > 0

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Self-play throughput (BASELINE.json configs[2] / [3]): `--self-play N --num-rollout 800` with G concurrent games on
+one B200 engine per process.  Fixed-duration sample of the full run (games with random-init weights go to the 722-ply
+cap), stated in the output.
+
+    python tools/bench_selfplay.py [--games 100] [--parallel 32] [--rollouts 800] [--probes 8] [--seconds 60]
+    torchrun --nproc-per-node N tools/bench_selfplay.py ...      # one engine + one set of games per GPU, no collective
+
+Prints ONE JSON line (rank 0): moves/s, NN evals/s, mean device batch, plus the host-only ceiling (same search with the
+RandomPredictor, no device) so that the split between search cost and evaluation cost is visible.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--games", type=int, default=100)
+    ap.add_argument("--parallel", type=int, default=32)
+    ap.add_argument("--rollouts", type=int, default=800)
+    ap.add_argument("--probes", type=int, default=8)
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--blocks", type=int, default=9)
+    ap.add_argument("--ex-it", action="store_true")
+    ap.add_argument("--host-only", action="store_true", help="RandomPredictor instead of the engine (no GPU needed)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from dream_go_b200 import mcts, nn, weights
+    cores = os.cpu_count() or 1
+    threads = args.threads or max(1, cores // world)
+
+    kw = dict(num_games=args.games, num_parallel=args.parallel, num_rollout=args.rollouts, probes_per_round=args.probes,
+              num_threads=threads, ex_it=args.ex_it, num_ex_it_rollout=args.rollouts, seed=20261017 + rank,
+              max_seconds=args.seconds)
+    host, _ = mcts.self_play(mcts.RandomPredictor(), **{**kw, "max_seconds": min(args.seconds, 15.0)})
+    line = {"metric": "self_play_moves_per_s", "unit": "moves/s", "n_gpus": world, "higher_is_better": True,
+            "config": {"workload": f"--self-play {args.games} --num-rollout {args.rollouts}, {args.parallel} concurrent games per GPU"
+                                   + (" --ex-it" if args.ex_it else ""),
+                       "sample": f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-ply cap)",
+                       "probes_per_round": args.probes, "host_threads_per_gpu": threads, "host_cores": cores,
+                       "weights": f"{args.blocks} blocks x 128 filters, seeded random init", "data": "synthetic"},
+            "host_only": {"evals_per_s": host["evals"] / host["seconds"], "moves_per_s": host["moves"] / host["seconds"],
+                          "mean_batch": host["mean_batch"], "predictor": "RandomPredictor (no device)"}}
+    if not args.host_only:
+        dist = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        tensors = weights.synthetic_network(seed=20261017, num_blocks=args.blocks)
+        net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=512, num_workspaces=2)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        st, sgf = mcts.self_play(mcts.EnginePredictor(net), **kw)
+        wall = time.perf_counter() - t0
+        vals = [st["moves"], st["evals"], st["games_finished"], st["seconds"], st["eval_seconds"], st["rounds"]]
+        if dist is not None:
+            import torch
+            t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local_rank}")
+            mx = t.clone()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            moves, evals, games, _, eval_s, rounds = t.tolist()
+            seconds = mx[3].item()
+            dist.destroy_process_group()
+        else:
+            moves, evals, games, seconds, eval_s, rounds = vals
+        line.update({"value": moves / seconds, "nn_evals_per_s": evals / seconds, "games_finished": games, "moves": moves,
+                     "evals": evals, "seconds": seconds, "mean_batch": evals / max(rounds, 1),
+                     "device_busy_frac": eval_s / (seconds * world), "wall_s": wall,
+                     "first_game": sgf[0][:200] if sgf else None})
+        net.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
