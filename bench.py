@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH = 256
+SELF_PLAY_GAMES = 128
 NUM_BLOCKS = 9
 METRIC = "nn_evals_per_s"
 UNIT = "evals/s"
@@ -119,6 +120,38 @@ def oracle_rate(seconds_target: float, steps: int = 1, warmup: int = 0):
                                  "sample": f"{sample} of the {BATCH} positions of one batch x {steps} step(s), same weights/inputs distribution"}
 
 
+def host_feature_rates(positions: int = 512):
+    """BASELINE.json configs[0] (CPU only): V1 feature planes + legal moves for batches of 32 boards -- the product's
+    host code next to the oracle port of the reference's libdg_go, on real game positions (tools/bench_go.py)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_go
+        from dream_go_b200 import go as pgo
+        from oracle import go as ogo
+        items = bench_go.collect_positions(positions)["corpus"]
+        boards = [p for p, _, _ in items]
+        tm = np.array([c for _, _, c in items], np.uint8)
+        cores = os.cpu_count() or 1
+        out = {"unit": "positions/s", "workload": "feature-plane extract + legal-move gen, batch=32, fixture-game positions", "cores": cores}
+        for label, threads in (("product_1_thread", 1), ("product_all_cores", cores)):
+            batches = [pgo.PreparedBatch(boards[i:i + 32], tm[i:i + 32], legal=True, threads=threads) for i in range(0, len(boards), 32)]
+            for b in batches:
+                b.run()
+            t0 = time.perf_counter()
+            for rep in range(4):
+                for b in batches:
+                    b.run()
+            out[label] = 4 * len(boards) / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _, oo, c in items:
+            oo.features(c)
+            oo.legal_mask(c)
+        out["oracle_port_1_thread"] = len(items) / (time.perf_counter() - t0)
+        return out
+    except Exception as exc:   # noqa: BLE001
+        return {"unavailable": repr(exc)[:200]}
+
+
 def cudnn_baseline(tensors, feats, steps: int):
     """The reference's own GPU path restated call for call on the image's cuDNN (baseline/cudnn_ref.cu),
     same weights, same positions, same box: device-resident and end-to-end (blocking H2D/D2H) rates."""
@@ -146,6 +179,8 @@ def run_reference(args, rank: int):
     reference cannot be built in this image) on the host cores."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     rate, info = oracle_rate(seconds_target=60.0, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
     per_step_ms = 1e3 * info["seconds"] / max(args.steps, 1)
     line = {
@@ -174,6 +209,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if dist is not None:
             dist.barrier()
 
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     def max_over_ranks(x: float) -> float:
         if dist is None:
             return x
@@ -183,7 +226,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         return float(t.item())
 
     tensors = weights.synthetic_network(seed=20261017, num_blocks=NUM_BLOCKS)
-    net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=BATCH, num_workspaces=2)
+    net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=4 * BATCH, num_workspaces=2)
     feats = net.pinned((BATCH, 361, 32), np.float16)
     feats[...] = weights.bernoulli_features(BATCH, seed=1000 + rank)       # each rank (shard) has its own positions
     value = net.pinned((BATCH,), np.float16)
@@ -245,6 +288,26 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     e2e_packed_s = max_over_ranks(time.perf_counter() - t0)
     clocks.__exit__()
 
+    # ---- the metric's other half: self-play moves/s through the whole hot path (BASELINE.json configs[2]/[3]) -----
+    self_play = None
+    if args.self_play_seconds > 0:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_selfplay
+        threads = max(1, (os.cpu_count() or 1) // world)
+        barrier()
+        st, _ = bench_selfplay.sample(net, games=100000, parallel=SELF_PLAY_GAMES, rollouts=800, probes=8,
+                                      seconds=args.self_play_seconds, threads=threads, seed=20261017 + rank)
+        sp_seconds = max_over_ranks(st["seconds"])
+        sp_moves = sum_over_ranks(float(st["moves"]))
+        sp_evals = sum_over_ranks(float(st["evals"]))
+        sp_rounds = sum_over_ranks(float(st["rounds"]))
+        sp_busy = sum_over_ranks(float(st["eval_seconds"]))
+        self_play = {"moves_per_s": sp_moves / sp_seconds, "nn_evals_per_s": sp_evals / sp_seconds, "unit": "moves/s, evals/s",
+                     "mean_device_batch": sp_evals / max(sp_rounds, 1.0), "device_busy_frac": sp_busy / (sp_seconds * world),
+                     "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU, real feature planes from "
+                                 f"the host Go code, random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
+                     "host_threads_per_gpu": threads, "host_cores": os.cpu_count()}
+
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -280,10 +343,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "us_per_launch": tower_launch_s * 1e6, "us_per_conv_layer": tower_launch_s * 1e6 / (2 * NUM_BLOCKS),
                      "whole_net_frac": (value_evals / world) * FLOP_PER_EVAL / (peak_tf * 1e12)},
     }
+    if self_play is not None:
+        line["self_play"] = self_play
     if world == 1 and not os.environ.get("DG_BENCH_SKIP_CPU"):      # skipped only under the profiler
         line["cudnn_baseline"] = cudnn_baseline(tensors, feats, args.steps)
         rate, info = oracle_rate(seconds_target=15.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+        line["host_features"] = host_feature_rates()
     print(json.dumps(line), flush=True)
 
 
@@ -293,6 +359,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--self-play-seconds", type=float, default=0.0 if os.environ.get("DG_BENCH_SKIP_CPU") else 12.0,
+                    help="length of the self-play sample appended to the line (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -585,6 +585,7 @@ const char* dg_engine_last_error(dg_engine* e) {
 }
 
 int32_t dg_engine_num_blocks(dg_engine* e) { return e ? e->net.num_blocks : 0; }
+int32_t dg_engine_max_batch(dg_engine* e) { return e ? e->cfg.max_batch : 0; }
 
 int32_t dg_engine_load_weights_json(dg_engine* e, const char* path) {
     if (!e || !path) return DG_ERR_INVALID_ARGUMENT;

@@ -1,4 +1,5 @@
 // go_api.cpp -- C ABI (include/dg_go.h) over go_board.h.
+#include <atomic>
 #include <cmath>
 #include <limits>
 #include <thread>
@@ -6,6 +7,7 @@
 
 #include "../../include/dg_go.h"
 #include "go_board.h"
+#include "thread_pool.h"
 
 using dg::Board;
 
@@ -91,16 +93,20 @@ void dg_go_extract_batch(const dg_board* const* boards, const uint8_t* to_move, 
                          dg_packed_position* out, uint8_t* legal, int32_t threads) {
     int hw = (int)std::thread::hardware_concurrency();
     if (threads <= 0) threads = hw > 0 ? hw : 1;
-    if (threads > count) threads = count;
-    auto work = [&](int t) {
-        for (int i = t; i < count; i += threads)
+    std::atomic<int> next{0};
+    std::function<void()> work = [&] {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= count) break;
             dg_board_features_packed(boards[i], to_move[i], symmetry ? symmetry[i] : 0, out + i, legal ? legal + (size_t)i * 361 : nullptr);
+        }
     };
-    if (threads <= 1) { work(0); return; }
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
-    work(0);
-    for (auto& th : pool) th.join();
+    if (threads <= 1 || count <= 1) { work(); return; }
+    // one process-wide pool (created on first use, sized to the machine); callers take turns
+    static std::mutex turn;
+    static dg::Helpers* pool = new dg::Helpers(std::max(1, hw - 1));
+    std::lock_guard<std::mutex> g(turn);
+    pool->run(work);
 }
 
 int32_t dg_go_replay(float komi, const uint8_t* colors, const uint16_t* moves, int32_t n, dg_packed_position* features,

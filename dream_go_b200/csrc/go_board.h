@@ -327,6 +327,20 @@ struct Board {
         }
         return L.count();
     }
+
+    // liberties_if for both colours from one scan of the neighbourhood (the feature loop asks for both at every
+    // empty point; most empty points touch no stone at all).
+    void liberties_if_both(int c, int p, const uint16_t* nl, int* mine, int* theirs) const {
+        const Tables& T = tables();
+        int n_empty = 0, n_stone = 0;
+        for (int k = 0; k < T.n_nbr[p]; ++k) {
+            int q = T.nbr_list[p][k];
+            if (color[q]) ++n_stone; else ++n_empty;
+        }
+        if (!n_stone) { *mine = *theirs = n_empty; return; }
+        *mine = liberties_if(c, p, nl);
+        *theirs = liberties_if(opposite(c), p, nl);
+    }
 };
 
 // ---- ladder reader (utils/ladder.rs) ---------------------------------------------------------------------------
@@ -625,7 +639,6 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
                         uint8_t* legal /* [361] or null, identity orientation */) {
     const Tables& T = tables();
     const uint16_t* sym = T.sym[symmetry];
-    int opp = opposite(to_move);
     uint32_t global = to_move == BLACK ? 1u : 2u;
     uint16_t nl[N_POINTS];                                  // liberties per chain slot, counted once
     for (int i = 0; i < b.n_slots; ++i) nl[i] = 0;
@@ -642,8 +655,8 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
             m = ge_mask[n > 6 ? 6 : n] << (col == to_move ? 5 : 17);
             if (legal) legal[p] = 0;
         } else {
-            int mine = b.liberties_if(to_move, p, nl);
-            int theirs = b.liberties_if(opp, p, nl);
+            int mine, theirs;
+            b.liberties_if_both(to_move, p, nl, &mine, &theirs);
             if (mine >= 0) m |= ge_mask[mine > 6 ? 6 : mine] << 11;
             if (theirs >= 0) m |= ge_mask[theirs > 6 ? 6 : theirs] << 23;
             bool ko = false;

@@ -92,10 +92,13 @@ struct Node {
     Node& operator=(const Node&) = delete;
 
     void set_prior(const float* prior) {       // lib.rs:170-182 replaces the prior of a re-used root
-        cand_move.clear();
-        cand_prior.clear();
+        int n = 0;
+        for (int i = 0; i < 362; ++i) n += std::isfinite(prior[i]);
+        cand_move.resize(n);
+        cand_prior.resize(n);
+        n = 0;
         for (int i = 0; i < 362; ++i)
-            if (std::isfinite(prior[i])) { cand_move.push_back((uint16_t)i); cand_prior.push_back(prior[i]); }
+            if (std::isfinite(prior[i])) { cand_move[n] = (uint16_t)i; cand_prior[n] = prior[i]; ++n; }
         cand_edge.assign(cand_move.size(), 0);
         sorted_n = 0;
         for (Edge& e : edges) {

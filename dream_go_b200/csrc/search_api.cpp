@@ -17,6 +17,7 @@
 
 #include "../../include/dg_mcts.h"
 #include "search_task.h"
+#include "thread_pool.h"
 
 using namespace dg;
 
@@ -92,53 +93,6 @@ static void tromp_taylor(const Board& b, int* black, int* white) {
 }
 
 namespace {
-
-// Persistent helper threads: every round hands the same job to all of them (each pulls game indices from an atomic
-// counter); creating threads per round would cost more than the round itself.
-class Helpers {
-  public:
-    explicit Helpers(int n) {
-        for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); });
-    }
-    ~Helpers() {
-        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++generation_; }
-        cv_.notify_all();
-        for (auto& t : threads_) t.join();
-    }
-    void run(const std::function<void()>& job) {          // the caller works too; returns when everybody is done
-        if (threads_.empty()) { job(); return; }
-        { std::lock_guard<std::mutex> g(m_); job_ = &job; remaining_ = (int)threads_.size(); ++generation_; }
-        cv_.notify_all();
-        job();
-        std::unique_lock<std::mutex> lk(m_);
-        done_cv_.wait(lk, [this] { return remaining_ == 0; });
-        job_ = nullptr;
-    }
-
-  private:
-    void loop() {
-        uint64_t seen = 0;
-        for (;;) {
-            const std::function<void()>* job;
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return generation_ != seen; });
-                seen = generation_;
-                if (stop_) return;
-                job = job_;
-            }
-            (*job)();
-            { std::lock_guard<std::mutex> g(m_); if (--remaining_ == 0) done_cv_.notify_one(); }
-        }
-    }
-    std::vector<std::thread> threads_;
-    std::mutex m_;
-    std::condition_variable cv_, done_cv_;
-    const std::function<void()>* job_ = nullptr;
-    uint64_t generation_ = 0;
-    int remaining_ = 0;
-    bool stop_ = false;
-};
 
 struct Player {                                                  // self_play.rs:217-241
     float winrate = 0.5f;
@@ -293,7 +247,15 @@ struct Driver {
 extern "C" {
 
 int32_t dg_engine_predict(void* engine, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy) {
-    return dg_engine_forward_packed(static_cast<dg_engine*>(engine), positions, n, value, policy);
+    dg_engine* e = static_cast<dg_engine*>(engine);
+    const int32_t chunk = dg_engine_max_batch(e);
+    if (chunk <= 0) return DG_ERR_INVALID_ARGUMENT;
+    for (int32_t at = 0; at < n; at += chunk) {
+        int32_t m = n - at < chunk ? n - at : chunk;
+        int32_t rc = dg_engine_forward_packed(e, positions + at, m, value + at, policy + (size_t)at * 362);
+        if (rc) return rc;
+    }
+    return DG_OK;
 }
 
 // `RandomPredictor` (predictors/random.rs:30-59) made a function of the position: value uniform in (-1, 1), policy

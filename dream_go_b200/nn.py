@@ -77,6 +77,7 @@ ABI = {
     "dg_engine_free_host": (None, [C.c_void_p, C.c_void_p]),
     "dg_engine_last_error": (C.c_char_p, [C.c_void_p]),
     "dg_engine_num_blocks": (C.c_int32, [C.c_void_p]),
+    "dg_engine_max_batch": (C.c_int32, [C.c_void_p]),
     "dg_engine_time_resident": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "dg_engine_debug_read_tower": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

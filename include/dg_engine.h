@@ -141,6 +141,8 @@ void    dg_engine_free_host(dg_engine* engine, void* ptr);
 const char* dg_engine_last_error(dg_engine* engine);
 /* Network shape discovered from the weights (graph.rs:76-96). */
 int32_t dg_engine_num_blocks(dg_engine* engine);
+/* The max_batch the engine was created with. */
+int32_t dg_engine_max_batch(dg_engine* engine);
 /* Library/ABI version, for the FFI shim to assert on. */
 int32_t dg_engine_abi_version(void);
 

