@@ -226,7 +226,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         return float(t.item())
 
     tensors = weights.synthetic_network(seed=20261017, num_blocks=NUM_BLOCKS)
-    net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=4 * BATCH, num_workspaces=2)
+    net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=BATCH, num_workspaces=2)
     feats = net.pinned((BATCH, 361, 32), np.float16)
     feats[...] = weights.bernoulli_features(BATCH, seed=1000 + rank)       # each rank (shard) has its own positions
     value = net.pinned((BATCH,), np.float16)
@@ -294,16 +294,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_selfplay
         threads = max(1, (os.cpu_count() or 1) // world)
+        sp_net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=2 * BATCH, num_workspaces=2)   # its own engine
         barrier()
-        st, _ = bench_selfplay.sample(net, games=100000, parallel=SELF_PLAY_GAMES, rollouts=800, probes=8,
+        st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=SELF_PLAY_GAMES, rollouts=800, probes=8,
                                       seconds=args.self_play_seconds, threads=threads, seed=20261017 + rank)
         sp_seconds = max_over_ranks(st["seconds"])
         sp_moves = sum_over_ranks(float(st["moves"]))
         sp_evals = sum_over_ranks(float(st["evals"]))
         sp_rounds = sum_over_ranks(float(st["rounds"]))
         sp_busy = sum_over_ranks(float(st["eval_seconds"]))
+        sp_net.close()
         self_play = {"moves_per_s": sp_moves / sp_seconds, "nn_evals_per_s": sp_evals / sp_seconds, "unit": "moves/s, evals/s",
-                     "mean_device_batch": sp_evals / max(sp_rounds, 1.0), "device_busy_frac": sp_busy / (sp_seconds * world),
+                     "mean_device_batch": sp_evals / max(sp_rounds, 1.0), "predictor_time_frac": sp_busy / (sp_seconds * world),   # two alternating groups overlap, so this can exceed 1
                      "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU, real feature planes from "
                                  f"the host Go code, random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
                      "host_threads_per_gpu": threads, "host_cores": os.cpu_count()}
