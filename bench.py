@@ -226,7 +226,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         return float(t.item())
 
     tensors = weights.synthetic_network(seed=20261017, num_blocks=NUM_BLOCKS)
-    net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=BATCH, num_workspaces=2)
+    net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=BATCH, num_workspaces=3)
     feats = net.pinned((BATCH, 361, 32), np.float16)
     feats[...] = weights.bernoulli_features(BATCH, seed=1000 + rank)       # each rank (shard) has its own positions
     value = net.pinned((BATCH,), np.float16)
@@ -257,28 +257,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         net.forward_into(feats, value, policy)
     e2e_single_s = max_over_ranks(time.perf_counter() - t0)
     # (b) two callers, as the reference drives one device (`max_num_threads() = 2 x device_count`,
-    #     predictors/nn.rs:64-67): each call is still a blocking H2D + forward + D2H of its own batch, but one
-    #     caller's copies overlap the other's kernels.  Same total number of steps.
-    feats2 = net.pinned((BATCH, 361, 32), np.float16)
-    feats2[...] = weights.bernoulli_features(BATCH, seed=5000 + rank)
-    value2 = net.pinned((BATCH,), np.float16)
-    policy2 = net.pinned((BATCH, 362), np.float16)
-    net.forward_into(feats2, value2, policy2)
-
-    def caller(f, v, p, n):
-        for _ in range(n):
-            net.forward_into(f, v, p)
-
+    #     predictors/nn.rs:64-67): each call is still a blocking H2D + forward + D2H of its own batch from its own
+    #     pinned buffers, but one caller's copies overlap the other's kernels.  Native host threads inside the library
+    #     (dg_engine_time_e2e) so that the Python GIL is not part of the measurement.  Same total number of steps.
     barrier()
-    threads = [threading.Thread(target=caller, args=(feats, value, policy, (args.steps + 1) // 2)),
-               threading.Thread(target=caller, args=(feats2, value2, policy2, args.steps // 2))]
-    t0 = time.perf_counter()
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = max_over_ranks(net.time_e2e(feats, args.steps, callers=2))
     e2e_evals = world * BATCH * args.steps / e2e_s
+    barrier()
+    e2e3_s = max_over_ranks(net.time_e2e(feats, args.steps, callers=3))
     packed = net.pinned((BATCH,), nn.PACKED_DTYPE)
     packed[...] = nn.pack_positions(feats)
     net.forward_into(packed, value, policy, packed=True)
@@ -334,7 +320,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_evals, "unit": UNIT, "h2d_bytes_per_step": BATCH * 11552 * 2, "d2h_bytes_per_step": BATCH * 363 * 2,
                 "call": "dg_engine_forward_f16 (pinned host buffers, blocking), 2 concurrent callers per device as in predictors/nn.rs:64-67",
-                "single_caller": world * BATCH * args.steps / e2e_single_s},
+                "single_caller": world * BATCH * args.steps / e2e_single_s,
+                "three_callers": world * BATCH * args.steps / e2e3_s},
         "e2e_packed": {"value": world * BATCH * args.steps / e2e_packed_s, "unit": UNIT,
                        "h2d_bytes_per_step": BATCH * nn.PACKED_DTYPE.itemsize, "d2h_bytes_per_step": BATCH * 363 * 2,
                        "call": "dg_engine_forward_packed"},

@@ -761,6 +761,37 @@ int32_t dg_engine_queue_wait(dg_engine* e, int64_t ticket, uint16_t* value_out, 
 
 // ---------------------------------------------------------------------------------- measurement
 
+// `callers` host threads each issue blocking dg_engine_forward_f16 calls from their own pinned buffers until `steps`
+// calls have been made in total; seconds = wall time from the first call to the last return.
+int32_t dg_engine_time_e2e(dg_engine* e, const uint16_t* features, int32_t batch, int32_t steps, int32_t callers, double* seconds) {
+    if (!e || !features || !seconds || batch < 1 || steps < 1 || callers < 1 || callers > 16) return DG_ERR_INVALID_ARGUMENT;
+    struct Bufs { uint16_t *in, *value, *policy; };
+    std::vector<Bufs> bufs(callers);
+    const size_t in_bytes = static_cast<size_t>(batch) * kFeatBytes;
+    for (auto& b : bufs) {
+        b.in = static_cast<uint16_t*>(dg_engine_alloc_host(e, in_bytes));
+        b.value = static_cast<uint16_t*>(dg_engine_alloc_host(e, static_cast<size_t>(batch) * 2));
+        b.policy = static_cast<uint16_t*>(dg_engine_alloc_host(e, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2));
+        if (!b.in || !b.value || !b.policy) return fail(e, DG_ERR_CUDA, "pinned allocation failed");
+        memcpy(b.in, features, in_bytes);
+    }
+    for (auto& b : bufs) { int32_t rc = dg_engine_forward_f16(e, b.in, batch, b.value, b.policy); if (rc) return rc; }
+    std::atomic<int32_t> next{0}, failed{0};
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (int c = 0; c < callers; c++)
+        threads.emplace_back([&, c] {
+            while (next.fetch_add(1) < steps) {
+                int32_t rc = dg_engine_forward_f16(e, bufs[c].in, batch, bufs[c].value, bufs[c].policy);
+                if (rc) { failed.store(rc); break; }
+            }
+        });
+    for (auto& t : threads) t.join();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (auto& b : bufs) { dg_engine_free_host(e, b.in); dg_engine_free_host(e, b.value); dg_engine_free_host(e, b.policy); }
+    return failed.load();
+}
+
 int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, int32_t flush_l2, float* ms_total, float* tower_ms,
                                 int32_t* launches) {
     if (!e || iters < 1) return DG_ERR_INVALID_ARGUMENT;

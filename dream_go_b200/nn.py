@@ -80,6 +80,7 @@ ABI = {
     "dg_engine_max_batch": (C.c_int32, [C.c_void_p]),
     "dg_engine_time_resident": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "dg_engine_time_e2e": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "dg_engine_debug_read_tower": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dg_engine_debug_conv_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "dg_engine_debug_tower_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
@@ -240,6 +241,13 @@ class Network:
         self._check(lib().dg_engine_time_resident(self._handle, batch, iters, int(flush_l2), C.byref(ms),
                                                   C.byref(tms) if tower else None, C.byref(launches)))
         return ms.value, tms.value, launches.value
+
+    def time_e2e(self, features: np.ndarray, steps: int, callers: int = 2) -> float:
+        """Wall seconds for `steps` blocking forward_f16 calls issued by `callers` native host threads."""
+        feats = np.ascontiguousarray(features, np.float16)
+        seconds = C.c_double()
+        self._check(lib().dg_engine_time_e2e(self._handle, feats.ctypes.data, feats.shape[0], steps, callers, C.byref(seconds)))
+        return seconds.value
 
     def debug_read_tower(self, layer: int, batch: int) -> np.ndarray:
         out = np.empty((batch, 361, 128), np.float16)

@@ -156,6 +156,11 @@ int32_t dg_engine_abi_version(void);
  * measured in a second pass.  launches (optional) = kernels launched per forward. */
 int32_t dg_engine_time_resident(dg_engine* engine, int32_t batch, int32_t iters, int32_t flush_l2,
                                 float* ms_total, float* tower_ms, int32_t* launches);
+/* End-to-end rate of the blocking call: `callers` host threads (the reference runs 2 per device,
+ * predictors/nn.rs:64-67) each issue dg_engine_forward_f16 from their own pinned buffers (filled with `features`)
+ * until `steps` calls have been made in total.  seconds = wall time of those calls. */
+int32_t dg_engine_time_e2e(dg_engine* engine, const uint16_t* features, int32_t batch, int32_t steps, int32_t callers,
+                           double* seconds);
 /* Re-evaluates the resident batch up to `layer` (0 = up-sample, i = residual block i,
  * -1 = last block) and copies that activation into out[batch][361][128] fp16 (tests). */
 int32_t dg_engine_debug_read_tower(dg_engine* engine, int32_t layer, int32_t batch, uint16_t* out);
