@@ -308,6 +308,15 @@ struct Board {
         }
         if (!(ok || n_empty || nc)) return -1;
         if (!nf && !nc) return n_empty;                     // a lone stone: its empty neighbours
+        if (nf == 1 && !nc) {                               // joins one chain: its liberties minus `p` plus the new ones
+            const Bits& fl = libs[friends[0]];
+            int n = (nl ? nl[friends[0]] : fl.count()) - 1;
+            for (int k = 0; k < T.n_nbr[p]; ++k) {
+                int q = T.nbr_list[p][k];
+                if (!color[q] && !fl.test(q)) ++n;
+            }
+            return n;
+        }
         Bits L = empty_neighbours(p);
         for (int j = 0; j < nf; ++j) L.or_with(libs[friends[j]]);
         L.reset(p);
@@ -639,11 +648,24 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
                         uint8_t* legal /* [361] or null, identity orientation */) {
     const Tables& T = tables();
     const uint16_t* sym = T.sym[symmetry];
+    const int opp = opposite(to_move);
     uint32_t global = to_move == BLACK ? 1u : 2u;
     uint16_t nl[N_POINTS];                                  // liberties per chain slot, counted once
     for (int i = 0; i < b.n_slots; ++i) nl[i] = 0;
-    for (int p = 0; p < N_POINTS; ++p)
-        if (b.color[p] && !nl[b.slot[p]]) nl[b.slot[p]] = (uint16_t)b.libs[b.slot[p]].count();
+    // where a ladder can start: the liberties of enemy chains with exactly two liberties (the move puts them in
+    // atari) / of own chains in atari (the move extends them) -- straight from the chains' liberty sets
+    Bits capture_at, escape_at;
+    capture_at.clear();
+    escape_at.clear();
+    for (int p = 0; p < N_POINTS; ++p) {
+        if (!b.color[p] || nl[b.slot[p]]) continue;
+        int sl = b.slot[p];
+        int n = b.libs[sl].count();
+        nl[sl] = (uint16_t)n;
+        if (b.color[p] == to_move) { if (n < 2) escape_at.or_with(b.libs[sl]); }
+        else if (n == 2) capture_at.or_with(b.libs[sl]);
+    }
+    const Bits touched = dilate(b.stones[1] | b.stones[2]);  // points next to a stone
     uint32_t local[N_POINTS];
     bool any_ko = false;
     static const uint32_t ge_mask[7] = {0, 1, 3, 7, 15, 31, 63};   // ">= 1 .. >= n" thermometer code
@@ -656,15 +678,19 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
             if (legal) legal[p] = 0;
         } else {
             int mine, theirs;
-            b.liberties_if_both(to_move, p, nl, &mine, &theirs);
+            if (!touched.test(p)) mine = theirs = T.n_nbr[p];     // open point: its neighbours are its liberties
+            else {
+                mine = b.liberties_if(to_move, p, nl);
+                theirs = b.liberties_if(opp, p, nl);
+            }
             if (mine >= 0) m |= ge_mask[mine > 6 ? 6 : mine] << 11;
             if (theirs >= 0) m |= ge_mask[theirs > 6 ? 6 : theirs] << 23;
             bool ko = false;
             if (mine >= 0) {
                 ko = b.is_ko(to_move, p);
                 if (ko) { m |= 1u << 29; any_ko = true; }
-                if (is_ladder_capture(b, to_move, p, nl)) m |= 1u << 30;
-                if (is_ladder_escape(b, to_move, p, nl)) m |= 1u << 31;
+                if (capture_at.test(p) && is_ladder_capture(b, to_move, p, nl)) m |= 1u << 30;
+                if (escape_at.test(p) && is_ladder_escape(b, to_move, p, nl)) m |= 1u << 31;
             }
             if (legal) legal[p] = mine >= 0 && !ko;
         }
