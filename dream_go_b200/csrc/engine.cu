@@ -19,6 +19,7 @@
 
 #include "../../include/dg_engine.h"
 #include "conv_tc.h"
+#include "go_board.h"
 #include "kernels.h"
 #include "layout.h"
 #include "weights_file.h"
@@ -43,6 +44,7 @@ struct Workspace {
     float* part = nullptr;             // [K split][batch rounded to 128][384] fp32 partial sums
     CUtensorMap tm_pa;                 // [batch][3200] view of pbuf
     __half *d_policy = nullptr, *d_value = nullptr;
+    uint8_t* h_legal = nullptr;       // pinned: legal masks of the raw-position path
     uint8_t* h_in = nullptr;          // pinned staging
     __half *h_policy = nullptr, *h_value = nullptr;
     CUtensorMap tm_feat, tm_x, tm_y;           // 170-row load windows
@@ -173,6 +175,7 @@ int32_t create_workspace(dg_engine* e, Workspace& w) {
     DG_CUDA(e, cudaHostAlloc(&w.h_in, static_cast<size_t>(mb) * kFeatBytes, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_policy, static_cast<size_t>(mb) * DG_POLICY_SIZE * 2, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_value, static_cast<size_t>(mb) * 2, cudaHostAllocDefault));
+    DG_CUDA(e, cudaHostAlloc(&w.h_legal, static_cast<size_t>(mb) * 361, cudaHostAllocDefault));
     if (!make_tmap(e, &w.tm_feat, w.feat, 64, rows, DG_WINDOW_ROWS) || !make_tmap(e, &w.tm_x, w.x, kChan, rows, DG_WINDOW_ROWS) ||
         !make_tmap(e, &w.tm_y, w.y, kChan, rows, DG_WINDOW_ROWS) ||
         !make_tmap(e, &w.tm_pa, w.pbuf + static_cast<size_t>(DG_GUARD_ROWS) * 8, dg::kPolicyFcK, mb, 128))
@@ -186,7 +189,7 @@ void destroy_workspace(Workspace& w) {
     if (w.ev1) cudaEventDestroy(w.ev1);
     cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
     cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done); cudaFree(w.pbuf); cudaFree(w.vbuf); cudaFree(w.part);
-    cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value);
+    cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value); cudaFreeHost(w.h_legal);
 }
 
 Workspace* acquire(dg_engine* e) {
@@ -423,6 +426,10 @@ int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMa
     return DG_OK;
 }
 
+// Raw-position path: d_in (max_batch x 23,104 B) holds [raw positions | compact planes | legal masks].
+inline uint8_t* raw_planes(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 512; }
+inline uint8_t* raw_legal(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 2048; }
+
 // Enqueues pack + tower (+ heads) of the batch resident in w.d_in.  blocks < 0 = whole network.
 // stage: 0 = everything, 1 = pack only, 2 = residual convolutions only (timing), 3 = everything but pack.
 int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int stage) {
@@ -430,7 +437,11 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
     int32_t rc;
     if (stage == 0 || stage == 1) {
         if (w.resident_kind == 1) DG_CUDA(e, dg::launch_pack_features(w.d_in, w.feat, batch, w.stream));
-        else DG_CUDA(e, dg::launch_pack_compact(w.d_in, w.feat, batch, w.stream));
+        else if (w.resident_kind == 3) {
+            // raw positions at d_in; compact planes and legal masks behind them in the same buffer
+            DG_CUDA(e, dg::launch_planes_from_stones(w.d_in, raw_planes(e, w), raw_legal(e, w), batch, w.stream));
+            DG_CUDA(e, dg::launch_pack_compact(raw_planes(e, w), w.feat, batch, w.stream));
+        } else DG_CUDA(e, dg::launch_pack_compact(w.d_in, w.feat, batch, w.stream));
         if (stage == 1) return DG_OK;
     }
     const int nb = (blocks < 0 || blocks > n.num_blocks) ? n.num_blocks : blocks;
@@ -544,6 +555,17 @@ int32_t dg_engine_create(const dg_engine_config* config, dg_engine** out) {
     DG_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(e, DG_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
     e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    {   // constants of the device feature kernel: the engine's zobrist keys and the 8 symmetry maps (csrc/go_board.h)
+        static_assert(sizeof(dg_raw_position) == 384, "dg_raw_position is 384 bytes");
+        const dg::Tables& T = dg::tables();
+        std::vector<unsigned long long> z(2 * 361);
+        std::vector<uint16_t> sym(8 * 361);
+        for (int c = 0; c < 2; c++)
+            for (int p = 0; p < 361; p++) z[c * 361 + p] = T.zobrist[c + 1][p];
+        for (int t = 0; t < 8; t++)
+            for (int p = 0; p < 361; p++) sym[t * 361 + p] = T.sym[t][p];
+        DG_CUDA(e, dg::upload_feature_tables(z.data(), sym.data()));
+    }
     e->ws.resize(e->cfg.num_workspaces);
     for (auto& w : e->ws) {
         int32_t rc = create_workspace(e, w);
@@ -640,6 +662,51 @@ int32_t dg_engine_forward_f16(dg_engine* e, const uint16_t* features, int32_t ba
 
 int32_t dg_engine_forward_packed(dg_engine* e, const dg_packed_position* positions, int32_t batch, uint16_t* value_out, uint16_t* policy_out) {
     return forward_impl(e, positions, sizeof(dg_packed_position), 2, batch, value_out, policy_out);
+}
+
+static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t batch, uint16_t* value_out, uint16_t* policy_out,
+                        dg_packed_position* planes_out, uint8_t* legal_out) {
+    if (!e) return DG_ERR_INVALID_ARGUMENT;
+    if (!positions || !legal_out) return fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch < 1 || batch > e->cfg.max_batch) return fail(e, DG_ERR_INVALID_ARGUMENT, "batch %d outside 1..%d", batch, e->cfg.max_batch);
+    const bool network = value_out && policy_out;
+    if (network && !e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    WsGuard guard(e);
+    Workspace& w = *guard.w;
+    const size_t in_bytes = sizeof(dg_raw_position) * static_cast<size_t>(batch);
+    memcpy(w.h_in, positions, in_bytes);
+    DG_CUDA(e, cudaMemcpyAsync(w.d_in, w.h_in, in_bytes, cudaMemcpyHostToDevice, w.stream));
+    w.resident_kind = 3;
+    w.resident_batch = batch;
+    int32_t rc = enqueue_network(e, w, batch, -1, network ? 0 : 1);
+    if (rc) { cudaStreamSynchronize(w.stream); return rc; }
+    DG_CUDA(e, cudaMemcpyAsync(w.h_legal, raw_legal(e, w), static_cast<size_t>(batch) * 361, cudaMemcpyDeviceToHost, w.stream));
+    if (network) {
+        DG_CUDA(e, cudaMemcpyAsync(w.h_value, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream));
+        DG_CUDA(e, cudaMemcpyAsync(w.h_policy, w.d_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2, cudaMemcpyDeviceToHost, w.stream));
+    }
+    if (planes_out)
+        DG_CUDA(e, cudaMemcpyAsync(planes_out, raw_planes(e, w), sizeof(dg_packed_position) * static_cast<size_t>(batch), cudaMemcpyDeviceToHost, w.stream));
+    DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    memcpy(legal_out, w.h_legal, static_cast<size_t>(batch) * 361);
+    if (network) {
+        memcpy(value_out, w.h_value, static_cast<size_t>(batch) * 2);
+        memcpy(policy_out, w.h_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2);
+    }
+    return DG_OK;
+}
+
+int32_t dg_engine_forward_raw(dg_engine* e, const dg_raw_position* positions, int32_t batch, uint16_t* value_out, uint16_t* policy_out,
+                              uint8_t* legal_out) {
+    if (!value_out || !policy_out) return e ? fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer") : DG_ERR_INVALID_ARGUMENT;
+    return raw_impl(e, positions, batch, value_out, policy_out, nullptr, legal_out);
+}
+
+int32_t dg_engine_features_raw(dg_engine* e, const dg_raw_position* positions, int32_t batch, dg_packed_position* planes_out,
+                               uint8_t* legal_out) {
+    if (!planes_out) return e ? fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer") : DG_ERR_INVALID_ARGUMENT;
+    return raw_impl(e, positions, batch, nullptr, nullptr, planes_out, legal_out);
 }
 
 int32_t dg_engine_synchronize(dg_engine* e) {

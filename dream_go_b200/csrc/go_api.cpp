@@ -77,6 +77,10 @@ void dg_board_features_packed(const dg_board* board, int32_t to_move, int32_t sy
     out->reserved = 0;
 }
 
+void dg_board_raw_position(const dg_board* board, int32_t to_move, int32_t symmetry, dg_raw_position* out) {
+    dg::raw_position(*B(board), to_move, symmetry, out);
+}
+
 void dg_board_features_f16(const dg_board* board, int32_t to_move, int32_t symmetry, uint16_t* out) {
     dg_packed_position pos;
     dg::features_v1(*B(board), to_move, symmetry, pos.planes, &pos.k_bits, nullptr);

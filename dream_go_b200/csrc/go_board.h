@@ -704,4 +704,44 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
     *k_bits = komi_plane_bits(b.komi);
 }
 
+// ---- raw position for the device feature kernel (csrc/features.cu) ----------------------------------------------------
+// Everything the device needs to rebuild the planes: stones, visited bits, hashes, last moves -- plus the two ladder
+// planes, which are read here (sequential search) for the points that can start a ladder and are legal.
+template <class Raw>
+inline void raw_position(const Board& b, int to_move, int symmetry, Raw* out) {
+    static_assert(sizeof(Bits) == 48, "Bits is 12 x u32");
+    memcpy(out->black, b.stones[BLACK].w, 48);
+    memcpy(out->white, b.stones[WHITE].w, 48);
+    memcpy(out->visited, b.visited.w, 48);
+    uint16_t nl[N_POINTS];
+    for (int i = 0; i < b.n_slots; ++i) nl[i] = 0;
+    Bits capture_at, escape_at, capture, escape;
+    capture_at.clear(); escape_at.clear(); capture.clear(); escape.clear();
+    for (int p = 0; p < N_POINTS; ++p) {
+        if (!b.color[p] || nl[b.slot[p]]) continue;
+        int sl = b.slot[p];
+        int n = b.libs[sl].count();
+        nl[sl] = (uint16_t)n;
+        if (b.color[p] == to_move) { if (n < 2) escape_at.or_with(b.libs[sl]); }
+        else if (n == 2) capture_at.or_with(b.libs[sl]);
+    }
+    Bits todo = capture_at | escape_at;
+    while (todo.any()) {
+        int p = todo.first();
+        todo.reset(p);
+        if (!b.is_valid_fast(to_move, p)) continue;
+        if (capture_at.test(p) && is_ladder_capture(b, to_move, p, nl)) capture.set(p);
+        if (escape_at.test(p) && is_ladder_escape(b, to_move, p, nl)) escape.set(p);
+    }
+    memcpy(out->ladder_capture, capture.w, 48);
+    memcpy(out->ladder_escape, escape.w, 48);
+    out->hash = b.hash;
+    for (int i = 0; i < 16; ++i) out->hash_history[i] = b.hash_history[i];
+    out->last_move[0] = (int16_t)b.recent_move(0);
+    out->last_move[1] = (int16_t)b.recent_move(1);
+    out->k_bits = komi_plane_bits(b.komi);
+    out->to_move = (uint8_t)to_move;
+    out->symmetry = (uint8_t)symmetry;
+}
+
 }  // namespace dg

@@ -29,7 +29,7 @@ ABI = {
     "dg_board_is_ladder_capture": (_I, [_P, _I, _I]), "dg_board_is_ladder_escape": (_I, [_P, _I, _I]),
     "dg_board_is_symmetric": (_I, [_P, _I]), "dg_board_legal_moves": (None, [_P, _I, _P]),
     "dg_symmetry_apply": (_I, [_I, _I]), "dg_symmetry_inverse": (_I, [_I]),
-    "dg_board_features_packed": (None, [_P, _I, _I, _P, _P]), "dg_board_features_f16": (None, [_P, _I, _I, _P]),
+    "dg_board_features_packed": (None, [_P, _I, _I, _P, _P]), "dg_board_raw_position": (None, [_P, _I, _I, _P]), "dg_board_features_f16": (None, [_P, _I, _I, _P]),
     "dg_go_extract_batch": (None, [_P, _P, _P, _I, _P, _P, _I]),
     "dg_go_replay": (_I, [_F, _P, _P, _I, _P, _P, _P]),
     "dg_board_prior": (None, [_P, _I, _I, _P, _P, _I, _F, _P]),
@@ -121,6 +121,12 @@ class Board:
         lg = np.empty(361, np.uint8) if legal else None
         lib().dg_board_features_packed(self._h, to_move, symmetry, out.ctypes.data, lg.ctypes.data if legal else None)
         return (out, lg) if legal else out
+
+    def raw_position(self, to_move: int, symmetry: int = IDENTITY) -> np.ndarray:
+        """One `dg_raw_position` (what `dg_engine_forward_raw` takes): the device derives planes and legal moves."""
+        out = np.zeros(1, nn.RAW_DTYPE)
+        lib().dg_board_raw_position(self._h, to_move, symmetry, out.ctypes.data)
+        return out
 
     def features(self, to_move: int, symmetry: int = IDENTITY) -> np.ndarray:
         """`features::V1::get_features::<HWC, f16>` -> [361, 32] fp16."""

@@ -56,6 +56,11 @@ class _TensorView(C.Structure):
 
 PACKED_DTYPE = np.dtype([("planes", "<u4", (361,)), ("k_bits", "<u2"), ("reserved", "<u2")])   # dg_packed_position
 
+RAW_DTYPE = np.dtype([("black", "<u4", (12,)), ("white", "<u4", (12,)), ("visited", "<u4", (12,)),
+                      ("ladder_capture", "<u4", (12,)), ("ladder_escape", "<u4", (12,)), ("hash", "<u8"),
+                      ("hash_history", "<u8", (16,)), ("last_move", "<i2", (2,)), ("k_bits", "<u2"), ("to_move", "u1"),
+                      ("symmetry", "u1")])   # dg_raw_position, 384 bytes
+
 _lib = None
 
 # every symbol include/dg_engine.h declares: name -> (restype, argtypes)
@@ -67,6 +72,8 @@ ABI = {
     "dg_engine_load_weights_raw": (C.c_int32, [C.c_void_p, C.POINTER(_TensorView), C.c_int32]),
     "dg_engine_forward_f16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dg_engine_forward_packed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dg_engine_forward_raw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dg_engine_features_raw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dg_engine_queue_push": (C.c_int64, [C.c_void_p, C.c_void_p]),
     "dg_engine_queue_flush": (C.c_int32, [C.c_void_p]),
     "dg_engine_queue_wait": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -218,6 +225,25 @@ class Network:
         policy = np.empty((pos.shape[0], POLICY_SIZE), np.float16)
         self.forward_into(pos, value, policy, packed=True)
         return OutputMap(value, policy)
+
+    def forward_raw(self, positions: np.ndarray):
+        """Raw positions -> (OutputMap, legal [n, 361] u8): planes and legal moves are derived on the device."""
+        pos = np.ascontiguousarray(positions, dtype=RAW_DTYPE).reshape(-1)
+        n = pos.shape[0]
+        value = np.empty((n,), np.float16)
+        policy = np.empty((n, POLICY_SIZE), np.float16)
+        legal = np.empty((n, 361), np.uint8)
+        self._check(lib().dg_engine_forward_raw(self._handle, pos.ctypes.data, n, value.ctypes.data, policy.ctypes.data, legal.ctypes.data))
+        return OutputMap(value, policy), legal
+
+    def features_raw(self, positions: np.ndarray):
+        """Feature stage only: (compact planes [n] PACKED_DTYPE, legal [n, 361] u8)."""
+        pos = np.ascontiguousarray(positions, dtype=RAW_DTYPE).reshape(-1)
+        n = pos.shape[0]
+        planes = np.zeros(n, PACKED_DTYPE)
+        legal = np.empty((n, 361), np.uint8)
+        self._check(lib().dg_engine_features_raw(self._handle, pos.ctypes.data, n, planes.ctypes.data, legal.ctypes.data))
+        return planes, legal
 
     def queue_push(self, position: np.ndarray) -> int:
         pos = np.ascontiguousarray(position, dtype=PACKED_DTYPE).reshape(1)

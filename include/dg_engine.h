@@ -80,6 +80,21 @@ typedef struct dg_packed_position {
     uint16_t reserved;
 } dg_packed_position;
 
+/* The smallest description of a position from which the DEVICE computes the V1 feature planes and the legal moves
+ * (csrc/features.cu): stones, which points have ever held a stone (the super-ko rule only looks at those,
+ * board.rs:135), the zobrist hash of the position and of the last 16 positions (board.rs:132-141; the keys are the
+ * engine's own, csrc/go_board.h), the last two moves (361 = none) and -- computed on the host, a ladder is a sequential
+ * search -- the two ladder planes.  Bit p of a mask = point p = 19*y + x.  `dg_board_raw_position` (dg_go.h) fills it. */
+typedef struct dg_raw_position {
+    uint32_t black[12], white[12], visited[12], ladder_capture[12], ladder_escape[12];
+    uint64_t hash;
+    uint64_t hash_history[16];
+    int16_t  last_move[2];
+    uint16_t k_bits;               /* fp16 bits of k (features.rs:236) */
+    uint8_t  to_move;              /* 1 black, 2 white */
+    uint8_t  symmetry;             /* orientation the planes are produced in (symmetry::ALL order) */
+} dg_raw_position;                 /* 384 bytes */
+
 /* ---- lifetime ------------------------------------------------------------------------------ */
 
 /* `Network::new()` minus the file search.  Fails with DG_ERR_CUDA when the device is missing
@@ -110,6 +125,15 @@ int32_t dg_engine_forward_f16(dg_engine* engine, const uint16_t* features, int32
  * (replaces the 23,104-byte-per-leaf host copy of pool/batch.rs:87-96 with 1,448 bytes). */
 int32_t dg_engine_forward_packed(dg_engine* engine, const dg_packed_position* positions, int32_t batch,
                                  uint16_t* value_out, uint16_t* policy_out);
+
+/* The same evaluation from raw positions: the device derives the feature planes itself and also returns
+ * `Board::is_valid(to_move, .)` for the 361 points of every position (identity orientation) -- what
+ * create_initial_policy (pool/policy_helper.rs:39-43) asks the board for.  384 bytes H2D per position. */
+int32_t dg_engine_forward_raw(dg_engine* engine, const dg_raw_position* positions, int32_t batch,
+                              uint16_t* value_out, uint16_t* policy_out, uint8_t* legal_out /* [batch][361] */);
+/* Only the feature stage of dg_engine_forward_raw: the planes as compact positions + the legal masks (tests, tools). */
+int32_t dg_engine_features_raw(dg_engine* engine, const dg_raw_position* positions, int32_t batch,
+                               dg_packed_position* planes_out, uint8_t* legal_out /* [batch][361] */);
 
 /* ---- leaf-batch queue (replaces pool::Batcher, src/libdg_mcts/pool/batch.rs:61-124) ---------- */
 

@@ -61,6 +61,9 @@ int32_t   dg_symmetry_inverse(int32_t transform);                     /* Transfo
  * Board::is_valid(to_move, .) in identity orientation -- computed from the same pass at no extra cost. */
 void      dg_board_features_packed(const dg_board* board, int32_t to_move, int32_t symmetry,
                                    dg_packed_position* out, uint8_t* legal);
+/* The raw form for dg_engine_forward_raw: stones, visited bits, hashes, last moves and the two ladder planes; the
+ * device derives the other 30 planes and the legal moves from it (csrc/features.cu). */
+void      dg_board_raw_position(const dg_board* board, int32_t to_move, int32_t symmetry, dg_raw_position* out);
 /* Bit-identical to `get_features::<HWC, f16>`: 11,552 fp16, index 32*(19y+x)+c. */
 void      dg_board_features_f16(const dg_board* board, int32_t to_move, int32_t symmetry, uint16_t* out);
 /* The same for `count` boards on up to `threads` host threads (<= 0: all cores); this is BASELINE.json configs[0]

@@ -1,0 +1,93 @@
+"""Device feature kernel (csrc/features.cu): V1 planes + legal moves from raw stones, bit for bit against the host
+code and the oracle restatement of the reference (features.rs:154-250, board.rs:151-153) -- every ply of the fixture
+games, capture-heavy random playouts, all 8 symmetries; and the whole network from raw positions against the
+compact-position path."""
+import numpy as np
+import pytest
+
+from dream_go_b200 import go as pgo, nn, weights
+from oracle import go as ogo
+
+pytestmark = pytest.mark.gpu
+BLACK, WHITE = 1, 2
+
+
+@pytest.fixture(scope="module")
+def engine(small_net):
+    net = nn.Network.from_tensors(small_net, max_batch=512, num_workspaces=2)
+    yield net
+    net.close()
+
+
+def replay_raw(colors, moves, komi, symmetries=None):
+    """Raw positions, host planes and host legal masks for every ply of a game (to_move = the move's colour)."""
+    board = pgo.Board(komi)
+    raws, planes, legal = [], [], []
+    for i, (c, m) in enumerate(zip(colors, moves)):
+        s = 0 if symmetries is None else int(symmetries[i])
+        raws.append(board.raw_position(int(c), s)[0])
+        p, lg = board.features_packed(int(c), s, legal=True)
+        planes.append(p[0])
+        legal.append(lg)
+        if m < 361:
+            board.place_index(int(c), int(m))
+    return np.array(raws, nn.RAW_DTYPE), np.array(planes, nn.PACKED_DTYPE), np.array(legal)
+
+
+def check(engine, raws, planes, legal):
+    for at in range(0, len(raws), 512):
+        got_planes, got_legal = engine.features_raw(raws[at:at + 512])
+        want = planes[at:at + 512]
+        bad = np.argwhere(got_planes["planes"] != want["planes"])
+        assert len(bad) == 0, f"first mismatch (position, point) = {bad[0]}: {got_planes['planes'][tuple(bad[0])]:#x} != {want['planes'][tuple(bad[0])]:#x}"
+        assert (got_planes["k_bits"] == want["k_bits"]).all()
+        assert (got_legal == legal[at:at + 512]).all()
+
+
+def test_fixture_games_bit_exact(engine):
+    ogo.use_default_zobrist()
+    games = ogo.load_games()
+    n = 0
+    for colors, moves, komi in games[::4]:
+        raws, planes, legal = replay_raw(colors, moves, komi)
+        check(engine, raws, planes, legal)
+        n += len(raws)
+    # and the host planes are the oracle's (tests/test_go_parity.py does all 99 games on the CPU)
+    colors, moves, komi = games[0]
+    raws, planes, legal = replay_raw(colors, moves, komi)
+    want = ogo.replay(colors, moves, komi, features=True, legal=True)
+    got_planes, got_legal = engine.features_raw(raws[:512])
+    assert (pgo.unpack_features(got_planes).view(np.uint16) == want["features"][:512].view(np.uint16)).all()
+    assert (got_legal == want["legal"][:512]).all()
+    assert n > 4000
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_playouts_and_symmetries_bit_exact(engine, seed):
+    from test_go_parity import random_playout
+    colors, moves = random_playout(977 + seed, 420, komi=6.5)
+    rng = np.random.default_rng(seed)
+    raws, planes, legal = replay_raw(colors, moves, 6.5, symmetries=rng.integers(0, 8, size=len(moves)))
+    check(engine, raws, planes, legal)
+
+
+def test_ko_and_capture_positions(engine):
+    b = pgo.Board(7.5)
+    for c, x, y in [(1, 0, 0), (1, 0, 2), (1, 1, 1), (2, 1, 0), (2, 0, 1)]:     # board.rs:341-351: ko at (0, 0)
+        b.place(c, x, y)
+    raws = np.concatenate([b.raw_position(BLACK, t) for t in range(8)] + [b.raw_position(WHITE, t) for t in range(8)])
+    planes = np.concatenate([b.features_packed(BLACK, t) for t in range(8)] + [b.features_packed(WHITE, t) for t in range(8)])
+    legal = np.stack([b.legal_moves(BLACK)] * 8 + [b.legal_moves(WHITE)] * 8)
+    check(engine, raws, planes, legal)
+    got, _ = engine.features_raw(raws[:1])
+    assert (got["planes"][0] & 4).all() and got["planes"][0][0] & (1 << 29)     # the ko planes are really set
+
+
+def test_network_from_raw_positions_matches_compact_path(engine):
+    colors, moves, komi = ogo.load_games()[5]
+    raws, planes, legal = replay_raw(colors[:96], moves[:96], komi)
+    out, got_legal = engine.forward_raw(raws)
+    want = engine.forward_packed(planes)
+    assert (out.value.view(np.uint16) == want.value.view(np.uint16)).all()
+    assert (out.policy.view(np.uint16) == want.policy.view(np.uint16)).all()
+    assert (got_legal == legal).all()
