@@ -119,7 +119,8 @@ struct Game {
     SearchTask task;
     std::string sgf;
     std::vector<uint16_t> moves;
-    std::vector<dg_packed_position> batch;                       // this round's leaves
+    std::vector<dg_packed_position> batch;                       // this round's leaves (host feature planes) ...
+    std::vector<dg_raw_position> raw_batch;                      // ... or raw positions (planes derived on the device)
     int n_emitted = 0;
     size_t batch_offset = 0;
     // result of the main search, kept while an ex-it search replaces the recorded statistics
@@ -323,9 +324,10 @@ void dg_tree_children(const dg_tree* tree, int32_t* count, float* value, float* 
 }
 int64_t dg_tree_num_nodes(const dg_tree* tree) { return tree ? count_nodes(N(tree)) : 0; }
 
-int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
-                        char* sgf_out, int64_t sgf_capacity) {
-    if (!predictor || !config || config->num_games <= 0 || config->num_parallel <= 0) return DG_ERR_INVALID_ARGUMENT;
+static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_predictor, void* ctx, const dg_selfplay_config* config,
+                             dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity) {
+    if ((!predictor && !raw_predictor) || !config || config->num_games <= 0 || config->num_parallel <= 0) return DG_ERR_INVALID_ARGUMENT;
+    const bool raw_mode = raw_predictor != nullptr;
     Driver d;
     d.cfg = *config;
     if (d.cfg.max_plies <= 0 || d.cfg.max_plies > 722) d.cfg.max_plies = 722;
@@ -339,8 +341,11 @@ int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_co
     struct Group {
         std::vector<int> slots;
         std::vector<dg_packed_position> batch;
+        std::vector<dg_raw_position> raw_batch;
         std::vector<uint16_t> value, policy;
+        std::vector<uint8_t> legal;
         std::future<int32_t> pending;
+        size_t size() const { return batch.size() + raw_batch.size(); }
         bool in_flight = false;
     } groups[2];
     for (int i = 0; i < n_slots; ++i) groups[i % n_groups].slots.push_back(i);
@@ -372,21 +377,22 @@ int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_co
     };
 
     // Advances one game until it has leaves for the device (returns with g.batch filled) or has nothing to do.
-    auto advance = [&](Game& g, const uint16_t* value, const uint16_t* policy) {
+    auto advance = [&](Game& g, const uint16_t* value, const uint16_t* policy, const uint8_t* legal) {
         if (!g.active) return;
         if (g.n_emitted > 0) {
-            g.task.absorb(value + g.batch_offset, policy + g.batch_offset * 362);
+            g.task.absorb(value + g.batch_offset, policy + g.batch_offset * 362, legal ? legal + g.batch_offset * 361 : nullptr);
             g.evals += g.n_emitted;
             g.n_emitted = 0;
         }
         g.batch.clear();
+        g.raw_batch.clear();
         for (;;) {
             if (g.mode == Game::IDLE) {
                 if ((int)g.board.count >= d.cfg.max_plies) { g.mode = Game::IDLE; g.active = false; g.n_emitted = -1; return; }   // ended: 722 plies
                 g.allow_pass = is_scorable(g.board);
                 d.begin_search(g, false);
             }
-            int n = g.task.emit(g.batch);
+            int n = raw_mode ? g.task.emit(nullptr, &g.raw_batch) : g.task.emit(&g.batch, nullptr);
             if (n > 0) { g.n_emitted = n; return; }
             // the search is done
             Player& me = g.players[0];
@@ -435,12 +441,14 @@ int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_co
             for (;;) {
                 size_t i = next.fetch_add(1);
                 if (i >= grp.slots.size()) break;
-                advance(d.games[grp.slots[i]], absorb_results ? grp.value.data() : nullptr, absorb_results ? grp.policy.data() : nullptr);
+                advance(d.games[grp.slots[i]], absorb_results ? grp.value.data() : nullptr, absorb_results ? grp.policy.data() : nullptr,
+                        absorb_results && raw_mode ? grp.legal.data() : nullptr);
             }
         };
         helpers.run(worker);
         // serial part: finished games are replaced, leaves are gathered in slot order
         grp.batch.clear();
+        grp.raw_batch.clear();
         for (int s : grp.slots) {
             Game& g = d.games[s];
             if (g.n_emitted == -1) {
@@ -450,27 +458,31 @@ int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_co
                 bool time_left = d.cfg.max_seconds <= 0 || seconds() < d.cfg.max_seconds;
                 if (d.started < d.cfg.num_games && time_left) {
                     d.start_game(g);
-                    advance(g, nullptr, nullptr);
+                    advance(g, nullptr, nullptr, nullptr);
                     if (g.n_emitted == -1) { g.n_emitted = 0; g.active = false; }
                 }
             }
             if (g.active && g.n_emitted > 0) {
-                g.batch_offset = grp.batch.size();
+                g.batch_offset = grp.size();
                 grp.batch.insert(grp.batch.end(), g.batch.begin(), g.batch.end());
+                grp.raw_batch.insert(grp.raw_batch.end(), g.raw_batch.begin(), g.raw_batch.end());
             }
         }
     };
 
     auto launch = [&](Group& grp) {
-        if (grp.batch.empty()) { grp.in_flight = false; return; }
-        grp.value.resize(grp.batch.size());
-        grp.policy.resize(grp.batch.size() * 362);
+        if (grp.size() == 0) { grp.in_flight = false; return; }
+        grp.value.resize(grp.size());
+        grp.policy.resize(grp.size() * 362);
+        if (raw_mode) grp.legal.resize(grp.size() * 361);
         ++rounds;
-        positions += (int64_t)grp.batch.size();
+        positions += (int64_t)grp.size();
         grp.in_flight = true;
-        grp.pending = std::async(std::launch::async, [&grp, predictor, ctx, &eval_ns] {
+        grp.pending = std::async(std::launch::async, [&grp, predictor, raw_predictor, ctx, &eval_ns] {
             auto t0 = std::chrono::steady_clock::now();
-            int32_t r = predictor(ctx, grp.batch.data(), (int32_t)grp.batch.size(), grp.value.data(), grp.policy.data());
+            int32_t r = raw_predictor
+                ? raw_predictor(ctx, grp.raw_batch.data(), (int32_t)grp.raw_batch.size(), grp.value.data(), grp.policy.data(), grp.legal.data())
+                : predictor(ctx, grp.batch.data(), (int32_t)grp.batch.size(), grp.value.data(), grp.policy.data());
             eval_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
             return r;
         });
@@ -514,6 +526,57 @@ int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_co
         sgf_out[n] = 0;
     }
     return rc;
+}
+
+int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
+                        char* sgf_out, int64_t sgf_capacity) {
+    return selfplay_impl(predictor, nullptr, ctx, config, stats, sgf_out, sgf_capacity);
+}
+
+int32_t dg_selfplay_run_raw(dg_predict_raw_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
+                            char* sgf_out, int64_t sgf_capacity) {
+    return selfplay_impl(nullptr, predictor, ctx, config, stats, sgf_out, sgf_capacity);
+}
+
+int32_t dg_engine_predict_raw(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy, uint8_t* legal) {
+    dg_engine* e = static_cast<dg_engine*>(engine);
+    const int32_t chunk = dg_engine_max_batch(e);
+    if (chunk <= 0) return DG_ERR_INVALID_ARGUMENT;
+    for (int32_t at = 0; at < n; at += chunk) {
+        int32_t m = n - at < chunk ? n - at : chunk;
+        int32_t rc = dg_engine_forward_raw(e, positions + at, m, value + at, policy + (size_t)at * 362, legal + (size_t)at * 361);
+        if (rc) return rc;
+    }
+    return DG_OK;
+}
+
+int32_t dg_mcts_predict_raw(dg_predict_raw_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
+                            const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
+                            int64_t* evals_out) {
+    if (!predictor || !options || !board) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
+    SearchTask task;
+    task.start(*reinterpret_cast<const Board*>(board), color, convert(options), N(starting_tree), options->seed);
+    std::vector<dg_raw_position> batch;
+    std::vector<uint16_t> value, policy;
+    std::vector<uint8_t> legal;
+    for (;;) {
+        batch.clear();
+        int n = task.emit(nullptr, &batch);
+        if (n == 0) break;
+        value.resize(n);
+        policy.resize((size_t)n * 362);
+        legal.resize((size_t)n * 361);
+        int32_t rc = predictor(ctx, batch.data(), n, value.data(), policy.data(), legal.data());
+        if (rc) return rc;
+        task.absorb(value.data(), policy.data(), legal.data());
+    }
+    if (value_out) *value_out = task.value();
+    if (index_out) *index_out = task.index();
+    if (evals_out) *evals_out = task.evals();
+    Node* root = task.take_root();
+    if (tree_out) *tree_out = reinterpret_cast<dg_tree*>(root);
+    else delete root;
+    return DG_OK;
 }
 
 }  // extern "C"

@@ -129,18 +129,28 @@ class SearchTask {
     bool policy_only() const { return opt_.policy_only; }
     const float* root_policy() const { return root_policy_; }
 
-    // Appends this round's leaf positions to `out` and returns how many; 0 with done() == true ends the search.
-    int emit(std::vector<dg_packed_position>& out) {
+    // Appends this round's leaf positions and returns how many; 0 with done() == true ends the search.
+    // Exactly one of `packed` / `raw` is given: compact feature planes computed here on the host, or raw positions
+    // whose planes and legal moves the device derives (csrc/features.cu) -- then absorb() receives the legal masks.
+    int emit(std::vector<dg_packed_position>* packed, std::vector<dg_raw_position>* raw = nullptr) {
         if (phase_ == DONE) return 0;
         if (phase_ == ROOT) {
-            uint8_t legal[N_POINTS];
-            size_t at = out.size();
-            out.resize(at + 8);
-            for (int t = 0; t < 8; ++t) {
-                features_v1(board_, color_, t, out[at + t].planes, &out[at + t].k_bits, t == 0 ? legal : nullptr);
-                out[at + t].reserved = 0;
+            if (raw) {
+                size_t at = raw->size();
+                raw->resize(at + 8);
+                raw_position(board_, color_, 0, &(*raw)[at]);
+                for (int t = 1; t < 8; ++t) { (*raw)[at + t] = (*raw)[at]; (*raw)[at + t].symmetry = (uint8_t)t; }
+            } else {
+                uint8_t legal[N_POINTS];
+                size_t at = packed->size();
+                packed->resize(at + 8);
+                for (int t = 0; t < 8; ++t) {
+                    dg_packed_position& pos = (*packed)[at + t];
+                    features_v1(board_, color_, t, pos.planes, &pos.k_bits, t == 0 ? legal : nullptr);
+                    pos.reserved = 0;
+                }
+                root_plan_.build(board_, color_, opt_.search_kind, legal);
             }
-            root_plan_.build(board_, color_, opt_.search_kind, legal);
             n_pending_ = 8;
             return 8;
         }
@@ -155,23 +165,31 @@ class SearchTask {
             if (st == PROBE_NO_RESULT) break;
             p.to_move = opposite(p.trace.back().node->to_move);
             p.symmetry = next_leaf_symmetry();
-            uint8_t legal[N_POINTS];
-            out.emplace_back();
-            dg_packed_position& pos = out.back();
-            features_v1(p.board, p.to_move, p.symmetry, pos.planes, &pos.k_bits, legal);
-            pos.reserved = 0;
-            p.plan.build(p.board, p.to_move, opt_.search_kind, legal);
+            if (raw) {
+                raw->emplace_back();
+                raw_position(p.board, p.to_move, p.symmetry, &raw->back());
+            } else {
+                uint8_t legal[N_POINTS];
+                packed->emplace_back();
+                dg_packed_position& pos = packed->back();
+                features_v1(p.board, p.to_move, p.symmetry, pos.planes, &pos.k_bits, legal);
+                pos.reserved = 0;
+                p.plan.build(p.board, p.to_move, opt_.search_kind, legal);
+            }
             ++emitted;
         }
         n_pending_ = emitted;
         if (emitted == 0) finish();
         return emitted;
     }
+    int emit(std::vector<dg_packed_position>& out) { return emit(&out, nullptr); }
 
-    // Evaluations of the leaves of the last emit(), in the same order.
-    void absorb(const uint16_t* value, const uint16_t* policy /* [n][362] */) {
+    // Evaluations of the leaves of the last emit(), in the same order; `legal` ([n][361], identity orientation) is the
+    // device's legal-move mask in raw mode, null otherwise.
+    void absorb(const uint16_t* value, const uint16_t* policy /* [n][362] */, const uint8_t* legal = nullptr) {
         evals_ += n_pending_;
         if (phase_ == ROOT) {
+            if (legal) root_plan_.build(board_, color_, opt_.search_kind, legal);
             float prior[368], acc[368];
             for (int i = 0; i < 368; ++i) acc[i] = NEG_INF;
             for (int p = 0; p <= N_POINTS; ++p) if (root_plan_.candidate[p]) acc[p] = 0.0f;
@@ -209,6 +227,7 @@ class SearchTask {
         float prior[368];
         for (int k = 0; k < n_pending_; ++k) {               // pool/worker_thread.rs:88-98
             Pending& p = pending_[k];
+            if (legal) p.plan.build(p.board, p.to_move, opt_.search_kind, legal + (size_t)k * N_POINTS);
             p.plan.apply(policy + (size_t)k * 362, p.symmetry, 1.0f, prior);
             float winrate = 0.5f * f16_to_f32(value[k]) + 0.5f;
             insert(p.trace, p.to_move, winrate, prior);

@@ -16,6 +16,7 @@ import numpy as np
 from . import go, nn
 
 PREDICT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p)
+PREDICT_RAW_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 class _SearchOptions(C.Structure):
@@ -43,6 +44,10 @@ _P, _I = C.c_void_p, C.c_int32
 ABI = {
     "dg_engine_predict": (_I, [_P, _P, _I, _P, _P]),
     "dg_random_predict": (_I, [_P, _P, _I, _P, _P]),
+    "dg_engine_predict_raw": (_I, [_P, _P, _I, _P, _P, _P]),
+    "dg_mcts_predict_raw": (_I, [PREDICT_RAW_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "dg_selfplay_run_raw": (_I, [PREDICT_RAW_FN, _P, C.POINTER(_SelfPlayConfig), C.POINTER(_SelfPlayStats), _P, C.c_int64]),
     "dg_mcts_predict": (_I, [PREDICT_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
                              C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "dg_tree_free": (None, [_P]), "dg_tree_forward": (_P, [_P, _I]), "dg_tree_disqualify": (None, [_P, _I]),
@@ -87,6 +92,16 @@ class EnginePredictor:
     def __init__(self, network: "nn.Network"):
         self.network = network
         self.fn = C.cast(lib().dg_engine_predict, PREDICT_FN)
+        self.ctx = network._handle
+
+
+class EngineRawPredictor:
+    """The engine fed with raw positions: feature planes and legal moves are computed on the device."""
+    raw = True
+
+    def __init__(self, network: "nn.Network"):
+        self.network = network
+        self.fn = C.cast(lib().dg_engine_predict_raw, PREDICT_RAW_FN)
         self.ctx = network._handle
 
 
@@ -145,7 +160,7 @@ class Tree:
 
 
 def _fn_ctx(predictor):
-    if isinstance(predictor, (EnginePredictor, RandomPredictor)):
+    if isinstance(predictor, (EnginePredictor, EngineRawPredictor, RandomPredictor)):
         return predictor.fn, predictor.ctx
     return predictor, None
 
@@ -169,8 +184,9 @@ def predict(predictor, board: "go.Board", color: int, *, search: int = go.STANDA
         opt.leaf_symmetries = ls.ctypes.data
         opt.n_leaf_symmetries = len(ls)
     value, index, tree, evals = C.c_float(), C.c_int32(), C.c_void_p(), C.c_int64()
-    rc = lib().dg_mcts_predict(fn, ctx, C.byref(opt), starting_tree.release() if starting_tree is not None else None,
-                               board._h, color, C.byref(value), C.byref(index), C.byref(tree), C.byref(evals))
+    call = lib().dg_mcts_predict_raw if getattr(predictor, "raw", False) else lib().dg_mcts_predict
+    rc = call(fn, ctx, C.byref(opt), starting_tree.release() if starting_tree is not None else None,
+              board._h, color, C.byref(value), C.byref(index), C.byref(tree), C.byref(evals))
     if rc:
         raise nn.Error(rc, "predictor failed")
     return value.value, index.value, Tree(tree.value), evals.value
@@ -186,7 +202,8 @@ def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout:
                           num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds)
     stats = _SelfPlayStats()
     buf = C.create_string_buffer(sgf_capacity)
-    rc = lib().dg_selfplay_run(fn, ctx, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
+    run = lib().dg_selfplay_run_raw if getattr(predictor, "raw", False) else lib().dg_selfplay_run
+    rc = run(fn, ctx, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
     if rc:
         raise nn.Error(rc, "self-play failed")
     out = {name: getattr(stats, name) for name, _ in _SelfPlayStats._fields_}

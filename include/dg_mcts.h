@@ -27,6 +27,14 @@ typedef int32_t (*dg_predict_fn)(void* ctx, const dg_packed_position* positions,
 /* The predictor that is the product: ctx = dg_engine*, evaluation through dg_engine_forward_packed. */
 int32_t dg_engine_predict(void* engine, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
 
+/* The same over raw positions: the predictor derives the feature planes itself and also returns the legal-move mask
+ * of every position ([n][361], `Board::is_valid(to_move, .)`), which the search needs for the prior. */
+typedef int32_t (*dg_predict_raw_fn)(void* ctx, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy,
+                                     uint8_t* legal);
+/* ctx = dg_engine*, evaluation through dg_engine_forward_raw (feature planes and legal moves computed on the device). */
+int32_t dg_engine_predict_raw(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy,
+                              uint8_t* legal);
+
 /* `RandomPredictor` (predictors/random.rs:30-59) as a deterministic function of the position; ctx = NULL or a
  * uint64_t* salt.  No device involved: it measures the host half of self-play alone. */
 int32_t dg_random_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
@@ -53,6 +61,10 @@ typedef struct dg_tree dg_tree;   /* `tree::Node` */
 int32_t  dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
                          const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                          int64_t* evals_out);
+/* The same search with a raw-position predictor: identical trees, the host skips the feature planes. */
+int32_t  dg_mcts_predict_raw(dg_predict_raw_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
+                             const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
+                             int64_t* evals_out);
 void     dg_tree_free(dg_tree* tree);
 dg_tree* dg_tree_forward(dg_tree* tree, int32_t index);            /* Node::forward (tree.rs:1198-1225); consumes `tree` */
 void     dg_tree_disqualify(dg_tree* tree, int32_t index);         /* Node::disqualify (tree.rs:1296-1301) */
@@ -89,6 +101,10 @@ typedef struct dg_selfplay_stats {
  * appended to `sgf_out` (NUL-terminated, truncated at sgf_capacity; may be NULL).  Returns 0 or the predictor's error. */
 int32_t  dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                          char* sgf_out, int64_t sgf_capacity);
+
+/* The same with a raw-position predictor (dg_engine_predict_raw): same games for the same seed. */
+int32_t  dg_selfplay_run_raw(dg_predict_raw_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
+                             char* sgf_out, int64_t sgf_capacity);
 
 #ifdef __cplusplus
 }

@@ -64,3 +64,25 @@ def test_self_play_on_engine_is_reproducible(engine):
     b, sgf_b = pm.self_play(pm.EnginePredictor(engine), num_threads=4, **kw)
     assert a["digest"] == b["digest"] and sorted(sgf_a) == sorted(sgf_b)
     assert a["games_finished"] == 4 and a["moves"] == 64 and a["evals"] == b["evals"] > 0
+
+
+def test_device_features_give_the_same_search_and_games(engine):
+    """Raw positions (planes + legal moves derived on the device) vs host feature planes: identical trees, identical games."""
+    colors, moves, komi = ogo.load_games()[13]
+    po = pgo.Board(komi)
+    for c, m in zip(colors[:70], moves[:70]):
+        if m < 361:
+            po.place_index(int(c), int(m))
+    color = po.to_move()
+    for kw in (dict(deterministic=True, num_rollout=120, probes_per_round=4, leaf_symmetries=[2, 0, 7, 5]),
+               dict(search=1, deterministic=False, num_rollout=80, probes_per_round=2, seed=9)):
+        v1, i1, t1, e1 = pm.predict(pm.EnginePredictor(engine), po, color, **kw)
+        v2, i2, t2, e2 = pm.predict(pm.EngineRawPredictor(engine), po, color, **kw)
+        c1, val1, p1 = t1.children()
+        c2, val2, p2 = t2.children()
+        assert (c1 == c2).all() and i1 == i2 and e1 == e2 and v1 == v2
+        assert (p1.view(np.uint32) == p2.view(np.uint32)).all() and (val1.view(np.uint32) == val2.view(np.uint32)).all()
+    kw = dict(num_games=4, num_parallel=4, num_rollout=40, probes_per_round=4, max_plies=24, seed=11, num_threads=4)
+    a, sgf_a = pm.self_play(pm.EnginePredictor(engine), **kw)
+    b, sgf_b = pm.self_play(pm.EngineRawPredictor(engine), **kw)
+    assert a["digest"] == b["digest"] and sorted(sgf_a) == sorted(sgf_b) and a["evals"] == b["evals"]

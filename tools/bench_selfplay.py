@@ -22,10 +22,11 @@ sys.path.insert(0, ROOT)
 
 
 def sample(net, *, games: int, parallel: int, rollouts: int, probes: int, seconds: float, threads: int, seed: int,
-           ex_it: bool = False):
+           ex_it: bool = False, device_features: bool = True):
     """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics."""
     from dream_go_b200 import mcts
-    st, sgf = mcts.self_play(mcts.EnginePredictor(net), num_games=games, num_parallel=parallel, num_rollout=rollouts,
+    predictor = mcts.EngineRawPredictor(net) if device_features else mcts.EnginePredictor(net)
+    st, sgf = mcts.self_play(predictor, num_games=games, num_parallel=parallel, num_rollout=rollouts,
                              probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=rollouts, seed=seed,
                              max_seconds=seconds)
     return st, sgf
@@ -42,6 +43,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=9)
     ap.add_argument("--ex-it", action="store_true")
     ap.add_argument("--host-only", action="store_true", help="RandomPredictor instead of the engine (no GPU needed)")
+    ap.add_argument("--host-features", action="store_true",
+                    help="compute the feature planes on the host (compact positions) instead of on the device (raw positions)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -59,7 +62,7 @@ def main():
             "config": {"workload": f"--self-play {args.games} --num-rollout {args.rollouts}, {args.parallel} concurrent games per GPU"
                                    + (" --ex-it" if args.ex_it else ""),
                        "sample": f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-ply cap)",
-                       "probes_per_round": args.probes, "host_threads_per_gpu": threads, "host_cores": cores,
+                       "probes_per_round": args.probes, "feature_planes": "host" if args.host_features else "device (csrc/features.cu)", "host_threads_per_gpu": threads, "host_cores": cores,
                        "weights": f"{args.blocks} blocks x 128 filters, seeded random init", "data": "synthetic"},
             "host_only": {"evals_per_s": host["evals"] / host["seconds"], "moves_per_s": host["moves"] / host["seconds"],
                           "mean_batch": host["mean_batch"], "predictor": "RandomPredictor (no device)"}}
@@ -76,7 +79,8 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
-                         seconds=args.seconds, threads=threads, seed=20261017 + rank, ex_it=args.ex_it)
+                         seconds=args.seconds, threads=threads, seed=20261017 + rank, ex_it=args.ex_it,
+                         device_features=not args.host_features)
         wall = time.perf_counter() - t0
         vals = [st["moves"], st["evals"], st["games_finished"], st["seconds"], st["eval_seconds"], st["rounds"]]
         if dist is not None:
