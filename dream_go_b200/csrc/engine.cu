@@ -36,6 +36,7 @@ constexpr int kHeadChan = 16;
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_done = nullptr;    // blocking-sync event (DG_FLAG_BLOCKING_SYNC)
     uint8_t* d_in = nullptr;          // raw NHWC features or compact positions of the current batch
     __half *feat = nullptr, *x = nullptr, *y = nullptr;
     __half *h = nullptr;               // [row][16] head-conv output of the debug direct path only
@@ -154,6 +155,7 @@ int32_t create_workspace(dg_engine* e, Workspace& w) {
     DG_CUDA(e, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     DG_CUDA(e, cudaEventCreate(&w.ev0));
     DG_CUDA(e, cudaEventCreate(&w.ev1));
+    DG_CUDA(e, cudaEventCreateWithFlags(&w.ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
     DG_CUDA(e, cudaMalloc(&w.d_in, static_cast<size_t>(mb) * kFeatBytes));
     DG_CUDA(e, cudaMalloc(&w.feat, rows * 64 * 2));
     DG_CUDA(e, cudaMalloc(&w.x, rows * kChan * 2));
@@ -187,6 +189,7 @@ void destroy_workspace(Workspace& w) {
     if (w.stream) cudaStreamDestroy(w.stream);
     if (w.ev0) cudaEventDestroy(w.ev0);
     if (w.ev1) cudaEventDestroy(w.ev1);
+    if (w.ev_done) cudaEventDestroy(w.ev_done);
     cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
     cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done); cudaFree(w.pbuf); cudaFree(w.vbuf); cudaFree(w.part);
     cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value); cudaFreeHost(w.h_legal);
@@ -426,6 +429,14 @@ int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMa
     return DG_OK;
 }
 
+// Waits for everything enqueued on the workspace's stream.  With DG_FLAG_BLOCKING_SYNC the calling thread sleeps on an
+// event instead of spinning in the driver: self-play runs as many host threads as cores and a spinning waiter steals one.
+inline cudaError_t wait_stream(dg_engine* e, Workspace& w) {
+    if (!(e->cfg.flags & DG_FLAG_BLOCKING_SYNC)) return cudaStreamSynchronize(w.stream);
+    cudaError_t rc = cudaEventRecord(w.ev_done, w.stream);
+    return rc != cudaSuccess ? rc : cudaEventSynchronize(w.ev_done);
+}
+
 // Raw-position path: d_in (max_batch x 23,104 B) holds [raw positions | compact planes | legal masks].
 inline uint8_t* raw_planes(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 512; }
 inline uint8_t* raw_legal(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 2048; }
@@ -521,7 +532,7 @@ int32_t forward_impl(dg_engine* e, const void* input, size_t bytes_per_pos, int 
     const bool pv = is_pinned(value_out), pp = is_pinned(policy_out);
     DG_CUDA(e, cudaMemcpyAsync(pv ? static_cast<void*>(value_out) : w.h_value, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream));
     DG_CUDA(e, cudaMemcpyAsync(pp ? static_cast<void*>(policy_out) : w.h_policy, w.d_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2, cudaMemcpyDeviceToHost, w.stream));
-    DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    DG_CUDA(e, wait_stream(e, w));
     if (!pv) memcpy(value_out, w.h_value, static_cast<size_t>(batch) * 2);
     if (!pp) memcpy(policy_out, w.h_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2);
     return DG_OK;
@@ -688,7 +699,7 @@ static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t 
     }
     if (planes_out)
         DG_CUDA(e, cudaMemcpyAsync(planes_out, raw_planes(e, w), sizeof(dg_packed_position) * static_cast<size_t>(batch), cudaMemcpyDeviceToHost, w.stream));
-    DG_CUDA(e, cudaStreamSynchronize(w.stream));
+    DG_CUDA(e, wait_stream(e, w));
     memcpy(legal_out, w.h_legal, static_cast<size_t>(batch) * 361);
     if (network) {
         memcpy(value_out, w.h_value, static_cast<size_t>(batch) * 2);

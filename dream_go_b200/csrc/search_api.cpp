@@ -337,7 +337,12 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     d.games = std::vector<Game>(n_slots);
     for (Game& g : d.games) d.start_game(g);
 
-    const int n_groups = n_slots >= 2 ? 2 : 1;
+    // games alternate in groups: while the device evaluates one group's leaves the host works on the others
+    int want_groups = 4;
+    if (const char* env = getenv("DG_SELFPLAY_GROUPS")) want_groups = atoi(env);
+    if (want_groups < 1) want_groups = 1;
+    if (want_groups > 8) want_groups = 8;
+    const int n_groups = std::min(want_groups, n_slots);
     struct Group {
         std::vector<int> slots;
         std::vector<dg_packed_position> batch;
@@ -347,7 +352,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         std::future<int32_t> pending;
         size_t size() const { return batch.size() + raw_batch.size(); }
         bool in_flight = false;
-    } groups[2];
+    } groups[8];
     for (int i = 0; i < n_slots; ++i) groups[i % n_groups].slots.push_back(i);
 
     auto t_start = std::chrono::steady_clock::now();

@@ -32,6 +32,7 @@ FLAG_DEBUG_DIRECT_CONV = 0x1
 FLAG_NO_PDL = 0x2
 FLAG_LAYERWISE = 0x4
 FLAG_NO_ROTATE = 0x8
+FLAG_BLOCKING_SYNC = 0x10
 
 
 class Error(Exception):

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=9)
     ap.add_argument("--ex-it", action="store_true")
     ap.add_argument("--host-only", action="store_true", help="RandomPredictor instead of the engine (no GPU needed)")
+    ap.add_argument("--blocking-sync", action="store_true", help="blocking engine calls sleep on an event instead of spinning in the driver")
     ap.add_argument("--host-features", action="store_true",
                     help="compute the feature planes on the host (compact positions) instead of on the device (raw positions)")
     args = ap.parse_args()
@@ -74,7 +75,8 @@ def main():
             torch.cuda.set_device(local_rank)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         tensors = weights.synthetic_network(seed=20261017, num_blocks=args.blocks)
-        net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=512, num_workspaces=2)
+        net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=512, num_workspaces=8,
+                                      flags=nn.FLAG_BLOCKING_SYNC if args.blocking_sync else 0)
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
