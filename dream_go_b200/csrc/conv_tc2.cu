@@ -318,7 +318,7 @@ cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUte
 //   * the unit -> pair assignment rotates by `rot` pairs per layer so that the pairs that get the
 //     extra (6th) unit differ from layer to layer.
 // The grid must be fully co-resident (<= one CTA per SM, cooperative launch).
-constexpr int kTowerSmem = t2::Smem<2>::kBarOff + 256 + 4 * 512 + 1024;   // + barriers + bias[2][2][128] + alignment slack
+constexpr int kTowerSmem = t2::Smem<2>::kBarOff + 512 + 4 * 512 + 1024;   // + barriers + bias[2][2][128] + alignment slack
 
 template <int UNUSED = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2::kThreads, 1)
@@ -335,11 +335,11 @@ tower_kernel(const __grid_constant__ TowerParams p) {
     uint64_t* a_empty = bars + kStages;      // [kStages]
     uint64_t* acc_full = bars + 2 * kStages; // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
-    uint64_t* w_full = acc_empty + 2;        // [2] per k-half
-    uint64_t* w_free = w_full + 2;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    float* bias_s = reinterpret_cast<float*>(bars + 32);      // [2 groups][2][128]
-    // barriers (256 B) + two bias buffers (1 KiB) follow the activation ring; see kTowerSmem
+    uint64_t* w_full = acc_empty + 2;        // [18] one per filter slab (tap, k-half): slab = tap * 2 + h
+    uint64_t* w_free = w_full + 18;          // [18]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+    float* bias_s = reinterpret_cast<float*>(bars + 64);      // [2 groups][2][128]
+    // barriers (512 B) + two bias buffers (1 KiB) follow the activation ring; see kTowerSmem
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -358,6 +358,8 @@ tower_kernel(const __grid_constant__ TowerParams p) {
         for (int i = 0; i < 2; i++) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 8);           // 4 warps of one epilogue group x 2 CTAs
+        }
+        for (int i = 0; i < 18; i++) {
             mbar_init(&w_full[i], 1);
             mbar_init(&w_free[i], 1);
         }
@@ -378,7 +380,6 @@ tower_kernel(const __grid_constant__ TowerParams p) {
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
         if (lane == 0) {
-            const uint32_t w_full0[2] = {mapa_shared(smem_u32(&w_full[0]), 0), mapa_shared(smem_u32(&w_full[1]), 0)};
             uint32_t a_full0[kStages];
             for (int i = 0; i < kStages; i++) a_full0[i] = mapa_shared(smem_u32(&a_full[i]), 0);
             int stage = 0;
@@ -388,11 +389,15 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                 const int nh = p.layer[l].nh;
                 const CUtensorMap* tm_w = &p.w[l];
                 const CUtensorMap* tm_a = &p.act[p.layer[l].in_map];
+                // slab by slab, in the order the MMAs consume them: a slab of layer l is fetched as soon as the last unit
+                // of layer l-1 is done with it, so the reload spreads over a whole unit time instead of two bursts
                 auto load_weights = [&](int h) {
-                    if (l > 0) mbar_wait(&w_free[h], (l - 1) & 1);      // layer l-1 no longer reads these slabs
-                    if (rank == 0) mbar_expect_tx(&w_full[h], 2 * kHalfBytes);
-                    for (int tap = 0; tap < 9; tap++)
-                        tma_load_2d_pair(w_s + (tap * 2 + h) * kSlab, tm_w, w_full0[h], h * 64, tap * 128 + rank * 64);
+                    for (int tap = 0; tap < 9; tap++) {
+                        const int s = tap * 2 + h;
+                        if (l > 0) mbar_wait(&w_free[s], (l - 1) & 1);      // layer l-1 no longer reads this slab
+                        if (rank == 0) mbar_expect_tx(&w_full[s], 2 * kSlab);
+                        tma_load_2d_pair(w_s + s * kSlab, tm_w, mapa_shared(smem_u32(&w_full[s]), 0), h * 64, tap * 128 + rank * 64);
+                    }
                 };
                 load_weights(0);
                 if (l == 0) { griddep_wait(); DG_TRACE(0); }
@@ -437,35 +442,63 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                     tc_fence_after();
                     if (lane == 0) DG_TRACE(1);
                     const uint32_t d_tmem = tmem_base + as * 128;
+                    const bool first = (u == u0);
+                    // In the first unit of a layer every tap waits for its own slab of the new filter bank; in the
+                    // last unit every tap hands its slab back as soon as its MMAs have retired.
+#define DG_TAP(H, T)                                                                                          \
+    do {                                                                                                      \
+        if (first) { mbar_wait(&w_full[(T) * 2 + (H)], wfull_phase[H]); tc_fence_after(); }                    \
+        if (elect_one()) {                                                                                    \
+            issue_half<2, H>(d_tmem, a_lo, w_lo, std::integer_sequence<int, (T) * 4, (T) * 4 + 1, (T) * 4 + 2, (T) * 4 + 3>{}); \
+            if (last) umma_commit_pair(&w_free[(T) * 2 + (H)], 3);                                             \
+        }                                                                                                     \
+        __syncwarp();                                                                                         \
+    } while (0)
+#define DG_TAPS(H) DG_TAP(H, 0); DG_TAP(H, 1); DG_TAP(H, 2); DG_TAP(H, 3); DG_TAP(H, 4); DG_TAP(H, 5); DG_TAP(H, 6); DG_TAP(H, 7); DG_TAP(H, 8)
                     // k-half 0
-                    if (u == u0) { mbar_wait(&w_full[0], wfull_phase[0]); wfull_phase[0] ^= 1; }
                     mbar_wait(&a_full[stage], phase);
                     tc_fence_after();
                     if (lane == 0) DG_TRACE(1);
-                    if (elect_one()) {
-                        issue_half<2, 0>(d_tmem, umma_desc_lo(smem_u32(a_s + stage * kStageBytes)), w_lo, std::make_integer_sequence<int, 36>{});
-                        umma_commit_pair(&a_empty[stage], 3);
-                        if (last) umma_commit_pair(&w_free[0], 3);
-                        if (nh == 1) {
-                            if (last) umma_commit_pair(&w_free[1], 3);
-                            umma_commit_pair(&acc_full[as], 3);
+                    {
+                        const uint32_t a_lo = umma_desc_lo(smem_u32(a_s + stage * kStageBytes));
+                        if (first || last) {
+                            DG_TAPS(0);
+                            if (first) wfull_phase[0] ^= 1;
+                        } else if (elect_one()) {
+                            issue_half<2, 0>(d_tmem, a_lo, w_lo, std::make_integer_sequence<int, 36>{});
                         }
+                        __syncwarp();
+                        if (elect_one()) {
+                            umma_commit_pair(&a_empty[stage], 3);
+                            if (nh == 1) {
+                                if (last)
+                                    for (int t = 0; t < 9; t++) umma_commit_pair(&w_free[t * 2 + 1], 3);
+                                umma_commit_pair(&acc_full[as], 3);
+                            }
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                     if (nh == 2) {   // k-half 1
-                        if (u == u0) { mbar_wait(&w_full[1], wfull_phase[1]); wfull_phase[1] ^= 1; }
                         mbar_wait(&a_full[stage], phase);
                         tc_fence_after();
+                        const uint32_t a_lo = umma_desc_lo(smem_u32(a_s + stage * kStageBytes));
+                        if (first || last) {
+                            DG_TAPS(1);
+                            if (first) wfull_phase[1] ^= 1;
+                        } else if (elect_one()) {
+                            issue_half<2, 1>(d_tmem, a_lo, w_lo, std::make_integer_sequence<int, 36>{});
+                        }
+                        __syncwarp();
                         if (elect_one()) {
-                            issue_half<2, 1>(d_tmem, umma_desc_lo(smem_u32(a_s + stage * kStageBytes)), w_lo, std::make_integer_sequence<int, 36>{});
                             umma_commit_pair(&a_empty[stage], 3);
-                            if (last) umma_commit_pair(&w_free[1], 3);
                             umma_commit_pair(&acc_full[as], 3);
                         }
                         __syncwarp();
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
+#undef DG_TAPS
+#undef DG_TAP
                     if (lane == 0) DG_TRACE(1);
                     if (++as == 2) { as = 0; aphase ^= 1; }
                 }
