@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <functional>
 #include <future>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -36,6 +37,7 @@ static SearchOptions convert(const dg_search_options* o) {
     s.leaf_symmetries = o->leaf_symmetries;
     s.n_leaf_symmetries = o->n_leaf_symmetries;
     s.choose_at = o->choose_at;
+    s.cache = reinterpret_cast<PredictionCache*>(o->cache);
     return s;
 }
 
@@ -117,6 +119,8 @@ struct Game {
     bool allow_pass = false;
     Rng rng;
     SearchTask task;
+    std::unique_ptr<PredictionCache> cache;
+    int64_t cache_hits = 0;
     std::string sgf;
     std::vector<uint16_t> moves;
     std::vector<dg_packed_position> batch;                       // this round's leaves (host feature planes) ...
@@ -151,7 +155,7 @@ struct Driver {
     int64_t started = 0, finished = 0;
     std::string sgf_all;
     uint64_t digest = 0;
-    int64_t total_moves = 0, total_evals = 0, total_searches = 0;
+    int64_t total_moves = 0, total_evals = 0, total_searches = 0, total_cache_hits = 0;
 
     void start_game(Game& g) {
         g.clear_trees();
@@ -167,6 +171,7 @@ struct Driver {
         g.mode = Game::IDLE;
         g.sgf.clear();
         g.moves.clear();
+        g.cache.reset(cfg.cache_capacity > 0 ? new PredictionCache((size_t)cfg.cache_capacity) : nullptr);
     }
 
     void finish_game(Game& g) {                                  // game_result.rs:23-43 (Ended)
@@ -187,6 +192,7 @@ struct Driver {
         total_moves += g.n_moves;
         total_evals += g.evals;
         total_searches += g.searches;
+        if (g.cache) { total_cache_hits += g.cache->hits; g.cache.reset(); }
         g.n_moves = g.evals = g.searches = 0;
         g.active = false;
         g.clear_trees();
@@ -203,6 +209,7 @@ struct Driver {
         opt.temperature = cfg.temperature;
         opt.num_rollout = ex_it ? cfg.num_ex_it_rollout : p.num_rollout(cfg.num_rollout);
         opt.policy_only = !ex_it && opt.num_rollout <= 1;
+        opt.cache = g.cache.get();
         Node* tree = p.root;
         p.root = nullptr;
         if (tree && !g.allow_pass) tree->disqualify(PASS);
@@ -301,6 +308,15 @@ int32_t dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_opti
     if (tree_out) *tree_out = reinterpret_cast<dg_tree*>(root);
     else delete root;
     return DG_OK;
+}
+
+dg_cache* dg_cache_new(int32_t capacity) { return reinterpret_cast<dg_cache*>(new PredictionCache(capacity > 0 ? (size_t)capacity : 0)); }
+void dg_cache_free(dg_cache* cache) { delete reinterpret_cast<PredictionCache*>(cache); }
+void dg_cache_stats(const dg_cache* cache, int64_t* hits, int64_t* misses, int64_t* size) {
+    const PredictionCache* c = reinterpret_cast<const PredictionCache*>(cache);
+    if (hits) *hits = c->hits;
+    if (misses) *misses = c->misses;
+    if (size) *size = (int64_t)c->size();
 }
 
 void dg_tree_free(dg_tree* tree) { delete N(tree); }
@@ -513,7 +529,10 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     for (int gi = 0; gi < n_groups; ++gi) if (groups[gi].in_flight) groups[gi].pending.wait();
 
     // account for the games that were cut off by max_seconds
-    for (Game& g : d.games) { d.total_moves += g.n_moves; d.total_evals += g.evals; d.total_searches += g.searches; }
+    for (Game& g : d.games) {
+        d.total_moves += g.n_moves; d.total_evals += g.evals; d.total_searches += g.searches;
+        if (g.cache) d.total_cache_hits += g.cache->hits;
+    }
     if (stats) {
         stats->games_finished = d.finished;
         stats->moves = d.total_moves;
@@ -524,6 +543,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         stats->eval_seconds = (double)eval_ns.load() * 1e-9;
         stats->mean_batch = rounds ? (double)positions / (double)rounds : 0.0;
         stats->digest = d.digest;
+        stats->cache_hits = d.total_cache_hits;
     }
     if (sgf_out && sgf_capacity > 0) {
         size_t n = std::min<size_t>(d.sgf_all.size(), (size_t)sgf_capacity - 1);

@@ -9,6 +9,7 @@
 //   DONE     move chosen (Node::best, lib.rs:190-194)
 #pragma once
 
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dg_engine.h"
@@ -31,6 +32,86 @@ inline float f16_to_f32(uint16_t h) {
     memcpy(&f, &x, 4);
     return f;
 }
+
+// Transposition table of network evaluations: `NnPredictor::{fetch, cache}` + `LruCache` (predictors/nn.rs:29-82,
+// lru_cache.rs).  Key = (zobrist hash, colour to move); the value is kept in IDENTITY orientation
+// (`cache` stores with_transform(response, symmetry.inverse()), `fetch` returns with_transform(entry, symmetry),
+// predictor.rs:30-44), so one evaluation answers the position under every symmetry.  `get` makes the entry the most
+// recent one, `insert` of an existing key does nothing, the least recent entry is dropped beyond `capacity`.
+// One table per game (the reference shares one behind a mutex; per-game tables keep the games reproducible).
+class PredictionCache {
+  public:
+    struct Entry {
+        uint64_t hash;
+        uint16_t value;
+        uint8_t to_move;
+        uint16_t policy[362];
+        int32_t prev, next;
+    };
+    explicit PredictionCache(size_t capacity) : capacity_(capacity) {}
+    size_t size() const { return map_.size(); }
+    long hits = 0, misses = 0;
+
+    const Entry* get(uint64_t hash, int to_move) {
+        auto it = map_.find(Key{hash, (uint8_t)to_move});
+        if (it == map_.end()) { ++misses; return nullptr; }
+        ++hits;
+        detach(it->second);
+        attach(it->second);
+        return &pool_[it->second];
+    }
+    // `policy` is in orientation `symmetry`; it is stored un-transformed
+    void insert(uint64_t hash, int to_move, int symmetry, uint16_t value, const uint16_t* policy) {
+        if (capacity_ == 0) return;
+        Key key{hash, (uint8_t)to_move};
+        if (map_.count(key)) return;
+        int32_t idx;
+        if (!free_.empty()) { idx = free_.back(); free_.pop_back(); }
+        else { idx = (int32_t)pool_.size(); pool_.emplace_back(); }
+        Entry& e = pool_[idx];
+        e.hash = hash;
+        e.to_move = (uint8_t)to_move;
+        e.value = value;
+        const uint16_t* inv = tables().sym[tables().sym_inverse[symmetry]];
+        for (int i = 0; i < N_POINTS; ++i) e.policy[inv[i]] = policy[i];     // with_transform(response, symmetry.inverse())
+        e.policy[PASS] = policy[PASS];
+        attach(idx);
+        map_.emplace(key, idx);
+        if (map_.size() > capacity_) {
+            int32_t t = tail_;
+            detach(t);
+            map_.erase(Key{pool_[t].hash, pool_[t].to_move});
+            free_.push_back(t);
+        }
+    }
+
+  private:
+    struct Key {
+        uint64_t hash;
+        uint8_t to_move;
+        bool operator==(const Key& o) const { return hash == o.hash && to_move == o.to_move; }
+    };
+    struct KeyHash { size_t operator()(const Key& k) const { return (size_t)(k.hash * 0x9e3779b97f4a7c15ull) ^ k.to_move; } };
+    void attach(int32_t i) {
+        pool_[i].prev = -1;
+        pool_[i].next = head_;
+        if (head_ >= 0) pool_[head_].prev = i;
+        head_ = i;
+        if (tail_ < 0) tail_ = i;
+    }
+    void detach(int32_t i) {
+        Entry& e = pool_[i];
+        if (e.prev >= 0) pool_[e.prev].next = e.next;
+        if (e.next >= 0) pool_[e.next].prev = e.prev;
+        if (head_ == i) head_ = e.next;
+        if (tail_ == i) tail_ = e.prev;
+    }
+    size_t capacity_;
+    std::vector<Entry> pool_;
+    std::vector<int32_t> free_;
+    std::unordered_map<Key, int32_t, KeyHash> map_;
+    int32_t head_ = -1, tail_ = -1;
+};
 
 // What create_initial_policy (pool/policy_helper.rs:28-75) derives from the board alone; computed when the leaf is
 // emitted (the feature pass already produced the legal mask), applied when its evaluation arrives.
@@ -91,6 +172,7 @@ struct SearchOptions {
     int n_leaf_symmetries = 0;
     double choose_at = -1.0;                   // injected uniform number for the stochastic move choice
     bool policy_only = false;                  // no tree: play from the averaged policy (self_play.rs:360-396)
+    PredictionCache* cache = nullptr;          // transposition table (predictors/nn.rs:29-82); null = none
 };
 
 class SearchTask {
@@ -115,6 +197,7 @@ class SearchTask {
         n_pending_ = 0;
         leaf_counter_ = 0;
         evals_ = 0;
+        cache_inserts_ = 0;
         value_ = 0.5f;
         index_ = PASS;
     }
@@ -124,6 +207,7 @@ class SearchTask {
     float value() const { return value_; }
     int index() const { return index_; }
     long evals() const { return evals_; }
+    long cache_inserts() const { return cache_inserts_; }
     const Node* root() const { return root_; }
     Node* take_root() { Node* r = root_; root_ = nullptr; return r; }
     bool policy_only() const { return opt_.policy_only; }
@@ -134,6 +218,28 @@ class SearchTask {
     // whose planes and legal moves the device derives (csrc/features.cu) -- then absorb() receives the legal masks.
     int emit(std::vector<dg_packed_position>* packed, std::vector<dg_raw_position>* raw = nullptr) {
         if (phase_ == DONE) return 0;
+        if (phase_ == ROOT && opt_.cache) {
+            // full_forward (lib.rs:97-111): a cached evaluation answers all 8 symmetries without the network
+            const PredictionCache::Entry* hit = opt_.cache->get(board_.hash, color_);
+            if (hit) opt_.cache->hits += 7; else opt_.cache->misses += 7;      // the reference asks once per symmetry
+            if (hit) {
+                uint8_t legal[N_POINTS];
+                for (int p = 0; p < N_POINTS; ++p) legal[p] = (uint8_t)board_.is_valid(color_, p);
+                root_plan_.build(board_, color_, opt_.search_kind, legal);
+                uint16_t value[8], policy[8 * 362];
+                const Tables& T = tables();
+                for (int t = 0; t < 8; ++t) {              // Prediction::with_transform(entry, t)
+                    value[t] = hit->value;
+                    for (int i = 0; i < N_POINTS; ++i) policy[t * 362 + T.sym[t][i]] = hit->policy[i];
+                    policy[t * 362 + PASS] = hit->policy[PASS];
+                }
+                n_pending_ = 0;
+                root_cached_ = true;
+                absorb(value, policy, nullptr);
+                root_cached_ = false;
+                if (phase_ == DONE) return 0;
+            }
+        }
         if (phase_ == ROOT) {
             if (raw) {
                 size_t at = raw->size();
@@ -154,7 +260,7 @@ class SearchTask {
             n_pending_ = 8;
             return 8;
         }
-        int emitted = 0;
+        int emitted = 0, hits_this_round = 0;
         if (pending_.size() < (size_t)opt_.probes_per_round) pending_.resize(opt_.probes_per_round);
         while (emitted < opt_.probes_per_round) {
             if (is_done(*root_, opt_.num_rollout)) break;
@@ -165,6 +271,19 @@ class SearchTask {
             if (st == PROBE_NO_RESULT) break;
             p.to_move = opposite(p.trace.back().node->to_move);
             p.symmetry = next_leaf_symmetry();
+            if (opt_.cache) {                                // Event::predict (pool/event.rs:50-52): fetch before extracting
+                if (const PredictionCache::Entry* hit = opt_.cache->get(p.board.hash, p.to_move)) {
+                    uint8_t legal[N_POINTS];
+                    for (int q = 0; q < N_POINTS; ++q) legal[q] = (uint8_t)p.board.is_valid(p.to_move, q);
+                    p.plan.build(p.board, p.to_move, opt_.search_kind, legal);
+                    float prior[368];
+                    p.plan.apply(hit->policy, 0, 1.0f, prior);   // the entry is in identity orientation
+                    insert(p.trace, p.to_move, 0.5f * f16_to_f32(hit->value) + 0.5f, prior);
+                    ++cache_inserts_;
+                    if (++hits_this_round > 4 * opt_.probes_per_round) break;   // leave the round eventually
+                    continue;
+                }
+            }
             if (raw) {
                 raw->emplace_back();
                 raw_position(p.board, p.to_move, p.symmetry, &raw->back());
@@ -179,7 +298,10 @@ class SearchTask {
             ++emitted;
         }
         n_pending_ = emitted;
-        if (emitted == 0) finish();
+        if (emitted == 0) {
+            if (hits_this_round > 0 && !is_done(*root_, opt_.num_rollout)) return emit(packed, raw);   // only cache hits: go on
+            finish();
+        }
         return emitted;
     }
     int emit(std::vector<dg_packed_position>& out) { return emit(&out, nullptr); }
@@ -190,6 +312,8 @@ class SearchTask {
         evals_ += n_pending_;
         if (phase_ == ROOT) {
             if (legal) root_plan_.build(board_, color_, opt_.search_kind, legal);
+            if (opt_.cache && !root_cached_)                 // lib.rs:124-131: every new response is offered to the table
+                for (int t = 0; t < 8; ++t) opt_.cache->insert(board_.hash, color_, t, value[t], policy + (size_t)t * 362);
             float prior[368], acc[368];
             for (int i = 0; i < 368; ++i) acc[i] = NEG_INF;
             for (int p = 0; p <= N_POINTS; ++p) if (root_plan_.candidate[p]) acc[p] = 0.0f;
@@ -231,6 +355,7 @@ class SearchTask {
             p.plan.apply(policy + (size_t)k * 362, p.symmetry, 1.0f, prior);
             float winrate = 0.5f * f16_to_f32(value[k]) + 0.5f;
             insert(p.trace, p.to_move, winrate, prior);
+            if (opt_.cache) opt_.cache->insert(p.board.hash, p.to_move, p.symmetry, value[k], policy + (size_t)k * 362);   // worker_thread.rs:96
         }
         n_pending_ = 0;
     }
@@ -265,7 +390,8 @@ class SearchTask {
     PriorPlan root_plan_;
     std::vector<Pending> pending_;
     int n_pending_ = 0;
-    long leaf_counter_ = 0, evals_ = 0;
+    long leaf_counter_ = 0, evals_ = 0, cache_inserts_ = 0;
+    bool root_cached_ = false;
     float value_ = 0.5f, root_value_ = 0.5f;
     float root_policy_[362];
     int index_ = PASS;

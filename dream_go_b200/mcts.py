@@ -23,20 +23,21 @@ class _SearchOptions(C.Structure):
     _fields_ = [("search", C.c_int32), ("deterministic", C.c_int32), ("num_rollout", C.c_int32),
                 ("probes_per_round", C.c_int32), ("dirichlet_noise", C.c_float), ("temperature", C.c_float),
                 ("seed", C.c_uint64), ("noise", C.c_void_p), ("leaf_symmetries", C.c_void_p),
-                ("n_leaf_symmetries", C.c_int32), ("choose_at", C.c_double)]
+                ("n_leaf_symmetries", C.c_int32), ("choose_at", C.c_double), ("cache", C.c_void_p)]
 
 
 class _SelfPlayConfig(C.Structure):
     _fields_ = [("num_games", C.c_int32), ("num_parallel", C.c_int32), ("num_rollout", C.c_int32),
                 ("probes_per_round", C.c_int32), ("max_plies", C.c_int32), ("num_threads", C.c_int32),
                 ("ex_it", C.c_int32), ("num_ex_it_rollout", C.c_int32), ("dirichlet_noise", C.c_float),
-                ("temperature", C.c_float), ("seed", C.c_uint64), ("max_seconds", C.c_double)]
+                ("temperature", C.c_float), ("seed", C.c_uint64), ("max_seconds", C.c_double),
+                ("cache_capacity", C.c_int32), ("reserved", C.c_int32)]
 
 
 class _SelfPlayStats(C.Structure):
     _fields_ = [("games_finished", C.c_int64), ("moves", C.c_int64), ("evals", C.c_int64), ("rounds", C.c_int64),
                 ("searches", C.c_int64), ("seconds", C.c_double), ("eval_seconds", C.c_double),
-                ("mean_batch", C.c_double), ("digest", C.c_uint64)]
+                ("mean_batch", C.c_double), ("digest", C.c_uint64), ("cache_hits", C.c_int64)]
 
 
 _P, _I = C.c_void_p, C.c_int32
@@ -50,6 +51,8 @@ ABI = {
     "dg_selfplay_run_raw": (_I, [PREDICT_RAW_FN, _P, C.POINTER(_SelfPlayConfig), C.POINTER(_SelfPlayStats), _P, C.c_int64]),
     "dg_mcts_predict": (_I, [PREDICT_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
                              C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "dg_cache_new": (_P, [_I]), "dg_cache_free": (None, [_P]),
+    "dg_cache_stats": (None, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dg_tree_free": (None, [_P]), "dg_tree_forward": (_P, [_P, _I]), "dg_tree_disqualify": (None, [_P, _I]),
     "dg_tree_total_count": (_I, [_P]), "dg_tree_to_move": (_I, [_P]), "dg_tree_initial_value": (C.c_float, [_P]),
     "dg_tree_children": (None, [_P, _P, _P, _P]), "dg_tree_num_nodes": (C.c_int64, [_P]),
@@ -113,6 +116,23 @@ class RandomPredictor:
         self.ctx = None
 
 
+class Cache:
+    """Transposition table of evaluations (`NnPredictor`'s `LruCache`, predictors/nn.rs:29-82)."""
+
+    def __init__(self, capacity: int = 200_000):
+        self._h = lib().dg_cache_new(capacity)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().dg_cache_free(self._h)
+            self._h = None
+
+    def stats(self):
+        hits, misses, size = C.c_int64(), C.c_int64(), C.c_int64()
+        lib().dg_cache_stats(self._h, C.byref(hits), C.byref(misses), C.byref(size))
+        return {"hits": hits.value, "misses": misses.value, "size": size.value}
+
+
 class Tree:
     """`tree::Node` owned by the caller."""
 
@@ -168,11 +188,11 @@ def _fn_ctx(predictor):
 def predict(predictor, board: "go.Board", color: int, *, search: int = go.STANDARD_SEARCH, deterministic: bool = False,
             num_rollout: int = 800, probes_per_round: int = 1, starting_tree: Optional[Tree] = None, seed: int = 1,
             noise: Optional[np.ndarray] = None, dirichlet_noise: float = 0.25, temperature: float = 0.8,
-            leaf_symmetries=None, choose_at: float = -1.0):
+            leaf_symmetries=None, choose_at: float = -1.0, cache: Optional["Cache"] = None):
     """`dg_mcts::predict`.  Returns (value, index, Tree, evals)."""
     fn, ctx = _fn_ctx(predictor)
     opt = _SearchOptions(search, int(deterministic), num_rollout, probes_per_round, dirichlet_noise, temperature, seed,
-                         None, None, 0, choose_at)
+                         None, None, 0, choose_at, cache._h if cache is not None else None)
     keep = []
     if noise is not None:
         eta = np.ascontiguousarray(noise, np.float32)
@@ -195,11 +215,11 @@ def predict(predictor, board: "go.Board", color: int, *, search: int = go.STANDA
 def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout: int = 800, probes_per_round: int = 8,
               max_plies: int = 722, num_threads: int = 0, ex_it: bool = False, num_ex_it_rollout: int = 800,
               dirichlet_noise: float = 0.25, temperature: float = 0.8, seed: int = 1, max_seconds: float = 0.0,
-              sgf_capacity: int = 1 << 24):
+              cache_capacity: int = 0, sgf_capacity: int = 1 << 24):
     """`dg_mcts::self_play`: returns (stats dict, list of SGF records)."""
     fn, ctx = _fn_ctx(predictor)
     cfg = _SelfPlayConfig(num_games, num_parallel, num_rollout, probes_per_round, max_plies, num_threads, int(ex_it),
-                          num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds)
+                          num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds, cache_capacity, 0)
     stats = _SelfPlayStats()
     buf = C.create_string_buffer(sgf_capacity)
     run = lib().dg_selfplay_run_raw if getattr(predictor, "raw", False) else lib().dg_selfplay_run

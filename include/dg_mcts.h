@@ -39,6 +39,7 @@ int32_t dg_engine_predict_raw(void* engine, const dg_raw_position* positions, in
  * uint64_t* salt.  No device involved: it measures the host half of self-play alone. */
 int32_t dg_random_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
 
+struct dg_cache;
 typedef struct dg_search_options {
     int32_t  search;              /* DG_STANDARD_SEARCH / DG_SCORING_SEARCH (options.rs:66-81, 141-162)                 */
     int32_t  deterministic;       /* SearchOptions::deterministic(): no Dirichlet noise, greedy move choice             */
@@ -51,7 +52,15 @@ typedef struct dg_search_options {
     const uint8_t* leaf_symmetries; /* optional: symmetry of the k-th leaf = leaf_symmetries[k % n] (tests)            */
     int32_t  n_leaf_symmetries;
     double   choose_at;           /* optional: the uniform number of the stochastic move choice; < 0 = draw it          */
+    struct dg_cache* cache;       /* optional: transposition table of evaluations (NnPredictor::fetch / cache)          */
 } dg_search_options;
+
+/* Transposition table `LruCache<(zobrist hash, to_move), Prediction>` (src/libdg_mcts/predictors/nn.rs:29-82,
+ * lru_cache.rs): entries are kept in identity orientation and answer every symmetry (predictor.rs:30-44). */
+typedef struct dg_cache dg_cache;
+dg_cache* dg_cache_new(int32_t capacity);                 /* the reference: 200,000, one table for the process */
+void      dg_cache_free(dg_cache* cache);
+void      dg_cache_stats(const dg_cache* cache, int64_t* hits, int64_t* misses, int64_t* size);
 
 typedef struct dg_tree dg_tree;   /* `tree::Node` */
 
@@ -88,6 +97,8 @@ typedef struct dg_selfplay_config {
     float    dirichlet_noise, temperature;
     uint64_t seed;
     double   max_seconds;         /* stop starting new rounds after this much wall time (<= 0: no limit)                */
+    int32_t  cache_capacity;      /* entries of each game's transposition table (0 = none); see dg_cache                */
+    int32_t  reserved;
 } dg_selfplay_config;
 
 typedef struct dg_selfplay_stats {
@@ -95,6 +106,7 @@ typedef struct dg_selfplay_stats {
     double  seconds, eval_seconds;        /* wall time total / spent inside the predictor                              */
     double  mean_batch;                   /* positions per predictor call                                              */
     uint64_t digest;                      /* order-independent hash of every finished game's move list (determinism)   */
+    int64_t cache_hits;                   /* leaf / root evaluations answered by the transposition tables              */
 } dg_selfplay_stats;
 
 /* Plays `num_games` games, `num_parallel` at a time, all sharing one predictor; one SGF record per finished game is

@@ -309,23 +309,83 @@ def normalize_policy(policy: np.ndarray, sum_to) -> None:   # :113-134 (asm/sum_
         policy[:] = (policy * recip).astype(F)
 
 
+class Cache:
+    """`LruCache<BoardTuple, Prediction>` as `NnPredictor` uses it (predictors/nn.rs:29-82, lru_cache.rs:96-150):
+    key (zobrist hash, to_move); `get` makes the entry most recent; `insert` of a present key does nothing; the least
+    recent entry is dropped beyond `capacity`.  Entries are stored through `Prediction::with_transform`
+    (predictor.rs:30-44) in identity orientation."""
+
+    def __init__(self, capacity: int = 200_000):
+        from collections import OrderedDict
+        self.capacity = capacity
+        self.entries = OrderedDict()          # last = most recent
+        self.hits = 0
+        self.misses = 0
+
+    @staticmethod
+    def with_transform(policy: np.ndarray, transform: int) -> np.ndarray:
+        out = np.zeros(362, np.float16)
+        for i in range(361):
+            out[go.symmetry_apply(transform, i)] = policy[i]
+        out[361] = policy[361]
+        return out
+
+    def fetch(self, board: "go.Board", to_move: int, symmetry: int):      # NnPredictor::fetch
+        key = (board.zobrist_hash(), to_move)
+        if key not in self.entries:
+            self.misses += 1
+            return None
+        self.hits += 1
+        self.entries.move_to_end(key)
+        value, policy = self.entries[key]
+        return value, self.with_transform(policy, symmetry)
+
+    def cache(self, board: "go.Board", to_move: int, symmetry: int, value, policy: np.ndarray) -> None:   # NnPredictor::cache
+        key = (board.zobrist_hash(), to_move)
+        if self.capacity == 0 or key in self.entries:
+            return
+        inv = go.lib().dgo_symmetry_inverse(symmetry)
+        self.entries[key] = (np.float16(value), self.with_transform(np.asarray(policy, np.float16), inv))
+        if len(self.entries) > self.capacity:
+            self.entries.popitem(last=False)
+
+
 Predictor = Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray]]   # features [n,361,32] f16 -> (value [n] f16, policy [n,362] f16)
 
 
-def full_forward(predictor: Predictor, search: int, board: "go.Board", to_move: int):   # lib.rs:83-133 (no cache)
+def full_forward(predictor: Predictor, search: int, board: "go.Board", to_move: int, cache: Optional[Cache] = None):   # lib.rs:83-133
+    """Returns (value, policy, evaluated positions)."""
     initial, indices = create_initial_policy(board, to_move, search)
     policy = initial.copy()
     value = F(0.0)
-    feats = np.stack([board.features(to_move, t) for t in range(8)])
-    values, policies = predictor(feats)
+    responses, missing = {}, []
     for t in range(8):
+        hit = cache.fetch(board, to_move, t) if cache is not None else None
+        if hit is not None:
+            responses[t] = hit
+        else:
+            missing.append(t)
+
+    def add(t, v, p):
+        nonlocal value, policy
         new_policy = initial.copy()
-        add_valid_candidates(new_policy, policies[t].astype(F), indices, t)
+        add_valid_candidates(new_policy, np.asarray(p).astype(F), indices, t)
         normalize_policy(new_policy, 0.125)
-        winrate = F(F(0.5) * F(values[t]) + F(0.5))
+        winrate = F(F(0.5) * F(v) + F(0.5))
         value = F(value + F(winrate * F(0.125)))
         policy[:362] = (policy[:362] + new_policy[:362]).astype(F)
-    return value, policy
+
+    for t in range(8):                       # cached symmetries first (lib.rs:97-111) ...
+        if t in responses:
+            add(t, *responses[t])
+    if missing:                              # ... then one batch for the rest (lib.rs:114-131)
+        feats = np.stack([board.features(to_move, t) for t in missing])
+        values, policies = predictor(feats)
+        for k, t in enumerate(missing):
+            add(t, values[k], policies[k])
+            if cache is not None:
+                cache.cache(board, to_move, t, values[k], policies[k])
+    return value, policy, len(missing)
 
 
 def dirichlet_mix(x: np.ndarray, eta: np.ndarray, beta) -> None:   # dirichlet.rs:70-75 with g/g_sum = eta supplied
@@ -338,11 +398,10 @@ def dirichlet_mix(x: np.ndarray, eta: np.ndarray, beta) -> None:   # dirichlet.r
 def predict(predictor: Predictor, board: "go.Board", color: int, *, search: int = 0, deterministic: bool = False,
             num_rollout: int = 800, probes_per_round: int = 1, starting_tree: Optional[Node] = None,
             noise: Optional[np.ndarray] = None, dirichlet_noise: float = 0.25, temperature: float = 0.8,
-            leaf_symmetries: Sequence[int] = (0,), choose_at: float = 0.0):
+            leaf_symmetries: Sequence[int] = (0,), choose_at: float = 0.0, cache: Optional[Cache] = None):
     """`dg_mcts::predict` (lib.rs:145-200) + the worker loop of pool/worker_thread.rs in its sequential schedule.
     Returns (value, index, root, evals)."""
-    value, policy = full_forward(predictor, search, board, color)
-    evals = 8
+    value, policy, evals = full_forward(predictor, search, board, color, cache)
     if not deterministic:
         dirichlet_mix(policy[:362], noise, dirichlet_noise)
     if starting_tree is not None:
@@ -354,6 +413,7 @@ def predict(predictor: Predictor, board: "go.Board", color: int, *, search: int 
     leaf = 0
     while True:
         pending = []
+        hits_this_round = 0
         while len(pending) < probes_per_round:
             if is_done(root, num_rollout):
                 break
@@ -364,8 +424,20 @@ def predict(predictor: Predictor, board: "go.Board", color: int, *, search: int 
             to_move = 3 - trace[-1][0].to_move
             sym = leaf_symmetries[leaf % len(leaf_symmetries)]
             leaf += 1
+            hit = cache.fetch(b, to_move, sym) if cache is not None else None      # Event::predict (pool/event.rs:50-52)
+            if hit is not None:
+                prior, indices = create_initial_policy(b, to_move, search)
+                add_valid_candidates(prior, hit[1].astype(F), indices, sym)
+                normalize_policy(prior, 1.0)
+                insert(trace, to_move, F(F(0.5) * F(hit[0]) + F(0.5)), prior)
+                hits_this_round += 1
+                if hits_this_round > 4 * probes_per_round:
+                    break
+                continue
             pending.append((trace, b, to_move, sym, b.features(to_move, sym)))
         if not pending:
+            if hits_this_round > 0 and not is_done(root, num_rollout):
+                continue
             break
         values, policies = predictor(np.stack([p[4] for p in pending]))
         evals += len(pending)
@@ -374,6 +446,8 @@ def predict(predictor: Predictor, board: "go.Board", color: int, *, search: int 
             add_valid_candidates(prior, policies[k].astype(F), indices, sym)
             normalize_policy(prior, 1.0)
             insert(trace, to_move, F(F(0.5) * F(values[k]) + F(0.5)), prior)
+            if cache is not None:
+                cache.cache(b, to_move, sym, values[k], policies[k])
     t = temperature if (not deterministic and board.count() < 8) else 0.0
     v, index = best(root, t, choose_at)
     return v, index, root, evals

@@ -52,7 +52,7 @@ def test_midgame_with_noise_and_temperature(probes):
     plays, komi = corpus_position(5, 6)          # count < 8: the stochastic move choice is active
     po, oo = boards(plays, komi)
     color = po.to_move()
-    _, policy = om.full_forward(hash_predictor(), 0, oo, color)
+    _, policy, _ = om.full_forward(hash_predictor(), 0, oo, color)
     noise = dirichlet_sample(3, policy[:362])
     assert_same_search(hash_predictor(), po, oo, color, deterministic=False, num_rollout=100, probes_per_round=probes,
                        noise=noise, leaf_symmetries=[2, 2, 7, 0, 4], choose_at=0.37)
@@ -164,3 +164,60 @@ def test_gamma_sampler_statistics():
     assert abs(float(p1[f].sum()) - 1.0) < 1e-3
     base = 0.75 / f.sum()
     assert (p1[f] >= base * 0.999).all() and p1[f].max() > 0.05      # 25 % of the mass on a few points
+
+
+# ---- transposition table (predictors/nn.rs:29-82, lru_cache.rs) ---------------------------------------------------------
+
+def test_lru_kats_on_oracle_cache():       # lru_cache.rs:153-183
+    c = om.Cache(1000)
+    b = ogo.Board(7.5)
+    class FakeBoard:
+        def __init__(self, h): self.h = h
+        def zobrist_hash(self): return self.h
+    for i in range(20000):
+        c.cache(FakeBoard(i), 1, 0, 0.0, np.zeros(362, np.float16))
+    assert len(c.entries) == 1000
+    c = om.Cache(10)
+    for i in range(10): c.cache(FakeBoard(i), 1, 0, 0.0, np.zeros(362, np.float16))
+    for i in range(2): c.fetch(FakeBoard(i), 1, 0)
+    for i in range(6): c.cache(FakeBoard(i + 20), 1, 0, 0.0, np.zeros(362, np.float16))
+    assert all(c.fetch(FakeBoard(i), 1, 0) is not None for i in (0, 1, 8, 9))
+    assert all(c.fetch(FakeBoard(i), 1, 0) is None for i in range(2, 8))
+
+
+@pytest.mark.parametrize("capacity", [200000, 48])
+def test_search_with_transposition_table_bit_exact(capacity):
+    """Two consecutive searches of one game share a table: root hits on the second search, leaf hits and (with the
+    small capacity) evictions inside both -- visit counts, evaluated-position counts and hit counts are identical."""
+    plays, komi = corpus_position(30, 50)
+    po, oo = boards(plays, komi)
+    color = po.to_move()
+    stub = hash_predictor(1.2)
+    pc, oc = pm.Cache(capacity), om.Cache(capacity)
+    kw = dict(deterministic=True, num_rollout=110, probes_per_round=3, leaf_symmetries=[0, 4, 7, 2, 5])
+    gv, gi, tree, ge = pm.predict(pm.python_predictor(stub), po, color, cache=pc, **kw)
+    wv, wi, root, we = om.predict(stub, oo, color, cache=oc, **kw)
+    count, _, _ = tree.children()
+    assert (count == root.count[:362]).all() and gi == wi and ge == we
+    assert pc.stats()["hits"] == oc.hits and pc.stats()["misses"] == oc.misses and pc.stats()["size"] == len(oc.entries)
+    po.place_index(color, gi)
+    oo.place_index(color, wi)
+    sub, want_sub = tree.forward(gi), om.forward(root, wi)
+    gv, gi, tree2, ge2 = pm.predict(pm.python_predictor(stub), po, 3 - color, starting_tree=sub, cache=pc, **kw)
+    wv, wi, root2, we2 = om.predict(stub, oo, 3 - color, starting_tree=want_sub, cache=oc, **kw)
+    count2, value2, prior2 = tree2.children()
+    assert (count2 == root2.count[:362]).all() and gi == wi and ge2 == we2
+    assert (prior2.view(np.uint32) == root2.prior[:362].view(np.uint32)).all()
+    assert pc.stats()["hits"] == oc.hits > 0 and pc.stats()["size"] == len(oc.entries) <= capacity
+    if capacity >= 200000:
+        assert ge2 < ge                    # the second root (a leaf of the first search) came out of the table
+
+
+def test_self_play_with_tables_is_reproducible_and_saves_evaluations():
+    stub = pm.python_predictor(hash_predictor())
+    kw = dict(num_games=2, num_parallel=2, num_rollout=16, probes_per_round=2, max_plies=10, seed=3)
+    a, _ = pm.self_play(stub, num_threads=1, cache_capacity=4096, **kw)
+    b, _ = pm.self_play(stub, num_threads=2, cache_capacity=4096, **kw)
+    c, _ = pm.self_play(stub, num_threads=2, cache_capacity=0, **kw)
+    assert a["digest"] == b["digest"] and a["cache_hits"] == b["cache_hits"] > 0
+    assert a["evals"] < c["evals"] and c["cache_hits"] == 0

@@ -22,13 +22,13 @@ sys.path.insert(0, ROOT)
 
 
 def sample(net, *, games: int, parallel: int, rollouts: int, probes: int, seconds: float, threads: int, seed: int,
-           ex_it: bool = False, device_features: bool = True):
+           ex_it: bool = False, device_features: bool = True, cache_capacity: int = 0):
     """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics."""
     from dream_go_b200 import mcts
     predictor = mcts.EngineRawPredictor(net) if device_features else mcts.EnginePredictor(net)
     st, sgf = mcts.self_play(predictor, num_games=games, num_parallel=parallel, num_rollout=rollouts,
                              probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=rollouts, seed=seed,
-                             max_seconds=seconds)
+                             max_seconds=seconds, cache_capacity=cache_capacity)
     return st, sgf
 
 
@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=9)
     ap.add_argument("--ex-it", action="store_true")
     ap.add_argument("--host-only", action="store_true", help="RandomPredictor instead of the engine (no GPU needed)")
+    ap.add_argument("--cache", type=int, default=0, help="entries of each game's transposition table (0 = none)")
     ap.add_argument("--blocking-sync", action="store_true", help="blocking engine calls sleep on an event instead of spinning in the driver")
     ap.add_argument("--host-features", action="store_true",
                     help="compute the feature planes on the host (compact positions) instead of on the device (raw positions)")
@@ -82,7 +83,7 @@ def main():
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
                          seconds=args.seconds, threads=threads, seed=20261017 + rank, ex_it=args.ex_it,
-                         device_features=not args.host_features)
+                         device_features=not args.host_features, cache_capacity=args.cache)
         wall = time.perf_counter() - t0
         vals = [st["moves"], st["evals"], st["games_finished"], st["seconds"], st["eval_seconds"], st["rounds"]]
         if dist is not None:
@@ -97,7 +98,7 @@ def main():
         else:
             moves, evals, games, seconds, eval_s, rounds = vals
         line.update({"value": moves / seconds, "nn_evals_per_s": evals / seconds, "games_finished": games, "moves": moves,
-                     "evals": evals, "seconds": seconds, "mean_batch": evals / max(rounds, 1),
+                     "evals": evals, "seconds": seconds, "mean_batch": evals / max(rounds, 1), "cache_hits_rank0": st.get("cache_hits", 0), "cache_capacity_per_game": args.cache,
                      "device_busy_frac": eval_s / (seconds * world), "wall_s": wall,
                      "first_game": sgf[0][:200] if sgf else None})
         net.close()
