@@ -221,3 +221,54 @@ def test_self_play_with_tables_is_reproducible_and_saves_evaluations():
     c, _ = pm.self_play(stub, num_threads=2, cache_capacity=0, **kw)
     assert a["digest"] == b["digest"] and a["cache_hits"] == b["cache_hits"] > 0
     assert a["evals"] < c["evals"] and c["cache_hits"] == 0
+
+
+# ---- self-play records (self_play.rs:187-214, game_result.rs:23-43) --------------------------------------------------
+
+def parse_record(sgf: str):
+    import re
+    from oracle import oracle as onn
+    assert sgf.startswith("(;GM[1]FF[4]") and sgf.endswith(")")
+    komi = float(re.search(r"KM\[([-0-9.]+)\]", sgf).group(1))
+    moves = []
+    for m in re.finditer(r";([BW])\[([a-s]{0,2})\]((?:[A-Z]+\[[^\]]*\])*)", sgf):
+        color = 1 if m.group(1) == "B" else 2
+        xy = m.group(2)
+        index = 361 if not xy else (ord(xy[1]) - 97) * 19 + (ord(xy[0]) - 97)        # CGoban: x letter, y letter (sgf.rs:36-43)
+        props = dict(re.findall(r"([A-Z]+)\[([^\]]*)\]", m.group(3)))
+        moves.append((color, index, props))
+    return komi, moves
+
+
+@pytest.mark.parametrize("mode", ["search", "ex_it", "policy_only"])
+def test_self_play_records_replay_legally_on_the_oracle(mode):
+    from oracle import oracle as onn
+    stub = pm.python_predictor(hash_predictor())
+    kw = dict(num_games=2, num_parallel=2, probes_per_round=2, max_plies=14, seed=21, num_threads=2)
+    if mode == "search":
+        st, games = pm.self_play(stub, num_rollout=24, **kw)
+    elif mode == "ex_it":
+        st, games = pm.self_play(stub, num_rollout=24, ex_it=True, num_ex_it_rollout=40, **{**kw, "max_plies": 40})
+    else:
+        st, games = pm.self_play(stub, num_rollout=1, **kw)       # `--num-rollout 1`: play from the averaged policy
+    assert st["games_finished"] == 2 and len(games) == 2
+    for sgf in games:
+        komi, moves = parse_record(sgf)
+        assert len(moves) == (40 if mode == "ex_it" else 14)
+        board = ogo.Board(komi)
+        for ply, (color, index, props) in enumerate(moves):
+            assert color == (1 if ply % 2 == 0 else 2)
+            if index < 361:
+                assert board.is_valid(color, index % 19, index // 19), (ply, index)
+                board.place_index(color, index)
+            assert "V" in props and -1.0 <= float(props["V"]) <= 1.0
+            if mode != "policy_only":
+                assert int(props["TV"]) >= 1
+                dist = np.frombuffer(onn.b85_decode(props["P"].encode("ascii")), "<f2")[:362].astype(np.float32)   # as contrib/trainer reads it
+                assert abs(float(dist.sum()) - 1.0) < 2e-2 and (dist >= 0).all()
+                if index < 361:
+                    assert dist[index] > 0
+            else:
+                assert "TV" not in props and "P" not in props
+    if mode == "ex_it":
+        assert st["searches"] > st["moves"]          # some positions were searched twice
