@@ -292,8 +292,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         sp_net.close()
         self_play = {"moves_per_s": sp_moves / sp_seconds, "nn_evals_per_s": sp_evals / sp_seconds, "unit": "moves/s, evals/s",
                      "mean_device_batch": sp_evals / max(sp_rounds, 1.0), "predictor_time_frac": sp_busy / (sp_seconds * world),   # two alternating groups overlap, so this can exceed 1
-                     "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU, real feature planes from "
-                                 f"the host Go code, random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
+                     "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU in 4 alternating groups, real positions: "
+                                 f"feature planes + legal moves derived on the device from raw stones (ladder planes on the host), random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
                      "host_threads_per_gpu": threads, "host_cores": os.cpu_count()}
 
     if dist is not None:
