@@ -195,35 +195,10 @@ def run_reference(args, rank: int):
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
-    from dream_go_b200 import nn, weights
+    from dream_go_b200 import nn, shard, weights
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-        torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist = dist_mod
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    shards = shard.Shards(backend="nccl")       # plumbing only: start barrier + adding up the shards' counters
+    barrier, max_over_ranks, sum_over_ranks = shards.barrier, shards.max, shards.sum
 
     tensors = weights.synthetic_network(seed=20261017, num_blocks=NUM_BLOCKS)
     net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=BATCH, num_workspaces=3)
@@ -284,21 +259,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         barrier()
         st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=SELF_PLAY_GAMES, rollouts=800, probes=8,
                                       seconds=args.self_play_seconds, threads=threads, seed=20261017 + rank)
-        sp_seconds = max_over_ranks(st["seconds"])
-        sp_moves = sum_over_ranks(float(st["moves"]))
-        sp_evals = sum_over_ranks(float(st["evals"]))
-        sp_rounds = sum_over_ranks(float(st["rounds"]))
-        sp_busy = sum_over_ranks(float(st["eval_seconds"]))
+        tot = shards.selfplay_totals(st)
         sp_net.close()
-        self_play = {"moves_per_s": sp_moves / sp_seconds, "nn_evals_per_s": sp_evals / sp_seconds, "unit": "moves/s, evals/s",
-                     "mean_device_batch": sp_evals / max(sp_rounds, 1.0), "predictor_time_frac": sp_busy / (sp_seconds * world),   # two alternating groups overlap, so this can exceed 1
+        self_play = {"moves_per_s": tot["moves_per_s"], "nn_evals_per_s": tot["nn_evals_per_s"], "unit": "moves/s, evals/s",
+                     "mean_device_batch": tot["mean_device_batch"],
+                     "predictor_time_frac": tot["predictor_seconds"] / (tot["seconds"] * world),   # alternating groups overlap, so this can exceed 1
                      "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU in 4 alternating groups, real positions: "
                                  f"feature planes + legal moves derived on the device from raw stones (ladder planes on the host), random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
                      "host_threads_per_gpu": threads, "host_cores": os.cpu_count()}
 
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    shards.close()
     if rank != 0:
         return
     peak_tf, _peak_gbs, peak_kind = measured_peaks()

@@ -69,34 +69,21 @@ def main():
             "host_only": {"evals_per_s": host["evals"] / host["seconds"], "moves_per_s": host["moves"] / host["seconds"],
                           "mean_batch": host["mean_batch"], "predictor": "RandomPredictor (no device)"}}
     if not args.host_only:
-        dist = None
-        if world > 1:
-            import torch
-            import torch.distributed as dist
-            torch.cuda.set_device(local_rank)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from dream_go_b200 import shard
+        shards = shard.Shards(backend="nccl")
         tensors = weights.synthetic_network(seed=20261017, num_blocks=args.blocks)
         net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=512, num_workspaces=8,
                                       flags=nn.FLAG_BLOCKING_SYNC if args.blocking_sync else 0)
-        if dist is not None:
-            dist.barrier()
+        shards.barrier()
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
-                         seconds=args.seconds, threads=threads, seed=20261017 + rank, ex_it=args.ex_it,
+                         seconds=args.seconds, threads=threads, seed=shards.seed(20261017), ex_it=args.ex_it,
                          device_features=not args.host_features, cache_capacity=args.cache)
         wall = time.perf_counter() - t0
-        vals = [st["moves"], st["evals"], st["games_finished"], st["seconds"], st["eval_seconds"], st["rounds"]]
-        if dist is not None:
-            import torch
-            t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local_rank}")
-            mx = t.clone()
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            moves, evals, games, _, eval_s, rounds = t.tolist()
-            seconds = mx[3].item()
-            dist.destroy_process_group()
-        else:
-            moves, evals, games, seconds, eval_s, rounds = vals
+        tot = shards.selfplay_totals(st)
+        shards.close()
+        moves, evals, games, seconds, eval_s, rounds = (tot["moves"], tot["evals"], tot["games_finished"], tot["seconds"],
+                                                        tot["predictor_seconds"], tot["rounds"])
         line.update({"value": moves / seconds, "nn_evals_per_s": evals / seconds, "games_finished": games, "moves": moves,
                      "evals": evals, "seconds": seconds, "mean_batch": evals / max(rounds, 1), "cache_hits_rank0": st.get("cache_hits", 0), "cache_capacity_per_game": args.cache,
                      "device_busy_frac": eval_s / (seconds * world), "wall_s": wall,
