@@ -431,7 +431,9 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                     if (after_move(g)) return;
                     continue;
                 }
-                if (d.cfg.ex_it && g.rng.uniform() < 0.05) {     // is_good_candidate (self_play.rs:287-291); value is a winrate
+                // is_good_candidate (self_play.rs:287-291): value within [-0.8, 0.8] (a winrate: only the upper bound
+                // bites) and, only then, a 5 % draw
+                if (d.cfg.ex_it && g.value >= -0.80f && g.value <= 0.80f && (float)g.rng.uniform() < 0.05f) {
                     d.begin_search(g, true);
                     continue;
                 }
