@@ -398,11 +398,14 @@ def dirichlet_mix(x: np.ndarray, eta: np.ndarray, beta) -> None:   # dirichlet.r
 def predict(predictor: Predictor, board: "go.Board", color: int, *, search: int = 0, deterministic: bool = False,
             num_rollout: int = 800, probes_per_round: int = 1, starting_tree: Optional[Node] = None,
             noise: Optional[np.ndarray] = None, dirichlet_noise: float = 0.25, temperature: float = 0.8,
-            leaf_symmetries: Sequence[int] = (0,), choose_at: float = 0.0, cache: Optional[Cache] = None):
+            leaf_symmetries: Sequence[int] = (0,), choose_at: float = 0.0, cache: Optional[Cache] = None, rng=None,
+            dirichlet_shape: float = 0.03):
     """`dg_mcts::predict` (lib.rs:145-200) + the worker loop of pool/worker_thread.rs in its sequential schedule.
     Returns (value, index, root, evals)."""
     value, policy, evals = full_forward(predictor, search, board, color, cache)
     if not deterministic:
+        if noise is None:
+            noise = rng.dirichlet(policy, float(F(dirichlet_shape)))       # drawn here, as the product's search does
         dirichlet_mix(policy[:362], noise, dirichlet_noise)
     if starting_tree is not None:
         assert starting_tree.to_move == color
@@ -422,7 +425,7 @@ def predict(predictor: Predictor, board: "go.Board", color: int, *, search: int 
             if status != "found":
                 break
             to_move = 3 - trace[-1][0].to_move
-            sym = leaf_symmetries[leaf % len(leaf_symmetries)]
+            sym = rng.below(8) if rng is not None else leaf_symmetries[leaf % len(leaf_symmetries)]
             leaf += 1
             hit = cache.fetch(b, to_move, sym) if cache is not None else None      # Event::predict (pool/event.rs:50-52)
             if hit is not None:
@@ -449,5 +452,86 @@ def predict(predictor: Predictor, board: "go.Board", color: int, *, search: int 
             if cache is not None:
                 cache.cache(b, to_move, sym, values[k], policies[k])
     t = temperature if (not deterministic and board.count() < 8) else 0.0
+    if rng is not None and t > 9e-2:
+        choose_at = rng.uniform()
     v, index = best(root, t, choose_at)
     return v, index, root, evals
+
+
+# ---- self_play.rs:217-459 -----------------------------------------------------------------------------------------------
+
+class Player:                                          # self_play.rs:217-241
+    def __init__(self, color: int):
+        self.winrate = F(0.5)                          # MovingAverage(0.5, MOMENTUM = 0.2)
+        self.root: Optional[Node] = None
+        self.color = color
+
+    def num_rollout(self, max_rollout: int) -> int:
+        m = F(F(F(4.0) * self.winrate) * F(F(1.0) - self.winrate))
+        m = F(0.1) if m < 0.1 else m
+        return int(F(m * F(max_rollout)))
+
+    def update(self, value) -> None:
+        self.winrate = F(self.winrate - F(F(0.2) * F(self.winrate - F(value))))
+
+
+def get_random_komi(rng) -> float:                     # lib.rs:210-224
+    v = F(rng.uniform())
+    if v < F(0.4):
+        return 7.5
+    if v < F(0.8):
+        return 6.5
+    if v < F(0.9):
+        return 0.5
+    return float(rng.below(16) - 8) + 0.5
+
+
+def self_play_one(predictor: Predictor, game_rng, *, num_rollout: int = 800, probes_per_round: int = 1, max_plies: int = 722,
+                  dirichlet_noise: float = 0.25, temperature: float = 0.8, cache: Optional[Cache] = None):
+    """`self_play_one` (self_play.rs:423-459) without ex-it: returns (komi, [(color, index)])."""
+    from .rng import Rng
+    komi = get_random_komi(game_rng)
+    board = go.Board(komi)
+    players = [Player(go.BLACK), Player(go.WHITE)]
+    pass_count = 0
+    played = []
+    while board.count() < max_plies:
+        me = players[0]
+        allow_pass = board.is_scorable()
+        rollouts = me.num_rollout(num_rollout)
+        search_rng = Rng(game_rng.next())
+        tree = me.root
+        me.root = None
+        if rollouts > 1:
+            if tree is not None and not allow_pass:
+                tree.disqualify(361)                   # predict_aux (self_play.rs:252-256)
+            value, index, tree, _ = predict(predictor, board, me.color, search=0 if allow_pass else 1, deterministic=not allow_pass,
+                                            num_rollout=rollouts, probes_per_round=probes_per_round, starting_tree=tree,
+                                            dirichlet_noise=dirichlet_noise, temperature=temperature, cache=cache, rng=search_rng)
+            if not np.isfinite(value):
+                index, tree = 361, None
+            else:
+                me.update(value)
+                tree = forward(tree, index)
+            me.root = tree
+        else:                                          # self_play.rs:360-396: play from the averaged policy
+            value, policy, _ = full_forward(predictor, 0 if allow_pass else 1, board, me.color, cache)
+            if not allow_pass:
+                policy[361] = NEG_INF
+            pick = choose([float(x) for x in policy[:362]], 0.5, 1.0 / float(F(temperature)), search_rng.uniform())
+            index = 361 if pick is None else pick
+            me.update(value)
+            me.root = forward(tree, index) if tree is not None else None
+        played.append((me.color, index))
+        if index == 361:
+            pass_count += 1
+            if pass_count >= 2 and board.is_scorable():
+                break
+        else:
+            pass_count = 0
+            board.place_index(me.color, index)
+        other = players[1]
+        if other.root is not None:
+            other.root = forward(other.root, index)
+        players.reverse()
+    return komi, played

@@ -272,3 +272,37 @@ def test_self_play_records_replay_legally_on_the_oracle(mode):
                 assert "TV" not in props and "P" not in props
     if mode == "ex_it":
         assert st["searches"] > st["moves"]          # some positions were searched twice
+
+
+# ---- whole games: product driver vs the oracle's self_play_one, same random stream --------------------------------------
+
+def test_rng_restatement_matches_the_engine_stream():
+    """oracle/rng.py reproduces csrc/search.h: Rng -- checked through its visible effects: komi draw and Dirichlet noise."""
+    from oracle.rng import Rng
+    po = pgo.Board(7.5)
+    po.place(WHITE, 2, 3)
+    oo = ogo.Board(7.5)
+    oo.place(WHITE, 2, 3)
+    stub = uniform_predictor()
+    _, _, tree, _ = pm.predict(pm.python_predictor(stub), po, BLACK, deterministic=False, num_rollout=1, seed=77)
+    _, policy, _ = om.full_forward(stub, 0, oo, BLACK)
+    eta = Rng(77).dirichlet(policy, float(np.float32(0.03)))
+    om.dirichlet_mix(policy[:362], eta, 0.25)
+    assert (tree.children()[2].view(np.uint32) == policy[:362].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("probes,rollouts,cache", [(1, 20, 0), (3, 20, 0), (2, 20, 512), (2, 1, 0)])
+def test_whole_game_matches_the_oracle_game(probes, rollouts, cache):
+    """One self-play game, move for move: komi, Dirichlet noise, leaf symmetries, stochastic opening moves, tree re-use,
+    scoring search with pass disqualified, the per-move rollout budget -- everything drawn from the same seeded stream."""
+    from oracle.rng import Rng
+    stub = hash_predictor()
+    seed, plies = 5, 12
+    st, games = pm.self_play(pm.python_predictor(stub), num_games=1, num_parallel=1, num_rollout=rollouts, probes_per_round=probes,
+                             max_plies=plies, seed=seed, num_threads=1, cache_capacity=cache)
+    komi, moves = parse_record(games[0])
+    game_rng = Rng((seed * 0x9e3779b97f4a7c15 + 0 * 0xd1342543de82ef95 + 1) & ((1 << 64) - 1))     # Driver::start_game, game id 0
+    want_komi, want_moves = om.self_play_one(stub, game_rng, num_rollout=rollouts, probes_per_round=probes, max_plies=plies,
+                                             cache=om.Cache(cache) if cache else None)
+    assert komi == want_komi
+    assert [(c, i) for c, i, _ in moves] == want_moves

@@ -86,3 +86,27 @@ def test_device_features_give_the_same_search_and_games(engine):
     a, sgf_a = pm.self_play(pm.EnginePredictor(engine), **kw)
     b, sgf_b = pm.self_play(pm.EngineRawPredictor(engine), **kw)
     assert a["digest"] == b["digest"] and sorted(sgf_a) == sorted(sgf_b) and a["evals"] == b["evals"]
+
+
+def test_whole_game_on_engine_matches_oracle_game(engine):
+    """A self-play game on the engine, move for move against the oracle's self_play_one fed by the same engine."""
+    import re
+    from oracle.rng import Rng
+    ogo.use_default_zobrist()
+
+    def engine_on_features(feats):
+        with engine.get_workspace(len(feats)) as ws:
+            value, policy = nn.forward(ws, np.ascontiguousarray(feats)).unwrap()
+        return value, policy.reshape(-1, 362)
+
+    seed, plies, rollouts = 3, 10, 48
+    kw = dict(num_games=1, num_parallel=1, num_rollout=rollouts, probes_per_round=2, max_plies=plies, seed=seed, num_threads=1)
+    _, games = pm.self_play(pm.EngineRawPredictor(engine), **kw)
+    _, games_packed = pm.self_play(pm.EnginePredictor(engine), **kw)
+    assert games == games_packed
+    komi = float(re.search(r"KM\[([-0-9.]+)\]", games[0]).group(1))
+    moves = [(1 if m.group(1) == "B" else 2, 361 if not m.group(2) else (ord(m.group(2)[1]) - 97) * 19 + ord(m.group(2)[0]) - 97)
+             for m in re.finditer(r";([BW])\[([a-s]{0,2})\]", games[0])]
+    game_rng = Rng((seed * 0x9e3779b97f4a7c15 + 1) & ((1 << 64) - 1))
+    want_komi, want_moves = om.self_play_one(engine_on_features, game_rng, num_rollout=rollouts, probes_per_round=2, max_plies=plies)
+    assert komi == want_komi and moves == want_moves
