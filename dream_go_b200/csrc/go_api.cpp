@@ -137,6 +137,8 @@ int32_t dg_go_replay(float komi, const uint8_t* colors, const uint16_t* moves, i
 
 int32_t dg_board_is_scorable(const dg_board* board) { return dg::is_scorable(*B(board)); }
 
+void dg_board_territory(const dg_board* board, uint8_t* out) { dg::territory_status(*B(board), out); }
+
 void dg_board_benson(const dg_board* board, int32_t color, uint8_t* out) {
     dg::Bits alive, eyes;
     dg::benson(*B(board), color, alive, eyes);

@@ -581,6 +581,30 @@ inline bool is_scorable(const Board& b) {
     return true;
 }
 
+// Whose territory the game record counts each point as (utils/score.rs:148-195 with `finished` = the board itself,
+// game_result.rs:45-93): stones belong to their owner unless they sit dead inside an unconditionally alive enemy eye;
+// empty points belong to the colour whose unconditionally alive stones alone reach them.  1 black, 2 white, 0 none.
+inline void territory_status(const Board& b, uint8_t out[N_POINTS]) {
+    Bits alive[3], eyes[3];
+    benson(b, BLACK, alive[BLACK], eyes[BLACK]);
+    benson(b, WHITE, alive[WHITE], eyes[WHITE]);
+    Bits reach[3];
+    const Bits open = tables().board.andnot(alive[BLACK] | alive[WHITE]);   // the cleaned board: everything else is empty
+    for (int c = BLACK; c <= WHITE; ++c) {
+        reach[c] = alive[c];
+        for (;;) {
+            Bits grow = (dilate(reach[c]) & open).andnot(reach[c]);
+            if (!grow.any()) break;
+            reach[c].or_with(grow);
+        }
+    }
+    for (int p = 0; p < N_POINTS; ++p) {
+        int c = b.color[p];
+        if (c) out[p] = (uint8_t)(alive[c].test(p) ? c : eyes[opposite(c)].test(p) ? opposite(c) : c);
+        else out[p] = (uint8_t)(reach[BLACK].test(p) && !reach[WHITE].test(p) ? BLACK : reach[WHITE].test(p) && !reach[BLACK].test(p) ? WHITE : 0);
+    }
+}
+
 // The own-eye heuristic of ScoringSearch (libdg_mcts/options.rs:180-214).
 inline bool is_simple_eye(const Board& b, int color, int p) {
     const Tables& T = tables();

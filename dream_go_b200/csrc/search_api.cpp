@@ -70,30 +70,6 @@ static void sgf_point(int index, std::string& out) {                        // u
     out.push_back((char)('a' + index / 19));
 }
 
-// Tromp-Taylor area score without komi (utils/score.rs:230-282): stones + empty regions that reach one colour only.
-static void tromp_taylor(const Board& b, int* black, int* white) {
-    const Tables& T = tables();
-    uint8_t reach[N_POINTS];
-    memset(reach, 0, sizeof(reach));
-    for (int c = BLACK; c <= WHITE; ++c) {
-        std::vector<int> stack;
-        for (int p = 0; p < N_POINTS; ++p) if (b.color[p] == c) stack.push_back(p);
-        while (!stack.empty()) {
-            int p = stack.back();
-            stack.pop_back();
-            for (int k = 0; k < T.n_nbr[p]; ++k) {
-                int q = T.nbr_list[p][k];
-                if (!b.color[q] && !(reach[q] & c)) { reach[q] |= (uint8_t)c; stack.push_back(q); }
-            }
-        }
-    }
-    *black = *white = 0;
-    for (int p = 0; p < N_POINTS; ++p) {
-        if (b.color[p] == BLACK || (!b.color[p] && reach[p] == BLACK)) ++*black;
-        else if (b.color[p] == WHITE || (!b.color[p] && reach[p] == WHITE)) ++*white;
-    }
-}
-
 namespace {
 
 struct Player {                                                  // self_play.rs:217-241
@@ -174,10 +150,16 @@ struct Driver {
         g.cache.reset(cfg.cache_capacity > 0 ? new PredictionCache((size_t)cfg.cache_capacity) : nullptr);
     }
 
-    void finish_game(Game& g) {                                  // game_result.rs:23-43 (Ended)
-        int black, white;
-        tromp_taylor(g.board, &black, &white);
-        float w = (float)white + g.board.komi, b = (float)black;
+    void finish_game(Game& g) {                                  // game_result.rs:23-93 (Ended)
+        uint8_t status[N_POINTS];
+        territory_status(g.board, status);
+        int black = 0, white = 0;
+        std::string tb, tw;                                      // get_territory_as_sgf (:45-66)
+        for (int p = 0; p < N_POINTS; ++p) {
+            if (status[p] == WHITE) { ++white; tw += "["; sgf_point(p, tw); tw += "]"; }
+            else if (status[p] == BLACK) { ++black; tb += "["; sgf_point(p, tb); tb += "]"; }
+        }
+        float w = (float)white + g.board.komi, b = (float)black;  // get_winner_as_sgf (:78-93)
         char head[160], res[32];
         if (b > w) snprintf(res, sizeof(res), "B+%.1f", b - w);
         else if (w > b) snprintf(res, sizeof(res), "W+%.1f", w - b);
@@ -185,6 +167,8 @@ struct Driver {
         snprintf(head, sizeof(head), "(;GM[1]FF[4]SZ[19]RU[Chinese]KM[%.1f]RE[%s]", g.board.komi, res);
         sgf_all += head;
         sgf_all += g.sgf;
+        if (!tb.empty()) { sgf_all += "TB"; sgf_all += tb; }
+        if (!tw.empty()) { sgf_all += "TW"; sgf_all += tw; }
         sgf_all += ")\n";
         uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)g.id;
         for (uint16_t m : g.moves) { h ^= m; h *= 0x100000001b3ull; }

@@ -33,7 +33,7 @@ ABI = {
     "dg_go_extract_batch": (None, [_P, _P, _P, _I, _P, _P, _I]),
     "dg_go_replay": (_I, [_F, _P, _P, _I, _P, _P, _P]),
     "dg_board_prior": (None, [_P, _I, _I, _P, _P, _I, _F, _P]),
-    "dg_board_is_scorable": (_I, [_P]), "dg_board_benson": (None, [_P, _I, _P]),
+    "dg_board_is_scorable": (_I, [_P]), "dg_board_territory": (None, [_P, _P]), "dg_board_benson": (None, [_P, _I, _P]),
     "dg_board_policy_candidates": (None, [_P, _I, _I, _P, _P]),
 }
 _ready = False
@@ -141,6 +141,12 @@ class Board:
     def benson(self, color: int) -> np.ndarray:
         out = np.empty(361, np.uint8)
         lib().dg_board_benson(self._h, color, out.ctypes.data)
+        return out
+
+    def territory(self) -> np.ndarray:
+        """Per point 1 / 2 / 0: whose territory the game record counts it as (`get_stone_status`, score.rs:148-195)."""
+        out = np.empty(361, np.uint8)
+        lib().dg_board_territory(self._h, out.ctypes.data)
         return out
 
     def policy_candidates(self, to_move: int, search: int = STANDARD_SEARCH) -> np.ndarray:

@@ -94,6 +94,9 @@ void      dg_board_prior(const dg_board* board, int32_t to_move, int32_t search,
 int32_t   dg_board_is_scorable(const dg_board* board);
 /* Benson status per point for `color`: 0 none, 1 unconditionally alive stone, 2 vital region (benson.rs:152-165) */
 void      dg_board_benson(const dg_board* board, int32_t color, uint8_t* out /* [361] */);
+/* Whose territory the game record counts each point as (utils/score.rs:148-195, game_result.rs:45-93): 1 black,
+ * 2 white, 0 neither -- `RE[]` and `TB[]/TW[]` of a finished game. */
+void      dg_board_territory(const dg_board* board, uint8_t* out /* [361] */);
 /* PolicyChecker::is_policy_candidate for moves 0..361 under `search`; `legal` optional as above. */
 void      dg_board_policy_candidates(const dg_board* board, int32_t to_move, int32_t search, const uint8_t* legal,
                                      uint8_t* out /* [362] */);

@@ -640,6 +640,50 @@ bool is_scorable(const Board& b) {
     return true;
 }
 
+// utils/score.rs:252-282: distance (through empty points) to the closest stone of `color`, 0xff = unreachable
+void territory_distance(const BoardFast& board, int color, uint8_t* territory /* [MAXP] */) {
+    memset(territory, 0xff, MAXP);
+    std::vector<int> probes;
+    for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+        int p = point_new(x, y);
+        if (v_color(board.vertices[p]) == color) { territory[p] = 0; probes.push_back(p); }
+    }
+    for (size_t i = 0; i < probes.size(); ++i) {
+        int index = probes[i];
+        int t = territory[index] + 1;
+        int adj[4];
+        int n = board.adjacent_to(index, adj);
+        for (int k = 0; k < n; ++k)
+            if (v_color(board.vertices[adj[k]]) == 0 && territory[adj[k]] > t) { probes.push_back(adj[k]); territory[adj[k]] = (uint8_t)t; }
+    }
+}
+
+// utils/score.rs:148-195 `get_stone_status(&self, finished = self)` reduced to what the game record needs: per point
+// 1 = counts as black territory, 2 = as white territory, 0 = neither (game_result.rs:45-93).
+void territory_status(const Board& b, uint8_t* out /* [361] */) {
+    Benson black(b.inner, BLACK), white(b.inner, WHITE);
+    BoardFast cleaned = b.inner;                                  // clear_board (score.rs:208-222)
+    for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+        int p = point_new(x, y);
+        int c = v_color(b.inner.vertices[p]);
+        if (c == WHITE && !white.is_alive(p)) v_set_color(cleaned.vertices[p], 0);
+        if (c == BLACK && !black.is_alive(p)) v_set_color(cleaned.vertices[p], 0);
+    }
+    uint8_t db[MAXP], dw[MAXP];
+    territory_distance(cleaned, BLACK, db);
+    territory_distance(cleaned, WHITE, dw);
+    for (int y = 0; y < 19; ++y) for (int x = 0; x < 19; ++x) {
+        int p = point_new(x, y);
+        int c = v_color(b.inner.vertices[p]);
+        uint8_t st = 0;
+        if (c == WHITE) st = white.is_alive(p) ? 2 : black.is_eye(p) ? 1 : 2;      // Alive / Dead / Seki
+        else if (c == BLACK) st = black.is_alive(p) ? 1 : white.is_eye(p) ? 2 : 1;
+        else if (db[p] != 0xff && dw[p] == 0xff) st = 1;
+        else if (dw[p] != 0xff && db[p] == 0xff) st = 2;
+        out[19 * y + x] = st;
+    }
+}
+
 // libdg_mcts/options.rs:180-214 (the "7 of 8 neighbours" own-eye heuristic of ScoringSearch)
 bool is_vertex_filled(const Board& b, int color, int p, int dx, int dy) {
     int other = point_offset(p, dx, dy);
@@ -683,6 +727,7 @@ dgo_board* dgo_board_new(float komi) { ensure_init(); return reinterpret_cast<dg
 dgo_board* dgo_board_clone(dgo_board* b) { return reinterpret_cast<dgo_board*>(new Board(*B(b))); }
 void dgo_board_free(dgo_board* b) { delete B(b); }
 void dgo_board_set_komi(dgo_board* b, float komi) { B(b)->komi = komi; }
+float dgo_board_komi(dgo_board* b) { return B(b)->komi; }
 void dgo_board_place(dgo_board* b, int color, int index) { B(b)->place(color, from_packed(index)); }
 int dgo_board_is_valid(dgo_board* b, int color, int index) { return B(b)->is_valid(color, from_packed(index)); }
 int dgo_board_is_valid_fast(dgo_board* b, int color, int index) { return B(b)->inner.is_valid(color, from_packed(index)); }
@@ -721,6 +766,8 @@ void dgo_board_benson(dgo_board* b, int color, uint8_t* out /* [361] */) {
     for (int i = 0; i < 361; ++i) out[i] = bn.points[from_packed(i)];
 }
 int dgo_board_is_scorable(dgo_board* b) { return is_scorable(*B(b)); }
+/* Territory per point as the game record counts it (score.rs:148-195, game_result.rs:45-93): 1 black, 2 white, 0 none */
+void dgo_board_territory(dgo_board* b, uint8_t* out /* [361] */) { territory_status(*B(b), out); }
 /* PolicyChecker::is_policy_candidate over 0..361.  kind 0 = StandardSearch (options.rs:53-57),
  * kind 1 = ScoringSearch (options.rs:109-138). */
 void dgo_board_policy_candidates(dgo_board* b, int to_move, int kind, uint8_t* out /* [362] */) {

@@ -27,7 +27,7 @@ def lib() -> C.CDLL:
         sig = {
             "dgo_set_zobrist_table": (None, [P]), "dgo_reset_zobrist_table": (None, []),
             "dgo_board_new": (P, [F]), "dgo_board_clone": (P, [P]), "dgo_board_free": (None, [P]),
-            "dgo_board_set_komi": (None, [P, F]),
+            "dgo_board_set_komi": (None, [P, F]), "dgo_board_komi": (F, [P]),
             "dgo_board_place": (None, [P, I, I]), "dgo_board_is_valid": (I, [P, I, I]),
             "dgo_board_is_valid_fast": (I, [P, I, I]), "dgo_board_is_ko": (I, [P, I, I]),
             "dgo_board_at": (I, [P, I]), "dgo_board_zobrist_hash": (U64, [P]), "dgo_board_to_move": (I, [P]),
@@ -38,7 +38,7 @@ def lib() -> C.CDLL:
             "dgo_board_is_symmetric": (I, [P, I]), "dgo_symmetry_apply": (I, [I, I]), "dgo_symmetry_inverse": (I, [I]),
             "dgo_ladder_nodes": (C.c_long, []), "dgo_f32_to_f16": (C.c_uint16, [F]),
             "dgo_replay": (I, [F, P, P, I, P, P, P]),
-            "dgo_board_benson": (None, [P, I, P]), "dgo_board_is_scorable": (I, [P]),
+            "dgo_board_benson": (None, [P, I, P]), "dgo_board_territory": (None, [P, P]), "dgo_board_is_scorable": (I, [P]),
             "dgo_board_policy_candidates": (None, [P, I, I, P]), "dgo_board_is_simple_eye": (I, [P, I, I]),
         }
         for name, (res, args) in sig.items():
@@ -141,6 +141,23 @@ class Board:
     def is_scorable(self) -> bool:
         return bool(lib().dgo_board_is_scorable(self._h))
 
+    def territory(self) -> np.ndarray:
+        """1 / 2 / 0 per point: whose territory the game record counts it as (score.rs:148-195)."""
+        out = np.empty(361, np.uint8)
+        lib().dgo_board_territory(self._h, out.ctypes.data)
+        return out
+
+    def result(self) -> str:
+        """`get_winner_as_sgf` (game_result.rs:78-93)."""
+        t = self.territory()
+        black = np.float32((t == 1).sum())
+        white = np.float32(np.float32((t == 2).sum()) + np.float32(lib_komi(self)))
+        if black > white:
+            return "B+%.1f" % float(np.float32(black - white))
+        if white > black:
+            return "W+%.1f" % float(np.float32(white - black))
+        return "0"
+
     def policy_candidates(self, to_move: int, kind: int = 0) -> np.ndarray:
         out = np.empty(362, np.uint8)
         lib().dgo_board_policy_candidates(self._h, to_move, kind, out.ctypes.data)
@@ -148,6 +165,10 @@ class Board:
 
     def is_simple_eye(self, color: int, x: int, y: int) -> bool:
         return bool(lib().dgo_board_is_simple_eye(self._h, color, idx(x, y)))
+
+
+def lib_komi(board: "Board") -> float:
+    return float(lib().dgo_board_komi(board._h))
 
 
 def symmetry_apply(transform: int, index: int) -> int:

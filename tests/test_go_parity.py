@@ -292,3 +292,22 @@ def test_scorable_kats_on_product():   # utils/score.rs:289-349
     b = pgo.Board(7.5)
     b.place(BLACK, 0, 0)
     assert not b.is_scorable()
+
+
+def test_territory_parity():                  # utils/score.rs:148-195
+    for seed in range(4):
+        po, oo = pgo.Board(6.5), ogo.Board(6.5)
+        for c, x, y in settled_position(seed):
+            if oo.at(x, y) == 0 and oo.is_valid(c, x, y):
+                po.place(c, x, y)
+                oo.place(c, x, y)
+        want = oo.territory()
+        assert (po.territory() == want).all()
+        assert (want == 1).any() and (want == 2).any()
+    for colors, moves, komi in ogo.load_games()[::9]:
+        po, oo = pgo.Board(komi), ogo.Board(komi)
+        for c, m in zip(colors, moves):
+            if m < 361:
+                po.place_index(int(c), int(m))
+                oo.place_index(int(c), int(m))
+        assert (po.territory() == oo.territory()).all()

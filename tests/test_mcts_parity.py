@@ -253,6 +253,7 @@ def test_self_play_records_replay_legally_on_the_oracle(mode):
         st, games = pm.self_play(stub, num_rollout=1, **kw)       # `--num-rollout 1`: play from the averaged policy
     assert st["games_finished"] == 2 and len(games) == 2
     for sgf in games:
+        import re
         komi, moves = parse_record(sgf)
         assert len(moves) == (40 if mode == "ex_it" else 14)
         board = ogo.Board(komi)
@@ -270,6 +271,13 @@ def test_self_play_records_replay_legally_on_the_oracle(mode):
                     assert dist[index] > 0
             else:
                 assert "TV" not in props and "P" not in props
+        # result and territory lists as game_result.rs:23-93 writes them, from the oracle's scoring of the final position
+        assert re.search(r"RE\[([^\]]*)\]", sgf).group(1) == board.result()
+        terr = board.territory()
+        for tag, color in (("TB", 1), ("TW", 2)):
+            m = re.search(tag + r"((?:\[[a-s]{2}\])+)", sgf)
+            got = sorted((ord(p[1]) - 97) * 19 + ord(p[0]) - 97 for p in re.findall(r"\[([a-s]{2})\]", m.group(1))) if m else []
+            assert got == np.flatnonzero(terr == color).tolist()
     if mode == "ex_it":
         assert st["searches"] > st["moves"]          # some positions were searched twice
 

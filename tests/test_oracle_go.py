@@ -357,3 +357,23 @@ def test_simple_eye_kats():   # libdg_mcts/options.rs:217-262
     assert b.is_simple_eye(BLACK, 1, 1) and not b.is_simple_eye(WHITE, 1, 1)
     b.place(BLACK, 0, 0)
     assert b.is_simple_eye(BLACK, 1, 1) and not b.is_simple_eye(WHITE, 1, 1)
+
+
+def test_eyes_should_be_territory():          # utils/score.rs:351-405
+    b = Board(0.5)
+    for x, y in [(0, 1), (1, 1), (2, 0), (2, 1), (3, 1), (4, 0), (4, 1)]:
+        b.place(WHITE, x, y)
+    b.place(BLACK, 0, 0)
+    b.place(BLACK, 9, 9)
+    t = b.territory()
+    for y in range(19):
+        for x in range(19):
+            want = 1 if (x, y) == (9, 9) else 2      # alive white stones, their eyes, the dead stone at (0,0), everything they reach;
+            assert t[go.idx(x, y)] == want, (x, y)   # the lone black stone counts for black ("seki")
+    assert b.result() == "W+359.5"             # 360 points + 0.5 komi against the one black stone
+
+
+def test_result_of_score_kats():              # utils/score.rs:289-330 positions through game_result.rs:78-93
+    b = Board(7.5)
+    b.place(BLACK, 0, 0)
+    assert b.result() == "W+6.5"              # one stone vs komi: nothing is unconditionally alive
