@@ -96,7 +96,6 @@ struct Game {
     Rng rng;
     SearchTask task;
     std::unique_ptr<PredictionCache> cache;
-    int64_t cache_hits = 0;
     std::string sgf;
     std::vector<uint16_t> moves;
     std::vector<dg_packed_position> batch;                       // this round's leaves (host feature planes) ...
