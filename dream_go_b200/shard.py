@@ -19,6 +19,8 @@ class Shards:
             import torch.distributed as dist
             backend = backend or "nccl"
             if backend == "nccl":
+                # NCCL announces its version on stdout; the benchmark's stdout is ONE JSON line, so send that to stderr
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
                 torch.cuda.set_device(self.local_rank)
                 self.device = torch.device("cuda", self.local_rank)
                 dist.init_process_group("nccl", device_id=self.device)
