@@ -19,8 +19,10 @@ class Shards:
             import torch.distributed as dist
             backend = backend or "nccl"
             if backend == "nccl":
-                # NCCL announces its version on stdout; the benchmark's stdout is ONE JSON line, so send that to stderr
-                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+                # with NCCL_DEBUG=VERSION (this image's default) NCCL prints a banner on stdout, but the benchmarks'
+                # stdout is ONE JSON line: keep warnings, drop the banner; any other NCCL_DEBUG setting is left alone
+                if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                    os.environ["NCCL_DEBUG"] = "WARN"
                 torch.cuda.set_device(self.local_rank)
                 self.device = torch.device("cuda", self.local_rank)
                 dist.init_process_group("nccl", device_id=self.device)
