@@ -19,10 +19,13 @@ class Shards:
             import torch.distributed as dist
             backend = backend or "nccl"
             if backend == "nccl":
-                # with NCCL_DEBUG=VERSION (this image's default) NCCL prints a banner on stdout, but the benchmarks'
-                # stdout is ONE JSON line: keep warnings, drop the banner; any other NCCL_DEBUG setting is left alone
+                # with NCCL_DEBUG=VERSION (this image's default) NCCL printf()s a banner on STDOUT, but the benchmarks'
+                # stdout is ONE JSON line: say the version on stderr instead; any other NCCL_DEBUG setting is left alone
                 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-                    os.environ["NCCL_DEBUG"] = "WARN"
+                    os.environ["NCCL_DEBUG"] = "NONE"
+                    if self.rank == 0:
+                        import sys
+                        print("NCCL version " + ".".join(str(v) for v in torch.cuda.nccl.version()), file=sys.stderr)
                 torch.cuda.set_device(self.local_rank)
                 self.device = torch.device("cuda", self.local_rank)
                 dist.init_process_group("nccl", device_id=self.device)
