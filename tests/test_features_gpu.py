@@ -91,3 +91,11 @@ def test_network_from_raw_positions_matches_compact_path(engine):
     assert (out.value.view(np.uint16) == want.value.view(np.uint16)).all()
     assert (out.policy.view(np.uint16) == want.policy.view(np.uint16)).all()
     assert (got_legal == legal).all()
+
+
+def test_long_random_game_bit_exact(engine):
+    """1,500 plies of random play (board fills, big captures, re-play on freed points, hash ring wrapping)."""
+    from test_go_parity import random_playout
+    colors, moves = random_playout(5, 1500, pass_rate=0.0)
+    raws, planes, legal = replay_raw(colors, moves, 7.5)
+    check(engine, raws, planes, legal)

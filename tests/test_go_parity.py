@@ -311,3 +311,13 @@ def test_territory_parity():                  # utils/score.rs:148-195
                 po.place_index(int(c), int(m))
                 oo.place_index(int(c), int(m))
         assert (po.territory() == oo.territory()).all()
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_long_random_games_bit_exact(seed):
+    """1,500 plies of random play: the board fills up, large groups die and the freed areas are played in again and again
+    (visited points, the 16-entry hash ring wrapping ~90 times, occasional kos) -- far beyond what real games reach."""
+    colors, moves = random_playout(seed, 1500, pass_rate=0.0)
+    stones = ogo.replay(colors, moves, 7.5, features=True)["features"].astype(np.float32)[:, :, 5].sum(axis=1)
+    assert (np.diff(stones) < -5).any()                     # big captures happen
+    assert_same_replay(colors, moves, 7.5)
