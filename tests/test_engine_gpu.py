@@ -247,3 +247,24 @@ def test_no_further_from_oracle_than_cudnn(full_engine, full_net):
     assert rel_l2(et, want_t) <= max(rel_l2(ct, want_t), 5e-4)
     assert np.abs(ev.astype(np.float32) - cv.astype(np.float32)).max() <= VALUE_TOL
     assert np.abs(ep.reshape(batch, 362).astype(np.float32) - cp.astype(np.float32)).max() <= 1e-3
+
+
+@pytest.mark.parametrize("batch", [300, 512, 1000])
+def test_large_and_ragged_batches_equal_split_evaluation(full_net, batch):
+    """BASELINE-size network at batches beyond 256 (self-play sends up to 512 leaves per forward): every position's
+    output is bit-identical to its output in a batch of 64 (batch-position independence at full size)."""
+    net = nn.Network.from_tensors(full_net, max_batch=1024, num_workspaces=2)
+    try:
+        feats = weights.bernoulli_features(batch, seed=batch)
+        with net.get_workspace(batch) as ws:
+            value, policy = nn.forward(ws, feats).unwrap()
+        policy = policy.reshape(batch, 362)
+        assert np.isfinite(policy.astype(np.float32)).all()
+        assert np.abs(policy.astype(np.float32).sum(axis=1) - 1.0).max() < 1e-2
+        for at in (0, batch // 2 - 17, batch - 64):
+            with net.get_workspace(64) as ws:
+                v, p = nn.forward(ws, feats[at:at + 64]).unwrap()
+            assert (v.view(np.uint16) == value[at:at + 64].view(np.uint16)).all()
+            assert (p.reshape(64, 362).view(np.uint16) == policy[at:at + 64].view(np.uint16)).all()
+    finally:
+        net.close()
