@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=9)
     ap.add_argument("--ex-it", action="store_true")
     ap.add_argument("--host-only", action="store_true", help="RandomPredictor instead of the engine (no GPU needed)")
+    ap.add_argument("--sgf-out", default=None, help="write the finished games' records (rank 0) to this file")
     ap.add_argument("--cache", type=int, default=0, help="entries of each game's transposition table (0 = none)")
     ap.add_argument("--blocking-sync", action="store_true", help="blocking engine calls sleep on an event instead of spinning in the driver")
     ap.add_argument("--host-features", action="store_true",
@@ -82,6 +83,9 @@ def main():
         wall = time.perf_counter() - t0
         tot = shards.selfplay_totals(st)
         shards.close()
+        if args.sgf_out and rank == 0:
+            with open(args.sgf_out, "w") as fh:
+                fh.write("\n".join(sgf) + "\n")
         moves, evals, games, seconds, eval_s, rounds = (tot["moves"], tot["evals"], tot["games_finished"], tot["seconds"],
                                                         tot["predictor_seconds"], tot["rounds"])
         line.update({"value": moves / seconds, "nn_evals_per_s": evals / seconds, "games_finished": games, "moves": moves,
