@@ -336,10 +336,14 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     d.games = std::vector<Game>(n_slots);
     for (Game& g : d.games) d.start_game(g);
 
-    // games alternate in groups: while the device evaluates one group's leaves the host works on the others
-    int want_groups = 4;
+    // games alternate in groups: while the device evaluates one group's leaves the host works on the others.  More
+    // groups hide more host time, fewer groups make larger device batches; aim at >= 128-256 leaves per batch
+    int want_groups = config->num_groups;
     if (const char* env = getenv("DG_SELFPLAY_GROUPS")) want_groups = atoi(env);
-    if (want_groups < 1) want_groups = 1;
+    if (want_groups <= 0) {
+        const int leaves = n_slots * (config->probes_per_round > 0 ? config->probes_per_round : 1);
+        want_groups = std::max(2, std::min(4, leaves / 256));
+    }
     if (want_groups > 8) want_groups = 8;
     const int n_groups = std::min(want_groups, n_slots);
     struct Group {

@@ -31,7 +31,7 @@ class _SelfPlayConfig(C.Structure):
                 ("probes_per_round", C.c_int32), ("max_plies", C.c_int32), ("num_threads", C.c_int32),
                 ("ex_it", C.c_int32), ("num_ex_it_rollout", C.c_int32), ("dirichlet_noise", C.c_float),
                 ("temperature", C.c_float), ("seed", C.c_uint64), ("max_seconds", C.c_double),
-                ("cache_capacity", C.c_int32), ("reserved", C.c_int32)]
+                ("cache_capacity", C.c_int32), ("num_groups", C.c_int32)]
 
 
 class _SelfPlayStats(C.Structure):
@@ -215,11 +215,11 @@ def predict(predictor, board: "go.Board", color: int, *, search: int = go.STANDA
 def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout: int = 800, probes_per_round: int = 8,
               max_plies: int = 722, num_threads: int = 0, ex_it: bool = False, num_ex_it_rollout: int = 800,
               dirichlet_noise: float = 0.25, temperature: float = 0.8, seed: int = 1, max_seconds: float = 0.0,
-              cache_capacity: int = 0, sgf_capacity: int = 1 << 24):
+              cache_capacity: int = 0, num_groups: int = 0, sgf_capacity: int = 1 << 24):
     """`dg_mcts::self_play`: returns (stats dict, list of SGF records)."""
     fn, ctx = _fn_ctx(predictor)
     cfg = _SelfPlayConfig(num_games, num_parallel, num_rollout, probes_per_round, max_plies, num_threads, int(ex_it),
-                          num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds, cache_capacity, 0)
+                          num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds, cache_capacity, num_groups)
     stats = _SelfPlayStats()
     buf = C.create_string_buffer(sgf_capacity)
     run = lib().dg_selfplay_run_raw if getattr(predictor, "raw", False) else lib().dg_selfplay_run
