@@ -64,7 +64,8 @@ def main():
     line = {"metric": "self_play_moves_per_s", "unit": "moves/s", "n_gpus": world, "higher_is_better": True,
             "config": {"workload": f"--self-play {args.games} --num-rollout {args.rollouts}, {args.parallel} concurrent games per GPU"
                                    + (" --ex-it" if args.ex_it else ""),
-                       "sample": f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-ply cap)",
+                       "sample": (f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-stone cap)"
+                                  if args.seconds > 0 else "all games played to the end"),
                        "probes_per_round": args.probes, "feature_planes": "host" if args.host_features else "device (csrc/features.cu)", "host_threads_per_gpu": threads, "host_cores": cores,
                        "weights": f"{args.blocks} blocks x 128 filters, seeded random init", "data": "synthetic"},
             "host_only": {"evals_per_s": host["evals"] / host["seconds"], "moves_per_s": host["moves"] / host["seconds"],
