@@ -450,8 +450,8 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
         if (w.resident_kind == 1) DG_CUDA(e, dg::launch_pack_features(w.d_in, w.feat, batch, w.stream));
         else if (w.resident_kind == 3) {
             // raw positions at d_in; compact planes and legal masks behind them in the same buffer
-            DG_CUDA(e, dg::launch_planes_from_stones(w.d_in, raw_planes(e, w), raw_legal(e, w), batch, w.stream));
-            DG_CUDA(e, dg::launch_pack_compact(raw_planes(e, w), w.feat, batch, w.stream));
+            // (the kernel also writes the tower's input rows: no separate pack launch)
+            DG_CUDA(e, dg::launch_planes_from_stones(w.d_in, raw_planes(e, w), raw_legal(e, w), w.feat, batch, w.stream));
         } else DG_CUDA(e, dg::launch_pack_compact(w.d_in, w.feat, batch, w.stream));
         if (stage == 1) return DG_OK;
     }

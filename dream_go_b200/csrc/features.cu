@@ -11,12 +11,14 @@
 //   3. per point the 32 plane bits: liberties of stones, legality + liberties-after-playing for both colours
 //      (board_fast.rs:216-243, 484-539: union of the joined chains' liberty sets, the point's empty neighbours and any
 //      captured stones that touch the new chain), super-ko against the last 16 hashes (board.rs:132-141),
-//   4. written as `dg_packed_position` (index = symmetry[p]) for pack_compact_kernel, plus the legal mask.
+//   4. written as `dg_packed_position` (index = symmetry[p]) plus the legal mask, and expanded in the same kernel into
+//      the tower's input rows (400 x 64 fp16 per position).
 // Integer work end to end; tests/test_features_gpu.py checks it bit for bit against the host code and the oracle.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "kernels.h"
+#include "layout.h"
 
 namespace dg {
 
@@ -35,8 +37,18 @@ __constant__ uint16_t c_symmetry[8][361];
 
 __device__ __forceinline__ bool bit(const uint32_t* m, int i) { return (m[i >> 5] >> (i & 31)) & 1u; }
 
+// Block n < batch handles position n and also expands its planes into the tower's input rows (what pack_compact_kernel
+// does for host-made planes: 400 rows x 64 fp16 channels, halo rows and channels 32..63 zero); block `batch` zeroes the
+// rows between the last position and the end of the last 128-row tile (stale after a larger batch).
 __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPosition* __restrict__ in, uint32_t* __restrict__ out_planes,
-                                                                 uint8_t* __restrict__ out_legal) {
+                                                                 uint8_t* __restrict__ out_legal, uint4* __restrict__ out_rows,
+                                                                 int batch, int total_rows) {
+    __shared__ uint32_t planes_s[361];
+    if (static_cast<int>(blockIdx.x) == batch) {
+        const long first = static_cast<long>(batch) * DG_POS_ROWS * 8, last = static_cast<long>(total_rows) * 8;
+        for (long i = first + threadIdx.x; i < last; i += 384) out_rows[static_cast<long>(DG_GUARD_ROWS) * 8 + i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
     __shared__ uint32_t lib[361][12];             // liberty set of the chain whose smallest point index is the row
     __shared__ unsigned long long chash[361];     // XOR of the zobrist keys of its stones
     __shared__ uint16_t lab[384];
@@ -201,9 +213,31 @@ __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPositi
     if (on) {
         const uint32_t global = (tm == 1 ? 1u : 2u) | (any_ko ? 4u : 0u);
         uint32_t* out = out_planes + static_cast<size_t>(blockIdx.x) * 362;
-        out[c_symmetry[r.symmetry][t]] = m | global;
+        const int target = c_symmetry[r.symmetry][t];
+        out[target] = m | global;
+        planes_s[target] = m | global;
         if (t == 0) out[361] = r.k_bits;
         out_legal[static_cast<size_t>(blockIdx.x) * 361 + t] = legal ? 1 : 0;
+    }
+    __syncthreads();
+    // 5. the tower's input rows of this position: one 16-byte chunk (8 channels) per thread and step, coalesced
+    const uint32_t kbits = r.k_bits;
+    uint4* rows = out_rows + (static_cast<long>(DG_GUARD_ROWS) + static_cast<long>(blockIdx.x) * DG_POS_ROWS) * 8;
+    for (int idx = t; idx < DG_POS_ROWS * 8; idx += 384) {
+        const int q = idx >> 3, chunk = idx & 7;
+        const int qx = q % DG_LINE_STRIDE, qy = q / DG_LINE_STRIDE;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (chunk < 4 && qx < 19 && qy < 19) {
+            const uint32_t mask = planes_s[qy * 19 + qx] >> (chunk * 8);
+            uint32_t h[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t one = (chunk == 0 && j < 2) ? kbits : 0x3c00u;
+                h[j] = ((mask >> j) & 1u) ? one : 0u;
+            }
+            v = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+        }
+        rows[idx] = v;
     }
 }
 
@@ -213,9 +247,10 @@ cudaError_t upload_feature_tables(const unsigned long long* zobrist /* [2][361] 
     return cudaMemcpyToSymbol(c_symmetry, symmetry, sizeof(c_symmetry));
 }
 
-cudaError_t launch_planes_from_stones(const void* raw, void* planes, void* legal, int batch, cudaStream_t s) {
-    planes_from_stones_kernel<<<batch, 384, 0, s>>>(static_cast<const RawPosition*>(raw), static_cast<uint32_t*>(planes),
-                                                    static_cast<uint8_t*>(legal));
+cudaError_t launch_planes_from_stones(const void* raw, void* planes, void* legal, void* rows64, int batch, cudaStream_t s) {
+    const int total = dg_num_tiles(batch) * DG_TILE_M;
+    planes_from_stones_kernel<<<batch + 1, 384, 0, s>>>(static_cast<const RawPosition*>(raw), static_cast<uint32_t*>(planes),
+                                                        static_cast<uint8_t*>(legal), static_cast<uint4*>(rows64), batch, total);
     return cudaGetLastError();
 }
 

@@ -91,6 +91,11 @@ def test_network_from_raw_positions_matches_compact_path(engine):
     assert (out.value.view(np.uint16) == want.value.view(np.uint16)).all()
     assert (out.policy.view(np.uint16) == want.policy.view(np.uint16)).all()
     assert (got_legal == legal).all()
+    # a smaller batch right after a larger one: no stale rows may survive behind the last position
+    out, _ = engine.forward_raw(raws[:5])
+    want = engine.forward_packed(planes[:5])
+    assert (out.value.view(np.uint16) == want.value.view(np.uint16)).all()
+    assert (out.policy.view(np.uint16) == want.policy.view(np.uint16)).all()
 
 
 def test_long_random_game_bit_exact(engine):
