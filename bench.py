@@ -270,12 +270,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                       seconds=args.self_play_seconds, threads=threads, seed=20261017 + rank)
         tot = shards.selfplay_totals(st)
         sp_net.close()
+        host_only = None
+        if rank == 0:      # the host half alone: same search and feature code, RandomPredictor instead of the device
+            from dream_go_b200 import mcts
+            ho, _ = mcts.self_play(mcts.RandomPredictor(), num_games=100000, num_parallel=SELF_PLAY_GAMES, num_rollout=800,
+                                   probes_per_round=8, num_threads=threads, seed=20261017, max_seconds=4.0)
+            host_only = {"nn_evals_per_s": ho["evals"] / ho["seconds"], "moves_per_s": ho["moves"] / ho["seconds"],
+                         "threads": threads, "predictor": "dg_random_predict (no device; feature planes on the host)"}
         self_play = {"moves_per_s": tot["moves_per_s"], "nn_evals_per_s": tot["nn_evals_per_s"], "unit": "moves/s, evals/s",
                      "mean_device_batch": tot["mean_device_batch"],
                      "predictor_time_frac": tot["predictor_seconds"] / (tot["seconds"] * world),   # alternating groups overlap, so this can exceed 1
                      "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU in 4 alternating groups, real positions: "
                                  f"feature planes + legal moves derived on the device from raw stones (ladder planes on the host), random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
-                     "host_threads_per_gpu": threads, "host_cores": os.cpu_count()}
+                     "host_threads_per_gpu": threads, "host_cores": os.cpu_count(), "host_only": host_only}
 
     shards.close()
     if rank != 0:
