@@ -128,3 +128,30 @@ def test_forward_argument_checks_need_no_device():
         nn.forward(ws, np.zeros((2 * 11552 - 1,), np.float16))
     with pytest.raises(nn.Error):
         nn.forward(ws, np.zeros((2 * 11552,), np.float32))
+
+
+def test_search_and_selfplay_reject_bad_arguments():
+    import ctypes as C
+    from dream_go_b200 import go, mcts
+    L = mcts.lib()
+    board = go.Board(7.5)
+    opt = mcts._SearchOptions(0, 1, 10, 1, 0.25, 0.8, 1, None, None, 0, -1.0, None)
+    null_fn = C.cast(None, mcts.PREDICT_FN)
+    assert L.dg_mcts_predict(null_fn, None, C.byref(opt), None, board._h, 1, None, None, None, None) == -5
+    cfg = mcts._SelfPlayConfig(0, 4, 10, 1, 10, 1, 0, 0, 0.25, 0.8, 1, 0.0, 0, 0)          # num_games = 0
+    stats = mcts._SelfPlayStats()
+    rnd = mcts.RandomPredictor()
+    assert L.dg_selfplay_run(rnd.fn, None, C.byref(cfg), C.byref(stats), None, 0) == -5
+    # a failing predictor's status comes back unchanged
+    failing = mcts.PREDICT_FN(lambda ctx, pos, n, v, p: -2)
+    assert L.dg_mcts_predict(failing, None, C.byref(opt), None, board._h, 1, None, None, None, None) == -2
+    cfg = mcts._SelfPlayConfig(2, 2, 10, 1, 10, 1, 0, 0, 0.25, 0.8, 1, 0.0, 0, 0)
+    assert L.dg_selfplay_run(failing, None, C.byref(cfg), C.byref(stats), None, 0) == -2
+
+
+def test_engine_entry_points_reject_null_engine():
+    L = nn.lib()
+    assert L.dg_engine_forward_f16(None, None, 1, None, None) == -5
+    assert L.dg_engine_forward_raw(None, None, 1, None, None, None) == -5
+    assert L.dg_engine_queue_push(None, None) == -5
+    assert L.dg_engine_max_batch(None) == 0
