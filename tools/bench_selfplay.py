@@ -22,12 +22,12 @@ sys.path.insert(0, ROOT)
 
 
 def sample(net, *, games: int, parallel: int, rollouts: int, probes: int, seconds: float, threads: int, seed: int,
-           ex_it: bool = False, device_features: bool = True, cache_capacity: int = 0):
+           ex_it: bool = False, device_features: bool = True, cache_capacity: int = 0, ex_it_rollouts: int = 0):
     """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics."""
     from dream_go_b200 import mcts
     predictor = mcts.EngineRawPredictor(net) if device_features else mcts.EnginePredictor(net)
     st, sgf = mcts.self_play(predictor, num_games=games, num_parallel=parallel, num_rollout=rollouts,
-                             probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=rollouts, seed=seed,
+                             probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=ex_it_rollouts or rollouts, seed=seed,
                              max_seconds=seconds, cache_capacity=cache_capacity)
     return st, sgf
 
@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks", type=int, default=9)
     ap.add_argument("--ex-it", action="store_true")
+    ap.add_argument("--ex-it-rollouts", type=int, default=0, help="`--num-ex-it-rollout` (default: same as --rollouts)")
     ap.add_argument("--host-only", action="store_true", help="RandomPredictor instead of the engine (no GPU needed)")
     ap.add_argument("--sgf-out", default=None, help="write the finished games' records (rank 0) to this file")
     ap.add_argument("--cache", type=int, default=0, help="entries of each game's transposition table (0 = none)")
@@ -80,7 +81,7 @@ def main():
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
                          seconds=args.seconds, threads=threads, seed=shards.seed(20261017), ex_it=args.ex_it,
-                         device_features=not args.host_features, cache_capacity=args.cache)
+                         device_features=not args.host_features, cache_capacity=args.cache, ex_it_rollouts=args.ex_it_rollouts)
         wall = time.perf_counter() - t0
         tot = shards.selfplay_totals(st)
         shards.close()
@@ -90,7 +91,8 @@ def main():
         moves, evals, games, seconds, eval_s, rounds = (tot["moves"], tot["evals"], tot["games_finished"], tot["seconds"],
                                                         tot["predictor_seconds"], tot["rounds"])
         line.update({"value": moves / seconds, "nn_evals_per_s": evals / seconds, "games_finished": games, "moves": moves,
-                     "evals": evals, "seconds": seconds, "mean_batch": evals / max(rounds, 1), "cache_hits_rank0": st.get("cache_hits", 0), "cache_capacity_per_game": args.cache,
+                     "evals": evals, "seconds": seconds, "mean_batch": evals / max(rounds, 1), "cache_hits_rank0": st.get("cache_hits", 0), "searches_rank0": st.get("searches", 0),
+                     "ex_it_expansions_rank0": (st.get("searches", 0) - st.get("moves", 0)) if args.ex_it else 0, "cache_capacity_per_game": args.cache,
                      "device_busy_frac": eval_s / (seconds * world), "wall_s": wall,
                      "first_game": sgf[0][:200] if sgf else None})
         net.close()
