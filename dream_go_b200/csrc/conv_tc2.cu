@@ -312,9 +312,10 @@ cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUte
 //     layer l-1, published through per-tile progress flags (st.release by the epilogue, ld.acquire
 //     + fence.proxy.async by the TMA producer).  The same RAW chain also covers every WAR hazard of
 //     the x/y ping-pong buffers;
-//   * the filter bank of layer l+1 replaces layer l's in shared memory half by half: the k-half-0
-//     slabs are reloaded while the last unit of layer l still runs its k-half-1 MMAs, the
-//     k-half-1 slabs while the first unit of layer l+1 runs its k-half-0 MMAs -- no weight bubble;
+//   * the filter bank of layer l+1 replaces layer l's in shared memory slab by slab (one 8 KiB slab per
+//     (tap, k-half), in the order the MMAs consume them): in the last unit of a layer every tap commits
+//     its own w_free barrier when its MMAs retire, the producer re-fetches that slab immediately, and in
+//     the first unit of the next layer every tap waits for its own w_full barrier;
 //   * the unit -> pair assignment rotates by `rot` pairs per layer so that the pairs that get the
 //     extra (6th) unit differ from layer to layer.
 // The grid must be fully co-resident (<= one CTA per SM, cooperative launch).
@@ -324,8 +325,7 @@ template <int UNUSED = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2::kThreads, 1)
 tower_kernel(const __grid_constant__ TowerParams p) {
     using namespace t2;
-    constexpr int kWeights = Smem<2>::kWeights, kAOff = Smem<2>::kAOff, kBarOff = Smem<2>::kBarOff;
-    constexpr uint32_t kHalfBytes = 9 * kSlab;           // one k-half of this CTA's filter slice
+    constexpr int kAOff = Smem<2>::kAOff, kBarOff = Smem<2>::kBarOff;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* w_s = smem;
