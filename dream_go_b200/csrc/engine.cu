@@ -46,6 +46,8 @@ struct Workspace {
     CUtensorMap tm_pa;                 // [batch][3200] view of pbuf
     __half *d_policy = nullptr, *d_value = nullptr;
     uint8_t* h_legal = nullptr;       // pinned: legal masks of the raw-position path
+    float* h_prior = nullptr;         // pinned: priors of the raw-position path
+    bool want_plan = false;           // the next raw feature launch also derives candidates / orbit representatives
     uint8_t* h_in = nullptr;          // pinned staging
     __half *h_policy = nullptr, *h_value = nullptr;
     CUtensorMap tm_feat, tm_x, tm_y;           // 170-row load windows
@@ -178,6 +180,7 @@ int32_t create_workspace(dg_engine* e, Workspace& w) {
     DG_CUDA(e, cudaHostAlloc(&w.h_policy, static_cast<size_t>(mb) * DG_POLICY_SIZE * 2, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_value, static_cast<size_t>(mb) * 2, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_legal, static_cast<size_t>(mb) * 361, cudaHostAllocDefault));
+    DG_CUDA(e, cudaHostAlloc(&w.h_prior, static_cast<size_t>(mb) * 368 * 4, cudaHostAllocDefault));
     if (!make_tmap(e, &w.tm_feat, w.feat, 64, rows, DG_WINDOW_ROWS) || !make_tmap(e, &w.tm_x, w.x, kChan, rows, DG_WINDOW_ROWS) ||
         !make_tmap(e, &w.tm_y, w.y, kChan, rows, DG_WINDOW_ROWS) ||
         !make_tmap(e, &w.tm_pa, w.pbuf + static_cast<size_t>(DG_GUARD_ROWS) * 8, dg::kPolicyFcK, mb, 128))
@@ -192,7 +195,7 @@ void destroy_workspace(Workspace& w) {
     if (w.ev_done) cudaEventDestroy(w.ev_done);
     cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
     cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done); cudaFree(w.pbuf); cudaFree(w.vbuf); cudaFree(w.part);
-    cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value); cudaFreeHost(w.h_legal);
+    cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value); cudaFreeHost(w.h_legal); cudaFreeHost(w.h_prior);
 }
 
 Workspace* acquire(dg_engine* e) {
@@ -440,6 +443,9 @@ inline cudaError_t wait_stream(dg_engine* e, Workspace& w) {
 // Raw-position path: d_in (max_batch x 23,104 B) holds [raw positions | compact planes | legal masks].
 inline uint8_t* raw_planes(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 512; }
 inline uint8_t* raw_legal(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 2048; }
+inline uint8_t* raw_cand(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 2560; }
+inline uint8_t* raw_rep(dg_engine* e, Workspace& w) { return w.d_in + static_cast<size_t>(e->cfg.max_batch) * 3072; }
+inline float* raw_prior(dg_engine* e, Workspace& w) { return reinterpret_cast<float*>(w.d_in + static_cast<size_t>(e->cfg.max_batch) * 4096); }
 
 // Enqueues pack + tower (+ heads) of the batch resident in w.d_in.  blocks < 0 = whole network.
 // stage: 0 = everything, 1 = pack only, 2 = residual convolutions only (timing), 3 = everything but pack.
@@ -451,7 +457,8 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
         else if (w.resident_kind == 3) {
             // raw positions at d_in; compact planes and legal masks behind them in the same buffer
             // (the kernel also writes the tower's input rows: no separate pack launch)
-            DG_CUDA(e, dg::launch_planes_from_stones(w.d_in, raw_planes(e, w), raw_legal(e, w), w.feat, batch, w.stream));
+            DG_CUDA(e, dg::launch_planes_from_stones(w.d_in, raw_planes(e, w), raw_legal(e, w), w.feat, w.want_plan ? raw_cand(e, w) : nullptr,
+                                                     w.want_plan ? raw_rep(e, w) : nullptr, batch, w.stream));
         } else DG_CUDA(e, dg::launch_pack_compact(w.d_in, w.feat, batch, w.stream));
         if (stage == 1) return DG_OK;
     }
@@ -676,7 +683,7 @@ int32_t dg_engine_forward_packed(dg_engine* e, const dg_packed_position* positio
 }
 
 static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t batch, uint16_t* value_out, uint16_t* policy_out,
-                        dg_packed_position* planes_out, uint8_t* legal_out) {
+                        dg_packed_position* planes_out, uint8_t* legal_out, float* prior_out = nullptr) {
     if (!e) return DG_ERR_INVALID_ARGUMENT;
     if (!positions || !legal_out) return fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer");
     if (batch < 1 || batch > e->cfg.max_batch) return fail(e, DG_ERR_INVALID_ARGUMENT, "batch %d outside 1..%d", batch, e->cfg.max_batch);
@@ -690,8 +697,14 @@ static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t 
     DG_CUDA(e, cudaMemcpyAsync(w.d_in, w.h_in, in_bytes, cudaMemcpyHostToDevice, w.stream));
     w.resident_kind = 3;
     w.resident_batch = batch;
+    w.want_plan = prior_out != nullptr;
     int32_t rc = enqueue_network(e, w, batch, -1, network ? 0 : 1);
+    w.want_plan = false;
     if (rc) { cudaStreamSynchronize(w.stream); return rc; }
+    if (prior_out) {
+        DG_CUDA(e, dg::launch_prior_from_policy(w.d_in, w.d_policy, raw_cand(e, w), raw_rep(e, w), raw_prior(e, w), batch, w.stream));
+        DG_CUDA(e, cudaMemcpyAsync(w.h_prior, raw_prior(e, w), static_cast<size_t>(batch) * 368 * 4, cudaMemcpyDeviceToHost, w.stream));
+    }
     DG_CUDA(e, cudaMemcpyAsync(w.h_legal, raw_legal(e, w), static_cast<size_t>(batch) * 361, cudaMemcpyDeviceToHost, w.stream));
     if (network) {
         DG_CUDA(e, cudaMemcpyAsync(w.h_value, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream));
@@ -701,6 +714,7 @@ static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t 
         DG_CUDA(e, cudaMemcpyAsync(planes_out, raw_planes(e, w), sizeof(dg_packed_position) * static_cast<size_t>(batch), cudaMemcpyDeviceToHost, w.stream));
     DG_CUDA(e, wait_stream(e, w));
     memcpy(legal_out, w.h_legal, static_cast<size_t>(batch) * 361);
+    if (prior_out) memcpy(prior_out, w.h_prior, static_cast<size_t>(batch) * 368 * 4);
     if (network) {
         memcpy(value_out, w.h_value, static_cast<size_t>(batch) * 2);
         memcpy(policy_out, w.h_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2);
@@ -712,6 +726,12 @@ int32_t dg_engine_forward_raw(dg_engine* e, const dg_raw_position* positions, in
                               uint8_t* legal_out) {
     if (!value_out || !policy_out) return e ? fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer") : DG_ERR_INVALID_ARGUMENT;
     return raw_impl(e, positions, batch, value_out, policy_out, nullptr, legal_out);
+}
+
+int32_t dg_engine_forward_raw_prior(dg_engine* e, const dg_raw_position* positions, int32_t batch, uint16_t* value_out,
+                                    uint16_t* policy_out, uint8_t* legal_out, float* prior_out) {
+    if (!value_out || !policy_out || !prior_out) return e ? fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer") : DG_ERR_INVALID_ARGUMENT;
+    return raw_impl(e, positions, batch, value_out, policy_out, nullptr, legal_out, prior_out);
 }
 
 int32_t dg_engine_features_raw(dg_engine* e, const dg_raw_position* positions, int32_t batch, dg_packed_position* planes_out,

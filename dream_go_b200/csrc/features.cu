@@ -14,6 +14,7 @@
 //   4. written as `dg_packed_position` (index = symmetry[p]) plus the legal mask, and expanded in the same kernel into
 //      the tower's input rows (400 x 64 fp16 per position).
 // Integer work end to end; tests/test_features_gpu.py checks it bit for bit against the host code and the oracle.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -37,11 +38,172 @@ __constant__ uint16_t c_symmetry[8][361];
 
 __device__ __forceinline__ bool bit(const uint32_t* m, int i) { return (m[i >> 5] >> (i & 31)) & 1u; }
 
+
+// ---- candidate mask + symmetry representatives on the device ---------------------------------------------------------------
+struct PlanScratch {                      // lives in the liberty-set storage once the planes are done (< 17 KB)
+    uint16_t rlab[384];                   // region label (smallest point index) of a point, 0xffff = none
+    uint16_t vch[361][4];                 // chains a region is vital to
+    int chain_cnt[361];                   // vital regions per chain (this iteration)
+    uint8_t other[384], dead[384], seeded[384], reg_on[384], nv[384], chain_alive[384];
+    uint8_t eye[2][384];
+    int symm[8];
+};
+static_assert(sizeof(PlanScratch) <= 361 * 12 * 4, "plan scratch must fit into the liberty-set storage");
+
+// Benson's unconditional life for colour c (utils/benson.rs as restated in csrc/go_board.h: benson()): marks eye[t] for the
+// points of the surviving vital regions.  All 384 threads call it; `flag` is a shared int.
+__device__ void device_benson(PlanScratch* S, const uint8_t* col, const uint16_t* lab, const int (&nb)[4], int t, bool on, int c,
+                              uint8_t* eye, int* flag) {
+    const bool is_other = on && col[t] != c;
+    bool near = false;
+    if (on)
+        for (int k = 0; k < 4; k++) near |= nb[k] >= 0 && col[nb[k]] == c;
+    S->other[t] = is_other;
+    S->dead[t] = is_other && !near;       // touches no stone of c: its whole region is vital to nobody
+    S->seeded[t] = 0;
+    S->reg_on[t] = 0;
+    S->nv[t] = 0;
+    S->chain_alive[t] = on && col[t] == c;
+    eye[t] = 0;
+    __syncthreads();
+    for (;;) {                            // flood the dead regions
+        if (t == 0) *flag = 0;
+        __syncthreads();
+        if (is_other && !S->dead[t]) {
+            bool d = false;
+            for (int k = 0; k < 4; k++) d |= nb[k] >= 0 && S->dead[nb[k]];
+            if (d) { S->dead[t] = 1; *flag = 1; }
+        }
+        __syncthreads();
+        const int again = *flag;
+        __syncthreads();
+        if (!again) break;
+    }
+    const bool rest = is_other && !S->dead[t];
+    S->rlab[t] = rest ? static_cast<uint16_t>(t) : 0xffffu;
+    __syncthreads();
+    for (;;) {                            // regions = connected components of what is left
+        if (t == 0) *flag = 0;
+        __syncthreads();
+        if (rest) {
+            int best = S->rlab[t];
+            for (int k = 0; k < 4; k++)
+                if (nb[k] >= 0 && S->rlab[nb[k]] != 0xffffu) best = min(best, static_cast<int>(S->rlab[nb[k]]));
+            best = min(best, static_cast<int>(S->rlab[best]));
+            if (best < S->rlab[t]) { S->rlab[t] = static_cast<uint16_t>(best); *flag = 1; }
+        }
+        __syncthreads();
+        const int again = *flag;
+        __syncthreads();
+        if (!again) break;
+    }
+    if (rest && col[t] == 0) S->seeded[S->rlab[t]] = 1;       // a region starts from an empty point (benson.rs:297-301)
+    __syncthreads();
+    const bool root = rest && S->rlab[t] == t && S->seeded[t];
+    if (root) {                           // chains this region is vital to: every point of the region touches the chain
+        int cand_ch[4], ncand = 0;
+        for (int k = 0; k < 4; k++)
+            if (nb[k] >= 0 && col[nb[k]] == c) {
+                const int ch = lab[nb[k]];
+                bool dup = false;
+                for (int j = 0; j < ncand; j++) dup |= cand_ch[j] == ch;
+                if (!dup) cand_ch[ncand++] = ch;
+            }
+        int nv = 0;
+        for (int j = 0; j < ncand; j++) {
+            bool vital = true;
+            for (int p = 0; p < 361 && vital; p++) {
+                if (S->rlab[p] != t) continue;
+                const int px = p % 19, py = p / 19;
+                const int pn[4] = {px < 18 ? p + 1 : -1, py > 0 ? p - 19 : -1, px > 0 ? p - 1 : -1, py < 18 ? p + 19 : -1};
+                bool touches = false;
+                for (int k = 0; k < 4; k++) touches |= pn[k] >= 0 && col[pn[k]] == c && lab[pn[k]] == cand_ch[j];
+                vital = touches;
+            }
+            if (vital) S->vch[t][nv++] = static_cast<uint16_t>(cand_ch[j]);
+        }
+        S->nv[t] = static_cast<uint8_t>(nv);
+        S->reg_on[t] = nv > 0;            // regions that are vital to nobody go first (benson.rs:128-143)
+    }
+    __syncthreads();
+    for (;;) {
+        if (t == 0) *flag = 0;
+        if (on) S->chain_cnt[t] = 0;
+        __syncthreads();
+        if (root && S->reg_on[t])
+            for (int j = 0; j < S->nv[t]; j++)
+                if (S->chain_alive[S->vch[t][j]]) atomicAdd(&S->chain_cnt[S->vch[t][j]], 1);
+        __syncthreads();
+        // a chain stays alive with two vital regions (benson.rs:95-111); chain_alive is indexed by the chain's label
+        if (on && col[t] == c && lab[t] == t && S->chain_alive[t] && S->chain_cnt[t] < 2) { S->chain_alive[t] = 0; *flag = 1; }
+        __syncthreads();
+        if (root && S->reg_on[t]) {       // a region stays while every stone around it is alive (benson.rs:115-131)
+            bool healthy = true;
+            for (int p = 0; p < 361 && healthy; p++) {
+                if (S->rlab[p] != t) continue;
+                const int px = p % 19, py = p / 19;
+                const int pn[4] = {px < 18 ? p + 1 : -1, py > 0 ? p - 19 : -1, px > 0 ? p - 1 : -1, py < 18 ? p + 19 : -1};
+                for (int k = 0; k < 4; k++)
+                    if (pn[k] >= 0 && col[pn[k]] == c && !S->chain_alive[lab[pn[k]]]) healthy = false;
+            }
+            if (!healthy) { S->reg_on[t] = 0; *flag = 1; }
+        }
+        __syncthreads();
+        const int again = *flag;
+        __syncthreads();
+        if (!again) break;
+    }
+    if (rest && S->seeded[S->rlab[t]] && S->reg_on[S->rlab[t]]) eye[t] = 1;
+    __syncthreads();
+}
+
+__device__ void plan_candidates(PlanScratch* S, const uint8_t* col, const uint16_t* lab, const int (&nb)[4], int t, bool on, bool legal,
+                                int to_move, int search, uint8_t* out_cand, uint16_t* out_rep, int* flag) {
+    // chain labels of stones only matter per colour; chain_alive[] is indexed by label, which is a stone of that chain
+    if (t < 8) S->symm[t] = 1;
+    __syncthreads();
+    if (on)
+        for (int tr = 1; tr < 8; tr++)
+            if (col[t] != col[c_symmetry[tr][t]]) S->symm[tr] = 0;        // symmetry::is_symmetric (utils/symmetry.rs:139-146)
+    bool cand = legal;
+    if (search == 1) {                    // ScoringSearch (libdg_mcts/options.rs:109-138)
+        device_benson(S, col, lab, nb, t, on, 1, S->eye[0], flag);
+        device_benson(S, col, lab, nb, t, on, 2, S->eye[1], flag);
+        if (cand && (S->eye[0][t] || S->eye[1][t])) cand = false;
+        if (cand) {                       // the own-eye heuristic (options.rs:180-214)
+            bool all_cross = true;
+            int n_cross = 0;
+            for (int k = 0; k < 4; k++)
+                if (nb[k] >= 0) { n_cross++; all_cross &= col[nb[k]] == to_move; }
+            if (all_cross) {
+                const int x = t % 19, y = t / 19;
+                int diag = 0;
+                for (int dy = -1; dy <= 1; dy += 2)
+                    for (int dx = -1; dx <= 1; dx += 2) {
+                        const int xx = x + dx, yy = y + dy;
+                        if (xx >= 0 && xx <= 18 && yy >= 0 && yy <= 18 && col[19 * yy + xx] == to_move) diag++;
+                    }
+                if (diag >= (n_cross == 2 ? 1 : n_cross == 3 ? 2 : 3)) cand = false;
+            }
+        }
+    }
+    __syncthreads();
+    if (on) {
+        int rep = t;                      // policy_helper.rs:54-72: the smallest index of the point's orbit
+        for (int tr = 1; tr < 8; tr++)
+            if (S->symm[tr]) rep = min(rep, static_cast<int>(c_symmetry[tr][t]));
+        out_rep[t] = static_cast<uint16_t>(rep);
+        out_cand[t] = cand && rep == t;
+    }
+    if (t == 361) { out_rep[361] = 361; out_cand[361] = search == 0; }
+}
+
 // Block n < batch handles position n and also expands its planes into the tower's input rows (what pack_compact_kernel
 // does for host-made planes: 400 rows x 64 fp16 channels, halo rows and channels 32..63 zero); block `batch` zeroes the
 // rows between the last position and the end of the last 128-row tile (stale after a larger batch).
 __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPosition* __restrict__ in, uint32_t* __restrict__ out_planes,
                                                                  uint8_t* __restrict__ out_legal, uint4* __restrict__ out_rows,
+                                                                 uint8_t* __restrict__ out_cand, uint16_t* __restrict__ out_rep,
                                                                  int batch, int total_rows) {
     __shared__ uint32_t planes_s[361];
     if (static_cast<int>(blockIdx.x) == batch) {
@@ -213,7 +375,7 @@ __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPositi
     if (on) {
         const uint32_t global = (tm == 1 ? 1u : 2u) | (any_ko ? 4u : 0u);
         uint32_t* out = out_planes + static_cast<size_t>(blockIdx.x) * 362;
-        const int target = c_symmetry[r.symmetry][t];
+        const int target = c_symmetry[r.symmetry & 7][t];
         out[target] = m | global;
         planes_s[target] = m | global;
         if (t == 0) out[361] = r.k_bits;
@@ -239,6 +401,69 @@ __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPositi
         }
         rows[idx] = v;
     }
+    // 6. optional: what create_initial_policy derives from the board (pool/policy_helper.rs:28-75) -- the candidate mask
+    //    of the position's search options and the orbit representatives of a symmetric board -- for the prior kernel
+    if (out_cand) {
+        __syncthreads();                              // everybody is done with lib[][]: it becomes scratch space
+        plan_candidates(reinterpret_cast<PlanScratch*>(&lib[0][0]), col, lab, nb, t, on, legal, tm, r.symmetry >> 4,
+                        out_cand + static_cast<size_t>(blockIdx.x) * 362, out_rep + static_cast<size_t>(blockIdx.x) * 362, &changed);
+    }
+}
+
+// add_valid_candidates + normalize_policy (pool/policy_helper.rs:87-134) on the device: the network's policy (fp16, in the
+// orientation the position was evaluated in) is un-transformed, folded onto the orbit representatives, masked by the
+// candidates and scaled to sum 1 -- in the host code's operation order (search_task.h: PriorPlan::apply), so that the result
+// is bit-identical and the search that consumes it builds the same tree.  One block per position.
+__constant__ uint8_t c_sym_inverse[8] = {0, 1, 2, 3, 4, 7, 6, 5};
+
+__global__ void __launch_bounds__(384) prior_from_policy_kernel(const RawPosition* __restrict__ raw, const __half* __restrict__ policy,
+                                                                const uint8_t* __restrict__ cand, const uint16_t* __restrict__ rep,
+                                                                float* __restrict__ prior_out) {
+    __shared__ float pol[362];
+    __shared__ float pri[368];
+    __shared__ uint16_t target[361];
+    __shared__ float lane[8];
+    __shared__ int n_finite;
+    const int n = blockIdx.x, t = threadIdx.x;
+    const int inv = c_sym_inverse[raw[n].symmetry & 7];
+    if (t < 362) pol[t] = __half2float(policy[static_cast<size_t>(n) * 362 + t]);
+    if (t < 361) target[t] = rep[static_cast<size_t>(n) * 362 + c_symmetry[inv][t]];
+    if (t == 0) n_finite = 0;
+    __syncthreads();
+    if (t < 368) {
+        float v = (t < 362 && cand[static_cast<size_t>(n) * 362 + t]) ? 0.0f : -INFINITY;
+        if (t == 361) v += pol[361];
+        if (t < 361)
+            for (int i = 0; i < 361; i++)
+                if (target[i] == t) v += pol[i];          // ascending source index, as the host loop adds them
+        pri[t] = v;
+        if (isfinite(v)) atomicAdd(&n_finite, 1);
+    }
+    __syncthreads();
+    if (t < 8) {                                           // asm/sum_finite.rs:23-57: eight interleaved lanes ...
+        float s = 0.0f;
+        for (int i = t; i < 368; i += 8)
+            if (isfinite(pri[i])) s += pri[i];
+        lane[t] = s;
+    }
+    __syncthreads();
+    if (t < 368) {
+        const float sum = ((lane[0] + lane[1]) + (lane[2] + lane[3])) + ((lane[4] + lane[5]) + (lane[6] + lane[7]));   // ... added pairwise
+        float v = pri[t];
+        if (sum < 1e-6f) {
+            if (isfinite(v)) v = __fdiv_rn(1.0f, static_cast<float>(n_finite));
+        } else {
+            v = __fmul_rn(v, __fdiv_rn(1.0f, sum));
+        }
+        prior_out[static_cast<size_t>(n) * 368 + t] = v;
+    }
+}
+
+cudaError_t launch_prior_from_policy(const void* raw, const void* policy, const void* cand, const void* rep, float* prior, int batch,
+                                     cudaStream_t s) {
+    prior_from_policy_kernel<<<batch, 384, 0, s>>>(static_cast<const RawPosition*>(raw), static_cast<const __half*>(policy),
+                                                   static_cast<const uint8_t*>(cand), static_cast<const uint16_t*>(rep), prior);
+    return cudaGetLastError();
 }
 
 cudaError_t upload_feature_tables(const unsigned long long* zobrist /* [2][361] */, const uint16_t* symmetry /* [8][361] */) {
@@ -247,10 +472,12 @@ cudaError_t upload_feature_tables(const unsigned long long* zobrist /* [2][361] 
     return cudaMemcpyToSymbol(c_symmetry, symmetry, sizeof(c_symmetry));
 }
 
-cudaError_t launch_planes_from_stones(const void* raw, void* planes, void* legal, void* rows64, int batch, cudaStream_t s) {
+cudaError_t launch_planes_from_stones(const void* raw, void* planes, void* legal, void* rows64, void* cand, void* rep, int batch,
+                                      cudaStream_t s) {
     const int total = dg_num_tiles(batch) * DG_TILE_M;
     planes_from_stones_kernel<<<batch + 1, 384, 0, s>>>(static_cast<const RawPosition*>(raw), static_cast<uint32_t*>(planes),
-                                                        static_cast<uint8_t*>(legal), static_cast<uint4*>(rows64), batch, total);
+                                                        static_cast<uint8_t*>(legal), static_cast<uint4*>(rows64),
+                                                        static_cast<uint8_t*>(cand), static_cast<uint16_t*>(rep), batch, total);
     return cudaGetLastError();
 }
 

@@ -11,7 +11,10 @@ cudaError_t launch_pack_features(const void* in_nhwc_f16, void* out_rows64, int 
 cudaError_t launch_pack_compact(const void* positions, void* out_rows64, int batch, cudaStream_t s);
 // features.cu -- V1 feature planes + legal mask from raw stones (dg_raw_position -> dg_packed_position)
 cudaError_t upload_feature_tables(const unsigned long long* zobrist, const uint16_t* symmetry);
-cudaError_t launch_planes_from_stones(const void* raw, void* planes, void* legal, void* rows64, int batch, cudaStream_t s);
+cudaError_t launch_planes_from_stones(const void* raw, void* planes, void* legal, void* rows64, void* cand, void* rep, int batch,
+                                      cudaStream_t s);
+cudaError_t launch_prior_from_policy(const void* raw, const void* policy, const void* cand, const void* rep, float* prior, int batch,
+                                     cudaStream_t s);
 cudaError_t launch_conv_direct(const __half* in, int cin, const __half* w, int ntot, const float* bias, float alpha, float beta,
                                const __half* skip, int skip_stride, __half* out, int out_stride, int batch, cudaStream_t s);
 cudaError_t launch_split_heads(const __half* h, __half* pbuf, __half* vbuf, int batch, cudaStream_t s);

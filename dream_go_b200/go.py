@@ -122,10 +122,11 @@ class Board:
         lib().dg_board_features_packed(self._h, to_move, symmetry, out.ctypes.data, lg.ctypes.data if legal else None)
         return (out, lg) if legal else out
 
-    def raw_position(self, to_move: int, symmetry: int = IDENTITY) -> np.ndarray:
-        """One `dg_raw_position` (what `dg_engine_forward_raw` takes): the device derives planes and legal moves."""
+    def raw_position(self, to_move: int, symmetry: int = IDENTITY, search: int = STANDARD_SEARCH) -> np.ndarray:
+        """One `dg_raw_position` (what `dg_engine_forward_raw` takes): the device derives planes and legal moves; `search`
+        (bits 4.. of the symmetry byte) only matters to `dg_engine_forward_raw_prior`."""
         out = np.zeros(1, nn.RAW_DTYPE)
-        lib().dg_board_raw_position(self._h, to_move, symmetry, out.ctypes.data)
+        lib().dg_board_raw_position(self._h, to_move, symmetry | (search << 4), out.ctypes.data)
         return out
 
     def features(self, to_move: int, symmetry: int = IDENTITY) -> np.ndarray:

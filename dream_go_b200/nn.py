@@ -74,6 +74,7 @@ ABI = {
     "dg_engine_forward_f16": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dg_engine_forward_packed": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dg_engine_forward_raw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dg_engine_forward_raw_prior": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dg_engine_features_raw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dg_engine_queue_push": (C.c_int64, [C.c_void_p, C.c_void_p]),
     "dg_engine_queue_flush": (C.c_int32, [C.c_void_p]),
@@ -236,6 +237,18 @@ class Network:
         legal = np.empty((n, 361), np.uint8)
         self._check(lib().dg_engine_forward_raw(self._handle, pos.ctypes.data, n, value.ctypes.data, policy.ctypes.data, legal.ctypes.data))
         return OutputMap(value, policy), legal
+
+    def forward_raw_prior(self, positions: np.ndarray):
+        """Raw positions -> (OutputMap, legal [n, 361] u8, prior [n, 368] f32): the prior construction runs on the device too."""
+        pos = np.ascontiguousarray(positions, dtype=RAW_DTYPE).reshape(-1)
+        n = pos.shape[0]
+        value = np.empty((n,), np.float16)
+        policy = np.empty((n, POLICY_SIZE), np.float16)
+        legal = np.empty((n, 361), np.uint8)
+        prior = np.empty((n, 368), np.float32)
+        self._check(lib().dg_engine_forward_raw_prior(self._handle, pos.ctypes.data, n, value.ctypes.data, policy.ctypes.data,
+                                                      legal.ctypes.data, prior.ctypes.data))
+        return OutputMap(value, policy), legal, prior
 
     def features_raw(self, positions: np.ndarray):
         """Feature stage only: (compact planes [n] PACKED_DTYPE, legal [n, 361] u8)."""

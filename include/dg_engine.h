@@ -94,7 +94,8 @@ typedef struct dg_raw_position {
     int16_t  last_move[2];
     uint16_t k_bits;               /* fp16 bits of k (features.rs:236) */
     uint8_t  to_move;              /* 1 black, 2 white */
-    uint8_t  symmetry;             /* orientation the planes are produced in (symmetry::ALL order) */
+    uint8_t  symmetry;             /* bits 0-2: orientation the planes are produced in (symmetry::ALL order);
+                                      bits 4-7: search options of the position (DG_STANDARD_SEARCH / DG_SCORING_SEARCH) */
 } dg_raw_position;                 /* 384 bytes */
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -133,6 +134,14 @@ int32_t dg_engine_forward_packed(dg_engine* engine, const dg_packed_position* po
  * create_initial_policy (pool/policy_helper.rs:39-43) asks the board for.  384 bytes H2D per position. */
 int32_t dg_engine_forward_raw(dg_engine* engine, const dg_raw_position* positions, int32_t batch,
                               uint16_t* value_out, uint16_t* policy_out, uint8_t* legal_out /* [batch][361] */);
+/* The same, and the priors the search inserts: `create_initial_policy` + `add_valid_candidates` + `normalize_policy(1.0)`
+ * (pool/policy_helper.rs:28-134, as the Insert event of pool/worker_thread.rs:88-93 runs them) computed on the device --
+ * candidate mask of the position's search options (bits 4.. of `symmetry`: 0 = StandardSearch, 1 = ScoringSearch incl.
+ * Benson's unconditional life and the own-eye heuristic, libdg_mcts/options.rs:53-138), orbit folding on symmetric
+ * boards, inverse symmetry, renormalisation.  prior_out: batch x 368 floats (-inf = not a candidate), bit-identical to
+ * dg_board_prior on the same policy. */
+int32_t dg_engine_forward_raw_prior(dg_engine* engine, const dg_raw_position* positions, int32_t batch,
+                                    uint16_t* value_out, uint16_t* policy_out, uint8_t* legal_out, float* prior_out);
 /* Only the feature stage of dg_engine_forward_raw: the planes as compact positions + the legal masks (tests, tools). */
 int32_t dg_engine_features_raw(dg_engine* engine, const dg_raw_position* positions, int32_t batch,
                                dg_packed_position* planes_out, uint8_t* legal_out /* [batch][361] */);

@@ -104,3 +104,56 @@ def test_long_random_game_bit_exact(engine):
     colors, moves = random_playout(5, 1500, pass_rate=0.0)
     raws, planes, legal = replay_raw(colors, moves, 7.5)
     check(engine, raws, planes, legal)
+
+
+# ---- prior construction on the device (pool/policy_helper.rs) ------------------------------------------------------------
+
+def check_priors(engine, boards, to_moves, searches, symmetries):
+    raws = np.concatenate([b.raw_position(tm, s, search=k) for b, tm, k, s in zip(boards, to_moves, searches, symmetries)])
+    out, legal, prior = engine.forward_raw_prior(raws)
+    policy = out.policy.reshape(-1, 362)
+    for i, (b, tm, k, s) in enumerate(zip(boards, to_moves, searches, symmetries)):
+        want = b.prior(tm, policy[i], s, 1.0, search=k)
+        assert (np.isfinite(prior[i]) == np.isfinite(want)).all(), (i, k, s, np.flatnonzero(np.isfinite(prior[i]) != np.isfinite(want)))
+        f = np.isfinite(want)
+        assert (prior[i][f].view(np.uint32) == want[f].view(np.uint32)).all(), (i, k, s)
+        assert (legal[i] == b.legal_moves(tm)).all()
+    return prior
+
+
+def test_device_priors_bit_exact_on_games(engine):
+    games = ogo.load_games()
+    boards, tms, kinds, syms = [], [], [], []
+    rng = np.random.default_rng(3)
+    for g in range(0, 99, 7):
+        colors, moves, komi = games[g]
+        b = pgo.Board(komi)
+        for ply, (c, m) in enumerate(zip(colors, moves)):
+            if ply % 23 == 0 or ply == len(moves) - 1:
+                boards.append(b.clone()); tms.append(int(c)); kinds.append(int(rng.integers(0, 2))); syms.append(int(rng.integers(0, 8)))
+            if m < 361:
+                b.place_index(int(c), int(m))
+    check_priors(engine, boards[:512], tms[:512], kinds[:512], syms[:512])
+    assert len(boards) > 100
+
+
+def test_device_priors_symmetric_and_settled_positions(engine):
+    from test_go_parity import settled_position
+    boards, tms, kinds, syms = [], [], [], []
+    empty = pgo.Board(7.5)
+    tengen = pgo.Board(7.5); tengen.place(1, 9, 9)
+    for b, tm in ((empty, 1), (tengen, 2)):                # full symmetry group: orbit folding (policy_helper.rs:54-72)
+        for s in range(8):
+            for k in (0, 1):
+                boards.append(b); tms.append(tm); kinds.append(k); syms.append(s)
+    for seed in range(8):                                  # alive groups, eyes, dead stones: Benson on the device
+        b = pgo.Board(6.5)
+        for c, x, y in settled_position(seed):
+            if b.at(x, y) == 0 and b.is_valid(c, x, y):
+                b.place(c, x, y)
+        assert (b.benson(1) == 2).any() and (b.benson(2) == 2).any()
+        for tm in (1, 2):
+            for k in (0, 1):
+                boards.append(b); tms.append(tm); kinds.append(k); syms.append((seed + tm) % 8)
+    prior = check_priors(engine, boards, tms, kinds, syms)
+    assert np.isfinite(prior[0][:361]).sum() == 55         # empty board, standard search: one candidate per orbit
