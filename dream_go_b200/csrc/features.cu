@@ -44,7 +44,9 @@ struct PlanScratch {                      // lives in the liberty-set storage on
     uint16_t rlab[384];                   // region label (smallest point index) of a point, 0xffff = none
     uint16_t vch[361][4];                 // chains a region is vital to
     int chain_cnt[361];                   // vital regions per chain (this iteration)
-    uint8_t other[384], dead[384], seeded[384], reg_on[384], nv[384], chain_alive[384];
+    int size[361];                        // points per region
+    int touch[361][4];                    // points of the region that touch candidate chain j
+    uint8_t other[384], dead[384], seeded[384], reg_on[384], nv[384], chain_alive[384], veto[384];
     uint8_t eye[2][384];
     int symm[8];
 };
@@ -63,6 +65,7 @@ __device__ void device_benson(PlanScratch* S, const uint8_t* col, const uint16_t
     S->seeded[t] = 0;
     S->reg_on[t] = 0;
     S->nv[t] = 0;
+    S->veto[t] = 0;
     S->chain_alive[t] = on && col[t] == c;
     eye[t] = 0;
     __syncthreads();
@@ -98,30 +101,40 @@ __device__ void device_benson(PlanScratch* S, const uint8_t* col, const uint16_t
         if (!again) break;
     }
     if (rest && col[t] == 0) S->seeded[S->rlab[t]] = 1;       // a region starts from an empty point (benson.rs:297-301)
+    if (on) { S->size[t] = 0; for (int j = 0; j < 4; j++) S->touch[t][j] = 0; }
     __syncthreads();
     const bool root = rest && S->rlab[t] == t && S->seeded[t];
-    if (root) {                           // chains this region is vital to: every point of the region touches the chain
-        int cand_ch[4], ncand = 0;
+    int ncand = 0;
+    if (root) {                           // the chains next to the root point are the only ones the region can be vital to
         for (int k = 0; k < 4; k++)
             if (nb[k] >= 0 && col[nb[k]] == c) {
-                const int ch = lab[nb[k]];
+                const uint16_t ch = lab[nb[k]];
                 bool dup = false;
-                for (int j = 0; j < ncand; j++) dup |= cand_ch[j] == ch;
-                if (!dup) cand_ch[ncand++] = ch;
+                for (int j = 0; j < ncand; j++) dup |= S->vch[t][j] == ch;
+                if (!dup) S->vch[t][ncand++] = ch;
             }
-        int nv = 0;
-        for (int j = 0; j < ncand; j++) {
-            bool vital = true;
-            for (int p = 0; p < 361 && vital; p++) {
-                if (S->rlab[p] != t) continue;
-                const int px = p % 19, py = p / 19;
-                const int pn[4] = {px < 18 ? p + 1 : -1, py > 0 ? p - 19 : -1, px > 0 ? p - 1 : -1, py < 18 ? p + 19 : -1};
-                bool touches = false;
-                for (int k = 0; k < 4; k++) touches |= pn[k] >= 0 && col[pn[k]] == c && lab[pn[k]] == cand_ch[j];
-                vital = touches;
-            }
-            if (vital) S->vch[t][nv++] = static_cast<uint16_t>(cand_ch[j]);
+        S->nv[t] = static_cast<uint8_t>(ncand);
+    }
+    __syncthreads();
+    // every point of a region votes: which of the region's candidate chains does it touch?
+    const int my_region = rest ? S->rlab[t] : 0xffff;
+    const bool in_region = rest && S->seeded[my_region];
+    if (in_region) {
+        atomicAdd(&S->size[my_region], 1);
+        for (int j = 0; j < S->nv[my_region]; j++) {
+            const int ch = S->vch[my_region][j];
+            bool touches = false;
+            for (int k = 0; k < 4; k++) touches |= nb[k] >= 0 && col[nb[k]] == c && lab[nb[k]] == ch;
+            if (touches) atomicAdd(&S->touch[my_region][j], 1);
         }
+    }
+    __syncthreads();
+    if (root) {                           // vital = every point of the region touches the chain (benson.rs:188-208)
+        int nv = 0;
+        uint16_t keep[4];
+        for (int j = 0; j < ncand; j++)
+            if (S->touch[t][j] == S->size[t]) keep[nv++] = S->vch[t][j];
+        for (int j = 0; j < nv; j++) S->vch[t][j] = keep[j];
         S->nv[t] = static_cast<uint8_t>(nv);
         S->reg_on[t] = nv > 0;            // regions that are vital to nobody go first (benson.rs:128-143)
     }
@@ -137,17 +150,14 @@ __device__ void device_benson(PlanScratch* S, const uint8_t* col, const uint16_t
         // a chain stays alive with two vital regions (benson.rs:95-111); chain_alive is indexed by the chain's label
         if (on && col[t] == c && lab[t] == t && S->chain_alive[t] && S->chain_cnt[t] < 2) { S->chain_alive[t] = 0; *flag = 1; }
         __syncthreads();
-        if (root && S->reg_on[t]) {       // a region stays while every stone around it is alive (benson.rs:115-131)
-            bool healthy = true;
-            for (int p = 0; p < 361 && healthy; p++) {
-                if (S->rlab[p] != t) continue;
-                const int px = p % 19, py = p / 19;
-                const int pn[4] = {px < 18 ? p + 1 : -1, py > 0 ? p - 19 : -1, px > 0 ? p - 1 : -1, py < 18 ? p + 19 : -1};
-                for (int k = 0; k < 4; k++)
-                    if (pn[k] >= 0 && col[pn[k]] == c && !S->chain_alive[lab[pn[k]]]) healthy = false;
-            }
-            if (!healthy) { S->reg_on[t] = 0; *flag = 1; }
+        // a region stays while every stone around it is alive (benson.rs:115-131): any point that sees a dead neighbour vetoes
+        if (in_region && S->reg_on[my_region]) {
+            bool bad = false;
+            for (int k = 0; k < 4; k++) bad |= nb[k] >= 0 && col[nb[k]] == c && !S->chain_alive[lab[nb[k]]];
+            if (bad) S->veto[my_region] = 1;
         }
+        __syncthreads();
+        if (root && S->reg_on[t] && S->veto[t]) { S->reg_on[t] = 0; *flag = 1; }
         __syncthreads();
         const int again = *flag;
         __syncthreads();
@@ -195,7 +205,12 @@ __device__ void plan_candidates(PlanScratch* S, const uint8_t* col, const uint16
         out_rep[t] = static_cast<uint16_t>(rep);
         out_cand[t] = cand && rep == t;
     }
-    if (t == 361) { out_rep[361] = 361; out_cand[361] = search == 0; }
+    if (t == 361) {                       // bit 15 of the pass entry: the board has a non-trivial symmetry (orbits to fold)
+        int any = 0;
+        for (int tr = 1; tr < 8; tr++) any |= S->symm[tr];
+        out_rep[361] = static_cast<uint16_t>(361 | (any ? 0x8000 : 0));
+        out_cand[361] = search == 0;
+    }
 }
 
 // Block n < batch handles position n and also expands its planes into the tower's input rows (what pack_compact_kernel
@@ -425,17 +440,21 @@ __global__ void __launch_bounds__(384) prior_from_policy_kernel(const RawPositio
     __shared__ float lane[8];
     __shared__ int n_finite;
     const int n = blockIdx.x, t = threadIdx.x;
-    const int inv = c_sym_inverse[raw[n].symmetry & 7];
+    const int sym = raw[n].symmetry & 7, inv = c_sym_inverse[sym];
+    const bool folded = (rep[static_cast<size_t>(n) * 362 + 361] & 0x8000u) != 0;
     if (t < 362) pol[t] = __half2float(policy[static_cast<size_t>(n) * 362 + t]);
-    if (t < 361) target[t] = rep[static_cast<size_t>(n) * 362 + c_symmetry[inv][t]];
+    if (t < 361 && folded) target[t] = rep[static_cast<size_t>(n) * 362 + c_symmetry[inv][t]];
     if (t == 0) n_finite = 0;
     __syncthreads();
     if (t < 368) {
         float v = (t < 362 && cand[static_cast<size_t>(n) * 362 + t]) ? 0.0f : -INFINITY;
         if (t == 361) v += pol[361];
-        if (t < 361)
-            for (int i = 0; i < 361; i++)
-                if (target[i] == t) v += pol[i];          // ascending source index, as the host loop adds them
+        if (t < 361) {
+            if (!folded) v += pol[c_symmetry[sym][t]];    // asymmetric board: point t receives exactly its own image
+            else
+                for (int i = 0; i < 361; i++)
+                    if (target[i] == t) v += pol[i];      // ascending source index, as the host loop adds them
+        }
         pri[t] = v;
         if (isfinite(v)) atomicAdd(&n_finite, 1);
     }

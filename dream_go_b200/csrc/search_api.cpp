@@ -323,10 +323,12 @@ void dg_tree_children(const dg_tree* tree, int32_t* count, float* value, float* 
 }
 int64_t dg_tree_num_nodes(const dg_tree* tree) { return tree ? count_nodes(N(tree)) : 0; }
 
-static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_predictor, void* ctx, const dg_selfplay_config* config,
-                             dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity) {
-    if ((!predictor && !raw_predictor) || !config || config->num_games <= 0 || config->num_parallel <= 0) return DG_ERR_INVALID_ARGUMENT;
-    const bool raw_mode = raw_predictor != nullptr;
+static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_predictor, dg_predict_prior_fn prior_predictor, void* ctx,
+                             const dg_selfplay_config* config, dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity) {
+    if ((!predictor && !raw_predictor && !prior_predictor) || !config || config->num_games <= 0 || config->num_parallel <= 0)
+        return DG_ERR_INVALID_ARGUMENT;
+    const bool raw_mode = raw_predictor != nullptr || prior_predictor != nullptr;
+    const bool prior_mode = prior_predictor != nullptr;
     Driver d;
     d.cfg = *config;
     if (d.cfg.max_plies <= 0 || d.cfg.max_plies > 722) d.cfg.max_plies = 722;
@@ -352,6 +354,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         std::vector<dg_raw_position> raw_batch;
         std::vector<uint16_t> value, policy;
         std::vector<uint8_t> legal;
+        std::vector<float> prior;
         std::future<int32_t> pending;
         size_t size() const { return batch.size() + raw_batch.size(); }
         bool in_flight = false;
@@ -385,10 +388,11 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     };
 
     // Advances one game until it has leaves for the device (returns with g.batch filled) or has nothing to do.
-    auto advance = [&](Game& g, const uint16_t* value, const uint16_t* policy, const uint8_t* legal) {
+    auto advance = [&](Game& g, const uint16_t* value, const uint16_t* policy, const uint8_t* legal, const float* prior) {
         if (!g.active) return;
         if (g.n_emitted > 0) {
-            g.task.absorb(value + g.batch_offset, policy + g.batch_offset * 362, legal ? legal + g.batch_offset * 361 : nullptr);
+            g.task.absorb(value + g.batch_offset, policy + g.batch_offset * 362, legal ? legal + g.batch_offset * 361 : nullptr,
+                          prior ? prior + g.batch_offset * 368 : nullptr);
             g.evals += g.n_emitted;
             g.n_emitted = 0;
         }
@@ -452,7 +456,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 size_t i = next.fetch_add(1);
                 if (i >= grp.slots.size()) break;
                 advance(d.games[grp.slots[i]], absorb_results ? grp.value.data() : nullptr, absorb_results ? grp.policy.data() : nullptr,
-                        absorb_results && raw_mode ? grp.legal.data() : nullptr);
+                        absorb_results && raw_mode ? grp.legal.data() : nullptr, absorb_results && prior_mode ? grp.prior.data() : nullptr);
             }
         };
         helpers.run(worker);
@@ -468,7 +472,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 bool time_left = d.cfg.max_seconds <= 0 || seconds() < d.cfg.max_seconds;
                 if (d.started < d.cfg.num_games && time_left) {
                     d.start_game(g);
-                    advance(g, nullptr, nullptr, nullptr);
+                    advance(g, nullptr, nullptr, nullptr, nullptr);
                     if (g.n_emitted == -1) { g.n_emitted = 0; g.active = false; }
                 }
             }
@@ -485,12 +489,16 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         grp.value.resize(grp.size());
         grp.policy.resize(grp.size() * 362);
         if (raw_mode) grp.legal.resize(grp.size() * 361);
+        if (prior_mode) grp.prior.resize(grp.size() * 368);
         ++rounds;
         positions += (int64_t)grp.size();
         grp.in_flight = true;
-        grp.pending = std::async(std::launch::async, [&grp, predictor, raw_predictor, ctx, &eval_ns] {
+        grp.pending = std::async(std::launch::async, [&grp, predictor, raw_predictor, prior_predictor, ctx, &eval_ns] {
             auto t0 = std::chrono::steady_clock::now();
-            int32_t r = raw_predictor
+            int32_t r = prior_predictor
+                ? prior_predictor(ctx, grp.raw_batch.data(), (int32_t)grp.raw_batch.size(), grp.value.data(), grp.policy.data(), grp.legal.data(),
+                                  grp.prior.data())
+                : raw_predictor
                 ? raw_predictor(ctx, grp.raw_batch.data(), (int32_t)grp.raw_batch.size(), grp.value.data(), grp.policy.data(), grp.legal.data())
                 : predictor(ctx, grp.batch.data(), (int32_t)grp.batch.size(), grp.value.data(), grp.policy.data());
             eval_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
@@ -544,12 +552,62 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
 
 int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                         char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(predictor, nullptr, ctx, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(predictor, nullptr, nullptr, ctx, config, stats, sgf_out, sgf_capacity);
 }
 
 int32_t dg_selfplay_run_raw(dg_predict_raw_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                             char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(nullptr, predictor, ctx, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(nullptr, predictor, nullptr, ctx, config, stats, sgf_out, sgf_capacity);
+}
+
+int32_t dg_selfplay_run_prior(dg_predict_prior_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
+                              char* sgf_out, int64_t sgf_capacity) {
+    return selfplay_impl(nullptr, nullptr, predictor, ctx, config, stats, sgf_out, sgf_capacity);
+}
+
+int32_t dg_engine_predict_prior(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy, uint8_t* legal,
+                                float* prior) {
+    dg_engine* e = static_cast<dg_engine*>(engine);
+    const int32_t chunk = dg_engine_max_batch(e);
+    if (chunk <= 0) return DG_ERR_INVALID_ARGUMENT;
+    for (int32_t at = 0; at < n; at += chunk) {
+        int32_t m = n - at < chunk ? n - at : chunk;
+        int32_t rc = dg_engine_forward_raw_prior(e, positions + at, m, value + at, policy + (size_t)at * 362, legal + (size_t)at * 361,
+                                                 prior + (size_t)at * 368);
+        if (rc) return rc;
+    }
+    return DG_OK;
+}
+
+int32_t dg_mcts_predict_prior(dg_predict_prior_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
+                              const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
+                              int64_t* evals_out) {
+    if (!predictor || !options || !board) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
+    SearchTask task;
+    task.start(*reinterpret_cast<const Board*>(board), color, convert(options), N(starting_tree), options->seed);
+    std::vector<dg_raw_position> batch;
+    std::vector<uint16_t> value, policy;
+    std::vector<uint8_t> legal;
+    std::vector<float> prior;
+    for (;;) {
+        batch.clear();
+        int n = task.emit(nullptr, &batch);
+        if (n == 0) break;
+        value.resize(n);
+        policy.resize((size_t)n * 362);
+        legal.resize((size_t)n * 361);
+        prior.resize((size_t)n * 368);
+        int32_t rc = predictor(ctx, batch.data(), n, value.data(), policy.data(), legal.data(), prior.data());
+        if (rc) return rc;
+        task.absorb(value.data(), policy.data(), legal.data(), prior.data());
+    }
+    if (value_out) *value_out = task.value();
+    if (index_out) *index_out = task.index();
+    if (evals_out) *evals_out = task.evals();
+    Node* root = task.take_root();
+    if (tree_out) *tree_out = reinterpret_cast<dg_tree*>(root);
+    else delete root;
+    return DG_OK;
 }
 
 int32_t dg_engine_predict_raw(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy, uint8_t* legal) {

@@ -244,8 +244,8 @@ class SearchTask {
             if (raw) {
                 size_t at = raw->size();
                 raw->resize(at + 8);
-                raw_position(board_, color_, 0, &(*raw)[at]);
-                for (int t = 1; t < 8; ++t) { (*raw)[at + t] = (*raw)[at]; (*raw)[at + t].symmetry = (uint8_t)t; }
+                raw_position(board_, color_, opt_.search_kind << 4, &(*raw)[at]);
+                for (int t = 1; t < 8; ++t) { (*raw)[at + t] = (*raw)[at]; (*raw)[at + t].symmetry = (uint8_t)(t | (opt_.search_kind << 4)); }
             } else {
                 uint8_t legal[N_POINTS];
                 size_t at = packed->size();
@@ -286,7 +286,7 @@ class SearchTask {
             }
             if (raw) {
                 raw->emplace_back();
-                raw_position(p.board, p.to_move, p.symmetry, &raw->back());
+                raw_position(p.board, p.to_move, p.symmetry | (opt_.search_kind << 4), &raw->back());
             } else {
                 uint8_t legal[N_POINTS];
                 packed->emplace_back();
@@ -308,7 +308,10 @@ class SearchTask {
 
     // Evaluations of the leaves of the last emit(), in the same order; `legal` ([n][361], identity orientation) is the
     // device's legal-move mask in raw mode, null otherwise.
-    void absorb(const uint16_t* value, const uint16_t* policy /* [n][362] */, const uint8_t* legal = nullptr) {
+    // `priors` ([n][368], optional): ready-to-insert priors of the leaves computed on the device (dg_engine_forward_raw_prior);
+    // the root evaluation always goes through the host (8 symmetries averaged with weight 0.125 each).
+    void absorb(const uint16_t* value, const uint16_t* policy /* [n][362] */, const uint8_t* legal = nullptr,
+                const float* priors = nullptr) {
         evals_ += n_pending_;
         if (phase_ == ROOT) {
             if (legal) root_plan_.build(board_, color_, opt_.search_kind, legal);
@@ -351,10 +354,14 @@ class SearchTask {
         float prior[368];
         for (int k = 0; k < n_pending_; ++k) {               // pool/worker_thread.rs:88-98
             Pending& p = pending_[k];
-            if (legal) p.plan.build(p.board, p.to_move, opt_.search_kind, legal + (size_t)k * N_POINTS);
-            p.plan.apply(policy + (size_t)k * 362, p.symmetry, 1.0f, prior);
             float winrate = 0.5f * f16_to_f32(value[k]) + 0.5f;
-            insert(p.trace, p.to_move, winrate, prior);
+            if (priors) {
+                insert(p.trace, p.to_move, winrate, priors + (size_t)k * 368);
+            } else {
+                if (legal) p.plan.build(p.board, p.to_move, opt_.search_kind, legal + (size_t)k * N_POINTS);
+                p.plan.apply(policy + (size_t)k * 362, p.symmetry, 1.0f, prior);
+                insert(p.trace, p.to_move, winrate, prior);
+            }
             if (opt_.cache) opt_.cache->insert(p.board.hash, p.to_move, p.symmetry, value[k], policy + (size_t)k * 362);   // worker_thread.rs:96
         }
         n_pending_ = 0;

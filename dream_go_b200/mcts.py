@@ -17,6 +17,7 @@ from . import go, nn
 
 PREDICT_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p)
 PREDICT_RAW_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
+PREDICT_PRIOR_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 class _SearchOptions(C.Structure):
@@ -46,6 +47,10 @@ ABI = {
     "dg_engine_predict": (_I, [_P, _P, _I, _P, _P]),
     "dg_random_predict": (_I, [_P, _P, _I, _P, _P]),
     "dg_engine_predict_raw": (_I, [_P, _P, _I, _P, _P, _P]),
+    "dg_engine_predict_prior": (_I, [_P, _P, _I, _P, _P, _P, _P]),
+    "dg_mcts_predict_prior": (_I, [PREDICT_PRIOR_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "dg_selfplay_run_prior": (_I, [PREDICT_PRIOR_FN, _P, C.POINTER(_SelfPlayConfig), C.POINTER(_SelfPlayStats), _P, C.c_int64]),
     "dg_mcts_predict_raw": (_I, [PREDICT_RAW_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "dg_selfplay_run_raw": (_I, [PREDICT_RAW_FN, _P, C.POINTER(_SelfPlayConfig), C.POINTER(_SelfPlayStats), _P, C.c_int64]),
@@ -105,6 +110,17 @@ class EngineRawPredictor:
     def __init__(self, network: "nn.Network"):
         self.network = network
         self.fn = C.cast(lib().dg_engine_predict_raw, PREDICT_RAW_FN)
+        self.ctx = network._handle
+
+
+class EnginePriorPredictor:
+    """The engine fed with raw positions, returning ready-to-insert priors as well (planes, legal moves, candidate masks,
+    inverse symmetry and renormalisation all on the device)."""
+    raw = "prior"
+
+    def __init__(self, network: "nn.Network"):
+        self.network = network
+        self.fn = C.cast(lib().dg_engine_predict_prior, PREDICT_PRIOR_FN)
         self.ctx = network._handle
 
 
@@ -180,7 +196,7 @@ class Tree:
 
 
 def _fn_ctx(predictor):
-    if isinstance(predictor, (EnginePredictor, EngineRawPredictor, RandomPredictor)):
+    if isinstance(predictor, (EnginePredictor, EngineRawPredictor, EnginePriorPredictor, RandomPredictor)):
         return predictor.fn, predictor.ctx
     return predictor, None
 
@@ -204,7 +220,8 @@ def predict(predictor, board: "go.Board", color: int, *, search: int = go.STANDA
         opt.leaf_symmetries = ls.ctypes.data
         opt.n_leaf_symmetries = len(ls)
     value, index, tree, evals = C.c_float(), C.c_int32(), C.c_void_p(), C.c_int64()
-    call = lib().dg_mcts_predict_raw if getattr(predictor, "raw", False) else lib().dg_mcts_predict
+    kind = getattr(predictor, "raw", False)
+    call = lib().dg_mcts_predict_prior if kind == "prior" else lib().dg_mcts_predict_raw if kind else lib().dg_mcts_predict
     rc = call(fn, ctx, C.byref(opt), starting_tree.release() if starting_tree is not None else None,
               board._h, color, C.byref(value), C.byref(index), C.byref(tree), C.byref(evals))
     if rc:
@@ -222,7 +239,8 @@ def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout:
                           num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds, cache_capacity, num_groups)
     stats = _SelfPlayStats()
     buf = C.create_string_buffer(sgf_capacity)
-    run = lib().dg_selfplay_run_raw if getattr(predictor, "raw", False) else lib().dg_selfplay_run
+    kind = getattr(predictor, "raw", False)
+    run = lib().dg_selfplay_run_prior if kind == "prior" else lib().dg_selfplay_run_raw if kind else lib().dg_selfplay_run
     rc = run(fn, ctx, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
     if rc:
         raise nn.Error(rc, "self-play failed")

@@ -35,6 +35,13 @@ typedef int32_t (*dg_predict_raw_fn)(void* ctx, const dg_raw_position* positions
 int32_t dg_engine_predict_raw(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy,
                               uint8_t* legal);
 
+/* ... and with the leaves' ready-to-insert priors ([n][368] floats; dg_engine_forward_raw_prior): the host then only walks
+ * the tree.  policy and legal are still returned (the root evaluation and the transposition table use them). */
+typedef int32_t (*dg_predict_prior_fn)(void* ctx, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy,
+                                       uint8_t* legal, float* prior);
+int32_t dg_engine_predict_prior(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy,
+                                uint8_t* legal, float* prior);
+
 /* `RandomPredictor` (predictors/random.rs:30-59) as a deterministic function of the position; ctx = NULL or a
  * uint64_t* salt.  No device involved: it measures the host half of self-play alone. */
 int32_t dg_random_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
@@ -74,6 +81,9 @@ int32_t  dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_opt
 int32_t  dg_mcts_predict_raw(dg_predict_raw_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
                              const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                              int64_t* evals_out);
+int32_t  dg_mcts_predict_prior(dg_predict_prior_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
+                               const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
+                               int64_t* evals_out);
 void     dg_tree_free(dg_tree* tree);
 dg_tree* dg_tree_forward(dg_tree* tree, int32_t index);            /* Node::forward (tree.rs:1198-1225); consumes `tree` */
 void     dg_tree_disqualify(dg_tree* tree, int32_t index);         /* Node::disqualify (tree.rs:1296-1301) */
@@ -117,6 +127,9 @@ int32_t  dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_c
 /* The same with a raw-position predictor (dg_engine_predict_raw): same games for the same seed. */
 int32_t  dg_selfplay_run_raw(dg_predict_raw_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                              char* sgf_out, int64_t sgf_capacity);
+
+int32_t  dg_selfplay_run_prior(dg_predict_prior_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
+                               char* sgf_out, int64_t sgf_capacity);
 
 #ifdef __cplusplus
 }

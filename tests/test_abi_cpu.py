@@ -40,7 +40,7 @@ def test_library_exports_every_go_symbol():
 def test_library_exports_every_mcts_symbol():
     from dream_go_b200 import mcts
     handle = ctypes.CDLL(nn.LIB_PATH)
-    names = [n for n in header_functions("dg_mcts.h") if n not in ("dg_predict_fn", "dg_predict_raw_fn")]
+    names = [n for n in header_functions("dg_mcts.h") if n not in ("dg_predict_fn", "dg_predict_raw_fn", "dg_predict_prior_fn")]
     assert len(names) >= 11
     for name in names:
         assert hasattr(handle, name), f"{name} declared in include/dg_mcts.h but not exported"

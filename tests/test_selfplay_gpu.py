@@ -77,15 +77,18 @@ def test_device_features_give_the_same_search_and_games(engine):
     for kw in (dict(deterministic=True, num_rollout=120, probes_per_round=4, leaf_symmetries=[2, 0, 7, 5]),
                dict(search=1, deterministic=False, num_rollout=80, probes_per_round=2, seed=9)):
         v1, i1, t1, e1 = pm.predict(pm.EnginePredictor(engine), po, color, **kw)
-        v2, i2, t2, e2 = pm.predict(pm.EngineRawPredictor(engine), po, color, **kw)
         c1, val1, p1 = t1.children()
-        c2, val2, p2 = t2.children()
-        assert (c1 == c2).all() and i1 == i2 and e1 == e2 and v1 == v2
-        assert (p1.view(np.uint32) == p2.view(np.uint32)).all() and (val1.view(np.uint32) == val2.view(np.uint32)).all()
+        for predictor in (pm.EngineRawPredictor(engine), pm.EnginePriorPredictor(engine)):     # planes / planes + priors on the device
+            v2, i2, t2, e2 = pm.predict(predictor, po, color, **kw)
+            c2, val2, p2 = t2.children()
+            assert (c1 == c2).all() and i1 == i2 and e1 == e2 and v1 == v2
+            assert (p1.view(np.uint32) == p2.view(np.uint32)).all() and (val1.view(np.uint32) == val2.view(np.uint32)).all()
     kw = dict(num_games=4, num_parallel=4, num_rollout=40, probes_per_round=4, max_plies=24, seed=11, num_threads=4)
     a, sgf_a = pm.self_play(pm.EnginePredictor(engine), **kw)
     b, sgf_b = pm.self_play(pm.EngineRawPredictor(engine), **kw)
-    assert a["digest"] == b["digest"] and sorted(sgf_a) == sorted(sgf_b) and a["evals"] == b["evals"]
+    c, sgf_c = pm.self_play(pm.EnginePriorPredictor(engine), **kw)
+    assert a["digest"] == b["digest"] == c["digest"] and sorted(sgf_a) == sorted(sgf_b) == sorted(sgf_c)
+    assert a["evals"] == b["evals"] == c["evals"]
 
 
 def test_whole_game_on_engine_matches_oracle_game(engine):

@@ -25,7 +25,8 @@ def sample(net, *, games: int, parallel: int, rollouts: int, probes: int, second
            ex_it: bool = False, device_features: bool = True, cache_capacity: int = 0, ex_it_rollouts: int = 0):
     """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics."""
     from dream_go_b200 import mcts
-    predictor = mcts.EngineRawPredictor(net) if device_features else mcts.EnginePredictor(net)
+    predictor = (mcts.EnginePriorPredictor(net) if device_features == "prior" else mcts.EngineRawPredictor(net) if device_features
+                 else mcts.EnginePredictor(net))
     st, sgf = mcts.self_play(predictor, num_games=games, num_parallel=parallel, num_rollout=rollouts,
                              probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=ex_it_rollouts or rollouts, seed=seed,
                              max_seconds=seconds, cache_capacity=cache_capacity)
@@ -47,6 +48,7 @@ def main():
     ap.add_argument("--sgf-out", default=None, help="write the finished games' records (rank 0) to this file")
     ap.add_argument("--cache", type=int, default=0, help="entries of each game's transposition table (0 = none)")
     ap.add_argument("--blocking-sync", action="store_true", help="blocking engine calls sleep on an event instead of spinning in the driver")
+    ap.add_argument("--device-priors", action="store_true", help="also build the priors on the device (dg_engine_forward_raw_prior)")
     ap.add_argument("--host-features", action="store_true",
                     help="compute the feature planes on the host (compact positions) instead of on the device (raw positions)")
     args = ap.parse_args()
@@ -67,7 +69,8 @@ def main():
                                    + (" --ex-it" if args.ex_it else ""),
                        "sample": (f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-stone cap)"
                                   if args.seconds > 0 else "all games played to the end"),
-                       "probes_per_round": args.probes, "feature_planes": "host" if args.host_features else "device (csrc/features.cu)", "host_threads_per_gpu": threads, "host_cores": cores,
+                       "probes_per_round": args.probes, "feature_planes": "host" if args.host_features else "device (csrc/features.cu)",
+                       "priors": "device" if args.device_priors else "host", "host_threads_per_gpu": threads, "host_cores": cores,
                        "weights": f"{args.blocks} blocks x 128 filters, seeded random init", "data": "synthetic"},
             "host_only": {"evals_per_s": host["evals"] / host["seconds"], "moves_per_s": host["moves"] / host["seconds"],
                           "mean_batch": host["mean_batch"], "predictor": "RandomPredictor (no device)"}}
@@ -81,7 +84,8 @@ def main():
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
                          seconds=args.seconds, threads=threads, seed=shards.seed(20261017), ex_it=args.ex_it,
-                         device_features=not args.host_features, cache_capacity=args.cache, ex_it_rollouts=args.ex_it_rollouts)
+                         device_features="prior" if args.device_priors else not args.host_features, cache_capacity=args.cache,
+                         ex_it_rollouts=args.ex_it_rollouts)
         wall = time.perf_counter() - t0
         tot = shards.selfplay_totals(st)
         shards.close()
