@@ -215,13 +215,9 @@ template <int NH, int BN>
 static cudaError_t launch_one(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
                               cudaStream_t stream, bool pdl) {
     using L = ConvSmem<NH, BN>;
-    static bool configured = false;   // per (NH, BN) instantiation; engine creation is serialised
+    static std::atomic<unsigned long long> configured{0};   // per (NH, BN) instantiation, one bit per device
     auto kernel = conv3x3_tc_kernel<NH, BN>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = opt_in_shared_memory(kernel, L::kTotal, configured); e != cudaSuccess) return e;
     constexpr int nsplit = (BN == 64) ? 2 : 1;
     int grid = num_sms - (num_sms % nsplit);
     const int work = p.ntiles * nsplit;

@@ -3,7 +3,23 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 namespace dg {
+
+// cudaFuncSetAttribute applies to the CURRENT device only, and one process may hold an engine per device
+// (the reference drives every GPU from one process, predictors/nn.rs:84-92): `done` keeps one bit per device.
+template <typename Kernel>
+inline cudaError_t opt_in_shared_memory(Kernel kernel, int bytes, std::atomic<unsigned long long>& done) {
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 struct ConvTcParams {
     int ntiles;                 // 128-row tiles to process

@@ -275,13 +275,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_con
 template <int NH, bool SKIP>
 static cudaError_t launch_pair(const CUtensorMap& tm_act, const CUtensorMap& tm_w, const ConvTcParams& p, int num_sms,
                                cudaStream_t stream, bool pdl) {
-    static bool configured = false;
+    static std::atomic<unsigned long long> configured{0};
     auto kernel = conv3x3_pair_kernel<NH, SKIP>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::Smem<NH>::kTotal);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = opt_in_shared_memory(kernel, t2::Smem<NH>::kTotal, configured); e != cudaSuccess) return e;
     const int nunits = (p.ntiles + 1) / 2;
     int pairs = num_sms / 2;
     if (pairs > nunits) pairs = nunits;
@@ -640,13 +636,9 @@ tower_kernel(const __grid_constant__ TowerParams p) {
 }
 
 cudaError_t launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
+    static std::atomic<unsigned long long> configured{0};
     auto kernel = tower_kernel<0>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTowerSmem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = opt_in_shared_memory(kernel, kTowerSmem, configured); e != cudaSuccess) return e;
     const int nunits = (p.ntiles + 1) / 2;
     int pairs = num_sms / 2;
     if (pairs > nunits) pairs = nunits;

@@ -553,6 +553,28 @@ extern "C" {
 
 int32_t dg_engine_abi_version(void) { return 1; }
 
+int32_t dg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int usable = 0;
+    for (; usable < n; usable++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, usable) != cudaSuccess || major != 10) break;
+    }
+    return usable;
+}
+
+int32_t dg_current_device(void) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+
+int32_t dg_set_current_device(int32_t device) {
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return DG_ERR_CUDA; }
+    return DG_OK;
+}
+
 int32_t dg_engine_create(const dg_engine_config* config, dg_engine** out) {
     if (!config || !out) return DG_ERR_INVALID_ARGUMENT;
     *out = nullptr;

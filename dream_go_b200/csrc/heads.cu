@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "conv_tc.h"
 #include "kernels.h"
 #include "layout.h"
 #include "ptx.cuh"
@@ -159,12 +160,8 @@ static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t sm
 }
 
 cudaError_t launch_policy_fc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, float* part, int batch, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(policy_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    if (cudaError_t e = opt_in_shared_memory(policy_fc_kernel, kFcSmem, configured); e != cudaSuccess) return e;
     const int m_tiles = (batch + 127) / 128;
     int m_total = m_tiles * 128;
     void* args[] = {const_cast<CUtensorMap*>(&tm_a), const_cast<CUtensorMap*>(&tm_b), &part, &m_total};

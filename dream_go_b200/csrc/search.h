@@ -4,9 +4,9 @@
 // lib.rs:83-200, time_control/mod.rs:47-97, choose.rs, dirichlet.rs, libdg_utils/config.rs:181-336, lcb.rs), with
 // the data organised for the batched engine instead of a pool of racing worker threads:
 //
-//   * a node stores only its candidate moves (finite prior) as sorted (move, prior) pairs plus one small edge
-//     record per VISITED child -- the reference keeps a dense prior[368] and an 8-slot / 362-slot child table
-//     (tree.rs:540-700);
+//   * a node stores only its candidate moves (finite prior) as sorted (move, prior) pairs plus one small record
+//     per VISITED child, field by field in parallel arrays that `select` scores eight children at a time (AVX2) --
+//     the reference keeps a dense prior[368] and an 8-slot / 362-slot child table (tree.rs:540-700);
 //   * a search advances in rounds: up to P probes are collected (virtual loss keeps them apart), their leaves are
 //     evaluated as ONE batch together with the leaves of every other game on the device, then inserted in probe
 //     order.  No locks, no atomics, and the result is a pure function of (position, weights, seed) -- the
@@ -15,6 +15,8 @@
 // Arithmetic is fp32 in the reference's operation order (compiled with -ffp-contract=off) so that visit counts
 // are bit-identical to the oracle restatement (tests/test_mcts_parity.py).
 #pragma once
+
+#include <immintrin.h>
 
 #include <algorithm>
 #include <cmath>
@@ -58,17 +60,19 @@ inline float lcb_critical_value(int visits) {
 
 struct Node;
 
-struct Edge {                                  // one visited (or disqualified) child
-    uint16_t move;
-    bool expanding;
-    float prior;                               // -inf = not (or no longer) a candidate
-    int32_t count;
-    int32_t vcount;
-    float value;
-    float value_s;
-    Node* child;
-};
+// Index of `x` in a[0..n) or -1; `a` is readable up to the next multiple of 16 entries (unused entries hold 0xffff).
+inline int find_u16(const uint16_t* a, int n, int x) {
+    const __m256i key = _mm256_set1_epi16((short)x);
+    for (int i = 0; i < n; i += 16) {
+        uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi16(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(a + i)), key));
+        if (m) { int k = i + (__builtin_ctz(m) >> 1); return k < n ? k : -1; }
+    }
+    return -1;
+}
 
+// A node keeps (a) its candidates and (b) one record per visited (or disqualified) child, in creation order.  Both are
+// stored as parallel arrays in one allocation each: the root of a search has hundreds of children and `select` scores
+// them eight at a time; records never move to another index, so a probe remembers the index instead of the move.
 struct Node {
     uint8_t to_move;
     int16_t pass_count;
@@ -77,38 +81,57 @@ struct Node {
     // Candidates (finite prior).  The first `sorted_n` are in DECREASING prior order (ties: increasing move); the
     // rest is unordered and gets selection-sorted only as far as a select() actually walks -- most nodes are
     // visited once or twice, so a full sort per node would cost more than the rest of the search.
-    std::vector<uint16_t> cand_move;
-    std::vector<float> cand_prior;
-    std::vector<uint8_t> cand_edge;            // 1 = the candidate has an edge record
-    int sorted_n = 0;
-    std::vector<Edge> edges;                   // in creation order, few
+    int n_cand = 0, sorted_n = 0;
+    int first_untouched = 0;                   // every sorted candidate before this one has a child record
+    float* cand_prior = nullptr;               // [n_cand]
+    uint16_t* cand_move = nullptr;             // [n_cand rounded up to 16]
+    uint8_t* cand_edge = nullptr;              // [n_cand] 1 = the candidate has a child record
+    // child records
+    int n_edges = 0, edge_cap = 0;
+    float *e_prior = nullptr;                  // -inf = not (or no longer) a candidate
+    float *e_value = nullptr, *e_value_s = nullptr;
+    int32_t *e_count = nullptr, *e_vcount = nullptr;
+    Node** e_child = nullptr;
+    uint16_t* e_move = nullptr;
+    uint8_t* e_expanding = nullptr;
 
     Node(int to_move_, float value, const float* prior /* [362] */)
         : to_move((uint8_t)to_move_), pass_count(0), initial_value(value), total_count(0), vtotal_count(0) {
         set_prior(prior);
     }
-    ~Node() { for (Edge& e : edges) delete e.child; }
+    ~Node() {
+        for (int i = 0; i < n_edges; ++i) delete e_child[i];
+        free(cand_prior);
+        free(e_child);
+    }
     Node(const Node&) = delete;
     Node& operator=(const Node&) = delete;
 
     void set_prior(const float* prior) {       // lib.rs:170-182 replaces the prior of a re-used root
         int n = 0;
         for (int i = 0; i < 362; ++i) n += std::isfinite(prior[i]);
-        cand_move.resize(n);
-        cand_prior.resize(n);
+        free(cand_prior);
+        const int n16 = (n + 15) & ~15;
+        char* mem = static_cast<char*>(malloc((size_t)n * 4 + (size_t)n16 * 2 + (size_t)n + 16));
+        cand_prior = reinterpret_cast<float*>(mem);
+        cand_move = reinterpret_cast<uint16_t*>(mem + (size_t)n * 4);
+        cand_edge = reinterpret_cast<uint8_t*>(mem + (size_t)n * 4 + (size_t)n16 * 2);
+        n_cand = n;
         n = 0;
         for (int i = 0; i < 362; ++i)
             if (std::isfinite(prior[i])) { cand_move[n] = (uint16_t)i; cand_prior[n] = prior[i]; ++n; }
-        cand_edge.assign(cand_move.size(), 0);
+        for (int i = n; i < n16; ++i) cand_move[i] = 0xffff;
+        memset(cand_edge, 0, (size_t)n_cand);
         sorted_n = 0;
-        for (Edge& e : edges) {
-            e.prior = std::isfinite(prior[e.move]) ? prior[e.move] : NEG_INF;
-            int c = cand_index(e.move);
+        first_untouched = 0;
+        for (int k = 0; k < n_edges; ++k) {
+            e_prior[k] = std::isfinite(prior[e_move[k]]) ? prior[e_move[k]] : NEG_INF;
+            int c = cand_index(e_move[k]);
             if (c >= 0) cand_edge[c] = 1;
         }
     }
     void sort_up_to(int k) {                   // makes positions [0, k] final
-        const int n = (int)cand_move.size();
+        const int n = n_cand;
         while (sorted_n <= k && sorted_n < n) {
             int best = sorted_n;
             for (int i = sorted_n + 1; i < n; ++i)
@@ -119,40 +142,75 @@ struct Node {
             ++sorted_n;
         }
     }
-    int cand_index(int move) const {
-        for (size_t k = 0; k < cand_move.size(); ++k) if (cand_move[k] == move) return (int)k;
-        return -1;
+    int cand_index(int move) const { return find_u16(cand_move, n_cand, move); }
+    int find(int move) const { return find_u16(e_move, n_edges, move); }       // index of the child record or -1
+    void grow() {
+        const int cap = edge_cap ? 2 * edge_cap : 16;                          // multiples of 16: find_u16 / the 8-wide scoring read whole blocks
+        char* mem = static_cast<char*>(malloc((size_t)cap * (8 + 5 * 4 + 2 + 1)));
+        Node** child = reinterpret_cast<Node**>(mem);
+        float* prior = reinterpret_cast<float*>(mem + (size_t)cap * 8);
+        float* value = prior + cap;
+        float* value_s = value + cap;
+        int32_t* count = reinterpret_cast<int32_t*>(value_s + cap);
+        int32_t* vcount = count + cap;
+        uint16_t* move = reinterpret_cast<uint16_t*>(vcount + cap);
+        uint8_t* expanding = reinterpret_cast<uint8_t*>(move + cap);
+        if (n_edges) {
+            memcpy(child, e_child, (size_t)n_edges * 8);
+            memcpy(prior, e_prior, (size_t)n_edges * 4);
+            memcpy(value, e_value, (size_t)n_edges * 4);
+            memcpy(value_s, e_value_s, (size_t)n_edges * 4);
+            memcpy(count, e_count, (size_t)n_edges * 4);
+            memcpy(vcount, e_vcount, (size_t)n_edges * 4);
+            memcpy(move, e_move, (size_t)n_edges * 2);
+            memcpy(expanding, e_expanding, (size_t)n_edges);
+        }
+        for (int i = n_edges; i < cap; ++i) {                                  // unused records never match and never score
+            move[i] = 0xffff;
+            prior[i] = NEG_INF;
+            value[i] = 0.0f;
+            count[i] = vcount[i] = 0;
+        }
+        free(e_child);
+        e_child = child; e_prior = prior; e_value = value; e_value_s = value_s; e_count = count; e_vcount = vcount;
+        e_move = move; e_expanding = expanding;
+        edge_cap = cap;
     }
-    Edge* find(int move) {
-        for (Edge& e : edges) if (e.move == move) return &e;
-        return nullptr;
-    }
-    const Edge* find(int move) const { return const_cast<Node*>(this)->find(move); }
-    Edge& edge(int move) {                     // tree.rs:276-285: an absent child reads as (count 0, value = initial)
-        if (Edge* e = find(move)) return *e;
+    int edge(int move) {                       // tree.rs:276-285: an absent child reads as (count 0, value = initial)
+        int k = find(move);
+        if (k >= 0) return k;
+        if (n_edges == edge_cap) grow();
         int c = cand_index(move);
         if (c >= 0) cand_edge[c] = 1;
-        edges.push_back(Edge{(uint16_t)move, false, c >= 0 ? cand_prior[c] : NEG_INF, 0, 0, initial_value, 0.0f, nullptr});
-        return edges.back();
+        k = n_edges++;
+        e_move[k] = (uint16_t)move;
+        e_expanding[k] = 0;
+        e_prior[k] = c >= 0 ? cand_prior[c] : NEG_INF;
+        e_count[k] = 0;
+        e_vcount[k] = 0;
+        e_value[k] = initial_value;
+        e_value_s[k] = 0.0f;
+        e_child[k] = nullptr;
+        return k;
     }
     float prior_of(int move) const { int c = cand_index(move); return c >= 0 ? cand_prior[c] : NEG_INF; }
-    int count_of(int move) const { const Edge* e = find(move); return e ? e->count : 0; }
-    float value_of(int move) const { const Edge* e = find(move); return e ? e->value : initial_value; }
+    int count_of(int move) const { int k = find(move); return k >= 0 ? e_count[k] : 0; }
+    float value_of(int move) const { int k = find(move); return k >= 0 ? e_value[k] : initial_value; }
 
     void disqualify(int move) {                // tree.rs:1296-1301
-        Edge& e = edge(move);
-        e.value = NEG_INF;
-        e.count = 0;
+        int k = edge(move);
+        e_value[k] = NEG_INF;
+        e_count[k] = 0;
     }
 };
 
 enum ProbeStatus { PROBE_FOUND = 0, PROBE_CONFLICT = 1, PROBE_NO_RESULT = 2 };
-struct TraceEntry { Node* node; int move; };
+struct TraceEntry { Node* node; int move; int edge; };      // edge = index of the child record of `move` in `node`
 typedef std::vector<TraceEntry> Trace;
 
 // Node::select (tree.rs:1311-1385) and asm/argmax.rs:23-76: the reference scans 368 scores in blocks of 8; among
 // equal maxima the LAST block wins and inside a block the FIRST lane.
-inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move) {
+inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move, int* out_edge) {
     const int n = node.total_count + node.vtotal_count;
     const float sqrt_n = std::sqrt((float)(1 + n));
     const float u = uct_exp(n) * sqrt_n;
@@ -172,50 +230,61 @@ inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move) {
             best_move = move;
         }
     };
-    // children with an edge record: their own value / visit count (an edge whose move is not a candidate any more
-    // has prior -inf in the reference and never wins)
-    for (const Edge& e : node.edges) {
-        if (!(e.prior > NEG_INF)) continue;
-        float value, bonus = u;
-        int total = e.count + e.vcount;
-        if (total != 0) {
-            value = e.value;
-            bonus = u / (float)(1 + total);
-        } else if (apply_fpu) {
-            float v = e.value - reduce;
-            value = v > 0.0f ? v : 0.0f;
-        } else {
-            value = e.value;
+    // children with a record: their own value / visit count (a record whose move is not a candidate any more has
+    // prior -inf in the reference and never wins).  score = value + prior * (u / (1 + count + vcount)), where an
+    // unvisited child's value is reduced (first-play urgency) -- eight records at a time, IEEE operation for operation
+    // what the scalar code computes (u / 1 == u, so the division needs no special case for unvisited children).
+    {
+        const __m256 vu = _mm256_set1_ps(u), vreduce = _mm256_set1_ps(reduce), zero = _mm256_setzero_ps();
+        const __m256i one = _mm256_set1_epi32(1);
+        float score[8];
+        for (int k0 = 0; k0 < node.n_edges; k0 += 8) {
+            const __m256i total = _mm256_add_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(node.e_count + k0)),
+                                                   _mm256_loadu_si256(reinterpret_cast<const __m256i*>(node.e_vcount + k0)));
+            const __m256 bonus = _mm256_div_ps(vu, _mm256_cvtepi32_ps(_mm256_add_epi32(total, one)));
+            __m256 value = _mm256_loadu_ps(node.e_value + k0);
+            if (apply_fpu) {
+                const __m256 fresh = _mm256_castsi256_ps(_mm256_cmpeq_epi32(total, _mm256_setzero_si256()));
+                value = _mm256_blendv_ps(value, _mm256_max_ps(_mm256_sub_ps(value, vreduce), zero), fresh);
+            }
+            const __m256 prior = _mm256_loadu_ps(node.e_prior + k0);
+            _mm256_storeu_ps(score, _mm256_add_ps(value, _mm256_mul_ps(prior, bonus)));
+            const int live = _mm256_movemask_ps(_mm256_cmp_ps(prior, _mm256_set1_ps(NEG_INF), _CMP_GT_OQ));
+            const int kn = std::min(8, node.n_edges - k0);
+            for (int j = 0; j < kn; ++j)
+                if (live >> j & 1) consider(node.e_move[k0 + j], score[j]);
         }
-        consider(e.move, value + e.prior * bonus);
     }
     // untouched children all score `unvisited + prior * u`, which never increases along the prior-sorted list:
     // stop at the first one that falls strictly below the best score seen
-    const size_t nc = node.cand_move.size();
-    for (size_t i = 0; i < nc; ++i) {
-        node.sort_up_to((int)i);
+    const int nc = node.n_cand;
+    int i = node.first_untouched;
+    while (i < node.sorted_n && node.cand_edge[i]) ++i;
+    node.first_untouched = i;
+    for (; i < nc; ++i) {
+        node.sort_up_to(i);
         if (node.cand_edge[i]) continue;
         float score = unvisited + node.cand_prior[i] * u;
         if (best_move >= 0 && score < best) break;
         consider(node.cand_move[i], score);
     }
     if (best_move < 0 || !std::isfinite(best)) return PROBE_NO_RESULT;
-    Edge& e = node.edge(best_move);
-    bool was_expanding = e.expanding;
-    e.expanding = true;
-    if (was_expanding && !e.child) return PROBE_CONFLICT;
-    e.vcount += VLOSS_CNT;
+    const int k = node.edge(best_move);
+    bool was_expanding = node.e_expanding[k];
+    node.e_expanding[k] = 1;
+    if (was_expanding && !node.e_child[k]) return PROBE_CONFLICT;
+    node.e_vcount[k] += VLOSS_CNT;
     node.vtotal_count += VLOSS_CNT;
     *out_move = best_move;
+    *out_edge = k;
     return PROBE_FOUND;
 }
 
 inline void undo(const Trace& trace, bool undo_expanding) {    // tree.rs:1397-1409
     for (const TraceEntry& t : trace) {
         t.node->vtotal_count -= VLOSS_CNT;
-        Edge& e = t.node->edge(t.move);
-        e.vcount -= VLOSS_CNT;
-        if (undo_expanding && !e.child) e.expanding = false;
+        t.node->e_vcount[t.edge] -= VLOSS_CNT;
+        if (undo_expanding && !t.node->e_child[t.edge]) t.node->e_expanding[t.edge] = 0;
     }
 }
 
@@ -224,14 +293,14 @@ inline ProbeStatus probe(Node& root, Board& board, Trace& trace) {
     trace.clear();
     Node* current = &root;
     for (;;) {
-        int move;
-        ProbeStatus st = select(*current, !trace.empty(), &move);
+        int move, k;
+        ProbeStatus st = select(*current, !trace.empty(), &move, &k);
         if (st == PROBE_CONFLICT) { undo(trace, false); trace.clear(); return st; }
         if (st == PROBE_NO_RESULT) return st;
-        trace.push_back(TraceEntry{current, move});
+        trace.push_back(TraceEntry{current, move, k});
         if (move != PASS) board.place(current->to_move, move);
         else if (current->pass_count >= 1) break;
-        Node* child = current->edge(move).child;
+        Node* child = current->e_child[k];
         if (!child) break;
         current = child;
     }
@@ -242,25 +311,25 @@ inline ProbeStatus probe(Node& root, Board& board, Trace& trace) {
 inline void insert(const Trace& trace, int color, float value, const float* prior /* [362] */) {
     if (!trace.empty()) {
         const TraceEntry& last = trace.back();
-        Edge& e = last.node->edge(last.move);
-        if (!e.child) {
+        if (!last.node->e_child[last.edge]) {
             Node* next = new Node(color, value, prior);
             if (last.move == PASS) next->pass_count = (int16_t)(last.node->pass_count + 1);
-            e.child = next;
+            last.node->e_child[last.edge] = next;
         }
     }
     for (const TraceEntry& t : trace) {
         float v = color == t.node->to_move ? value : 1.0f - value;
-        t.node->total_count += 1;
-        t.node->vtotal_count -= VLOSS_CNT;
-        Edge& e = t.node->edge(t.move);
-        float prev = e.value, prev_s = e.value_s;
-        int prev_count = e.count;
-        e.count = prev_count + 1;
+        Node& nd = *t.node;
+        const int k = t.edge;
+        nd.total_count += 1;
+        nd.vtotal_count -= VLOSS_CNT;
+        float prev = nd.e_value[k], prev_s = nd.e_value_s[k];
+        int prev_count = nd.e_count[k];
+        nd.e_count[k] = prev_count + 1;
         float next = prev + (v - prev) / (float)(prev_count + 1);
-        e.value = next;
-        e.value_s = prev_s + (v - prev) * (v - next);
-        e.vcount -= VLOSS_CNT;
+        nd.e_value[k] = next;
+        nd.e_value_s[k] = prev_s + (v - prev) * (v - next);
+        nd.e_vcount[k] -= VLOSS_CNT;
     }
 }
 
@@ -272,9 +341,10 @@ inline bool is_done(const Node& root, int limit) {
     // min_promote_rollouts (:47-74): visits the runner-up needs to catch up = largest count - second largest
     // (whichever of two tied leaders the reference's argmax picks, the difference is the same)
     int c1 = 0, c2 = 0;
-    for (const Edge& e : root.edges) {
-        if (e.count > c1) { c2 = c1; c1 = e.count; }
-        else if (e.count > c2) c2 = e.count;
+    for (int k = 0; k < root.n_edges; ++k) {
+        const int c = root.e_count[k];
+        if (c > c1) { c2 = c1; c1 = c; }
+        else if (c > c2) c2 = c;
     }
     int min_promote = c1 > c2 ? c1 - c2 : 0;
     return min_promote > remaining;
@@ -290,13 +360,12 @@ inline float normal_lcb(float p_hat, float p_std, int n, int m) {      // libdg_
 
 // tree.rs:1524-1560; returns <0, 0, >0 like Ordering
 inline int compare_children(const Node& node, int a, int b) {
-    const Edge* ea = node.find(a);
-    const Edge* eb = node.find(b);
-    int ac = ea ? ea->count : 0, bc = eb ? eb->count : 0;
+    const int ea = node.find(a), eb = node.find(b);
+    int ac = ea >= 0 ? node.e_count[ea] : 0, bc = eb >= 0 ? node.e_count[eb] : 0;
     auto cmp = [](float x, float y) { return x < y ? -1 : x > y ? 1 : 0; };
     if (ac >= MIN_LCB_VISITS && bc >= MIN_LCB_VISITS) {
-        float as = std::sqrt(ea->value_s / ((float)ac + 1e-5f)), bs = std::sqrt(eb->value_s / ((float)bc + 1e-5f));
-        float al = normal_lcb(ea->value, as, ac, node.total_count), bl = normal_lcb(eb->value, bs, bc, node.total_count);
+        float as = std::sqrt(node.e_value_s[ea] / ((float)ac + 1e-5f)), bs = std::sqrt(node.e_value_s[eb] / ((float)bc + 1e-5f));
+        float al = normal_lcb(node.e_value[ea], as, ac, node.total_count), bl = normal_lcb(node.e_value[eb], bs, bc, node.total_count);
         if (al != bl) return cmp(al, bl);
     }
     if (ac != bc) return ac < bc ? -1 : 1;
@@ -335,8 +404,8 @@ inline int best(const Node& node, float temperature, double at, float* value_out
         // children.nonzero() (tree.rs:871-890) walks the 8-slot table in insertion order while the node is
         // sparse and the dense table in index order once a 9th child exists; it only matters for exact ties
         std::vector<int> visited;
-        for (const Edge& e : node.edges) if (e.count != 0) visited.push_back(e.move);
-        if (node.edges.size() > 8) std::sort(visited.begin(), visited.end());
+        for (int k = 0; k < node.n_edges; ++k) if (node.e_count[k] != 0) visited.push_back(node.e_move[k]);
+        if (node.n_edges > 8) std::sort(visited.begin(), visited.end());
         pick = PASS;
         bool first = true;
         for (int i : visited) {                // Iterator::max_by keeps the LAST of equal maxima
@@ -357,7 +426,7 @@ inline int best(const Node& node, float temperature, double at, float* value_out
 // the rest of `node` is destroyed.
 inline Node* forward(Node* node, int move) {
     Node* next = nullptr;
-    if (Edge* e = node->find(move)) { next = e->child; e->child = nullptr; }
+    if (int k = node->find(move); k >= 0) { next = node->e_child[k]; node->e_child[k] = nullptr; }
     if (!next && move == PASS) {
         float prior[362];
         for (int i = 0; i < 362; ++i) prior[i] = 0.0f;
@@ -373,7 +442,7 @@ inline void visit_distribution(const Node& node, float out[362]) {
     float total = 0.0f;
     for (int i = 0; i < 362; ++i) out[i] = 0.0f;
     std::vector<int> visited;
-    for (const Edge& e : node.edges) if (e.count != 0) visited.push_back(e.move);
+    for (int k = 0; k < node.n_edges; ++k) if (node.e_count[k] != 0) visited.push_back(node.e_move[k]);
     std::sort(visited.begin(), visited.end());
     for (int i : visited) total += (float)node.count_of(i);
     for (int i : visited) out[i] = (float)node.count_of(i) / total;

@@ -43,7 +43,7 @@ static SearchOptions convert(const dg_search_options* o) {
 
 static int64_t count_nodes(const Node* n) {
     int64_t c = 1;
-    for (const Edge& e : n->edges) if (e.child) c += count_nodes(e.child);
+    for (int k = 0; k < n->n_edges; ++k) if (n->e_child[k]) c += count_nodes(n->e_child[k]);
     return c;
 }
 
@@ -210,7 +210,7 @@ struct Driver {
             // Node::prior() = argmax_f32 over the dense prior (tree.rs:1266-1270, asm/argmax.rs tie rule)
             int arg = PASS;
             float bestp = NEG_INF;
-            for (size_t i = 0; i < tree->cand_move.size(); ++i) {
+            for (int i = 0; i < tree->n_cand; ++i) {
                 int m = tree->cand_move[i];
                 float p = tree->cand_prior[i];
                 if (p > bestp || (p == bestp && ((m >> 3) > (arg >> 3) || ((m >> 3) == (arg >> 3) && m < arg)))) { bestp = p; arg = m; }
@@ -315,11 +315,11 @@ void dg_tree_children(const dg_tree* tree, int32_t* count, float* value, float* 
         if (value) value[i] = n->initial_value;
         if (prior) prior[i] = NEG_INF;
     }
-    for (const Edge& e : n->edges) {
-        if (count) count[e.move] = e.count;
-        if (value) value[e.move] = e.value;
+    for (int k = 0; k < n->n_edges; ++k) {
+        if (count) count[n->e_move[k]] = n->e_count[k];
+        if (value) value[n->e_move[k]] = n->e_value[k];
     }
-    if (prior) for (size_t i = 0; i < n->cand_move.size(); ++i) prior[n->cand_move[i]] = n->cand_prior[i];
+    if (prior) for (int i = 0; i < n->n_cand; ++i) prior[n->cand_move[i]] = n->cand_prior[i];
 }
 int64_t dg_tree_num_nodes(const dg_tree* tree) { return tree ? count_nodes(N(tree)) : 0; }
 

@@ -9,6 +9,8 @@
 //   DONE     move chosen (Node::best, lib.rs:190-194)
 #pragma once
 
+#include <immintrin.h>
+
 #include <unordered_map>
 #include <vector>
 
@@ -17,21 +19,7 @@
 
 namespace dg {
 
-inline float f16_to_f32(uint16_t h) {
-    uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1f, m = h & 0x3ffu, x;
-    if (e == 0) {
-        if (m == 0) x = sign;
-        else {
-            int s = 0;
-            while (!(m & 0x400u)) { m <<= 1; ++s; }
-            x = sign | ((uint32_t)(113 - s) << 23) | ((m & 0x3ffu) << 13);
-        }
-    } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
-    else x = sign | ((e + 112) << 23) | (m << 13);
-    float f;
-    memcpy(&f, &x, 4);
-    return f;
-}
+inline float f16_to_f32(uint16_t h) { return _cvtsh_ss(h); }     // exact (F16C); the build targets x86-64-v3
 
 // Transposition table of network evaluations: `NnPredictor::{fetch, cache}` + `LruCache` (predictors/nn.rs:29-82,
 // lru_cache.rs).  Key = (zobrist hash, colour to move); the value is kept in IDENTITY orientation
@@ -118,6 +106,7 @@ class PredictionCache {
 struct PriorPlan {
     uint8_t candidate[N_POINTS + 1];           // after symmetry elimination
     uint16_t rep[N_POINTS + 1];                // orbit representative of each point (`indices`, :54-72)
+    bool folded;                               // the board has a symmetry: some rep[p] != p
 
     void build(const Board& b, int to_move, int search_kind, const uint8_t* legal) {
         const Tables& T = tables();
@@ -128,6 +117,11 @@ struct PriorPlan {
             const uint16_t* m = T.sym[t];
             for (int p = 0; p < N_POINTS && same; ++p) same = b.color[p] == b.color[m[p]];
             if (same) syms[ns++] = t;
+        }
+        folded = ns > 1;                           // syms[0] is the identity
+        if (!folded) {
+            for (int p = 0; p <= N_POINTS; ++p) rep[p] = (uint16_t)p;
+            return;
         }
         for (int p = 0; p < N_POINTS; ++p) {
             int best = p;
@@ -141,20 +135,39 @@ struct PriorPlan {
     // add_valid_candidates + normalize_policy (policy_helper.rs:87-134; lane order of asm/sum_finite.rs:23-57)
     void apply(const uint16_t* policy /* [362] fp16, orientation `symmetry` */, int symmetry, float sum_to, float* prior /* [368] */) const {
         const Tables& T = tables();
-        for (int i = 0; i < 368; ++i) prior[i] = NEG_INF;
-        for (int p = 0; p <= N_POINTS; ++p) if (candidate[p]) prior[p] = 0.0f;
-        prior[PASS] += f16_to_f32(policy[PASS]);
-        const uint16_t* inv = T.sym[T.sym_inverse[symmetry]];
-        for (int i = 0; i < N_POINTS; ++i) prior[rep[inv[i]]] += f16_to_f32(policy[i]);
-        float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (!folded) {
+            // every point is its own representative: prior[q] = 0 + policy[sym(q)] for the candidates, -inf elsewhere
+            const uint16_t* fwd = T.sym[symmetry];             // i = fwd[q]  <=>  q = inverse(symmetry)[i]
+            for (int q = 0; q < N_POINTS; ++q) prior[q] = candidate[q] ? 0.0f + f16_to_f32(policy[fwd[q]]) : NEG_INF;
+            prior[PASS] = candidate[PASS] ? 0.0f + f16_to_f32(policy[PASS]) : NEG_INF;
+            for (int i = N_POINTS + 1; i < 368; ++i) prior[i] = NEG_INF;
+        } else {
+            for (int i = 0; i < 368; ++i) prior[i] = NEG_INF;
+            for (int p = 0; p <= N_POINTS; ++p) if (candidate[p]) prior[p] = 0.0f;
+            prior[PASS] += f16_to_f32(policy[PASS]);
+            const uint16_t* inv = T.sym[T.sym_inverse[symmetry]];
+            for (int i = 0; i < N_POINTS; ++i) prior[rep[inv[i]]] += f16_to_f32(policy[i]);
+        }
+        // eight interleaved partial sums over the finite entries, as the reference's AVX code keeps them; a masked-out
+        // entry adds +0.0, which leaves a partial sum (never -0.0) unchanged
+        const __m256 inf = _mm256_set1_ps(std::numeric_limits<float>::infinity());
+        const __m256 absmask = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
+        __m256 acc = _mm256_setzero_ps();
         int finite = 0;
-        for (int i = 0; i < 368; ++i) if (std::isfinite(prior[i])) { lane[i & 7] += prior[i]; ++finite; }
+        for (int i = 0; i < 368; i += 8) {
+            const __m256 x = _mm256_loadu_ps(prior + i);
+            const __m256 ok = _mm256_cmp_ps(_mm256_and_ps(x, absmask), inf, _CMP_LT_OQ);     // finite: not inf, not NaN
+            acc = _mm256_add_ps(acc, _mm256_and_ps(x, ok));
+            finite += __builtin_popcount((unsigned)_mm256_movemask_ps(ok));
+        }
+        float lane[8];
+        _mm256_storeu_ps(lane, acc);
         float sum = ((lane[0] + lane[1]) + (lane[2] + lane[3])) + ((lane[4] + lane[5]) + (lane[6] + lane[7]));
         if (sum < 1e-6f) {
             for (int i = 0; i < 368; ++i) if (std::isfinite(prior[i])) prior[i] = sum_to / (float)finite;
         } else {
-            float recip = 1.0f / (sum / sum_to);
-            for (int i = 0; i < 368; ++i) prior[i] *= recip;
+            const __m256 recip = _mm256_set1_ps(1.0f / (sum / sum_to));
+            for (int i = 0; i < 368; i += 8) _mm256_storeu_ps(prior + i, _mm256_mul_ps(_mm256_loadu_ps(prior + i), recip));
         }
     }
 };

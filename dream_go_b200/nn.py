@@ -67,6 +67,9 @@ _lib = None
 # every symbol include/dg_engine.h declares: name -> (restype, argtypes)
 ABI = {
     "dg_engine_abi_version": (C.c_int32, []),
+    "dg_device_count": (C.c_int32, []),
+    "dg_current_device": (C.c_int32, []),
+    "dg_set_current_device": (C.c_int32, [C.c_int32]),
     "dg_engine_create": (C.c_int32, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
     "dg_engine_destroy": (None, [C.c_void_p]),
     "dg_engine_load_weights_json": (C.c_int32, [C.c_void_p, C.c_char_p]),

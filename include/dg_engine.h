@@ -98,6 +98,19 @@ typedef struct dg_raw_position {
                                       bits 4-7: search options of the position (DG_STANDARD_SEARCH / DG_SCORING_SEARCH) */
 } dg_raw_position;                 /* 384 bytes */
 
+/* ---- devices ------------------------------------------------------------------------------- */
+
+/* `Device::len()` / `Device::all()` (src/libdg_cuda/devices.rs:55-64) restricted to what this engine runs on: the number
+ * of CUDA devices if every one of them is an sm_100 part, else the number of leading sm_100 devices; 0 without a driver
+ * or device (the reference's `Device::all().expect(..)` then panics, predictors/nn.rs:65).  One process may hold one
+ * engine per device and call them from any thread. */
+int32_t dg_device_count(void);
+/* `cudaGetDevice` / `Device::set_current` (devices.rs:70-73) of the calling thread: the reference's NnPredictor picks a
+ * device per batch with set_current and then asks the network for a workspace (predictors/nn.rs:87-93); a shim maps the
+ * calling thread's current device to its engine with these.  -1 / DG_ERR_CUDA on failure. */
+int32_t dg_current_device(void);
+int32_t dg_set_current_device(int32_t device);
+
 /* ---- lifetime ------------------------------------------------------------------------------ */
 
 /* `Network::new()` minus the file search.  Fails with DG_ERR_CUDA when the device is missing

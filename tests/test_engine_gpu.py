@@ -193,6 +193,40 @@ def test_concurrent_forwards(small_engine, small_net):
     assert not errors, errors
 
 
+def test_one_process_two_devices(small_net):
+    """The reference drives every GPU from ONE process (`cudaSetDevice` per call, predictors/nn.rs:84-92): two engines on
+    two devices, used concurrently from two threads, give the results of one engine alone, bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nets = [nn.Network.from_tensors(small_net, device=d, max_batch=64, num_workspaces=2) for d in (1, 0)]
+    feats = [weights.bernoulli_features(40 + d, seed=70 + d) for d in range(2)]
+    alone = []
+    for net, f in zip(nets, feats):
+        with net.get_workspace(len(f)) as ws:
+            alone.append(nn.forward(ws, f).unwrap())
+    got, errors = [None, None], []
+
+    def worker(i):
+        try:
+            for _ in range(20):
+                with nets[i].get_workspace(len(feats[i])) as ws:
+                    got[i] = nn.forward(ws, feats[i]).unwrap()
+        except Exception as exc:   # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(2):
+        assert np.array_equal(got[i][0], alone[i][0]) and np.array_equal(got[i][1], alone[i][1])
+    want_v, want_p = oracle.OracleNetwork(small_net).forward(feats[0])
+    check_outputs(*got[0], want_v, want_p)
+    for net in nets:
+        net.close()
+
+
 def test_errors(tmp_path, small_net):
     net = nn.Network(max_batch=4)
     with pytest.raises(nn.Error) as err:      # forward before load
