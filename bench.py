@@ -264,7 +264,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_selfplay
         threads = max(1, (os.cpu_count() or 1) // world)
-        sp_net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=2 * BATCH, num_workspaces=4)   # its own engine, one workspace per group of games
+        # its own engine, one workspace per group of games; its calls nap while they wait instead of spinning on a core
+        sp_net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=2 * BATCH, num_workspaces=4, flags=nn.FLAG_BLOCKING_SYNC)
         barrier()
         st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=SELF_PLAY_GAMES, rollouts=800, probes=8,
                                       seconds=args.self_play_seconds, threads=threads, seed=20261017 + rank)

@@ -4,6 +4,9 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <sys/prctl.h>
+#include <time.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -36,7 +39,6 @@ constexpr int kHeadChan = 16;
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_done = nullptr;    // blocking-sync event (DG_FLAG_BLOCKING_SYNC)
     uint8_t* d_in = nullptr;          // raw NHWC features or compact positions of the current batch
     __half *feat = nullptr, *x = nullptr, *y = nullptr;
     __half *h = nullptr;               // [row][16] head-conv output of the debug direct path only
@@ -157,7 +159,6 @@ int32_t create_workspace(dg_engine* e, Workspace& w) {
     DG_CUDA(e, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     DG_CUDA(e, cudaEventCreate(&w.ev0));
     DG_CUDA(e, cudaEventCreate(&w.ev1));
-    DG_CUDA(e, cudaEventCreateWithFlags(&w.ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
     DG_CUDA(e, cudaMalloc(&w.d_in, static_cast<size_t>(mb) * kFeatBytes));
     DG_CUDA(e, cudaMalloc(&w.feat, rows * 64 * 2));
     DG_CUDA(e, cudaMalloc(&w.x, rows * kChan * 2));
@@ -192,7 +193,6 @@ void destroy_workspace(Workspace& w) {
     if (w.stream) cudaStreamDestroy(w.stream);
     if (w.ev0) cudaEventDestroy(w.ev0);
     if (w.ev1) cudaEventDestroy(w.ev1);
-    if (w.ev_done) cudaEventDestroy(w.ev_done);
     cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
     cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done); cudaFree(w.pbuf); cudaFree(w.vbuf); cudaFree(w.part);
     cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value); cudaFreeHost(w.h_legal); cudaFreeHost(w.h_prior);
@@ -432,12 +432,21 @@ int32_t run_conv(dg_engine* e, Workspace& w, ConvTcShape shape, const CUtensorMa
     return DG_OK;
 }
 
-// Waits for everything enqueued on the workspace's stream.  With DG_FLAG_BLOCKING_SYNC the calling thread sleeps on an
-// event instead of spinning in the driver: self-play runs as many host threads as cores and a spinning waiter steals one.
+// Waits for everything enqueued on the workspace's stream.  By default the calling thread spins in the driver
+// (cudaStreamSynchronize: lowest latency, one core per waiter).  With DG_FLAG_BLOCKING_SYNC it polls the stream between
+// short naps instead: self-play runs as many host threads as cores and a spinning waiter steals one (measured on a B200
+// with 4 host cores: 418 k evaluations/s spinning, 471 k sleeping on a cudaEventBlockingSync event, 490 k with naps; with
+// 16 cores naps equal spinning, the blocking event loses 10 %).
 inline cudaError_t wait_stream(dg_engine* e, Workspace& w) {
     if (!(e->cfg.flags & DG_FLAG_BLOCKING_SYNC)) return cudaStreamSynchronize(w.stream);
-    cudaError_t rc = cudaEventRecord(w.ev_done, w.stream);
-    return rc != cudaSuccess ? rc : cudaEventSynchronize(w.ev_done);
+    static thread_local bool slack_set = false;
+    if (!slack_set) { prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0); slack_set = true; }   // naps of ~20 us, not 20 + 50 us
+    for (;;) {
+        cudaError_t q = cudaStreamQuery(w.stream);
+        if (q != cudaErrorNotReady) return q;
+        timespec nap{0, 20000};
+        nanosleep(&nap, nullptr);
+    }
 }
 
 // Raw-position path: d_in (max_batch x 23,104 B) holds [raw positions | compact planes | legal masks].

@@ -631,8 +631,20 @@ inline void policy_candidates(const Board& b, int to_move, int kind, const uint8
     Bits alive, eyes_b, eyes_w;
     benson(b, BLACK, alive, eyes_b);
     benson(b, WHITE, alive, eyes_w);
-    for (int p = 0; p < N_POINTS; ++p)
-        out[p] = legal[p] && !eyes_b.test(p) && !eyes_w.test(p) && !is_simple_eye(b, to_move, p);
+    const Bits settled = eyes_b | eyes_w;                    // usually empty before the endgame
+    if (settled.any()) {
+        for (int p = 0; p < N_POINTS; ++p) out[p] = legal[p] && !settled.test(p);
+    } else {
+        memcpy(out, legal, N_POINTS);
+    }
+    // own eyes: only points whose on-board neighbours are all own stones can be one -- whole-board shifts find them
+    const Tables& T = tables();
+    Bits maybe_eye = T.board.andnot(dilate(T.board.andnot(b.stones[to_move])));
+    while (maybe_eye.any()) {
+        const int p = maybe_eye.first();
+        maybe_eye.reset(p);
+        if (out[p] && is_simple_eye(b, to_move, p)) out[p] = 0;
+    }
     out[PASS] = 0;
 }
 

@@ -108,18 +108,26 @@ struct Node {
     Node& operator=(const Node&) = delete;
 
     void set_prior(const float* prior) {       // lib.rs:170-182 replaces the prior of a re-used root
+        // `prior` has 362 entries; the callers' buffers are not padded, so the last 2 are counted one by one
+        const __m256 inf = _mm256_set1_ps(std::numeric_limits<float>::infinity());
+        const __m256 absmask = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
         int n = 0;
-        for (int i = 0; i < 362; ++i) n += std::isfinite(prior[i]);
+        for (int i = 0; i < 360; i += 8)
+            n += __builtin_popcount((unsigned)_mm256_movemask_ps(_mm256_cmp_ps(_mm256_and_ps(_mm256_loadu_ps(prior + i), absmask), inf, _CMP_LT_OQ)));
+        n += std::isfinite(prior[360]) + std::isfinite(prior[361]);
         free(cand_prior);
-        const int n16 = (n + 15) & ~15;
-        char* mem = static_cast<char*>(malloc((size_t)n * 4 + (size_t)n16 * 2 + (size_t)n + 16));
+        const int n16 = (n + 1 + 15) & ~15;    // one spare slot: the compaction below writes before it knows whether to keep
+        char* mem = static_cast<char*>(malloc((size_t)(n + 1) * 4 + (size_t)n16 * 2 + (size_t)n + 16));
         cand_prior = reinterpret_cast<float*>(mem);
-        cand_move = reinterpret_cast<uint16_t*>(mem + (size_t)n * 4);
-        cand_edge = reinterpret_cast<uint8_t*>(mem + (size_t)n * 4 + (size_t)n16 * 2);
+        cand_move = reinterpret_cast<uint16_t*>(mem + (size_t)(n + 1) * 4);
+        cand_edge = reinterpret_cast<uint8_t*>(mem + (size_t)(n + 1) * 4 + (size_t)n16 * 2);
         n_cand = n;
         n = 0;
-        for (int i = 0; i < 362; ++i)
-            if (std::isfinite(prior[i])) { cand_move[n] = (uint16_t)i; cand_prior[n] = prior[i]; ++n; }
+        for (int i = 0; i < 362; ++i) {
+            cand_move[n] = (uint16_t)i;
+            cand_prior[n] = prior[i];
+            n += std::isfinite(prior[i]);
+        }
         for (int i = n; i < n16; ++i) cand_move[i] = 0xffff;
         memset(cand_edge, 0, (size_t)n_cand);
         sorted_n = 0;

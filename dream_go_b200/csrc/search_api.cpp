@@ -355,9 +355,20 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         std::vector<uint16_t> value, policy;
         std::vector<uint8_t> legal;
         std::vector<float> prior;
-        std::future<int32_t> pending;
         size_t size() const { return batch.size() + raw_batch.size(); }
         bool in_flight = false;
+        // one persistent device thread per group: it makes the (blocking) predictor call of the group's batch
+        std::thread device_thread;
+        std::mutex m;
+        std::condition_variable cv;
+        enum { IDLE, SUBMITTED, FINISHED, QUIT } state = IDLE;
+        int32_t result = DG_OK;
+        int32_t wait() {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [this] { return state == FINISHED; });
+            state = IDLE;
+            return result;
+        }
     } groups[8];
     for (int i = 0; i < n_slots; ++i) groups[i % n_groups].slots.push_back(i);
 
@@ -449,7 +460,15 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     };
 
     Helpers helpers(std::max(0, std::min(n_threads, (n_slots + n_groups - 1) / n_groups) - 1));
+    // DG_SELFPLAY_TRACE=1: where the driver thread's time goes (stderr, at the end)
+    const bool trace_driver = getenv("DG_SELFPLAY_TRACE") != nullptr;
+    int64_t ns_wait = 0, ns_parallel = 0, ns_serial = 0;
+    std::mutex idle_mutex;                    // trace only: wall time during which no predictor call was in flight
+    int calls_in_flight = 0;
+    int64_t idle_since = 0, ns_idle = 0;
+    auto now_ns = [] { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     auto run_group = [&](Group& grp, bool absorb_results) {
+        const int64_t t_begin = now_ns();
         std::atomic<size_t> next{0};
         std::function<void()> worker = [&] {
             for (;;) {
@@ -460,6 +479,8 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
             }
         };
         helpers.run(worker);
+        const int64_t t_mid = now_ns();
+        ns_parallel += t_mid - t_begin;
         // serial part: finished games are replaced, leaves are gathered in slot order
         grp.batch.clear();
         grp.raw_batch.clear();
@@ -482,6 +503,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 grp.raw_batch.insert(grp.raw_batch.end(), g.raw_batch.begin(), g.raw_batch.end());
             }
         }
+        ns_serial += now_ns() - t_mid;
     };
 
     auto launch = [&](Group& grp) {
@@ -493,8 +515,21 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         ++rounds;
         positions += (int64_t)grp.size();
         grp.in_flight = true;
-        grp.pending = std::async(std::launch::async, [&grp, predictor, raw_predictor, prior_predictor, ctx, &eval_ns] {
+        { std::lock_guard<std::mutex> lk(grp.m); grp.state = Group::SUBMITTED; }
+        grp.cv.notify_all();
+    };
+    auto device_loop = [&](Group& grp) {
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(grp.m);
+                grp.cv.wait(lk, [&] { return grp.state == Group::SUBMITTED || grp.state == Group::QUIT; });
+                if (grp.state == Group::QUIT) return;
+            }
             auto t0 = std::chrono::steady_clock::now();
+            if (trace_driver) {
+                std::lock_guard<std::mutex> lk(idle_mutex);
+                if (calls_in_flight++ == 0 && idle_since) ns_idle += now_ns() - idle_since;
+            }
             int32_t r = prior_predictor
                 ? prior_predictor(ctx, grp.raw_batch.data(), (int32_t)grp.raw_batch.size(), grp.value.data(), grp.policy.data(), grp.legal.data(),
                                   grp.prior.data())
@@ -502,9 +537,15 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 ? raw_predictor(ctx, grp.raw_batch.data(), (int32_t)grp.raw_batch.size(), grp.value.data(), grp.policy.data(), grp.legal.data())
                 : predictor(ctx, grp.batch.data(), (int32_t)grp.batch.size(), grp.value.data(), grp.policy.data());
             eval_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-            return r;
-        });
+            if (trace_driver) {
+                std::lock_guard<std::mutex> lk(idle_mutex);
+                if (--calls_in_flight == 0) idle_since = now_ns();
+            }
+            { std::lock_guard<std::mutex> lk(grp.m); grp.result = r; grp.state = Group::FINISHED; }
+            grp.cv.notify_all();
+        }
     };
+    for (int gi = 0; gi < n_groups; ++gi) groups[gi].device_thread = std::thread(device_loop, std::ref(groups[gi]));
 
     for (int gi = 0; gi < n_groups; ++gi) { run_group(groups[gi], false); launch(groups[gi]); }
     for (;;) {
@@ -513,7 +554,9 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
             Group& grp = groups[gi];
             if (!grp.in_flight) continue;
             any = true;
-            rc = grp.pending.get();
+            const int64_t t_wait = now_ns();
+            rc = grp.wait();
+            ns_wait += now_ns() - t_wait;
             grp.in_flight = false;
             if (rc != DG_OK) break;
             bool out_of_time = d.cfg.max_seconds > 0 && seconds() >= d.cfg.max_seconds;
@@ -523,8 +566,18 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         }
         if (!any || rc != DG_OK) break;
     }
-    for (int gi = 0; gi < n_groups; ++gi) if (groups[gi].in_flight) groups[gi].pending.wait();
+    for (int gi = 0; gi < n_groups; ++gi) {
+        Group& grp = groups[gi];
+        if (grp.in_flight) grp.wait();
+        { std::lock_guard<std::mutex> lk(grp.m); grp.state = Group::QUIT; }
+        grp.cv.notify_all();
+        grp.device_thread.join();
+    }
 
+    if (trace_driver)
+        fprintf(stderr, "[dg_selfplay] %d groups, %d threads, %lld rounds: driver thread waited for the device %.3f s, parallel host work %.3f s, "
+                "serial gather %.3f s, predictor calls %.3f s (sum over device threads), no call in flight %.3f s, wall %.3f s\n", n_groups, n_threads,
+                (long long)rounds, ns_wait * 1e-9, ns_parallel * 1e-9, ns_serial * 1e-9, (double)eval_ns.load() * 1e-9, ns_idle * 1e-9, seconds());
     // account for the games that were cut off by max_seconds
     for (Game& g : d.games) {
         d.total_moves += g.n_moves; d.total_evals += g.evals; d.total_searches += g.searches;

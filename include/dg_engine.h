@@ -44,9 +44,9 @@ extern "C" {
 
 #define DG_FLAG_NO_PDL             0x2u  /* debug: launch the layers without programmatic dependent launch */
 #define DG_FLAG_LAYERWISE          0x4u  /* debug: one launch per convolution instead of the persistent tower kernel */
-#define DG_FLAG_NO_ROTATE          0x8u
-#define DG_FLAG_BLOCKING_SYNC     0x10u /* blocking calls sleep on an event instead of spinning in the driver (self-play:
-                                            every core is busy searching) */  /* debug: do not rotate the unit -> CTA-pair assignment between layers */
+#define DG_FLAG_NO_ROTATE          0x8u  /* debug: do not rotate the unit -> CTA-pair assignment between layers */
+#define DG_FLAG_BLOCKING_SYNC     0x10u  /* blocking calls poll the stream between 20 us naps instead of spinning in the driver
+                                            (self-play: every core is busy searching and a spinning waiter steals one) */
 
 typedef struct dg_engine dg_engine;
 

@@ -44,10 +44,13 @@ def main():
     ap.add_argument("--blocks", type=int, default=9)
     ap.add_argument("--ex-it", action="store_true")
     ap.add_argument("--ex-it-rollouts", type=int, default=0, help="`--num-ex-it-rollout` (default: same as --rollouts)")
+    ap.add_argument("--no-host-sample", action="store_true", help="skip the host-only (RandomPredictor) sample")
     ap.add_argument("--host-only", action="store_true", help="RandomPredictor instead of the engine (no GPU needed)")
     ap.add_argument("--sgf-out", default=None, help="write the finished games' records (rank 0) to this file")
     ap.add_argument("--cache", type=int, default=0, help="entries of each game's transposition table (0 = none)")
-    ap.add_argument("--blocking-sync", action="store_true", help="blocking engine calls sleep on an event instead of spinning in the driver")
+    ap.add_argument("--spin-sync", action="store_true",
+                    help="engine calls spin in the driver while they wait (default: they nap, DG_FLAG_BLOCKING_SYNC, and leave the cores to the search)")
+    ap.add_argument("--blocking-sync", action="store_true", help="(the default now; kept for old command lines)")
     ap.add_argument("--device-priors", action="store_true", help="also build the priors on the device (dg_engine_forward_raw_prior)")
     ap.add_argument("--host-features", action="store_true",
                     help="compute the feature planes on the host (compact positions) instead of on the device (raw positions)")
@@ -63,7 +66,10 @@ def main():
     kw = dict(num_games=args.games, num_parallel=args.parallel, num_rollout=args.rollouts, probes_per_round=args.probes,
               num_threads=threads, ex_it=args.ex_it, num_ex_it_rollout=args.rollouts, seed=20261017 + rank,
               max_seconds=args.seconds)
-    host, _ = mcts.self_play(mcts.RandomPredictor(), **{**kw, "max_seconds": min(args.seconds, 15.0)})
+    if args.no_host_sample and not args.host_only:
+        host = {"evals": 0, "moves": 0, "seconds": 1.0, "mean_batch": 0.0}
+    else:
+        host, _ = mcts.self_play(mcts.RandomPredictor(), **{**kw, "max_seconds": min(args.seconds, 15.0)})
     line = {"metric": "self_play_moves_per_s", "unit": "moves/s", "n_gpus": world, "higher_is_better": True,
             "config": {"workload": f"--self-play {args.games} --num-rollout {args.rollouts}, {args.parallel} concurrent games per GPU"
                                    + (" --ex-it" if args.ex_it else ""),
@@ -79,7 +85,7 @@ def main():
         shards = shard.Shards(backend="nccl")
         tensors = weights.synthetic_network(seed=20261017, num_blocks=args.blocks)
         net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=512, num_workspaces=8,
-                                      flags=nn.FLAG_BLOCKING_SYNC if args.blocking_sync else 0)
+                                      flags=0 if args.spin_sync else nn.FLAG_BLOCKING_SYNC)
         shards.barrier()
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
