@@ -70,6 +70,19 @@ inline int find_u16(const uint16_t* a, int n, int x) {
     return -1;
 }
 
+// permutation that moves the lanes selected by an 8-bit mask to the front, in order (AVX2 has no compress instruction)
+struct CompressLut {
+    alignas(32) int32_t idx[256][8];
+    CompressLut() {
+        for (int m = 0; m < 256; ++m) {
+            int k = 0;
+            for (int b = 0; b < 8; ++b) if (m >> b & 1) idx[m][k++] = b;
+            for (; k < 8; ++k) idx[m][k] = 0;
+        }
+    }
+};
+inline const CompressLut& compress_lut() { static const CompressLut t; return t; }
+
 // A node keeps (a) its candidates and (b) one record per visited (or disqualified) child, in creation order.  Both are
 // stored as parallel arrays in one allocation each: the root of a search has hundreds of children and `select` scores
 // them eight at a time; records never move to another index, so a probe remembers the index instead of the move.
@@ -116,18 +129,29 @@ struct Node {
             n += __builtin_popcount((unsigned)_mm256_movemask_ps(_mm256_cmp_ps(_mm256_and_ps(_mm256_loadu_ps(prior + i), absmask), inf, _CMP_LT_OQ)));
         n += std::isfinite(prior[360]) + std::isfinite(prior[361]);
         free(cand_prior);
-        const int n16 = (n + 1 + 15) & ~15;    // one spare slot: the compaction below writes before it knows whether to keep
-        char* mem = static_cast<char*>(malloc((size_t)(n + 1) * 4 + (size_t)n16 * 2 + (size_t)n + 16));
+        // the compaction below stores whole vectors of 8 at the running position: 8 spare slots in both arrays
+        const int n16 = (n + 8 + 15) & ~15;
+        char* mem = static_cast<char*>(malloc((size_t)(n + 8) * 4 + (size_t)n16 * 2 + (size_t)n + 16));
         cand_prior = reinterpret_cast<float*>(mem);
-        cand_move = reinterpret_cast<uint16_t*>(mem + (size_t)(n + 1) * 4);
-        cand_edge = reinterpret_cast<uint8_t*>(mem + (size_t)(n + 1) * 4 + (size_t)n16 * 2);
+        cand_move = reinterpret_cast<uint16_t*>(mem + (size_t)(n + 8) * 4);
+        cand_edge = reinterpret_cast<uint8_t*>(mem + (size_t)(n + 8) * 4 + (size_t)n16 * 2);
         n_cand = n;
         n = 0;
-        for (int i = 0; i < 362; ++i) {
-            cand_move[n] = (uint16_t)i;
-            cand_prior[n] = prior[i];
-            n += std::isfinite(prior[i]);
+        const CompressLut& lut = compress_lut();
+        __m256i moves = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+        const __m256i eight = _mm256_set1_epi32(8);
+        for (int i = 0; i < 360; i += 8) {         // keep the finite entries (and their indices), in order
+            const __m256 x = _mm256_loadu_ps(prior + i);
+            const unsigned keep = (unsigned)_mm256_movemask_ps(_mm256_cmp_ps(_mm256_and_ps(x, absmask), inf, _CMP_LT_OQ));
+            const __m256i order = _mm256_load_si256(reinterpret_cast<const __m256i*>(lut.idx[keep]));
+            _mm256_storeu_ps(cand_prior + n, _mm256_permutevar8x32_ps(x, order));
+            const __m256i m = _mm256_permutevar8x32_epi32(moves, order);
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(cand_move + n), _mm_packus_epi32(_mm256_castsi256_si128(m), _mm256_extracti128_si256(m, 1)));
+            n += __builtin_popcount(keep);
+            moves = _mm256_add_epi32(moves, eight);
         }
+        for (int i = 360; i < 362; ++i)
+            if (std::isfinite(prior[i])) { cand_move[n] = (uint16_t)i; cand_prior[n] = prior[i]; ++n; }
         for (int i = n; i < n16; ++i) cand_move[i] = 0xffff;
         memset(cand_edge, 0, (size_t)n_cand);
         sorted_n = 0;

@@ -348,6 +348,10 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     }
     if (want_groups > 8) want_groups = 8;
     const int n_groups = std::min(want_groups, n_slots);
+    // A group is either on the host (its games are advanced one by one by whichever worker is free; the worker that
+    // finishes the last one gathers the leaves and submits them) or on the device (its device thread is inside the
+    // blocking predictor call).  Nobody waits for a particular group: workers take the next game of ANY group that has
+    // results, so the host stays busy while at least one group is back and the device while at least one is submitted.
     struct Group {
         std::vector<int> slots;
         std::vector<dg_packed_position> batch;
@@ -356,19 +360,11 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         std::vector<uint8_t> legal;
         std::vector<float> prior;
         size_t size() const { return batch.size() + raw_batch.size(); }
-        bool in_flight = false;
-        // one persistent device thread per group: it makes the (blocking) predictor call of the group's batch
+        enum State { HOST, SUBMITTED, RETIRED } state = HOST;     // guarded by sched_m
+        size_t next = 0, done = 0;                                // games handed out / advanced in this round (sched_m)
+        bool absorb = false;                                      // the round starts from results of the device
         std::thread device_thread;
-        std::mutex m;
-        std::condition_variable cv;
-        enum { IDLE, SUBMITTED, FINISHED, QUIT } state = IDLE;
-        int32_t result = DG_OK;
-        int32_t wait() {
-            std::unique_lock<std::mutex> lk(m);
-            cv.wait(lk, [this] { return state == FINISHED; });
-            state = IDLE;
-            return result;
-        }
+        std::condition_variable cv;                               // wakes the device thread (with sched_m)
     } groups[8];
     for (int i = 0; i < n_slots; ++i) groups[i % n_groups].slots.push_back(i);
 
@@ -459,29 +455,32 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         }
     };
 
-    Helpers helpers(std::max(0, std::min(n_threads, (n_slots + n_groups - 1) / n_groups) - 1));
-    // DG_SELFPLAY_TRACE=1: where the driver thread's time goes (stderr, at the end)
+    // DG_SELFPLAY_TRACE=1: where the time goes (stderr, at the end)
     const bool trace_driver = getenv("DG_SELFPLAY_TRACE") != nullptr;
-    int64_t ns_wait = 0, ns_parallel = 0, ns_serial = 0;
-    std::mutex idle_mutex;                    // trace only: wall time during which no predictor call was in flight
-    int calls_in_flight = 0;
-    int64_t idle_since = 0, ns_idle = 0;
+    phase_clock().on = trace_driver;
     auto now_ns = [] { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    auto run_group = [&](Group& grp, bool absorb_results) {
-        const int64_t t_begin = now_ns();
-        std::atomic<size_t> next{0};
-        std::function<void()> worker = [&] {
-            for (;;) {
-                size_t i = next.fetch_add(1);
-                if (i >= grp.slots.size()) break;
-                advance(d.games[grp.slots[i]], absorb_results ? grp.value.data() : nullptr, absorb_results ? grp.policy.data() : nullptr,
-                        absorb_results && raw_mode ? grp.legal.data() : nullptr, absorb_results && prior_mode ? grp.prior.data() : nullptr);
-            }
-        };
-        helpers.run(worker);
-        const int64_t t_mid = now_ns();
-        ns_parallel += t_mid - t_begin;
-        // serial part: finished games are replaced, leaves are gathered in slot order
+    std::atomic<int64_t> ns_worker_idle{0}, ns_worker_busy{0}, ns_worker_cpu{0}, ns_device_cpu{0};
+    auto thread_cpu_ns = [] { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return (int64_t)ts.tv_sec * 1000000000 + ts.tv_nsec; };
+    int64_t ns_serial = 0;                    // guarded by gather_m
+    int calls_in_flight = 0;                  // trace: wall time during which no predictor call was in flight (sched_m)
+    int64_t idle_since = 0, ns_idle = 0;
+
+    std::mutex sched_m;                       // group states, task cursors, rc, stop
+    std::condition_variable sched_cv;         // workers: "a group came back from the device" / "stop"
+    std::mutex gather_m;                      // the Driver's shared state (game ids, records, totals) and the counters below
+    int live_groups = n_groups;
+    bool stop = false, quit = false;
+    auto out_of_time = [&] { return d.cfg.max_seconds > 0 && seconds() >= d.cfg.max_seconds; };
+    auto retire = [&](Group& grp) {           // sched_m held
+        grp.state = Group::RETIRED;
+        if (--live_groups == 0) stop = true;
+    };
+
+    // The worker that advanced the last game of a round: finished games are replaced, leaves are gathered in slot order,
+    // the batch goes to the group's device thread.
+    auto finalize = [&](Group& grp) {
+        std::unique_lock<std::mutex> gl(gather_m);
+        const int64_t t_begin = trace_driver ? now_ns() : 0;
         grp.batch.clear();
         grp.raw_batch.clear();
         for (int s : grp.slots) {
@@ -490,8 +489,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 g.n_emitted = 0;
                 g.active = true;
                 d.finish_game(g);
-                bool time_left = d.cfg.max_seconds <= 0 || seconds() < d.cfg.max_seconds;
-                if (d.started < d.cfg.num_games && time_left) {
+                if (d.started < d.cfg.num_games && !out_of_time()) {
                     d.start_game(g);
                     advance(g, nullptr, nullptr, nullptr, nullptr);
                     if (g.n_emitted == -1) { g.n_emitted = 0; g.active = false; }
@@ -503,33 +501,33 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 grp.raw_batch.insert(grp.raw_batch.end(), g.raw_batch.begin(), g.raw_batch.end());
             }
         }
-        ns_serial += now_ns() - t_mid;
+        const bool empty = grp.size() == 0;
+        if (!empty) {
+            grp.value.resize(grp.size());
+            grp.policy.resize(grp.size() * 362);
+            if (raw_mode) grp.legal.resize(grp.size() * 361);
+            if (prior_mode) grp.prior.resize(grp.size() * 368);
+            ++rounds;
+            positions += (int64_t)grp.size();
+        }
+        if (trace_driver) ns_serial += now_ns() - t_begin;
+        gl.unlock();
+        {
+            std::lock_guard<std::mutex> lk(sched_m);
+            if (empty) retire(grp); else grp.state = Group::SUBMITTED;
+        }
+        if (empty) sched_cv.notify_all(); else grp.cv.notify_one();
     };
 
-    auto launch = [&](Group& grp) {
-        if (grp.size() == 0) { grp.in_flight = false; return; }
-        grp.value.resize(grp.size());
-        grp.policy.resize(grp.size() * 362);
-        if (raw_mode) grp.legal.resize(grp.size() * 361);
-        if (prior_mode) grp.prior.resize(grp.size() * 368);
-        ++rounds;
-        positions += (int64_t)grp.size();
-        grp.in_flight = true;
-        { std::lock_guard<std::mutex> lk(grp.m); grp.state = Group::SUBMITTED; }
-        grp.cv.notify_all();
-    };
     auto device_loop = [&](Group& grp) {
         for (;;) {
             {
-                std::unique_lock<std::mutex> lk(grp.m);
-                grp.cv.wait(lk, [&] { return grp.state == Group::SUBMITTED || grp.state == Group::QUIT; });
-                if (grp.state == Group::QUIT) return;
+                std::unique_lock<std::mutex> lk(sched_m);
+                grp.cv.wait(lk, [&] { return grp.state == Group::SUBMITTED || quit; });
+                if (quit) { if (trace_driver) ns_device_cpu += thread_cpu_ns(); return; }
+                if (trace_driver && calls_in_flight++ == 0 && idle_since) ns_idle += now_ns() - idle_since;
             }
             auto t0 = std::chrono::steady_clock::now();
-            if (trace_driver) {
-                std::lock_guard<std::mutex> lk(idle_mutex);
-                if (calls_in_flight++ == 0 && idle_since) ns_idle += now_ns() - idle_since;
-            }
             int32_t r = prior_predictor
                 ? prior_predictor(ctx, grp.raw_batch.data(), (int32_t)grp.raw_batch.size(), grp.value.data(), grp.policy.data(), grp.legal.data(),
                                   grp.prior.data())
@@ -537,47 +535,78 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 ? raw_predictor(ctx, grp.raw_batch.data(), (int32_t)grp.raw_batch.size(), grp.value.data(), grp.policy.data(), grp.legal.data())
                 : predictor(ctx, grp.batch.data(), (int32_t)grp.batch.size(), grp.value.data(), grp.policy.data());
             eval_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-            if (trace_driver) {
-                std::lock_guard<std::mutex> lk(idle_mutex);
-                if (--calls_in_flight == 0) idle_since = now_ns();
+            {
+                std::lock_guard<std::mutex> lk(sched_m);
+                if (trace_driver && --calls_in_flight == 0) idle_since = now_ns();
+                if (r != DG_OK) {
+                    if (rc == DG_OK) rc = r;
+                    retire(grp);
+                    stop = true;
+                } else if (out_of_time()) {
+                    retire(grp);                                   // the work in flight at the deadline is dropped
+                } else {
+                    grp.absorb = true;
+                    grp.next = grp.done = 0;
+                    grp.state = Group::HOST;
+                }
             }
-            { std::lock_guard<std::mutex> lk(grp.m); grp.result = r; grp.state = Group::FINISHED; }
-            grp.cv.notify_all();
+            sched_cv.notify_all();
         }
     };
-    for (int gi = 0; gi < n_groups; ++gi) groups[gi].device_thread = std::thread(device_loop, std::ref(groups[gi]));
 
-    for (int gi = 0; gi < n_groups; ++gi) { run_group(groups[gi], false); launch(groups[gi]); }
-    for (;;) {
-        bool any = false;
-        for (int gi = 0; gi < n_groups && rc == DG_OK; ++gi) {
-            Group& grp = groups[gi];
-            if (!grp.in_flight) continue;
-            any = true;
-            const int64_t t_wait = now_ns();
-            rc = grp.wait();
-            ns_wait += now_ns() - t_wait;
-            grp.in_flight = false;
-            if (rc != DG_OK) break;
-            bool out_of_time = d.cfg.max_seconds > 0 && seconds() >= d.cfg.max_seconds;
-            if (out_of_time) continue;                            // drop the in-flight work, stop
-            run_group(grp, true);
-            launch(grp);
+    auto worker_loop = [&] {
+        int64_t t_mark = trace_driver ? now_ns() : 0;
+        for (;;) {
+            Group* grp = nullptr;
+            size_t i = 0;
+            {
+                std::unique_lock<std::mutex> lk(sched_m);
+                for (;;) {
+                    if (stop) { if (trace_driver) ns_worker_cpu += thread_cpu_ns(); return; }
+                    for (int gi = 0; gi < n_groups && !grp; ++gi)
+                        if (groups[gi].state == Group::HOST && groups[gi].next < groups[gi].slots.size()) { grp = &groups[gi]; i = grp->next++; }
+                    if (grp) break;
+                    if (trace_driver) { const int64_t t = now_ns(); ns_worker_busy += t - t_mark; t_mark = t; }
+                    sched_cv.wait(lk);
+                    if (trace_driver) { const int64_t t = now_ns(); ns_worker_idle += t - t_mark; t_mark = t; }
+                }
+            }
+            const bool absorb = grp->absorb;
+            advance(d.games[grp->slots[i]], absorb ? grp->value.data() : nullptr, absorb ? grp->policy.data() : nullptr,
+                    absorb && raw_mode ? grp->legal.data() : nullptr, absorb && prior_mode ? grp->prior.data() : nullptr);
+            bool last;
+            { std::lock_guard<std::mutex> lk(sched_m); last = ++grp->done == grp->slots.size(); }
+            if (last) finalize(*grp);
         }
-        if (!any || rc != DG_OK) break;
+    };
+
+    for (int gi = 0; gi < n_groups; ++gi) groups[gi].device_thread = std::thread(device_loop, std::ref(groups[gi]));
+    {
+        std::vector<std::thread> workers;
+        const int n_workers = std::max(1, std::min(n_threads, n_slots));
+        for (int i = 1; i < n_workers; ++i) workers.emplace_back(worker_loop);
+        const int64_t cpu_before = trace_driver ? thread_cpu_ns() : 0;   // the calling thread has a history
+        worker_loop();
+        if (trace_driver) ns_worker_cpu -= cpu_before;
+        sched_cv.notify_all();
+        for (auto& t : workers) t.join();
     }
-    for (int gi = 0; gi < n_groups; ++gi) {
-        Group& grp = groups[gi];
-        if (grp.in_flight) grp.wait();
-        { std::lock_guard<std::mutex> lk(grp.m); grp.state = Group::QUIT; }
-        grp.cv.notify_all();
-        grp.device_thread.join();
+    {   // device threads still inside a call (deadline, error) come back first
+        { std::lock_guard<std::mutex> lk(sched_m); quit = true; }
+        for (int gi = 0; gi < n_groups; ++gi) { groups[gi].cv.notify_all(); groups[gi].device_thread.join(); }
     }
 
     if (trace_driver)
-        fprintf(stderr, "[dg_selfplay] %d groups, %d threads, %lld rounds: driver thread waited for the device %.3f s, parallel host work %.3f s, "
-                "serial gather %.3f s, predictor calls %.3f s (sum over device threads), no call in flight %.3f s, wall %.3f s\n", n_groups, n_threads,
-                (long long)rounds, ns_wait * 1e-9, ns_parallel * 1e-9, ns_serial * 1e-9, (double)eval_ns.load() * 1e-9, ns_idle * 1e-9, seconds());
+        fprintf(stderr, "[dg_selfplay] %d groups, %d threads, %lld rounds: workers busy %.3f s / idle %.3f s (sum over threads), serial gather %.3f s, "
+                "predictor calls %.3f s (sum over device threads), no call in flight %.3f s, CPU time: workers %.3f s, device threads %.3f s, wall %.3f s\n",
+                n_groups, n_threads, (long long)rounds, ns_worker_busy.load() * 1e-9, ns_worker_idle.load() * 1e-9, ns_serial * 1e-9,
+                (double)eval_ns.load() * 1e-9, ns_idle * 1e-9, ns_worker_cpu.load() * 1e-9, ns_device_cpu.load() * 1e-9, seconds());
+    if (trace_driver) {
+        PhaseClock& c = phase_clock();
+        const double n = (double)std::max<uint64_t>(1, c.leaves.load());
+        fprintf(stderr, "[dg_selfplay] cycles per leaf: board copy %.0f, probe %.0f, extract %.0f, prior plan %.0f, prior apply %.0f, insert %.0f\n",
+                c.copy.load() / n, c.probe.load() / n, c.extract.load() / n, c.plan.load() / n, c.apply.load() / n, c.insert.load() / n);
+    }
     // account for the games that were cut off by max_seconds
     for (Game& g : d.games) {
         d.total_moves += g.n_moves; d.total_evals += g.evals; d.total_searches += g.searches;

@@ -11,6 +11,7 @@
 
 #include <immintrin.h>
 
+#include <atomic>
 #include <unordered_map>
 #include <vector>
 
@@ -172,6 +173,19 @@ struct PriorPlan {
     }
 };
 
+// DG_SELFPLAY_TRACE: cycles spent in the phases of a probe (summed over all threads; relaxed atomics, off by default)
+struct PhaseClock {
+    std::atomic<uint64_t> copy{0}, probe{0}, extract{0}, plan{0}, apply{0}, insert{0}, leaves{0};
+    bool on = false;
+};
+inline PhaseClock& phase_clock() { static PhaseClock c; return c; }
+struct PhaseTimer {
+    uint64_t t;
+    bool on;
+    PhaseTimer() : t(0), on(phase_clock().on) { if (on) t = __rdtsc(); }
+    void lap(std::atomic<uint64_t>& into) { if (on) { uint64_t n = __rdtsc(); into.fetch_add(n - t, std::memory_order_relaxed); t = n; } }
+};
+
 struct SearchOptions {
     int search_kind = STANDARD_SEARCH;         // which PolicyChecker (options.rs)
     bool deterministic = false;                // SearchOptions::deterministic()
@@ -278,8 +292,11 @@ class SearchTask {
         while (emitted < opt_.probes_per_round) {
             if (is_done(*root_, opt_.num_rollout)) break;
             Pending& p = pending_[emitted];
+            PhaseTimer pt;
             p.board.copy_from(board_);
+            pt.lap(phase_clock().copy);
             ProbeStatus st = probe(*root_, p.board, p.trace);
+            pt.lap(phase_clock().probe);
             if (st == PROBE_CONFLICT) break;                 // somebody (an earlier probe of this round) is expanding it
             if (st == PROBE_NO_RESULT) break;
             p.to_move = opposite(p.trace.back().node->to_move);
@@ -308,6 +325,7 @@ class SearchTask {
                 pos.reserved = 0;
                 p.plan.build(p.board, p.to_move, opt_.search_kind, legal);
             }
+            pt.lap(phase_clock().extract);
             ++emitted;
         }
         n_pending_ = emitted;
@@ -368,13 +386,18 @@ class SearchTask {
         for (int k = 0; k < n_pending_; ++k) {               // pool/worker_thread.rs:88-98
             Pending& p = pending_[k];
             float winrate = 0.5f * f16_to_f32(value[k]) + 0.5f;
+            PhaseTimer pt;
             if (priors) {
                 insert(p.trace, p.to_move, winrate, priors + (size_t)k * 368);
             } else {
                 if (legal) p.plan.build(p.board, p.to_move, opt_.search_kind, legal + (size_t)k * N_POINTS);
+                pt.lap(phase_clock().plan);
                 p.plan.apply(policy + (size_t)k * 362, p.symmetry, 1.0f, prior);
+                pt.lap(phase_clock().apply);
                 insert(p.trace, p.to_move, winrate, prior);
             }
+            pt.lap(phase_clock().insert);
+            if (pt.on) phase_clock().leaves.fetch_add(1, std::memory_order_relaxed);
             if (opt_.cache) opt_.cache->insert(p.board.hash, p.to_move, p.symmetry, value[k], policy + (size_t)k * 362);   // worker_thread.rs:96
         }
         n_pending_ = 0;
