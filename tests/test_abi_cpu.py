@@ -51,6 +51,17 @@ def test_abi_version():
     assert nn.lib().dg_engine_abi_version() == 1
 
 
+def test_device_helpers_without_gpu():
+    """`Device::all()` of the shim (INTEGRATION.md): no usable device here, and asking never throws."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = nn.lib()
+    assert L.dg_device_count() == 0
+    assert L.dg_current_device() == -1
+    assert L.dg_set_current_device(0) == -1      # DG_ERR_CUDA
+
+
 def test_create_without_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():

@@ -193,6 +193,14 @@ def test_concurrent_forwards(small_engine, small_net):
     assert not errors, errors
 
 
+def test_device_helpers():
+    import torch
+    L = nn.lib()
+    assert L.dg_device_count() == torch.cuda.device_count() >= 1      # every device of a B200 box is an sm_100 part
+    assert L.dg_set_current_device(0) == 0 and L.dg_current_device() == 0
+    assert L.dg_set_current_device(L.dg_device_count()) == -1
+
+
 def test_one_process_two_devices(small_net):
     """The reference drives every GPU from ONE process (`cudaSetDevice` per call, predictors/nn.rs:84-92): two engines on
     two devices, used concurrently from two threads, give the results of one engine alone, bit for bit."""
