@@ -58,6 +58,35 @@ def test_midgame_with_noise_and_temperature(probes):
                        noise=noise, leaf_symmetries=[2, 2, 7, 0, 4], choose_at=0.37)
 
 
+def tied_predictor():
+    """Near-uniform policy with only three distinct values (ties in every block of 8) and values close to 0: what a
+    random-init network gives -- the root ends up with hundreds of visited children."""
+    import zlib
+
+    def fn(feats: np.ndarray):
+        n = feats.shape[0]
+        v = np.empty(n, np.float16)
+        p = np.empty((n, 362), np.float16)
+        for i in range(n):
+            rng = np.random.default_rng(zlib.crc32(np.ascontiguousarray(feats[i]).tobytes()))
+            p[i] = (rng.integers(1, 4, size=362) / (2 * 362)).astype(np.float16)
+            v[i] = np.float16(rng.normal() * 0.03)
+        return v, p
+    return fn
+
+
+@pytest.mark.parametrize("game,plies,search,rollouts,min_children", [(5, 6, 0, 700, 257), (11, 150, 1, 300, 129)])
+def test_wide_roots_with_tied_priors(game, plies, search, rollouts, min_children):
+    """Hundreds of child records at the root (the parallel arrays grow 16 -> 512, eight records are scored at a time),
+    equal priors everywhere (the argmax tie rule and the lazy candidate order decide every probe)."""
+    plays, komi = corpus_position(game, plies)
+    po, oo = boards(plays, komi)
+    tree, _ = assert_same_search(tied_predictor(), po, oo, po.to_move(), search=search, deterministic=True, num_rollout=rollouts,
+                                 probes_per_round=8, leaf_symmetries=[1, 6, 3, 0, 5])
+    count, _, _ = tree.children()
+    assert (count > 0).sum() >= min_children
+
+
 def test_late_game_scoring_search_and_tree_reuse():
     plays, komi = corpus_position(11, 150)
     po, oo = boards(plays, komi)
@@ -146,6 +175,13 @@ def test_run_to_run_and_thread_count_determinism_of_self_play():
     c, _ = pm.self_play(stub, num_games=3, num_parallel=3, num_rollout=12, probes_per_round=2, max_plies=12, seed=8, num_threads=4)
     assert a["digest"] == b["digest"] and sorted(sgf_a) == sorted(sgf_b)
     assert a["digest"] != c["digest"]
+    # more games than slots, any number of groups and workers: whichever worker and group a game meets, it is the same game
+    kw = dict(num_games=7, num_parallel=5, num_rollout=10, probes_per_round=2, max_plies=8, seed=7)
+    ref, sgf_ref = pm.self_play(stub, num_threads=1, num_groups=1, **kw)
+    for groups, threads in ((2, 3), (5, 8), (3, 2)):
+        got, sgf_got = pm.self_play(stub, num_threads=threads, num_groups=groups, **kw)
+        assert got["digest"] == ref["digest"] and sorted(sgf_got) == sorted(sgf_ref) and got["moves"] == ref["moves"]
+        assert got["games_finished"] == 7
     assert a["games_finished"] == 3 and a["moves"] == 36
     assert all(g.startswith("(;GM[1]FF[4]SZ[19]RU[Chinese]KM[") and g.endswith(")") for g in sgf_a)
 
