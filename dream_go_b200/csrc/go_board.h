@@ -382,39 +382,50 @@ inline LadderArena& ladder_arena() {
     return arena;
 }
 
-// arena.boards[depth] already holds the attacker's stone at `p`.  ladder.rs:53-119.
-inline bool ladder_capture_after_place(LadderArena& arena, int depth, int c, int p) {
+// arena.boards[slot] already holds the attacker's stone at `p`.  ladder.rs:53-119.  `depth` counts the attacker's
+// stones of this reading (the cut-off below); the last attacker move of a step is played on the board itself
+// instead of on a copy, so `slot` grows more slowly than `depth`.
+inline bool ladder_capture_after_place(LadderArena& arena, int slot, int depth, int c, int p) {
     const Tables& T = tables();
-    Board& board = arena.boards[depth];
+    Board& board = arena.boards[slot];
     int opp = opposite(c);
-    int run = -1;
-    for (int k = 0; k < T.n_nbr[p] && run < 0; ++k) {
-        int q = T.nbr_list[p][k];
-        if (board.color[q] != opp) continue;
-        int sl = board.slot[q];
-        if (board.libs[sl].count() >= 2 || chain_can_capture(board, q)) continue;
-        int lib = board.libs[sl].first();                    // in atari: its only liberty
-        if (lib >= 0 && board.is_valid_fast(opp, lib)) run = lib;
+    for (;;) {
+        int run = -1, nl = 0;
+        for (int k = 0; k < T.n_nbr[p] && run < 0; ++k) {
+            int q = T.nbr_list[p][k];
+            if (board.color[q] != opp) continue;
+            int sl = board.slot[q];
+            if (board.libs[sl].count() >= 2 || chain_can_capture(board, q)) continue;
+            int lib = board.libs[sl].first();                // in atari: its only liberty
+            if (lib < 0) continue;
+            nl = board.liberties_if(opp, lib);               // -1: the extension is not a legal move
+            if (nl >= 0) run = lib;
+        }
+        if (run < 0) return false;
+        if (nl < 2) return true;                             // the liberties after extending decide before the stone is placed
+        if (nl >= 3) return false;
+        board.place(opp, run);
+        for (int k = 0; k < T.n_nbr[run]; ++k) {
+            int q = T.nbr_list[run][k];
+            if (board.color[q] == c && board.n_liberty(q) < 2) return false;
+        }
+        if (depth + 1 >= LadderArena::MAX_DEPTH) return false;
+        int tries[4], nt = 0;
+        for (int k = 0; k < T.n_nbr[run]; ++k) {
+            int q = T.nbr_list[run][k];
+            if (board.is_valid_fast(c, q)) tries[nt++] = q;
+        }
+        if (nt == 0) return false;
+        for (int t = 0; t + 1 < nt; ++t) {
+            Board& child = arena.boards[slot + 1];
+            child.copy_from(board);
+            child.place(c, tries[t]);
+            if (ladder_capture_after_place(arena, slot + 1, depth + 1, c, tries[t])) return true;
+        }
+        p = tries[nt - 1];                                   // nobody looks at this board again: continue on it
+        board.place(c, p);
+        ++depth;
     }
-    if (run < 0) return false;
-    board.place(opp, run);
-    int nl = board.n_liberty(run);
-    if (nl < 2) return true;
-    if (nl >= 3) return false;
-    for (int k = 0; k < T.n_nbr[run]; ++k) {
-        int q = T.nbr_list[run][k];
-        if (board.color[q] == c && board.n_liberty(q) < 2) return false;
-    }
-    if (depth + 1 >= LadderArena::MAX_DEPTH) return false;
-    for (int k = 0; k < T.n_nbr[run]; ++k) {
-        int q = T.nbr_list[run][k];
-        if (!board.is_valid_fast(c, q)) continue;
-        Board& child = arena.boards[depth + 1];
-        child.copy_from(board);
-        child.place(c, q);
-        if (ladder_capture_after_place(arena, depth + 1, c, q)) return true;
-    }
-    return false;
 }
 
 inline bool is_ladder_capture(const Board& b, int c, int p, const uint16_t* nl = nullptr) {       // ladder.rs:131-135
@@ -430,7 +441,7 @@ inline bool is_ladder_capture(const Board& b, int c, int p, const uint16_t* nl =
     LadderArena& arena = ladder_arena();
     arena.boards[0].copy_from(b);
     arena.boards[0].place(c, p);
-    return ladder_capture_after_place(arena, 0, c, p);
+    return ladder_capture_after_place(arena, 0, 0, c, p);
 }
 
 inline bool is_ladder_escape(const Board& b, int c, int p, const uint16_t* nl = nullptr) {        // ladder.rs:144-178
@@ -441,11 +452,11 @@ inline bool is_ladder_escape(const Board& b, int c, int p, const uint16_t* nl = 
         if (b.color[q] == c && (nl ? nl[b.slot[q]] : b.libs[b.slot[q]].count()) < 2) in_atari = true;
     }
     if (!in_atari) return false;
+    if (b.liberties_if(c, p, nl) != 2) return false;         // the callers only ask about legal moves
     LadderArena& arena = ladder_arena();
     Board& board = arena.boards[0];
     board.copy_from(b);
     board.place(c, p);
-    if (board.n_liberty(p) != 2) return false;
     int opp = opposite(c);
     for (int k = 0; k < T.n_nbr[p]; ++k) {
         int q = T.nbr_list[p][k];
@@ -453,7 +464,7 @@ inline bool is_ladder_escape(const Board& b, int c, int p, const uint16_t* nl = 
         Board& child = arena.boards[1];
         child.copy_from(board);
         child.place(opp, q);
-        if (ladder_capture_after_place(arena, 1, opp, q)) return false;
+        if (ladder_capture_after_place(arena, 1, 1, opp, q)) return false;
     }
     return true;
 }
