@@ -155,12 +155,17 @@ struct Board {
     uint16_t n_slots, n_free;       // slots ever handed out / currently on the free list
     float komi;
     Bits libs[N_POINTS];            // liberties of the chain in a slot; only [0, n_slots) is meaningful
+    struct ChainInfo {
+        uint16_t n;                 // number of liberties, kept up to date by place(); 0 = the slot is free
+        uint16_t head;              // one stone of the chain
+    } chain[N_POINTS];              // only [0, n_slots) is meaningful
 
     Board() {}
     Board(const Board& o) { copy_from(o); }
     Board& operator=(const Board& o) { if (this != &o) copy_from(o); return *this; }
     void copy_from(const Board& o) {
         memcpy(static_cast<void*>(this), static_cast<const void*>(&o), offsetof(Board, libs) + o.n_slots * sizeof(Bits));
+        memcpy(chain, o.chain, o.n_slots * sizeof(ChainInfo));
     }
 
     void init(float komi_) {
@@ -169,10 +174,10 @@ struct Board {
         for (int i = 0; i < 8; ++i) moves[i] = PASS;
     }
     int to_move() const { return last_played ? opposite(last_played) : BLACK; }        // board.rs:102-107
-    int n_liberty(int p) const { return libs[slot[p]].count(); }
+    int n_liberty(int p) const { return chain[slot[p]].n; }
     int recent_move(int i) const { return moves[(moves_pos + 7 - i) & 7]; }
     int alloc_slot() { return n_free ? free_list[--n_free] : n_slots++; }
-    void free_slot(int s) { free_list[n_free++] = (uint16_t)s; }
+    void free_slot(int s) { free_list[n_free++] = (uint16_t)s; chain[s].n = 0; }
 
     Bits empty_neighbours(int p) const {
         const Bits& m = tables().nbr_mask[p];
@@ -188,7 +193,7 @@ struct Board {
         for (int k = 0; k < T.n_nbr[p]; ++k) {
             int q = T.nbr_list[p][k];
             if (!color[q]) return true;
-            int nl = libs[slot[q]].count();
+            int nl = chain[slot[q]].n;
             if ((color[q] == c) == (nl >= 2)) return true;
         }
         return false;
@@ -204,7 +209,7 @@ struct Board {
             int q = T.nbr_list[p][k];
             if (color[q] != opp) continue;
             int sl = slot[q];
-            if (libs[sl].count() >= 2) continue;
+            if (chain[sl].n >= 2) continue;
             bool dup = false;
             for (int j = 0; j < ns; ++j) dup |= seen[j] == sl;
             if (dup) continue;
@@ -236,7 +241,7 @@ struct Board {
             hash ^= T.zobrist[own][s];
             for (int k = 0; k < T.n_nbr[s]; ++k) {
                 int q = T.nbr_list[s][k];
-                if (color[q] && color[q] != own) libs[slot[q]].set(s);
+                if (color[q] && color[q] != own && !libs[slot[q]].test(s)) { libs[slot[q]].set(s); ++chain[slot[q]].n; }
             }
             s = nx;
         } while (s != at);
@@ -253,13 +258,15 @@ struct Board {
         slot[p] = (uint16_t)mine;
         next[p] = (uint16_t)p;
         libs[mine].clear();
+        chain[mine].n = 0;
+        chain[mine].head = (uint16_t)p;
         hash ^= T.zobrist[c][p];
         for (int k = 0; k < T.n_nbr[p]; ++k) {               // enemies lose a liberty; captures first so that
             int q = T.nbr_list[p][k];                        // the freed points count as liberties below
             if (color[q] != opp) continue;
             int sl = slot[q];
-            libs[sl].reset(p);
-            if (!libs[sl].any()) remove_chain(q);
+            if (libs[sl].test(p)) { libs[sl].reset(p); --chain[sl].n; }
+            if (chain[sl].n == 0) remove_chain(q);
         }
         libs[mine] = empty_neighbours(p);
         for (int k = 0; k < T.n_nbr[p]; ++k) {               // merge with friends
@@ -274,6 +281,7 @@ struct Board {
             free_slot(a);
         }
         libs[slot[p]].reset(p);
+        chain[slot[p]].n = (uint16_t)libs[slot[p]].count();   // the one recount of a move: the chain the stone ended up in
         last_played = (uint8_t)c;
         count += 1;
         moves[moves_pos] = (int16_t)p;
@@ -284,8 +292,7 @@ struct Board {
 
     // Liberties the stone's chain would have after `c` plays the legal move `p` (board_fast.rs:484-539),
     // and whether the move is legal at all (fused: the feature loop needs both).  Returns -1 if illegal.
-    // `nl` (optional) = liberty count per slot, precomputed by the caller.
-    int liberties_if(int c, int p, const uint16_t* nl = nullptr) const {
+    int liberties_if(int c, int p) const {
         const Tables& T = tables();
         int n_empty = 0, nf = 0, nc = 0;
         int friends[4], captured[4], captured_at[4];
@@ -294,7 +301,7 @@ struct Board {
             int q = T.nbr_list[p][k];
             if (!color[q]) { ++n_empty; continue; }
             int sl = slot[q];
-            int n = nl ? nl[sl] : libs[sl].count();
+            int n = chain[sl].n;
             if (color[q] == c) {
                 ok |= n >= 2;
                 bool dup = false;
@@ -310,7 +317,7 @@ struct Board {
         if (!nf && !nc) return n_empty;                     // a lone stone: its empty neighbours
         if (nf == 1 && !nc) {                               // joins one chain: its liberties minus `p` plus the new ones
             const Bits& fl = libs[friends[0]];
-            int n = (nl ? nl[friends[0]] : fl.count()) - 1;
+            int n = chain[friends[0]].n - 1;
             for (int k = 0; k < T.n_nbr[p]; ++k) {
                 int q = T.nbr_list[p][k];
                 if (!color[q] && !fl.test(q)) ++n;
@@ -339,7 +346,7 @@ struct Board {
 
     // liberties_if for both colours from one scan of the neighbourhood (the feature loop asks for both at every
     // empty point; most empty points touch no stone at all).
-    void liberties_if_both(int c, int p, const uint16_t* nl, int* mine, int* theirs) const {
+    void liberties_if_both(int c, int p, int* mine, int* theirs) const {
         const Tables& T = tables();
         int n_empty = 0, n_stone = 0;
         for (int k = 0; k < T.n_nbr[p]; ++k) {
@@ -347,8 +354,8 @@ struct Board {
             if (color[q]) ++n_stone; else ++n_empty;
         }
         if (!n_stone) { *mine = *theirs = n_empty; return; }
-        *mine = liberties_if(c, p, nl);
-        *theirs = liberties_if(opposite(c), p, nl);
+        *mine = liberties_if(c, p);
+        *theirs = liberties_if(opposite(c), p);
     }
 };
 
@@ -362,7 +369,7 @@ inline bool chain_can_capture(const Board& b, int at) {      // ladder.rs:33-41
     do {
         for (int k = 0; k < T.n_nbr[s]; ++k) {
             int q = T.nbr_list[s][k];
-            if (b.color[q] && b.color[q] != own && b.libs[b.slot[q]].count() < 2) return true;
+            if (b.color[q] && b.color[q] != own && b.chain[b.slot[q]].n < 2) return true;
         }
         s = b.next[s];
     } while (s != at);
@@ -395,7 +402,7 @@ inline bool ladder_capture_after_place(LadderArena& arena, int slot, int depth, 
             int q = T.nbr_list[p][k];
             if (board.color[q] != opp) continue;
             int sl = board.slot[q];
-            if (board.libs[sl].count() >= 2 || chain_can_capture(board, q)) continue;
+            if (board.chain[sl].n >= 2 || chain_can_capture(board, q)) continue;
             int lib = board.libs[sl].first();                // in atari: its only liberty
             if (lib < 0) continue;
             nl = board.liberties_if(opp, lib);               // -1: the extension is not a legal move
@@ -428,31 +435,107 @@ inline bool ladder_capture_after_place(LadderArena& arena, int slot, int depth, 
     }
 }
 
-inline bool is_ladder_capture(const Board& b, int c, int p, const uint16_t* nl = nullptr) {       // ladder.rs:131-135
+// Where a ladder can start: the liberties of enemy chains with exactly two liberties (the move puts them in atari) and
+// of own chains in atari (the move extends them) -- one pass over the chain slots, no stone is looked at.
+inline void ladder_starts(const Board& b, int to_move, Bits& capture_at, Bits& escape_at) {
+    capture_at.clear();
+    escape_at.clear();
+    for (int sl = 0; sl < b.n_slots; ++sl) {
+        const int n = b.chain[sl].n;
+        if (n == 0 || n > 2) continue;                       // a free slot / nothing starts here
+        if (b.color[b.chain[sl].head] == to_move) { if (n < 2) escape_at.or_with(b.libs[sl]); }
+        else if (n == 2) capture_at.or_with(b.libs[sl]);
+    }
+}
+
+// The first step of ladder_capture_after_place read off the ORIGINAL board: four of five readings end there (the
+// chain put in atari extends to three or more liberties), and a board copy costs more than the rest of such a reading.
+// Exact whenever neither the attacker's stone at `p` nor the extension captures anything; otherwise, and when the
+// ladder goes on, the caller reads it on a copy.  Returns 0 = no ladder, 1 = captured, 2 = read it on a copy.
+inline int ladder_capture_first_step(const Board& b, int c, int p) {
+    const Tables& T = tables();
+    const int opp = opposite(c);
+    int merged[4], nm = 0;                                   // own chains the stone at `p` joins
+    Bits lm = b.empty_neighbours(p);                         // liberties of the joined chain
+    for (int k = 0; k < T.n_nbr[p]; ++k) {
+        int q = T.nbr_list[p][k];
+        if (b.color[q] == opp) { if (b.chain[b.slot[q]].n < 2) return 2; }          // `p` captures: not handled here
+        else if (b.color[q] == c) { merged[nm++] = b.slot[q]; lm.or_with(b.libs[b.slot[q]]); }
+    }
+    lm.reset(p);
+    if (lm.count() < 2) return 0;        // every chain next to `p` could capture the attacker's own stones (chain_can_capture)
+    auto in_merged = [&](int sl) { for (int j = 0; j < nm; ++j) if (merged[j] == sl) return true; return false; };
+    for (int k = 0; k < T.n_nbr[p]; ++k) {
+        int q = T.nbr_list[p][k];
+        if (b.color[q] != opp) continue;
+        const int sx = b.slot[q];
+        if (b.chain[sx].n != 2) continue;                    // two liberties, `p` is one: in atari after the stone
+        bool can_capture = false;                            // chain_can_capture on the board after the stone: the joined
+        int s = q;                                           // chain has >= 2 liberties, every other chain is as it was
+        do {
+            for (int j = 0; j < T.n_nbr[s] && !can_capture; ++j) {
+                int t = T.nbr_list[s][j];
+                if (b.color[t] == c && !in_merged(b.slot[t]) && b.chain[b.slot[t]].n < 2) can_capture = true;
+            }
+            s = b.next[s];
+        } while (s != q && !can_capture);
+        if (can_capture) continue;
+        Bits only = b.libs[sx];
+        only.reset(p);
+        const int lib = only.first();
+        // liberties_if(opp, lib) on the board after the stone
+        Bits l = b.empty_neighbours(lib);
+        l.reset(p);
+        bool legal = l.any();
+        for (int j = 0; j < T.n_nbr[lib]; ++j) {
+            int u = T.nbr_list[lib][j];
+            if (u == p) continue;                            // the joined chain: >= 2 liberties, not captured
+            if (b.color[u] == c) {
+                if (!in_merged(b.slot[u]) && b.chain[b.slot[u]].n < 2) return 2;        // the extension captures: not handled here
+            } else if (b.color[u] == opp) {
+                const Bits& fl = b.libs[b.slot[u]];
+                legal |= b.chain[b.slot[u]].n - (fl.test(p) ? 1 : 0) >= 2;
+                l.or_with(fl);
+            }
+        }
+        if (!legal) continue;                                // the extension would be suicide: look at the next chain
+        l.reset(p);
+        l.reset(lib);
+        const int n = l.count();
+        return n < 2 ? 1 : n >= 3 ? 0 : 2;
+    }
+    return 0;
+}
+
+inline bool is_ladder_capture(const Board& b, int c, int p) {                                     // ladder.rs:131-135
     // a ladder starts by putting an adjacent enemy chain in atari: it needs exactly two liberties now
     const Tables& T = tables();
     int opp = opposite(c);
     bool candidate = false;
     for (int k = 0; k < T.n_nbr[p]; ++k) {
         int q = T.nbr_list[p][k];
-        if (b.color[q] == opp && (nl ? nl[b.slot[q]] : b.libs[b.slot[q]].count()) == 2) candidate = true;
+        if (b.color[q] == opp && b.chain[b.slot[q]].n == 2) candidate = true;
     }
     if (!candidate) return false;
+    if (!b.color[p]) {
+        const int first = ladder_capture_first_step(b, c, p);
+        if (first != 2) return first == 1;
+    }
     LadderArena& arena = ladder_arena();
     arena.boards[0].copy_from(b);
     arena.boards[0].place(c, p);
     return ladder_capture_after_place(arena, 0, 0, c, p);
 }
 
-inline bool is_ladder_escape(const Board& b, int c, int p, const uint16_t* nl = nullptr) {        // ladder.rs:144-178
+inline bool is_ladder_escape(const Board& b, int c, int p) {                                      // ladder.rs:144-178
     const Tables& T = tables();
     bool in_atari = false;
     for (int k = 0; k < T.n_nbr[p]; ++k) {
         int q = T.nbr_list[p][k];
-        if (b.color[q] == c && (nl ? nl[b.slot[q]] : b.libs[b.slot[q]].count()) < 2) in_atari = true;
+        if (b.color[q] == c && b.chain[b.slot[q]].n < 2) in_atari = true;
     }
     if (!in_atari) return false;
-    if (b.liberties_if(c, p, nl) != 2) return false;         // the callers only ask about legal moves
+    if (b.liberties_if(c, p) != 2) return false;             // the callers only ask about legal moves
     LadderArena& arena = ladder_arena();
     Board& board = arena.boards[0];
     board.copy_from(b);
@@ -697,21 +780,10 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
     const uint16_t* sym = T.sym[symmetry];
     const int opp = opposite(to_move);
     uint32_t global = to_move == BLACK ? 1u : 2u;
-    uint16_t nl[N_POINTS];                                  // liberties per chain slot, counted once
-    for (int i = 0; i < b.n_slots; ++i) nl[i] = 0;
     // where a ladder can start: the liberties of enemy chains with exactly two liberties (the move puts them in
     // atari) / of own chains in atari (the move extends them) -- straight from the chains' liberty sets
     Bits capture_at, escape_at;
-    capture_at.clear();
-    escape_at.clear();
-    for (int p = 0; p < N_POINTS; ++p) {
-        if (!b.color[p] || nl[b.slot[p]]) continue;
-        int sl = b.slot[p];
-        int n = b.libs[sl].count();
-        nl[sl] = (uint16_t)n;
-        if (b.color[p] == to_move) { if (n < 2) escape_at.or_with(b.libs[sl]); }
-        else if (n == 2) capture_at.or_with(b.libs[sl]);
-    }
+    ladder_starts(b, to_move, capture_at, escape_at);
     const Bits touched = dilate(b.stones[1] | b.stones[2]);  // points next to a stone
     uint32_t local[N_POINTS];
     bool any_ko = false;
@@ -720,15 +792,15 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
         uint32_t m = 0;
         int col = b.color[p];
         if (col) {
-            int n = nl[b.slot[p]];
+            int n = b.chain[b.slot[p]].n;
             m = ge_mask[n > 6 ? 6 : n] << (col == to_move ? 5 : 17);
             if (legal) legal[p] = 0;
         } else {
             int mine, theirs;
             if (!touched.test(p)) mine = theirs = T.n_nbr[p];     // open point: its neighbours are its liberties
             else {
-                mine = b.liberties_if(to_move, p, nl);
-                theirs = b.liberties_if(opp, p, nl);
+                mine = b.liberties_if(to_move, p);
+                theirs = b.liberties_if(opp, p);
             }
             if (mine >= 0) m |= ge_mask[mine > 6 ? 6 : mine] << 11;
             if (theirs >= 0) m |= ge_mask[theirs > 6 ? 6 : theirs] << 23;
@@ -736,8 +808,8 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
             if (mine >= 0) {
                 ko = b.is_ko(to_move, p);
                 if (ko) { m |= 1u << 29; any_ko = true; }
-                if (capture_at.test(p) && is_ladder_capture(b, to_move, p, nl)) m |= 1u << 30;
-                if (escape_at.test(p) && is_ladder_escape(b, to_move, p, nl)) m |= 1u << 31;
+                if (capture_at.test(p) && is_ladder_capture(b, to_move, p)) m |= 1u << 30;
+                if (escape_at.test(p) && is_ladder_escape(b, to_move, p)) m |= 1u << 31;
             }
             if (legal) legal[p] = mine >= 0 && !ko;
         }
@@ -760,25 +832,16 @@ inline void raw_position(const Board& b, int to_move, int symmetry, Raw* out) {
     memcpy(out->black, b.stones[BLACK].w, 48);
     memcpy(out->white, b.stones[WHITE].w, 48);
     memcpy(out->visited, b.visited.w, 48);
-    uint16_t nl[N_POINTS];
-    for (int i = 0; i < b.n_slots; ++i) nl[i] = 0;
     Bits capture_at, escape_at, capture, escape;
-    capture_at.clear(); escape_at.clear(); capture.clear(); escape.clear();
-    for (int p = 0; p < N_POINTS; ++p) {
-        if (!b.color[p] || nl[b.slot[p]]) continue;
-        int sl = b.slot[p];
-        int n = b.libs[sl].count();
-        nl[sl] = (uint16_t)n;
-        if (b.color[p] == to_move) { if (n < 2) escape_at.or_with(b.libs[sl]); }
-        else if (n == 2) capture_at.or_with(b.libs[sl]);
-    }
+    capture.clear(); escape.clear();
+    ladder_starts(b, to_move, capture_at, escape_at);
     Bits todo = capture_at | escape_at;
     while (todo.any()) {
         int p = todo.first();
         todo.reset(p);
         if (!b.is_valid_fast(to_move, p)) continue;
-        if (capture_at.test(p) && is_ladder_capture(b, to_move, p, nl)) capture.set(p);
-        if (escape_at.test(p) && is_ladder_escape(b, to_move, p, nl)) escape.set(p);
+        if (capture_at.test(p) && is_ladder_capture(b, to_move, p)) capture.set(p);
+        if (escape_at.test(p) && is_ladder_escape(b, to_move, p)) escape.set(p);
     }
     memcpy(out->ladder_capture, capture.w, 48);
     memcpy(out->ladder_escape, escape.w, 48);
