@@ -268,9 +268,9 @@ inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move, int* out_ed
     // what the scalar code computes (u / 1 == u, so the division needs no special case for unvisited children).
     {
         const __m256 vu = _mm256_set1_ps(u), vreduce = _mm256_set1_ps(reduce), zero = _mm256_setzero_ps();
+        const __m256 ninf = _mm256_set1_ps(NEG_INF);
         const __m256i one = _mm256_set1_epi32(1);
-        float score[8];
-        for (int k0 = 0; k0 < node.n_edges; k0 += 8) {
+        auto score8 = [&](int k0, __m256* live) {
             const __m256i total = _mm256_add_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(node.e_count + k0)),
                                                    _mm256_loadu_si256(reinterpret_cast<const __m256i*>(node.e_vcount + k0)));
             const __m256 bonus = _mm256_div_ps(vu, _mm256_cvtepi32_ps(_mm256_add_epi32(total, one)));
@@ -280,11 +280,56 @@ inline ProbeStatus select(Node& node, bool apply_fpu, int* out_move, int* out_ed
                 value = _mm256_blendv_ps(value, _mm256_max_ps(_mm256_sub_ps(value, vreduce), zero), fresh);
             }
             const __m256 prior = _mm256_loadu_ps(node.e_prior + k0);
-            _mm256_storeu_ps(score, _mm256_add_ps(value, _mm256_mul_ps(prior, bonus)));
-            const int live = _mm256_movemask_ps(_mm256_cmp_ps(prior, _mm256_set1_ps(NEG_INF), _CMP_GT_OQ));
-            const int kn = std::min(8, node.n_edges - k0);
-            for (int j = 0; j < kn; ++j)
-                if (live >> j & 1) consider(node.e_move[k0 + j], score[j]);
+            *live = _mm256_cmp_ps(prior, ninf, _CMP_GT_OQ);          // unused records (prior -inf) are never live
+            return _mm256_add_ps(value, _mm256_mul_ps(prior, bonus));
+        };
+        bool done = false;
+        if (node.n_edges > 16) {
+            // Many records (the root): keep all scores, find the maximum with vector operations and apply the tie rule to
+            // the records that reach it -- without NaNs the order (score, block of 8 descending, lane ascending) is total,
+            // so that is what considering every record in turn gives.
+            alignas(32) float sc[512];
+            __m256 vmax = ninf;
+            int nan = 0, any_live = 0;
+            for (int k0 = 0; k0 < node.n_edges; k0 += 8) {
+                __m256 live;
+                const __m256 raw8 = score8(k0, &live);
+                const __m256 s8 = _mm256_blendv_ps(ninf, raw8, live);
+                nan |= _mm256_movemask_ps(_mm256_cmp_ps(s8, s8, _CMP_UNORD_Q));
+                any_live |= _mm256_movemask_ps(live);
+                _mm256_store_ps(sc + k0, s8);
+                vmax = _mm256_max_ps(vmax, s8);
+            }
+            if (!nan) {
+                done = true;
+                if (any_live) {
+                    alignas(32) float lanes[8];
+                    _mm256_store_ps(lanes, vmax);
+                    float m = lanes[0];
+                    for (int j = 1; j < 8; ++j) m = lanes[j] > m ? lanes[j] : m;
+                    const __m256 vm = _mm256_set1_ps(m);
+                    for (int k0 = 0; k0 < node.n_edges; k0 += 8) {
+                        const __m256 live = _mm256_cmp_ps(_mm256_loadu_ps(node.e_prior + k0), ninf, _CMP_GT_OQ);
+                        int hit = _mm256_movemask_ps(_mm256_and_ps(_mm256_cmp_ps(_mm256_load_ps(sc + k0), vm, _CMP_EQ_OQ), live));
+                        for (; hit; hit &= hit - 1) {
+                            const int k = k0 + __builtin_ctz((unsigned)hit);
+                            consider(node.e_move[k], sc[k]);
+                        }
+                    }
+                }
+            }
+        }
+        if (!done) {
+            float score[8];
+            for (int k0 = 0; k0 < node.n_edges; k0 += 8) {
+                __m256 live8;
+                const __m256 raw8 = score8(k0, &live8);
+                _mm256_storeu_ps(score, raw8);
+                const int live = _mm256_movemask_ps(live8);
+                const int kn = std::min(8, node.n_edges - k0);
+                for (int j = 0; j < kn; ++j)
+                    if (live >> j & 1) consider(node.e_move[k0 + j], score[j]);
+            }
         }
     }
     // untouched children all score `unvisited + prior * u`, which never increases along the prior-sorted list:
