@@ -7,11 +7,12 @@
 #include "../include/dg_mcts.h"
 extern "C" int32_t dg_engine_forward_packed(dg_engine*, const dg_packed_position*, int32_t, uint16_t*, uint16_t*) { return -1; }
 extern "C" int32_t dg_engine_forward_raw(dg_engine*, const dg_raw_position*, int32_t, uint16_t*, uint16_t*, uint8_t*) { return -1; }
+extern "C" int32_t dg_engine_forward_raw_prior(dg_engine*, const dg_raw_position*, int32_t, uint16_t*, uint16_t*, uint8_t*, float*) { return -1; }
 extern "C" int32_t dg_engine_max_batch(dg_engine*) { return 0; }
 int main(){
   for (int variant = 0; variant < 3; ++variant) {
     dg_selfplay_config c{}; c.num_games=5; c.num_parallel=3; c.num_rollout= variant==2 ? 1 : 60; c.probes_per_round=4; c.max_plies=30; c.num_threads=3; c.dirichlet_noise=0.25f; c.temperature=0.8f; c.seed=3+variant;
-    c.ex_it = variant==1; c.num_ex_it_rollout=80; c.cache_capacity = variant==0 ? 64 : 0;
+    c.ex_it = variant==1; c.num_ex_it_rollout=80; c.cache_capacity = variant==0 ? 64 : 0; c.num_groups = variant + 1;
     dg_selfplay_stats s{};
     std::vector<char> sgf(1<<20);
     int rc=dg_selfplay_run(dg_random_predict,nullptr,&c,&s,sgf.data(),sgf.size());
