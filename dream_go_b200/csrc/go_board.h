@@ -590,16 +590,21 @@ inline void benson(const Board& b, int color, Bits& alive, Bits& eyes) {
     int nr = 0;
     Bits around_all;
     around_all.clear();
-    while (seeds.any()) {
-        Region& r = regions[nr];
+    while (seeds.any()) {                                    // what is left are small enclosed regions: flood them point by
+        Region& r = regions[nr];                             // point (a whole-board shift per step costs more than they do)
         r.points.clear();
-        r.points.set(seeds.first());
-        for (;;) {
-            Bits grow = (dilate(r.points) & rest).andnot(r.points);
-            if (!grow.any()) break;
-            r.points.or_with(grow);
+        r.around.clear();
+        int stack[N_POINTS], top = 0;
+        stack[top++] = seeds.first();
+        r.points.set(stack[0]);
+        while (top) {
+            const int s = stack[--top];
+            for (int k = 0; k < T.n_nbr[s]; ++k) {
+                const int q = T.nbr_list[s][k];
+                if (own.test(q)) r.around.set(q);            // never empty: every point of `rest` touches `own`
+                else if (rest.test(q) && !r.points.test(q)) { r.points.set(q); stack[top++] = q; }
+            }
         }
-        r.around = dilate(r.points) & own;                   // never empty: every point of `rest` touches `own`
         around_all.or_with(r.around);
         seeds = seeds.andnot(r.points);
         ++nr;
@@ -618,9 +623,9 @@ inline void benson(const Board& b, int color, Bits& alive, Bits& eyes) {
             slot_seen[b.slot[p]] = 1;
             Chain& c = chains[nc++];
             c.stones.clear();
+            c.touch.clear();
             int s = p;
-            do { c.stones.set(s); s = b.next[s]; } while (s != p);
-            c.touch = dilate(c.stones);
+            do { c.stones.set(s); c.touch.or_with(T.nbr_mask[s]); s = b.next[s]; } while (s != p);
         }
     }
     auto vital = [](const Region& r, const Chain& c) {       // every point of the region touches the chain (:188-208)
