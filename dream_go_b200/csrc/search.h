@@ -83,6 +83,25 @@ struct CompressLut {
 };
 inline const CompressLut& compress_lut() { static const CompressLut t; return t; }
 
+// Candidate blocks all have the size of the largest (362 candidates), and a search frees and allocates thousands of them
+// per move: each thread keeps the blocks it frees for its next allocations (glibc's own per-thread cache stops at 1 KiB).
+constexpr size_t kCandBlock = (362 + 8) * 4 + 384 * 2 + 362 + 16;
+struct CandBlockCache {
+    std::vector<void*> blocks;
+    ~CandBlockCache() { for (void* b : blocks) free(b); }
+    void* get() {
+        if (blocks.empty()) return malloc(kCandBlock);
+        void* b = blocks.back();
+        blocks.pop_back();
+        return b;
+    }
+    void put(void* b) {
+        if (!b) return;
+        if (blocks.size() < 8192) blocks.push_back(b); else free(b);      // a thread that mostly frees keeps <= 21 MB
+    }
+};
+inline CandBlockCache& cand_blocks() { static thread_local CandBlockCache c; return c; }
+
 // A node keeps (a) its candidates and (b) one record per visited (or disqualified) child, in creation order.  Both are
 // stored as parallel arrays in one allocation each: the root of a search has hundreds of children and `select` scores
 // them eight at a time; records never move to another index, so a probe remembers the index instead of the move.
@@ -114,7 +133,7 @@ struct Node {
     }
     ~Node() {
         for (int i = 0; i < n_edges; ++i) delete e_child[i];
-        free(cand_prior);
+        cand_blocks().put(cand_prior);
         free(e_child);
     }
     Node(const Node&) = delete;
@@ -128,10 +147,10 @@ struct Node {
         for (int i = 0; i < 360; i += 8)
             n += __builtin_popcount((unsigned)_mm256_movemask_ps(_mm256_cmp_ps(_mm256_and_ps(_mm256_loadu_ps(prior + i), absmask), inf, _CMP_LT_OQ)));
         n += std::isfinite(prior[360]) + std::isfinite(prior[361]);
-        free(cand_prior);
         // the compaction below stores whole vectors of 8 at the running position: 8 spare slots in both arrays
         const int n16 = (n + 8 + 15) & ~15;
-        char* mem = static_cast<char*>(malloc((size_t)(n + 8) * 4 + (size_t)n16 * 2 + (size_t)n + 16));
+        static_assert(kCandBlock >= (362 + 8) * 4 + ((362 + 8 + 15) & ~15) * 2 + 362 + 16, "a block holds the largest node");
+        char* mem = cand_prior ? reinterpret_cast<char*>(cand_prior) : static_cast<char*>(cand_blocks().get());
         cand_prior = reinterpret_cast<float*>(mem);
         cand_move = reinterpret_cast<uint16_t*>(mem + (size_t)(n + 8) * 4);
         cand_edge = reinterpret_cast<uint8_t*>(mem + (size_t)(n + 8) * 4 + (size_t)n16 * 2);
