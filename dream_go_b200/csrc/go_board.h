@@ -72,6 +72,7 @@ struct Tables {
     int16_t nbr_list[N_POINTS][4];  // on-board neighbours only, same order
     Bits nbr_mask[N_POINTS];
     uint16_t sym[8][N_POINTS + 1];  // sym[t][i] = where point i goes under transform t; 361 -> 361
+    int32_t sym32[8][368];          // the same as gather indices, padded to whole vectors of 8 (the padding reads entry 0)
     uint8_t sym_inverse[8];
     uint64_t zobrist[3][N_POINTS];
     Bits board, not_col0, not_col18;   // all 361 points / without column x = 0 / without column x = 18
@@ -112,6 +113,7 @@ struct Tables {
                 sym[t][19 * y + x] = (uint16_t)(19 * (ty + 9) + (tx + 9));
             }
             sym[t][PASS] = PASS;
+            for (int i = 0; i < 368; ++i) sym32[t][i] = i <= PASS ? sym[t][i] : 0;
         }
         static const uint8_t inv[8] = {0, 1, 2, 3, 4, 7, 6, 5};     // symmetry.rs:78-89
         memcpy(sym_inverse, inv, 8);

@@ -175,6 +175,26 @@ struct Node {
         memset(cand_edge, 0, (size_t)n_cand);
         sorted_n = 0;
         first_untouched = 0;
+        // The first visits of a node ask for its best few candidates one at a time, each time by a scan of arrays that have
+        // gone cold in between: find the best four now, in one pass, while the arrays are in the cache.  (Candidates are in
+        // increasing move order here, so among equal priors the earlier one ranks higher: strict comparisons.)
+        if (n_cand > 4) {
+            int top[4] = {-1, -1, -1, -1};
+            for (int i = 0; i < n_cand; ++i) {
+                const float x = cand_prior[i];
+                if (top[3] >= 0 && !(x > cand_prior[top[3]])) continue;
+                int r = 3;
+                while (r > 0 && (top[r - 1] < 0 || x > cand_prior[top[r - 1]])) { top[r] = top[r - 1]; --r; }
+                top[r] = i;
+            }
+            for (int r = 0; r < 4; ++r) {
+                const int j = top[r];
+                std::swap(cand_prior[r], cand_prior[j]);
+                std::swap(cand_move[r], cand_move[j]);
+                for (int t = r + 1; t < 4; ++t) if (top[t] == r) top[t] = j;     // what stood at r now stands at j
+            }
+            sorted_n = 4;
+        }
         for (int k = 0; k < n_edges; ++k) {
             e_prior[k] = std::isfinite(prior[e_move[k]]) ? prior[e_move[k]] : NEG_INF;
             int c = cand_index(e_move[k]);

@@ -105,13 +105,14 @@ class PredictionCache {
 // What create_initial_policy (pool/policy_helper.rs:28-75) derives from the board alone; computed when the leaf is
 // emitted (the feature pass already produced the legal mask), applied when its evaluation arrives.
 struct PriorPlan {
-    uint8_t candidate[N_POINTS + 1];           // after symmetry elimination
+    uint8_t candidate[368];                    // after symmetry elimination; [362, 368) stays 0 (whole vectors of 8 below)
     uint16_t rep[N_POINTS + 1];                // orbit representative of each point (`indices`, :54-72)
     bool folded;                               // the board has a symmetry: some rep[p] != p
 
     void build(const Board& b, int to_move, int search_kind, const uint8_t* legal) {
         const Tables& T = tables();
         policy_candidates(b, to_move, search_kind, legal, candidate);
+        memset(candidate + N_POINTS + 1, 0, 368 - (N_POINTS + 1));
         int syms[8], ns = 0;
         for (int t = 0; t < 8; ++t) {
             bool same = true;
@@ -138,10 +139,20 @@ struct PriorPlan {
         const Tables& T = tables();
         if (!folded) {
             // every point is its own representative: prior[q] = 0 + policy[sym(q)] for the candidates, -inf elsewhere
-            const uint16_t* fwd = T.sym[symmetry];             // i = fwd[q]  <=>  q = inverse(symmetry)[i]
-            for (int q = 0; q < N_POINTS; ++q) prior[q] = candidate[q] ? 0.0f + f16_to_f32(policy[fwd[q]]) : NEG_INF;
-            prior[PASS] = candidate[PASS] ? 0.0f + f16_to_f32(policy[PASS]) : NEG_INF;
-            for (int i = N_POINTS + 1; i < 368; ++i) prior[i] = NEG_INF;
+            // i = fwd[q]  <=>  q = inverse(symmetry)[i]; fp16 -> fp32 for the whole vector first, then one gather per 8 points
+            alignas(32) float p32[368];
+            for (int i = 0; i < 360; i += 8)
+                _mm256_store_ps(p32 + i, _mm256_cvtph_ps(_mm_loadu_si128(reinterpret_cast<const __m128i*>(policy + i))));
+            p32[360] = f16_to_f32(policy[360]);
+            p32[361] = f16_to_f32(policy[361]);
+            const int32_t* fwd = T.sym32[symmetry];
+            const __m256 zero = _mm256_setzero_ps(), ninf = _mm256_set1_ps(NEG_INF);
+            for (int q = 0; q < 368; q += 8) {
+                const __m256 x = _mm256_i32gather_ps(p32, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(fwd + q)), 4);
+                const __m256i c8 = _mm256_cvtepu8_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i*>(candidate + q)));
+                const __m256 keep = _mm256_castsi256_ps(_mm256_cmpgt_epi32(c8, _mm256_setzero_si256()));
+                _mm256_storeu_ps(prior + q, _mm256_blendv_ps(ninf, _mm256_add_ps(zero, x), keep));
+            }
         } else {
             for (int i = 0; i < 368; ++i) prior[i] = NEG_INF;
             for (int p = 0; p <= N_POINTS; ++p) if (candidate[p]) prior[p] = 0.0f;
