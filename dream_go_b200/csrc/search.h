@@ -180,13 +180,20 @@ struct Node {
         // increasing move order here, so among equal priors the earlier one ranks higher: strict comparisons.)
         if (n_cand > 4) {
             int top[4] = {-1, -1, -1, -1};
-            for (int i = 0; i < n_cand; ++i) {
+            auto offer = [&](int i) {
                 const float x = cand_prior[i];
-                if (top[3] >= 0 && !(x > cand_prior[top[3]])) continue;
+                if (top[3] >= 0 && !(x > cand_prior[top[3]])) return;
                 int r = 3;
                 while (r > 0 && (top[r - 1] < 0 || x > cand_prior[top[r - 1]])) { top[r] = top[r - 1]; --r; }
                 top[r] = i;
+            };
+            for (int i = 0; i < 4; ++i) offer(i);
+            int i = 4;
+            for (; i + 8 <= n_cand; i += 8) {          // eight at a time against the fourth best so far; hits are rare
+                unsigned hit = (unsigned)_mm256_movemask_ps(_mm256_cmp_ps(_mm256_loadu_ps(cand_prior + i), _mm256_set1_ps(cand_prior[top[3]]), _CMP_GT_OQ));
+                for (; hit; hit &= hit - 1) offer(i + __builtin_ctz(hit));
             }
+            for (; i < n_cand; ++i) offer(i);
             for (int r = 0; r < 4; ++r) {
                 const int j = top[r];
                 std::swap(cand_prior[r], cand_prior[j]);

@@ -113,18 +113,16 @@ struct PriorPlan {
         const Tables& T = tables();
         policy_candidates(b, to_move, search_kind, legal, candidate);
         memset(candidate + N_POINTS + 1, 0, 368 - (N_POINTS + 1));
-        int syms[8], ns = 0;
-        for (int t = 0; t < 8; ++t) {
+        int syms[8], ns = 1;
+        syms[0] = 0;                               // the identity
+        for (int t = 1; t < 8; ++t) {
             bool same = true;
             const uint16_t* m = T.sym[t];
             for (int p = 0; p < N_POINTS && same; ++p) same = b.color[p] == b.color[m[p]];
             if (same) syms[ns++] = t;
         }
-        folded = ns > 1;                           // syms[0] is the identity
-        if (!folded) {
-            for (int p = 0; p <= N_POINTS; ++p) rep[p] = (uint16_t)p;
-            return;
-        }
+        folded = ns > 1;
+        if (!folded) return;                       // every point is its own representative: apply() does not look at `rep`
         for (int p = 0; p < N_POINTS; ++p) {
             int best = p;
             for (int k = 0; k < ns; ++k) { int q = T.sym[syms[k]][p]; if (q < best) best = q; }
