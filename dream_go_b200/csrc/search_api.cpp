@@ -1,16 +1,15 @@
 // search_api.cpp -- C ABI of include/dg_mcts.h: blocking single search (dg_mcts_predict) and the self-play driver.
 //
 // The driver is the engine-side replacement of `self_play` + `Pool` + `Batcher` (src/libdg_mcts/self_play.rs:423-500,
-// pool/pool.rs, pool/batch.rs): the games in flight are split into two groups that alternate -- while the device
-// evaluates the leaves of one group, the host threads insert the previous results of the other group, probe its
-// trees and extract the next features.  Every game owns its random stream, so the games played are a function of
-// the seed alone, whatever the thread count.
+// pool/pool.rs, pool/batch.rs): the games in flight are split into a few groups.  A group is either on the host -- any free
+// worker thread advances the next of its games (insert the evaluations, probe the tree, extract the next leaves), and the
+// worker that finishes the last one gathers the leaves and submits them -- or on the device, where the group's device
+// thread sits in the blocking predictor call.  Every game owns its random stream, so the games played are a function of
+// the seed alone, whatever the number of threads and groups.
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
-#include <functional>
-#include <future>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -18,7 +17,6 @@
 
 #include "../../include/dg_mcts.h"
 #include "search_task.h"
-#include "thread_pool.h"
 
 using namespace dg;
 

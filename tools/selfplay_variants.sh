@@ -1,5 +1,6 @@
 #!/bin/bash
-# Self-play throughput under scarce host cores (the 8-GPU box has 4 cores per GPU): blocking sync / device priors A/B.
+# Self-play throughput under scarce host cores (the 8-GPU box has 4 hardware threads per GPU): napping (default) vs spinning
+# engine calls, device priors A/B.
 #   tools/selfplay_variants.sh <out.jsonl> [seconds]
 out=${1:-gpurun_out/selfplay_variants.jsonl}
 secs=${2:-10}
@@ -13,10 +14,9 @@ run() {   # label, cpu list ('' = all), threads, extra args
     echo "$label: $(echo "$line" | python -c 'import sys,json; d=json.load(sys.stdin); print(round(d["value"],1), round(d["nn_evals_per_s"]), round(d["mean_batch"],1))')"
 }
 run "16 threads" "" 16
-run "16 threads, blocking sync" "" 16 --blocking-sync
+run "16 threads, spinning engine calls" "" 16 --spin-sync
 run "4 cores" 0-3 4
-run "4 cores, blocking sync" 0-3 4 --blocking-sync
+run "4 cores, spinning engine calls" 0-3 4 --spin-sync
 run "4 cores, device priors" 0-3 4 --device-priors
-run "4 cores, device priors, blocking sync" 0-3 4 --device-priors --blocking-sync
-run "4 cores, 64 games, blocking sync" 0-3 4 --blocking-sync --parallel 64
-run "8 cores, blocking sync" 0-7 8 --blocking-sync
+run "4 cores, 64 games" 0-3 4 --parallel 64
+run "8 cores" 0-7 8
