@@ -89,6 +89,35 @@ def test_ladder_kats_on_product():   # utils/ladder.rs:187-351
     assert b.is_ladder_escape(WHITE, 4, 13)
 
 
+def test_raw_positions_against_the_oracle():
+    """`dg_raw_position` (what the device feature kernel starts from): stones, visited points, hashes, last moves and the two
+    ladder planes -- the only planes the host still computes on that path -- against the ORACLE's board and feature planes,
+    on random play (weak chains everywhere: many ladder readings, most decided at the first step, some deep)."""
+    def bits(words):
+        return np.unpackbits(np.asarray(words, "<u4").view(np.uint8), bitorder="little")[:361]
+
+    colors, moves = random_playout(77, 260)
+    po, oo = pgo.Board(7.5), ogo.Board(7.5)
+    checked = ladders = 0
+    for ply, (c, m) in enumerate(zip(colors, moves)):
+        if m < 361:
+            po.place_index(int(c), int(m))
+            oo.place_index(int(c), int(m))
+        if ply % 3:
+            continue
+        to_move = 3 - int(c)
+        raw = po.raw_position(to_move)[0]
+        want = oo.features(to_move).reshape(361, 32).astype(np.float32)
+        stones = po.stones()
+        assert (bits(raw["black"]) == (stones == BLACK)).all() and (bits(raw["white"]) == (stones == WHITE)).all()
+        assert (bits(raw["ladder_capture"]) == (want[:, 30] != 0)).all(), ply
+        assert (bits(raw["ladder_escape"]) == (want[:, 31] != 0)).all(), ply
+        assert int(raw["hash"]) == po.zobrist_hash() and int(raw["to_move"]) == to_move
+        ladders += int(bits(raw["ladder_capture"]).sum() + bits(raw["ladder_escape"]).sum())
+        checked += 1
+    assert checked > 80 and ladders > 20
+
+
 @pytest.mark.parametrize("t", range(8))
 def test_symmetry_tables(t):
     assert [pgo.symmetry_apply(t, i) for i in range(362)] == [ogo.symmetry_apply(t, i) for i in range(362)]
