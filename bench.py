@@ -280,8 +280,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "threads": threads, "predictor": "dg_random_predict (no device; feature planes on the host)"}
         self_play = {"moves_per_s": tot["moves_per_s"], "nn_evals_per_s": tot["nn_evals_per_s"], "unit": "moves/s, evals/s",
                      "mean_device_batch": tot["mean_device_batch"],
-                     "predictor_time_frac": tot["predictor_seconds"] / (tot["seconds"] * world),   # alternating groups overlap, so this can exceed 1
-                     "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU in 4 alternating groups, real positions: "
+                     "predictor_time_frac": tot["predictor_seconds"] / (tot["seconds"] * world),   # the groups' device calls overlap, so this can exceed 1
+                     "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU in 4 groups (host and device stages overlap), engine calls napping while they wait, real positions: "
                                  f"feature planes + legal moves derived on the device from raw stones (ladder planes on the host), random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
                      "host_threads_per_gpu": threads, "host_cores": os.cpu_count(), "host_only": host_only}
 

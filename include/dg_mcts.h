@@ -108,7 +108,7 @@ typedef struct dg_selfplay_config {
     uint64_t seed;
     double   max_seconds;         /* stop starting new rounds after this much wall time (<= 0: no limit)                */
     int32_t  cache_capacity;      /* entries of each game's transposition table (0 = none); see dg_cache                */
-    int32_t  num_groups;          /* alternating groups of games (1..8); 0 = chosen from num_parallel * probes_per_round */
+    int32_t  num_groups;          /* groups of games, each either on the host or on the device (1..8); 0 = chosen from num_parallel * probes_per_round */
 } dg_selfplay_config;
 
 typedef struct dg_selfplay_stats {
