@@ -350,3 +350,17 @@ def test_whole_game_matches_the_oracle_game(probes, rollouts, cache):
                                              cache=om.Cache(cache) if cache else None)
     assert komi == want_komi
     assert [(c, i) for c, i, _ in moves] == want_moves
+
+
+# ---- the games themselves, pinned (tests/golden/selfplay_digests.json, tools/make_selfplay_digests.py) ---------------
+
+def test_self_play_digests_match_the_golden_file():
+    """Whole self-play runs with the RandomPredictor give the games they gave when the fixture was written -- for every
+    number of worker threads and groups."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "selfplay_digests.json")
+    for k, case in enumerate(json.load(open(path))):
+        st, games = pm.self_play(pm.RandomPredictor(), num_threads=1 + k % 3, num_groups=1 + k % 4, **case["config"])
+        assert f"{st['digest']:016x}" == case["digest"], case["config"]
+        assert int(st["moves"]) == case["moves"] and len(games) == case["games"]
