@@ -68,6 +68,29 @@ def test_full_network_matches_oracle(full_engine, full_net):
     assert full_engine.num_blocks == 9
 
 
+@pytest.mark.parametrize("inputs", ["bernoulli", "real"])
+def test_full_network_batch_256_matches_oracle(full_engine, full_net, inputs):
+    """BASELINE.json configs[1] at its stated size -- 9 blocks x 128 filters, batch 256 -- against the CPU oracle directly
+    (value, policy, final tower activation), on the reference benchmark's Bernoulli(0.2) inputs
+    (dg_tests/benches/batch_sizes.rs:44-49) and on real V1 feature planes of fixture-game positions."""
+    batch = 256
+    if inputs == "bernoulli":
+        feats = weights.bernoulli_features(batch, seed=256)
+    else:
+        from oracle import go as ogo
+        games = ogo.load_games()
+        feats = np.concatenate([ogo.replay(c[:160], m[:160], k, features=True)["features"][96:160] for c, m, k in games[3:7]])[:batch]
+        assert feats.shape == (batch, 361, 32)
+    with full_engine.get_workspace(batch) as ws:
+        value, policy = nn.forward(ws, np.ascontiguousarray(feats)).unwrap()
+    want_v, want_p, tower = oracle.OracleNetwork(full_net).forward(feats, want_tower=True)
+    check_outputs(value, policy, want_v, want_p)
+    got = full_engine.debug_read_tower(-1, batch)
+    assert rel_l2(got, tower) <= 2e-3
+    per_pos = [rel_l2(got[i], tower[i]) for i in range(batch)]       # no position of the batch is off (tile / pair boundaries)
+    assert max(per_pos) <= 4e-3, int(np.argmax(per_pos))
+
+
 def test_random_gates_full_depth():
     tensors = weights.synthetic_network(seed=5, num_blocks=9, gate="random")
     feats = weights.bernoulli_features(4, seed=10)

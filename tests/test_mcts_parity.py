@@ -87,6 +87,20 @@ def test_wide_roots_with_tied_priors(game, plies, search, rollouts, min_children
     assert (count > 0).sum() >= min_children
 
 
+@pytest.mark.parametrize("rollouts,probes", [(800, 8), (1700, 8), (900, 1)])
+def test_full_rollout_budget_past_the_interpolation_knots(rollouts, probes):
+    """Every BASELINE config searches with 800 rollouts: n = total + virtual visits then passes the knots at 800 and 1600 of
+    the piecewise-linear UCT_EXP / FPU_REDUCE tables (src/libdg_utils/config.rs:181-195, 297-336) -- the second and
+    third segment of the interpolation, which the short searches above never reach."""
+    plays, komi = corpus_position(7, 30)
+    po, oo = boards(plays, komi)
+    tree, want_root = assert_same_search(hash_predictor(1.0), po, oo, po.to_move(), deterministic=True, num_rollout=rollouts,
+                                         probes_per_round=probes, leaf_symmetries=[3, 0, 6, 1, 4, 7, 2, 5])
+    assert tree.total_count + 32 * probes > 800          # n = visits + virtual visits really crossed the first knot
+    if rollouts > 1600:
+        assert tree.total_count > 1600                   # ... and the second
+
+
 def test_late_game_scoring_search_and_tree_reuse():
     plays, komi = corpus_position(11, 150)
     po, oo = boards(plays, komi)

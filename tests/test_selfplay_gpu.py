@@ -32,8 +32,10 @@ def test_real_feature_planes_match_oracle_network(engine, small_net):
     assert (np.abs(p - want_p.astype(np.float32)) <= 1e-3 + 1e-2 * want_p.astype(np.float32)).all()
 
 
-@pytest.mark.parametrize("probes", [1, 4])
-def test_search_on_engine_matches_oracle_search(engine, probes):
+@pytest.mark.parametrize("probes,rollouts", [(1, 150), (4, 150), (8, 800)])
+def test_search_on_engine_matches_oracle_search(engine, probes, rollouts):
+    """(8, 800) is the search every BASELINE config runs: n passes the first knot of the UCT_EXP / FPU_REDUCE tables
+    (src/libdg_utils/config.rs:181-195, 297-336)."""
     ogo.use_default_zobrist()
     colors, moves, komi = ogo.load_games()[9]
     po, oo = pgo.Board(komi), ogo.Board(komi)
@@ -48,7 +50,7 @@ def test_search_on_engine_matches_oracle_search(engine, probes):
             value, policy = nn.forward(ws, np.ascontiguousarray(feats)).unwrap()
         return value, policy.reshape(-1, 362)
 
-    kw = dict(deterministic=True, num_rollout=150, probes_per_round=probes, leaf_symmetries=[0, 3, 6, 1, 5])
+    kw = dict(deterministic=True, num_rollout=rollouts, probes_per_round=probes, leaf_symmetries=[0, 3, 6, 1, 5])
     want_v, want_i, want_root, want_evals = om.predict(engine_on_features, oo, color, **kw)
     got_v, got_i, tree, got_evals = pm.predict(pm.EnginePredictor(engine), po, color, **kw)
     count, value, prior = tree.children()
