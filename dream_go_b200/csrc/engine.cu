@@ -651,8 +651,11 @@ void dg_engine_destroy(dg_engine* e) {
 
 const char* dg_engine_last_error(dg_engine* e) {
     if (!e) return "null engine";
+    // a copy per calling thread: a concurrent failing call on the same engine may replace the engine's text at any time
+    static thread_local std::string text;
     std::lock_guard<std::mutex> g(e->err_mutex);
-    return e->last_error.c_str();
+    text = e->last_error;
+    return text.c_str();
 }
 
 int32_t dg_engine_num_blocks(dg_engine* e) { return e ? e->net.num_blocks : 0; }

@@ -32,6 +32,17 @@ static inline float f16_bits_to_f32(uint16_t h) {
 
 extern "C" {
 
+// Argument checks of the boundary: the reference's types make these states unrepresentable (`Point`, `Color`,
+// `Transform`); here a caller can hand over any integer.
+static inline bool on_board(int32_t point) { return point >= 0 && point < dg::N_POINTS; }
+static inline bool is_color(int32_t color) { return color == dg::BLACK || color == dg::WHITE; }
+static inline bool is_transform(int32_t t) { return t >= 0 && t < 8; }
+
+void dg_go_set_zobrist(const uint64_t* table) {
+    if (table) dg::mutable_tables().load_zobrist(table);
+    else dg::mutable_tables().default_zobrist();
+}
+
 dg_board* dg_board_new(float komi) {
     Board* b = new Board();
     b->init(komi);
@@ -45,20 +56,26 @@ float dg_board_komi(const dg_board* board) { return B(board)->komi; }
 int32_t dg_board_count(const dg_board* board) { return B(board)->count; }
 uint64_t dg_board_zobrist_hash(const dg_board* board) { return B(board)->hash; }
 int32_t dg_board_to_move(const dg_board* board) { return B(board)->to_move(); }
-int32_t dg_board_at(const dg_board* board, int32_t point) { return B(board)->color[point]; }
-int32_t dg_board_is_valid(const dg_board* board, int32_t color, int32_t point) { return B(board)->is_valid(color, point); }
-void dg_board_place(dg_board* board, int32_t color, int32_t point) { B(board)->place(color, point); }
-int32_t dg_board_get_n_liberty(const dg_board* board, int32_t point) { return B(board)->n_liberty(point); }
+int32_t dg_board_at(const dg_board* board, int32_t point) { return on_board(point) ? B(board)->color[point] : -1; }
+int32_t dg_board_is_valid(const dg_board* board, int32_t color, int32_t point) {
+    return on_board(point) && is_color(color) ? B(board)->is_valid(color, point) : 0;
+}
+void dg_board_place(dg_board* board, int32_t color, int32_t point) {
+    if (on_board(point) && is_color(color)) B(board)->place(color, point);      // 361 (pass) is not played (self_play.rs:442-451)
+}
+int32_t dg_board_get_n_liberty(const dg_board* board, int32_t point) { return on_board(point) ? B(board)->n_liberty(point) : 0; }
 int32_t dg_board_get_n_liberty_if(const dg_board* board, int32_t color, int32_t point) {
+    if (!on_board(point) || !is_color(color)) return -1;
     return B(board)->color[point] ? -1 : B(board)->liberties_if(color, point);
 }
 int32_t dg_board_is_ladder_capture(const dg_board* board, int32_t color, int32_t point) {
-    return dg::is_ladder_capture(*B(board), color, point);
+    return on_board(point) && is_color(color) ? dg::is_ladder_capture(*B(board), color, point) : 0;
 }
 int32_t dg_board_is_ladder_escape(const dg_board* board, int32_t color, int32_t point) {
-    return dg::is_ladder_escape(*B(board), color, point);
+    return on_board(point) && is_color(color) ? dg::is_ladder_escape(*B(board), color, point) : 0;
 }
 int32_t dg_board_is_symmetric(const dg_board* board, int32_t transform) {
+    if (!is_transform(transform)) return 0;
     const uint16_t* t = dg::tables().sym[transform];
     const Board* b = B(board);
     for (int p = 0; p < dg::N_POINTS; ++p)
@@ -67,10 +84,12 @@ int32_t dg_board_is_symmetric(const dg_board* board, int32_t transform) {
 }
 void dg_board_legal_moves(const dg_board* board, int32_t color, uint8_t* out) {
     const Board* b = B(board);
-    for (int p = 0; p < dg::N_POINTS; ++p) out[p] = (uint8_t)b->is_valid(color, p);
+    for (int p = 0; p < dg::N_POINTS; ++p) out[p] = is_color(color) ? (uint8_t)b->is_valid(color, p) : 0;
 }
-int32_t dg_symmetry_apply(int32_t transform, int32_t point) { return dg::tables().sym[transform][point]; }
-int32_t dg_symmetry_inverse(int32_t transform) { return dg::tables().sym_inverse[transform]; }
+int32_t dg_symmetry_apply(int32_t transform, int32_t point) {
+    return is_transform(transform) && point >= 0 && point <= dg::PASS ? dg::tables().sym[transform][point] : -1;
+}
+int32_t dg_symmetry_inverse(int32_t transform) { return is_transform(transform) ? dg::tables().sym_inverse[transform] : -1; }
 
 void dg_board_features_packed(const dg_board* board, int32_t to_move, int32_t symmetry, dg_packed_position* out, uint8_t* legal) {
     dg::features_v1(*B(board), to_move, symmetry, out->planes, &out->k_bits, legal);

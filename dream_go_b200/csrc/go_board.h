@@ -120,6 +120,9 @@ struct Tables {
         // The reference's constants are arbitrary random numbers (zobrist.rs:16-17); any table gives the
         // same rules.  splitmix64 stream, laid out over the reference's padded indices so that the
         // oracle (which uses the same generator by default) produces identical hashes.
+        default_zobrist();
+    }
+    void default_zobrist() {
         uint64_t s = 0x6472656d2d676f21ull;
         for (int c = 0; c < 3; ++c)
             for (int i = 0; i < 420; ++i) {
@@ -131,12 +134,20 @@ struct Tables {
                 if (col >= 1 && row >= 1 && row <= 19) zobrist[c][19 * (row - 1) + (col - 1)] = z;
             }
     }
+    // A table in the reference's own layout, `zobrist::TABLE: [[u64; 420]; 3]` (zobrist.rs:18) indexed by the padded
+    // vertex 20 * (y + 1) + (x + 1) (board_fast.rs): with the reference's constants the hashes are the reference's.
+    void load_zobrist(const uint64_t* table /* [3][420] */) {
+        for (int c = 0; c < 3; ++c)
+            for (int y = 0; y < 19; ++y)
+                for (int x = 0; x < 19; ++x) zobrist[c][19 * y + x] = table[c * 420 + 20 * (y + 1) + (x + 1)];
+    }
 };
 
-inline const Tables& tables() {
-    static const Tables t;
+inline Tables& mutable_tables() {
+    static Tables t;
     return t;
 }
+inline const Tables& tables() { return mutable_tables(); }
 
 // One board = stones + chains + the history the features and the super-ko rule need
 // (board.rs:27-49: last 8 moves, last 16 whole-board hashes, komi, move count, last colour).

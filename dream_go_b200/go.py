@@ -35,6 +35,7 @@ ABI = {
     "dg_board_prior": (None, [_P, _I, _I, _P, _P, _I, _F, _P]),
     "dg_board_is_scorable": (_I, [_P]), "dg_board_territory": (None, [_P, _P]), "dg_board_benson": (None, [_P, _I, _P]),
     "dg_board_policy_candidates": (None, [_P, _I, _I, _P, _P]),
+    "dg_go_set_zobrist": (None, [_P]),
 }
 _ready = False
 
@@ -48,6 +49,16 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         _ready = True
     return L
+
+
+def set_zobrist(table) -> None:
+    """`zobrist::TABLE` ([3][420] u64, src/libdg_go/zobrist.rs:18) for every hash of the process; None = built-in table."""
+    if table is None:
+        lib().dg_go_set_zobrist(None)
+    else:
+        t = np.ascontiguousarray(table, np.uint64)
+        assert t.shape == (3, 420)
+        lib().dg_go_set_zobrist(t.ctypes.data)
 
 
 def idx(x: int, y: int) -> int:

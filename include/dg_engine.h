@@ -185,7 +185,7 @@ int32_t dg_engine_synchronize(dg_engine* engine);
 /* Pinned host memory the forward calls can DMA from/to directly. */
 void*   dg_engine_alloc_host(dg_engine* engine, uint64_t nbytes);
 void    dg_engine_free_host(dg_engine* engine, void* ptr);
-/* Last error text of this engine (valid until the next failing call on it). */
+/* Last error text of this engine: a copy owned by the calling thread, valid until that thread asks again. */
 const char* dg_engine_last_error(dg_engine* engine);
 /* Network shape discovered from the weights (graph.rs:76-96). */
 int32_t dg_engine_num_blocks(dg_engine* engine);

@@ -26,6 +26,17 @@ extern "C" {
 
 typedef struct dg_board dg_board;
 
+/* Out-of-range arguments (point outside 0..360, colour outside 1..2, transform outside 0..7) are rejected at this
+ * boundary: queries answer 0 / -1, dg_board_place does nothing -- in particular for 361, the pass index the search
+ * hands out as a move (the reference does not call `place` for a pass, self_play.rs:442-451). */
+
+/* The zobrist constants of the process, in the reference's layout `zobrist::TABLE: [[u64; 420]; 3]` (src/libdg_go/
+ * zobrist.rs:18; index 20 * (y + 1) + (x + 1), board_fast.rs).  The shim passes `&dg_go::zobrist::TABLE` once at start-up
+ * and every hash -- `Board::zobrist_hash`, the super-ko window, the transposition-table key, the hashes the device feature
+ * kernel compares -- is then the reference's (dg_tests/tests/real_games.rs:49,74,117).  NULL restores the built-in
+ * table.  Call before creating boards and engines (an engine uploads the table when it is created); not thread-safe. */
+void      dg_go_set_zobrist(const uint64_t* table /* [3][420] or NULL */);
+
 /* ---- `Board` (src/libdg_go/board.rs) ------------------------------------------------------------------ */
 dg_board* dg_board_new(float komi);                                   /* Board::new          board.rs:51-62   */
 dg_board* dg_board_clone(const dg_board* board);                      /* #[derive(Clone)]    board.rs:26      */
@@ -34,7 +45,7 @@ void      dg_board_free(dg_board* board);
 void      dg_board_set_komi(dg_board* board, float komi);             /* board.rs:78-81 */
 float     dg_board_komi(const dg_board* board);
 int32_t   dg_board_count(const dg_board* board);                      /* board.rs:84-87 */
-uint64_t  dg_board_zobrist_hash(const dg_board* board);               /* board.rs:90-93 (own constants, see go_board.h) */
+uint64_t  dg_board_zobrist_hash(const dg_board* board);               /* board.rs:90-93; constants: dg_go_set_zobrist */
 int32_t   dg_board_to_move(const dg_board* board);                    /* board.rs:102-107 */
 int32_t   dg_board_at(const dg_board* board, int32_t point);          /* board.rs:117-121; 0 = empty */
 /* Board::is_valid (board.rs:151-153): empty, not suicide, not a repetition of the last 16 positions. */

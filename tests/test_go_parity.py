@@ -350,3 +350,39 @@ def test_long_random_games_bit_exact(seed):
     stones = ogo.replay(colors, moves, 7.5, features=True)["features"].astype(np.float32)[:, :, 5].sum(axis=1)
     assert (np.diff(stones) < -5).any()                     # big captures happen
     assert_same_replay(colors, moves, 7.5)
+
+
+# ---- the reference's zobrist constants at the product boundary (dg_go_set_zobrist) ----------------------------------
+
+def test_real_game_hashes_through_the_product_board():
+    """dg_tests/tests/real_games.rs:49,74,117: with `zobrist::TABLE` (zobrist.rs:18) loaded through dg_go_set_zobrist the
+    PRODUCT board ends the three pinned games on the reference's hashes; afterwards the built-in table is back."""
+    import numpy as np
+    from dream_go_b200 import go as pgo
+    from oracle import go as ogo
+    z = np.load(ogo._GOLDEN)
+    before = pgo.replay(z["kat0_colors"], z["kat0_moves"], hashes=True)["hash"][-1]
+    pgo.set_zobrist(z["zobrist"])
+    try:
+        for i in range(3):
+            out = pgo.replay(z[f"kat{i}_colors"], z[f"kat{i}_moves"], hashes=True)
+            assert int(out["hash"][-1]) == int(z[f"kat{i}_hash"][0])
+    finally:
+        pgo.set_zobrist(None)
+    assert pgo.replay(z["kat0_colors"], z["kat0_moves"], hashes=True)["hash"][-1] == before != int(z["kat0_hash"][0])
+
+
+def test_out_of_range_arguments_are_rejected_at_the_boundary():
+    from dream_go_b200 import go as pgo
+    L = pgo.lib()
+    b = pgo.Board(7.5)
+    b.place(1, 3, 3)
+    h = b.zobrist_hash()
+    for point in (361, 362, -1, 100000):
+        L.dg_board_place(b._h, 2, point)                       # pass / garbage: not played, nothing corrupted
+        assert L.dg_board_is_valid(b._h, 2, point) == 0 and L.dg_board_at(b._h, point) == -1
+        assert L.dg_board_get_n_liberty_if(b._h, 2, point) == -1
+    L.dg_board_place(b._h, 3, 5)                               # not a colour
+    assert b.zobrist_hash() == h and b.count() == 1 and b.to_move() == 2
+    assert L.dg_symmetry_apply(8, 0) == -1 and L.dg_symmetry_apply(0, 362) == -1 and L.dg_symmetry_inverse(-1) == -1
+    assert L.dg_symmetry_apply(3, 361) == 361
