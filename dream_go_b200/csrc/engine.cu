@@ -10,11 +10,14 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
+#include <cstddef>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -54,11 +57,25 @@ struct Workspace {
     __half *h_policy = nullptr, *h_value = nullptr;
     CUtensorMap tm_feat, tm_x, tm_y;           // 170-row load windows
     uint32_t* done = nullptr;          // per-tile progress flags of the persistent tower kernel
-    uint32_t flag_gen = 0;
+    uint32_t flag_gen = 1u << 20;      // eager launches count up from here; a graph launch zeroes the flags and uses kGraphGen
     int resident_batch = 0;
     int resident_kind = 0;            // 0 none, 1 raw features, 2 compact positions
     bool busy = false;
+    // leaf batch (dg_leaf_batch): producers claim slots of h_in lock-free, one graph launch per submit, completion flag
+    dg_engine* owner = nullptr;
+    std::atomic<int32_t> fill{0};      // slots claimed so far
+    std::atomic<int32_t> committed{0}; // slots whose 384 bytes are complete
+    std::atomic<uint32_t> polls{0};    // dg_leaf_batch_ready calls (every 65536th asks the driver whether the stream failed)
+    int32_t submitted = 0;             // leaves of the submit in flight / last completed
+    uint32_t* h_flag = nullptr;        // pinned: 0 while a submit is in flight, 1 once its results are in the pinned outputs
+    std::map<uint32_t, cudaGraphExec_t> graphs;   // (bucket << 1 | want_prior) -> instantiated forward
+    bool capturing = false;
+    Workspace() = default;
+    Workspace(const Workspace&) = delete;
+    Workspace& operator=(const Workspace&) = delete;
 };
+constexpr uint32_t kGraphGen = 64;     // flag base of a captured tower launch (the graph zeroes the flags first)
+constexpr int kBucket = 16;            // captured forwards exist for batches rounded up to a multiple of this
 
 struct ConvWeights {
     __half* w = nullptr;              // [9][ntot][k] fp16
@@ -82,21 +99,6 @@ struct DeviceNet {
     bool loaded = false;
 };
 
-struct LeafQueue {
-    int64_t capacity = 0;
-    dg_packed_position* ring = nullptr;       // pinned + mapped
-    __half* res_policy = nullptr;             // pinned [capacity][362]
-    __half* res_value = nullptr;              // pinned [capacity]
-    std::atomic<int64_t>* ready = nullptr;    // ticket+1 once the slot is filled
-    std::atomic<int64_t>* done = nullptr;     // ticket+1 once the slot is evaluated
-    std::atomic<int64_t> head{0};
-    std::atomic<int64_t> completed{0};        // all tickets below are evaluated
-    int64_t claimed = 0;                      // guarded by claim_mutex
-    std::mutex claim_mutex;
-    std::mutex wait_mutex;
-    std::condition_variable wait_cv;
-};
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -107,11 +109,12 @@ struct dg_engine {
     dg_engine_config cfg;
     int num_sms = 0;
     EncodeTiledFn encode = nullptr;
-    std::vector<Workspace> ws;
+    std::vector<std::unique_ptr<Workspace>> ws;
     std::mutex ws_mutex;
     std::condition_variable ws_cv;
     DeviceNet net;
-    LeafQueue queue;
+    std::atomic<bool> kernels_configured{false};   // a raw forward has run once outside a capture (one-time kernel attributes)
+    std::mutex graph_mutex;           // captures, and the first (eager) forward
     std::mutex err_mutex;
     std::string last_error;
     std::vector<void*> host_allocs;
@@ -182,6 +185,10 @@ int32_t create_workspace(dg_engine* e, Workspace& w) {
     DG_CUDA(e, cudaHostAlloc(&w.h_value, static_cast<size_t>(mb) * 2, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_legal, static_cast<size_t>(mb) * 361, cudaHostAllocDefault));
     DG_CUDA(e, cudaHostAlloc(&w.h_prior, static_cast<size_t>(mb) * 368 * 4, cudaHostAllocDefault));
+    DG_CUDA(e, cudaHostAlloc(&w.h_flag, 64, cudaHostAllocDefault));
+    *w.h_flag = 1;
+    memset(w.h_in, 0, static_cast<size_t>(mb) * kFeatBytes);
+    w.owner = e;
     if (!make_tmap(e, &w.tm_feat, w.feat, 64, rows, DG_WINDOW_ROWS) || !make_tmap(e, &w.tm_x, w.x, kChan, rows, DG_WINDOW_ROWS) ||
         !make_tmap(e, &w.tm_y, w.y, kChan, rows, DG_WINDOW_ROWS) ||
         !make_tmap(e, &w.tm_pa, w.pbuf + static_cast<size_t>(DG_GUARD_ROWS) * 8, dg::kPolicyFcK, mb, 128))
@@ -196,13 +203,15 @@ void destroy_workspace(Workspace& w) {
     cudaFree(w.d_in); cudaFree(w.feat); cudaFree(w.x); cudaFree(w.y); cudaFree(w.h);
     cudaFree(w.d_policy); cudaFree(w.d_value); cudaFree(w.done); cudaFree(w.pbuf); cudaFree(w.vbuf); cudaFree(w.part);
     cudaFreeHost(w.h_in); cudaFreeHost(w.h_policy); cudaFreeHost(w.h_value); cudaFreeHost(w.h_legal); cudaFreeHost(w.h_prior);
+    cudaFreeHost(w.h_flag);
+    for (auto& g : w.graphs) cudaGraphExecDestroy(g.second);
 }
 
 Workspace* acquire(dg_engine* e) {
     std::unique_lock<std::mutex> lk(e->ws_mutex);
     for (;;) {
         for (auto& w : e->ws)
-            if (!w.busy) { w.busy = true; return &w; }
+            if (!w->busy) { w->busy = true; return w.get(); }
         e->ws_cv.wait(lk);
     }
 }
@@ -216,9 +225,9 @@ Workspace* acquire_resident(dg_engine* e, int batch) {
     for (;;) {
         bool any = false;
         for (auto& w : e->ws) {
-            if (w.resident_kind == 0 || w.resident_batch != batch) continue;
+            if (w->resident_kind == 0 || w->resident_batch != batch) continue;
             any = true;
-            if (!w.busy) { w.busy = true; return &w; }
+            if (!w->busy) { w->busy = true; return w.get(); }
         }
         if (!any) return nullptr;
         e->ws_cv.wait(lk);
@@ -496,8 +505,17 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
             const int nunits = (tp.ntiles + 1) / 2;
             const int pairs = std::min(e->num_sms / 2, nunits);
             tp.rot = (e->cfg.flags & DG_FLAG_NO_ROTATE) ? 0 : nunits % pairs;
-            w.flag_gen += 64;                         // > layers per launch; flags compare modulo 2^32
-            tp.gen = w.flag_gen;
+            if (w.capturing) {                        // a graph replays the same parameters: zero the flags, fixed base
+                DG_CUDA(e, cudaMemsetAsync(w.done, 0, (static_cast<size_t>(dg_num_tiles(e->cfg.max_batch)) + 2) * 4, w.stream));
+                tp.gen = kGraphGen;
+            } else {
+                w.flag_gen += 64;                     // > layers per launch; flags compare modulo 2^32
+                if (w.flag_gen < (1u << 20)) {        // wrapped: stay above what a graph launch leaves in the flags
+                    w.flag_gen = 1u << 20;
+                    DG_CUDA(e, cudaMemsetAsync(w.done, 0, (static_cast<size_t>(dg_num_tiles(e->cfg.max_batch)) + 2) * 4, w.stream));
+                }
+                tp.gen = w.flag_gen;
+            }
             tp.done = w.done;
             tp.trace = e->trace_buf;
             DG_CUDA(e, dg::launch_tower(tp, e->num_sms, w.stream));
@@ -546,9 +564,12 @@ int32_t forward_impl(dg_engine* e, const void* input, size_t bytes_per_pos, int 
     int32_t rc = enqueue_network(e, w, batch, -1, 0);
     if (rc) { cudaStreamSynchronize(w.stream); return rc; }
     const bool pv = is_pinned(value_out), pp = is_pinned(policy_out);
-    DG_CUDA(e, cudaMemcpyAsync(pv ? static_cast<void*>(value_out) : w.h_value, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream));
-    DG_CUDA(e, cudaMemcpyAsync(pp ? static_cast<void*>(policy_out) : w.h_policy, w.d_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2, cudaMemcpyDeviceToHost, w.stream));
-    DG_CUDA(e, wait_stream(e, w));
+    cudaError_t cerr = cudaMemcpyAsync(pv ? static_cast<void*>(value_out) : w.h_value, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream);
+    if (cerr == cudaSuccess)
+        cerr = cudaMemcpyAsync(pp ? static_cast<void*>(policy_out) : w.h_policy, w.d_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2, cudaMemcpyDeviceToHost, w.stream);
+    if (cerr != cudaSuccess) cudaStreamSynchronize(w.stream);     // the workspace goes back to the pool: nothing of this call may still run
+    else cerr = wait_stream(e, w);
+    if (cerr != cudaSuccess) return fail(e, DG_ERR_CUDA, "forward failed: %s", cudaGetErrorString(cerr));
     if (!pv) memcpy(value_out, w.h_value, static_cast<size_t>(batch) * 2);
     if (!pp) memcpy(policy_out, w.h_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2);
     return DG_OK;
@@ -615,21 +636,11 @@ int32_t dg_engine_create(const dg_engine_config* config, dg_engine** out) {
             for (int p = 0; p < 361; p++) sym[t * 361 + p] = T.sym[t][p];
         DG_CUDA(e, dg::upload_feature_tables(z.data(), sym.data()));
     }
-    e->ws.resize(e->cfg.num_workspaces);
-    for (auto& w : e->ws) {
-        int32_t rc = create_workspace(e, w);
+    for (int i = 0; i < e->cfg.num_workspaces; i++) {
+        e->ws.emplace_back(new Workspace());
+        int32_t rc = create_workspace(e, *e->ws.back());
         if (rc) return rc;
     }
-    // leaf queue
-    LeafQueue& q = e->queue;
-    q.capacity = 4096;
-    while (q.capacity < 8ll * e->cfg.max_batch) q.capacity *= 2;
-    DG_CUDA(e, cudaHostAlloc(&q.ring, q.capacity * sizeof(dg_packed_position), cudaHostAllocMapped));
-    DG_CUDA(e, cudaHostAlloc(&q.res_policy, q.capacity * DG_POLICY_SIZE * 2, cudaHostAllocDefault));
-    DG_CUDA(e, cudaHostAlloc(&q.res_value, q.capacity * 2, cudaHostAllocDefault));
-    q.ready = new std::atomic<int64_t>[q.capacity];
-    q.done = new std::atomic<int64_t>[q.capacity];
-    for (int64_t i = 0; i < q.capacity; i++) { q.ready[i].store(0); q.done[i].store(0); }
     return DG_OK;
 }
 
@@ -637,13 +648,8 @@ void dg_engine_destroy(dg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
-    for (auto& w : e->ws) destroy_workspace(w);
+    for (auto& w : e->ws) destroy_workspace(*w);
     free_net(e->net);
-    if (e->queue.ring) cudaFreeHost(e->queue.ring);
-    if (e->queue.res_policy) cudaFreeHost(e->queue.res_policy);
-    if (e->queue.res_value) cudaFreeHost(e->queue.res_value);
-    delete[] e->queue.ready;
-    delete[] e->queue.done;
     for (void* p : e->host_allocs) cudaFreeHost(p);
     cudaFree(e->flush_buf);
     delete e;
@@ -660,6 +666,7 @@ const char* dg_engine_last_error(dg_engine* e) {
 
 int32_t dg_engine_num_blocks(dg_engine* e) { return e ? e->net.num_blocks : 0; }
 int32_t dg_engine_max_batch(dg_engine* e) { return e ? e->cfg.max_batch : 0; }
+int32_t dg_engine_num_workspaces(dg_engine* e) { return e ? e->cfg.num_workspaces : 0; }
 
 int32_t dg_engine_load_weights_json(dg_engine* e, const char* path) {
     if (!e || !path) return DG_ERR_INVALID_ARGUMENT;
@@ -716,26 +723,18 @@ int32_t dg_engine_forward_packed(dg_engine* e, const dg_packed_position* positio
     return forward_impl(e, positions, sizeof(dg_packed_position), 2, batch, value_out, policy_out);
 }
 
-static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t batch, uint16_t* value_out, uint16_t* policy_out,
-                        dg_packed_position* planes_out, uint8_t* legal_out, float* prior_out = nullptr) {
-    if (!e) return DG_ERR_INVALID_ARGUMENT;
-    if (!positions || !legal_out) return fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer");
-    if (batch < 1 || batch > e->cfg.max_batch) return fail(e, DG_ERR_INVALID_ARGUMENT, "batch %d outside 1..%d", batch, e->cfg.max_batch);
-    const bool network = value_out && policy_out;
-    if (network && !e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
-    DG_CUDA(e, cudaSetDevice(e->cfg.device));
-    WsGuard guard(e);
-    Workspace& w = *guard.w;
+// The raw-position forward of the `batch` positions staged in w.h_in, enqueued on the workspace's stream: H2D, feature
+// kernel (+ network) (+ priors), D2H of every result into the workspace's pinned outputs.  No synchronisation.
+static int32_t enqueue_raw(dg_engine* e, Workspace& w, int batch, bool network, bool prior, dg_packed_position* planes_out) {
     const size_t in_bytes = sizeof(dg_raw_position) * static_cast<size_t>(batch);
-    memcpy(w.h_in, positions, in_bytes);
     DG_CUDA(e, cudaMemcpyAsync(w.d_in, w.h_in, in_bytes, cudaMemcpyHostToDevice, w.stream));
     w.resident_kind = 3;
     w.resident_batch = batch;
-    w.want_plan = prior_out != nullptr;
+    w.want_plan = prior;
     int32_t rc = enqueue_network(e, w, batch, -1, network ? 0 : 1);
     w.want_plan = false;
-    if (rc) { cudaStreamSynchronize(w.stream); return rc; }
-    if (prior_out) {
+    if (rc) return rc;
+    if (prior) {
         DG_CUDA(e, dg::launch_prior_from_policy(w.d_in, w.d_policy, raw_cand(e, w), raw_rep(e, w), raw_prior(e, w), batch, w.stream));
         DG_CUDA(e, cudaMemcpyAsync(w.h_prior, raw_prior(e, w), static_cast<size_t>(batch) * 368 * 4, cudaMemcpyDeviceToHost, w.stream));
     }
@@ -746,7 +745,24 @@ static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t 
     }
     if (planes_out)
         DG_CUDA(e, cudaMemcpyAsync(planes_out, raw_planes(e, w), sizeof(dg_packed_position) * static_cast<size_t>(batch), cudaMemcpyDeviceToHost, w.stream));
-    DG_CUDA(e, wait_stream(e, w));
+    return DG_OK;
+}
+
+static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t batch, uint16_t* value_out, uint16_t* policy_out,
+                        dg_packed_position* planes_out, uint8_t* legal_out, float* prior_out = nullptr) {
+    if (!e) return DG_ERR_INVALID_ARGUMENT;
+    if (!positions || !legal_out) return fail(e, DG_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch < 1 || batch > e->cfg.max_batch) return fail(e, DG_ERR_INVALID_ARGUMENT, "batch %d outside 1..%d", batch, e->cfg.max_batch);
+    const bool network = value_out && policy_out;
+    if (network && !e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    WsGuard guard(e);
+    Workspace& w = *guard.w;
+    memcpy(w.h_in, positions, sizeof(dg_raw_position) * static_cast<size_t>(batch));
+    int32_t rc = enqueue_raw(e, w, batch, network, prior_out != nullptr, planes_out);
+    if (rc) { cudaStreamSynchronize(w.stream); return rc; }      // nothing of this call may still run when the workspace goes back
+    cudaError_t werr = wait_stream(e, w);
+    if (werr != cudaSuccess) return fail(e, DG_ERR_CUDA, "forward failed: %s", cudaGetErrorString(werr));
     memcpy(legal_out, w.h_legal, static_cast<size_t>(batch) * 361);
     if (prior_out) memcpy(prior_out, w.h_prior, static_cast<size_t>(batch) * 368 * 4);
     if (network) {
@@ -801,94 +817,173 @@ void dg_engine_free_host(dg_engine* e, void* ptr) {
     cudaFreeHost(ptr);
 }
 
-// ---------------------------------------------------------------------------------- leaf queue
+// ---------------------------------------------------------------------------------- leaf-batch queue
+//
+// Replaces `pool::Batcher` (src/libdg_mcts/pool/batch.rs:61-124: a mutex, a Vec and a 23 KB memcpy per leaf, at most
+// `max_batches` batches alive) and the blocking `batch.forward(predictor)` of pool/worker_thread.rs:88-99.  A leaf batch is
+// one of the engine's workspaces: producers claim slots of its pinned input array lock-free (384 B per leaf), ONE graph
+// launch evaluates them (H2D, feature kernel, tower, heads, priors, D2H -- captured once per batch bucket), and completion
+// is a word in pinned host memory written by the last kernel of the launch, so waiting costs no driver call and any
+// thread can notice it.  The self-play driver (search_api.cpp) runs on this.
 
-int64_t dg_engine_queue_push(dg_engine* e, const dg_packed_position* position) {
-    if (!e || !position) return DG_ERR_INVALID_ARGUMENT;
-    LeafQueue& q = e->queue;
-    int64_t t = q.head.load(std::memory_order_relaxed);
-    for (;;) {
-        if (t - q.completed.load(std::memory_order_acquire) >= q.capacity) return fail(e, DG_ERR_INVALID_ARGUMENT, "leaf queue full");
-        if (q.head.compare_exchange_weak(t, t + 1, std::memory_order_acq_rel)) break;
-    }
-    const int64_t slot = t & (q.capacity - 1);
-    memcpy(&q.ring[slot], position, sizeof(dg_packed_position));
-    q.ready[slot].store(t + 1, std::memory_order_release);
-    return t;
-}
+namespace {
 
-int32_t dg_engine_queue_flush(dg_engine* e) {
-    if (!e) return DG_ERR_INVALID_ARGUMENT;
-    if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
-    LeafQueue& q = e->queue;
-    DG_CUDA(e, cudaSetDevice(e->cfg.device));
-    for (;;) {
-        int64_t start, end;
-        {   // claim a contiguous, fully written, non-wrapping range of at most max_batch leaves
-            std::lock_guard<std::mutex> g(q.claim_mutex);
-            start = q.claimed;
-            const int64_t head = q.head.load(std::memory_order_acquire);
-            end = start;
-            while (end < head && end - start < e->cfg.max_batch && ((end & (q.capacity - 1)) != 0 || end == start) &&
-                   q.ready[end & (q.capacity - 1)].load(std::memory_order_acquire) == end + 1)
-                end++;
-            q.claimed = end;
-        }
-        if (end == start) return DG_OK;
-        const int batch = static_cast<int>(end - start);
-        const int64_t slot = start & (q.capacity - 1);
-        int32_t rc;
-        {
-            WsGuard guard(e);
-            Workspace& w = *guard.w;
-            // the pack kernel gathers the leaves straight out of the mapped pinned ring
-            void* dev_ring = nullptr;
-            DG_CUDA(e, cudaHostGetDevicePointer(&dev_ring, q.ring + slot, 0));
-            w.resident_kind = 0;
-            w.resident_batch = 0;
-            DG_CUDA(e, dg::launch_pack_compact(dev_ring, w.feat, batch, w.stream));
-            rc = enqueue_network(e, w, batch, -1, 3);
-            if (rc == DG_OK) {
-                DG_CUDA(e, cudaMemcpyAsync(q.res_value + slot, w.d_value, static_cast<size_t>(batch) * 2, cudaMemcpyDeviceToHost, w.stream));
-                DG_CUDA(e, cudaMemcpyAsync(q.res_policy + slot * DG_POLICY_SIZE, w.d_policy, static_cast<size_t>(batch) * DG_POLICY_SIZE * 2, cudaMemcpyDeviceToHost, w.stream));
-            }
-            DG_CUDA(e, cudaStreamSynchronize(w.stream));
-        }
-        for (int64_t t = start; t < end; t++) q.done[t & (q.capacity - 1)].store(rc == DG_OK ? t + 1 : -(t + 1), std::memory_order_release);
-        {   // advance the completed prefix
-            std::lock_guard<std::mutex> g(q.wait_mutex);
-            int64_t c = q.completed.load(std::memory_order_relaxed);
-            while (c < q.head.load(std::memory_order_acquire)) {
-                const int64_t d = q.done[c & (q.capacity - 1)].load(std::memory_order_acquire);
-                if (d != c + 1 && d != -(c + 1)) break;
-                c++;
-            }
-            q.completed.store(c, std::memory_order_release);
-        }
-        q.wait_cv.notify_all();
-        if (rc) return rc;
-    }
-}
+constexpr int32_t kSealed = INT32_MIN;
 
-int32_t dg_engine_queue_wait(dg_engine* e, int64_t ticket, uint16_t* value_out, uint16_t* policy_out) {
-    if (!e || ticket < 0 || !value_out || !policy_out) return DG_ERR_INVALID_ARGUMENT;
-    LeafQueue& q = e->queue;
-    if (ticket >= q.head.load(std::memory_order_acquire)) return fail(e, DG_ERR_INVALID_ARGUMENT, "ticket %lld was never issued", static_cast<long long>(ticket));
-    const int64_t slot = ticket & (q.capacity - 1);
-    int64_t d;
-    {
-        std::unique_lock<std::mutex> lk(q.wait_mutex);
-        for (;;) {
-            d = q.done[slot].load(std::memory_order_acquire);
-            if (d == ticket + 1 || d == -(ticket + 1)) break;
-            if (d > ticket + 1 || d < -(ticket + 1)) return fail(e, DG_ERR_INVALID_ARGUMENT, "result of ticket %lld was overwritten", static_cast<long long>(ticket));
-            q.wait_cv.wait_for(lk, std::chrono::milliseconds(1));
-        }
-    }
-    if (d < 0) return fail(e, DG_ERR_KERNEL, "evaluation of ticket %lld failed", static_cast<long long>(ticket));
-    *value_out = reinterpret_cast<const uint16_t*>(q.res_value)[slot];
-    memcpy(policy_out, q.res_policy + slot * DG_POLICY_SIZE, DG_POLICY_SIZE * 2);
+// the opaque dg_leaf_batch of the ABI is a workspace of its engine
+inline dg_leaf_batch* LB(Workspace* w) { return reinterpret_cast<dg_leaf_batch*>(w); }
+inline Workspace& WS(dg_leaf_batch* b) { return *reinterpret_cast<Workspace*>(b); }
+inline const Workspace& WSC(const dg_leaf_batch* b) { return *reinterpret_cast<const Workspace*>(b); }
+
+// The forward of `bucket` staged positions as an executable graph (captured on first use).
+int32_t batch_graph(dg_engine* e, Workspace& w, int bucket, bool prior, cudaGraphExec_t* out) {
+    const uint32_t key = (static_cast<uint32_t>(bucket) << 1) | (prior ? 1u : 0u);
+    auto it = w.graphs.find(key);
+    if (it != w.graphs.end()) { *out = it->second; return DG_OK; }
+    std::lock_guard<std::mutex> g(e->graph_mutex);
+    cudaGraph_t graph = nullptr;
+    DG_CUDA(e, cudaStreamBeginCapture(w.stream, cudaStreamCaptureModeThreadLocal));
+    w.capturing = true;
+    int32_t rc = enqueue_raw(e, w, bucket, true, prior, nullptr);
+    if (rc == DG_OK && dg::launch_signal_host(w.h_flag, 1u, w.stream) != cudaSuccess) rc = fail(e, DG_ERR_CUDA, "signal launch failed during capture");
+    w.capturing = false;
+    cudaError_t cerr = cudaStreamEndCapture(w.stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    if (cerr != cudaSuccess || !graph) return fail(e, DG_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(cerr));
+    cudaGraphExec_t exec = nullptr;
+    cerr = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (cerr != cudaSuccess) return fail(e, DG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(cerr));
+    w.graphs[key] = exec;
+    *out = exec;
     return DG_OK;
+}
+
+}  // namespace
+
+int32_t dg_engine_batch_acquire(dg_engine* e, dg_leaf_batch** out) {
+    if (!e || !out) return DG_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    Workspace* w = acquire(e);
+    w->fill.store(0);
+    w->committed.store(0);
+    w->submitted = 0;
+    *w->h_flag = 1;
+    *out = LB(w);
+    return DG_OK;
+}
+
+void dg_engine_batch_release(dg_leaf_batch* b) {
+    if (!b) return;
+    Workspace& w = WS(b);
+    if (*static_cast<volatile uint32_t*>(w.h_flag) == 0) { cudaSetDevice(w.owner->cfg.device); cudaStreamSynchronize(w.stream); *w.h_flag = 1; }
+    release(w.owner, &w);
+}
+
+int32_t dg_leaf_batch_capacity(const dg_leaf_batch* b) { return b ? WSC(b).owner->cfg.max_batch : 0; }
+
+int32_t dg_leaf_batch_push(dg_leaf_batch* b, const dg_raw_position* positions, int32_t n) {
+    if (!b || !positions || n < 1) return DG_ERR_INVALID_ARGUMENT;
+    Workspace& w = WS(b);
+    const int32_t cap = w.owner->cfg.max_batch;
+    int32_t at = w.fill.load(std::memory_order_relaxed);
+    do {
+        if (at < 0 || at + n > cap) return -1;             // sealed (a submit is in flight) or full: submit / wait, then retry
+    } while (!w.fill.compare_exchange_weak(at, at + n, std::memory_order_acq_rel, std::memory_order_relaxed));
+    memcpy(reinterpret_cast<dg_raw_position*>(w.h_in) + at, positions, sizeof(dg_raw_position) * static_cast<size_t>(n));
+    w.committed.fetch_add(n, std::memory_order_release);
+    return at;
+}
+
+int32_t dg_leaf_batch_submit(dg_leaf_batch* b, uint32_t outputs) {
+    if (!b) return DG_ERR_INVALID_ARGUMENT;
+    Workspace& w = WS(b);
+    dg_engine* e = w.owner;
+    if (*static_cast<volatile uint32_t*>(w.h_flag) == 0) return fail(e, DG_ERR_INVALID_ARGUMENT, "the previous submit of this leaf batch has not been waited for");
+    const int32_t n = w.fill.exchange(kSealed, std::memory_order_acq_rel);      // later pushes fail until dg_leaf_batch_reset
+    if (n <= 0) { w.fill.store(n < 0 ? kSealed : 0); return n == 0 ? fail(e, DG_ERR_INVALID_ARGUMENT, "empty leaf batch") : fail(e, DG_ERR_INVALID_ARGUMENT, "leaf batch already submitted"); }
+    while (w.committed.load(std::memory_order_acquire) < n) {}               // producers that claimed a slot finish their 384-byte copy
+    DG_CUDA(e, cudaSetDevice(e->cfg.device));
+    const bool prior = (outputs & DG_LEAF_PRIOR) != 0;
+    const int cap = e->cfg.max_batch;
+    int bucket = (n + kBucket - 1) / kBucket * kBucket;
+    if (bucket > cap) bucket = cap;
+    dg_raw_position* slots = reinterpret_cast<dg_raw_position*>(w.h_in);
+    for (int i = n; i < bucket; i++) slots[i] = slots[0];                       // the padding of a bucket is evaluated too: keep it a position
+    w.submitted = n;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    *static_cast<volatile uint32_t*>(w.h_flag) = 0;
+    int32_t rc;
+    const bool eager = (e->cfg.flags & DG_FLAG_NO_GRAPH) != 0 || !e->kernels_configured.load(std::memory_order_acquire);
+    if (eager) {
+        // the first forward of an engine runs outside a capture: the kernels' one-time attribute calls are not capturable
+        std::unique_lock<std::mutex> g(e->graph_mutex, std::defer_lock);
+        if (!(e->cfg.flags & DG_FLAG_NO_GRAPH)) g.lock();
+        rc = enqueue_raw(e, w, bucket, true, prior, nullptr);
+        if (rc == DG_OK && dg::launch_signal_host(w.h_flag, 1u, w.stream) != cudaSuccess) rc = fail(e, DG_ERR_CUDA, "signal launch failed");
+        if (rc == DG_OK && g.owns_lock()) {
+            if (cudaStreamSynchronize(w.stream) != cudaSuccess) rc = fail(e, DG_ERR_CUDA, "first forward failed");
+            else e->kernels_configured.store(true, std::memory_order_release);
+        }
+    } else {
+        cudaGraphExec_t exec = nullptr;
+        rc = batch_graph(e, w, bucket, prior, &exec);
+        if (rc == DG_OK) {
+            cudaError_t cerr = cudaGraphLaunch(exec, w.stream);
+            if (cerr != cudaSuccess) rc = fail(e, DG_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(cerr));
+        }
+    }
+    if (rc) { cudaStreamSynchronize(w.stream); *w.h_flag = 1; w.submitted = 0; }
+    return rc;
+}
+
+int32_t dg_leaf_batch_ready(dg_leaf_batch* b) {
+    if (!b) return DG_ERR_INVALID_ARGUMENT;
+    Workspace& w = WS(b);
+    const uint32_t f = *static_cast<volatile uint32_t*>(w.h_flag);
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (f != 0) return 1;
+    // a launch that failed on the device never writes the flag: ask the driver once in a while
+    if ((w.polls.fetch_add(1, std::memory_order_relaxed) & 0xffff) == 0xffff) {
+        cudaSetDevice(w.owner->cfg.device);
+        const cudaError_t q = cudaStreamQuery(w.stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) { *w.h_flag = 1; return fail(w.owner, DG_ERR_CUDA, "leaf batch failed: %s", cudaGetErrorString(q)); }
+    }
+    return 0;
+}
+
+int32_t dg_leaf_batch_wait(dg_leaf_batch* b) {
+    if (!b) return DG_ERR_INVALID_ARGUMENT;
+    Workspace& w = WS(b);
+    dg_engine* e = w.owner;
+    const bool nap = (e->cfg.flags & DG_FLAG_BLOCKING_SYNC) != 0;
+    for (uint32_t spins = 1;; spins++) {
+        if (dg_leaf_batch_ready(b)) return DG_OK;
+        if ((spins & 1023) == 0 || nap) {
+            if (nap) { timespec ts{0, 20000}; nanosleep(&ts, nullptr); }
+            if ((spins & (nap ? 63 : 0xfffff)) == 0) {                          // a failed launch never writes the flag
+                cudaSetDevice(e->cfg.device);
+                cudaError_t q = cudaStreamQuery(w.stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) { *w.h_flag = 1; return fail(e, DG_ERR_CUDA, "leaf batch failed: %s", cudaGetErrorString(q)); }
+            }
+        } else {
+            __builtin_ia32_pause();
+        }
+    }
+}
+
+int32_t dg_leaf_batch_size(const dg_leaf_batch* b) { return b ? WSC(b).submitted : 0; }
+dg_raw_position* dg_leaf_batch_slots(dg_leaf_batch* b) { return b ? reinterpret_cast<dg_raw_position*>(WS(b).h_in) : nullptr; }
+const uint16_t* dg_leaf_batch_value(const dg_leaf_batch* b) { return reinterpret_cast<const uint16_t*>(WSC(b).h_value); }
+const uint16_t* dg_leaf_batch_policy(const dg_leaf_batch* b) { return reinterpret_cast<const uint16_t*>(WSC(b).h_policy); }
+const uint8_t* dg_leaf_batch_legal(const dg_leaf_batch* b) { return WSC(b).h_legal; }
+const float* dg_leaf_batch_prior(const dg_leaf_batch* b) { return WSC(b).h_prior; }
+
+void dg_leaf_batch_reset(dg_leaf_batch* b) {
+    if (!b) return;
+    WS(b).committed.store(0, std::memory_order_relaxed);
+    WS(b).fill.store(0, std::memory_order_release);
 }
 
 // ---------------------------------------------------------------------------------- measurement

@@ -129,4 +129,15 @@ cudaError_t launch_split_heads(const __half* h, __half* pbuf, __half* vbuf, int 
     return cudaGetLastError();
 }
 
+// Completion signal of a leaf batch: runs last on the batch's stream, after the device-to-host copies of the results,
+// and writes `value` into a word of pinned host memory that the host polls (no driver call per poll).
+__global__ void signal_host_kernel(volatile uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    *flag = value;
+}
+cudaError_t launch_signal_host(uint32_t* flag, uint32_t value, cudaStream_t s) {
+    signal_host_kernel<<<1, 1, 0, s>>>(flag, value);
+    return cudaGetLastError();
+}
+
 }  // namespace dg

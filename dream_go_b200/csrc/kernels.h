@@ -17,6 +17,7 @@ cudaError_t launch_prior_from_policy(const void* raw, const void* policy, const 
                                      cudaStream_t s);
 cudaError_t launch_conv_direct(const __half* in, int cin, const __half* w, int ntot, const float* bias, float alpha, float beta,
                                const __half* skip, int skip_stride, __half* out, int out_stride, int batch, cudaStream_t s);
+cudaError_t launch_signal_host(uint32_t* flag_in_pinned_host_memory, uint32_t value, cudaStream_t s);
 cudaError_t launch_split_heads(const __half* h, __half* pbuf, __half* vbuf, int batch, cudaStream_t s);
 // heads.cu -- policy FC as a K-split tcgen05 GEMM + finishing kernel (softmax, value head)
 constexpr int kPolicyFcK = DG_POS_ROWS_ * 8;        // 3200: 8 policy samples of each of the 400 board rows of a position

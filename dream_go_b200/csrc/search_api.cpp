@@ -15,6 +15,9 @@
 #include <string>
 #include <thread>
 
+#include <sys/prctl.h>
+#include <time.h>
+
 #include "../../include/dg_mcts.h"
 #include "search_task.h"
 
@@ -321,12 +324,19 @@ void dg_tree_children(const dg_tree* tree, int32_t* count, float* value, float* 
 }
 int64_t dg_tree_num_nodes(const dg_tree* tree) { return tree ? count_nodes(N(tree)) : 0; }
 
+// `engines` != nullptr: the product path -- every group of games owns a leaf batch (include/dg_engine.h) of one of the
+// engines (group g -> engine g mod n_engines, the round-robin of predictors/nn.rs:87-89): the worker that advanced the
+// group's last game pushes the leaves and submits them with one graph launch, and whichever worker looks for work next
+// notices the completion flag -- no device thread, no blocking call, no condition variable on that path.
 static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_predictor, dg_predict_prior_fn prior_predictor, void* ctx,
+                             dg_engine* const* engines, int32_t n_engines, bool engine_priors,
                              const dg_selfplay_config* config, dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity) {
-    if ((!predictor && !raw_predictor && !prior_predictor) || !config || config->num_games <= 0 || config->num_parallel <= 0)
+    const bool engine_mode = engines != nullptr;
+    if ((!predictor && !raw_predictor && !prior_predictor && !engine_mode) || (engine_mode && n_engines <= 0) || !config ||
+        config->num_games <= 0 || config->num_parallel <= 0)
         return DG_ERR_INVALID_ARGUMENT;
-    const bool raw_mode = raw_predictor != nullptr || prior_predictor != nullptr;
-    const bool prior_mode = prior_predictor != nullptr;
+    const bool raw_mode = raw_predictor != nullptr || prior_predictor != nullptr || engine_mode;
+    const bool prior_mode = prior_predictor != nullptr || (engine_mode && engine_priors);
     Driver d;
     d.cfg = *config;
     if (d.cfg.max_plies <= 0 || d.cfg.max_plies > 722) d.cfg.max_plies = 722;
@@ -340,16 +350,30 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     // groups hide more host time, fewer groups make larger device batches; aim at >= 128-256 leaves per batch
     int want_groups = config->num_groups;
     if (const char* env = getenv("DG_SELFPLAY_GROUPS")) want_groups = atoi(env);
+    const int round_leaves = std::max(8, config->probes_per_round);            // a game emits its probes or the 8 root symmetries
+    const int per_engine_slots = engine_mode ? (n_slots + n_engines - 1) / n_engines : n_slots;
     if (want_groups <= 0) {
-        const int leaves = n_slots * (config->probes_per_round > 0 ? config->probes_per_round : 1);
+        const int leaves = per_engine_slots * (config->probes_per_round > 0 ? config->probes_per_round : 1);
         want_groups = std::max(2, std::min(4, leaves / 256));
     }
     if (want_groups > 8) want_groups = 8;
+    if (engine_mode) {                        // a group owns a workspace of its engine and its leaves must fit one leaf batch
+        int cap = dg_engine_max_batch(engines[0]), max_groups = 8;
+        for (int i = 0; i < n_engines; ++i) {
+            cap = std::min(cap, (int)dg_engine_max_batch(engines[i]));
+            max_groups = std::min(max_groups, (int)dg_engine_num_workspaces(engines[i]));
+        }
+        if (want_groups > max_groups) want_groups = max_groups;
+        while (want_groups < max_groups && ((per_engine_slots + want_groups - 1) / want_groups) * round_leaves > cap) ++want_groups;
+        if (want_groups < 1 || ((per_engine_slots + want_groups - 1) / want_groups) * round_leaves > cap) return DG_ERR_INVALID_ARGUMENT;
+        want_groups *= n_engines;
+    }
     const int n_groups = std::min(want_groups, n_slots);
     // A group is either on the host (its games are advanced one by one by whichever worker is free; the worker that
     // finishes the last one gathers the leaves and submits them) or on the device (its device thread is inside the
-    // blocking predictor call).  Nobody waits for a particular group: workers take the next game of ANY group that has
-    // results, so the host stays busy while at least one group is back and the device while at least one is submitted.
+    // blocking predictor call / its leaf batch is in flight).  Nobody waits for a particular group: workers take the next
+    // game of ANY group that has results, so the host stays busy while at least one group is back and the device while at
+    // least one is submitted.
     struct Group {
         std::vector<int> slots;
         std::vector<dg_packed_position> batch;
@@ -357,14 +381,33 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         std::vector<uint16_t> value, policy;
         std::vector<uint8_t> legal;
         std::vector<float> prior;
-        size_t size() const { return batch.size() + raw_batch.size(); }
+        size_t n_leaves = 0;
+        size_t size() const { return n_leaves; }
+        // where the evaluations of the round are read from: the vectors above, or the pinned outputs of the leaf batch
+        const uint16_t *r_value = nullptr, *r_policy = nullptr;
+        const uint8_t* r_legal = nullptr;
+        const float* r_prior = nullptr;
+        dg_leaf_batch* lb = nullptr;                              // engine mode
+        int64_t t_submit = 0;
         enum State { HOST, SUBMITTED, RETIRED } state = HOST;     // guarded by sched_m
         size_t next = 0, done = 0;                                // games handed out / advanced in this round (sched_m)
         bool absorb = false;                                      // the round starts from results of the device
         std::thread device_thread;
         std::condition_variable cv;                               // wakes the device thread (with sched_m)
-    } groups[8];
-    for (int i = 0; i < n_slots; ++i) groups[i % n_groups].slots.push_back(i);
+    };
+    std::vector<std::unique_ptr<Group>> group_store;
+    for (int gi = 0; gi < n_groups; ++gi) group_store.emplace_back(new Group());
+    auto groups = [&](int gi) -> Group& { return *group_store[gi]; };
+    for (int i = 0; i < n_slots; ++i) groups(i % n_groups).slots.push_back(i);
+    if (engine_mode) {
+        for (int gi = 0; gi < n_groups; ++gi) {
+            int32_t arc = dg_engine_batch_acquire(engines[gi % n_engines], &groups(gi).lb);
+            if (arc) {
+                for (int k = 0; k < gi; ++k) dg_engine_batch_release(groups(k).lb);
+                return arc;
+            }
+        }
+    }
 
     auto t_start = std::chrono::steady_clock::now();
     auto seconds = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
@@ -481,6 +524,9 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         const int64_t t_begin = trace_driver ? now_ns() : 0;
         grp.batch.clear();
         grp.raw_batch.clear();
+        grp.n_leaves = 0;
+        if (grp.lb) dg_leaf_batch_reset(grp.lb);                 // every game of the group has consumed its results
+        int32_t push_rc = DG_OK;
         for (int s : grp.slots) {
             Game& g = d.games[s];
             if (g.n_emitted == -1) {
@@ -495,26 +541,71 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
             }
             if (g.active && g.n_emitted > 0) {
                 g.batch_offset = grp.size();
-                grp.batch.insert(grp.batch.end(), g.batch.begin(), g.batch.end());
-                grp.raw_batch.insert(grp.raw_batch.end(), g.raw_batch.begin(), g.raw_batch.end());
+                if (grp.lb) {                                    // straight into the pinned input array of the leaf batch
+                    if (dg_leaf_batch_push(grp.lb, g.raw_batch.data(), (int32_t)g.raw_batch.size()) != (int32_t)g.batch_offset) push_rc = DG_ERR_INVALID_ARGUMENT;
+                } else {
+                    grp.batch.insert(grp.batch.end(), g.batch.begin(), g.batch.end());
+                    grp.raw_batch.insert(grp.raw_batch.end(), g.raw_batch.begin(), g.raw_batch.end());
+                }
+                grp.n_leaves += g.batch.size() + g.raw_batch.size();
             }
         }
         const bool empty = grp.size() == 0;
         if (!empty) {
-            grp.value.resize(grp.size());
-            grp.policy.resize(grp.size() * 362);
-            if (raw_mode) grp.legal.resize(grp.size() * 361);
-            if (prior_mode) grp.prior.resize(grp.size() * 368);
+            if (!grp.lb) {
+                grp.value.resize(grp.size());
+                grp.policy.resize(grp.size() * 362);
+                if (raw_mode) grp.legal.resize(grp.size() * 361);
+                if (prior_mode) grp.prior.resize(grp.size() * 368);
+                grp.r_value = grp.value.data(); grp.r_policy = grp.policy.data();
+                grp.r_legal = grp.legal.data(); grp.r_prior = grp.prior.data();
+            }
             ++rounds;
             positions += (int64_t)grp.size();
         }
         if (trace_driver) ns_serial += now_ns() - t_begin;
         gl.unlock();
+        if (!empty && grp.lb) {
+            // one graph launch: H2D, planes + legal moves, tower, heads, (priors), D2H, completion flag
+            int32_t r = push_rc ? push_rc : dg_leaf_batch_submit(grp.lb, prior_mode ? DG_LEAF_PRIOR : 0u);
+            std::lock_guard<std::mutex> lk(sched_m);
+            if (r != DG_OK) {
+                if (rc == DG_OK) rc = r;
+                retire(grp);
+                stop = true;
+            } else {
+                grp.t_submit = now_ns();
+                if (trace_driver && calls_in_flight++ == 0 && idle_since) ns_idle += grp.t_submit - idle_since;
+                grp.state = Group::SUBMITTED;
+            }
+            if (r != DG_OK) sched_cv.notify_all();
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(sched_m);
             if (empty) retire(grp); else grp.state = Group::SUBMITTED;
         }
         if (empty) sched_cv.notify_all(); else grp.cv.notify_one();
+    };
+
+    // engine mode, sched_m held: the leaf batch of a submitted group has completed (or failed)
+    auto complete = [&](Group& grp, int32_t ready) {
+        const int64_t t = now_ns();
+        eval_ns += t - grp.t_submit;
+        if (trace_driver && --calls_in_flight == 0) idle_since = t;
+        if (ready < 0) {
+            if (rc == DG_OK) rc = ready;
+            retire(grp);
+            stop = true;
+        } else if (out_of_time()) {
+            retire(grp);                                       // the work in flight at the deadline is dropped
+        } else {
+            grp.r_value = dg_leaf_batch_value(grp.lb); grp.r_policy = dg_leaf_batch_policy(grp.lb);
+            grp.r_legal = dg_leaf_batch_legal(grp.lb); grp.r_prior = dg_leaf_batch_prior(grp.lb);
+            grp.absorb = true;
+            grp.next = grp.done = 0;
+            grp.state = Group::HOST;
+        }
     };
 
     auto device_loop = [&](Group& grp) {
@@ -554,31 +645,47 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
 
     auto worker_loop = [&] {
         int64_t t_mark = trace_driver ? now_ns() : 0;
+        prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);               // the short naps below are meant to be short
         for (;;) {
             Group* grp = nullptr;
             size_t i = 0;
             {
                 std::unique_lock<std::mutex> lk(sched_m);
-                for (;;) {
+                for (int idle_polls = 0;; ++idle_polls) {
                     if (stop) { if (trace_driver) ns_worker_cpu += thread_cpu_ns(); return; }
+                    if (engine_mode)                              // has a leaf batch come back?  (a read of pinned memory each)
+                        for (int gi = 0; gi < n_groups; ++gi)
+                            if (groups(gi).state == Group::SUBMITTED)
+                                if (int32_t ready = dg_leaf_batch_ready(groups(gi).lb)) complete(groups(gi), ready);
+                    if (stop) continue;
                     for (int gi = 0; gi < n_groups && !grp; ++gi)
-                        if (groups[gi].state == Group::HOST && groups[gi].next < groups[gi].slots.size()) { grp = &groups[gi]; i = grp->next++; }
+                        if (groups(gi).state == Group::HOST && groups(gi).next < groups(gi).slots.size()) { grp = &groups(gi); i = grp->next++; }
                     if (grp) break;
                     if (trace_driver) { const int64_t t = now_ns(); ns_worker_busy += t - t_mark; t_mark = t; }
-                    sched_cv.wait(lk);
+                    if (engine_mode) {
+                        // nothing to do until a batch returns: poll its flag -- a few pauses first, then naps that leave
+                        // the core to a sibling thread
+                        lk.unlock();
+                        if (idle_polls < 64) { for (int k = 0; k < 32; ++k) __builtin_ia32_pause(); }
+                        else { timespec nap{0, 5000}; nanosleep(&nap, nullptr); }
+                        lk.lock();
+                    } else {
+                        sched_cv.wait(lk);
+                    }
                     if (trace_driver) { const int64_t t = now_ns(); ns_worker_idle += t - t_mark; t_mark = t; }
                 }
             }
             const bool absorb = grp->absorb;
-            advance(d.games[grp->slots[i]], absorb ? grp->value.data() : nullptr, absorb ? grp->policy.data() : nullptr,
-                    absorb && raw_mode ? grp->legal.data() : nullptr, absorb && prior_mode ? grp->prior.data() : nullptr);
+            advance(d.games[grp->slots[i]], absorb ? grp->r_value : nullptr, absorb ? grp->r_policy : nullptr,
+                    absorb && raw_mode ? grp->r_legal : nullptr, absorb && prior_mode ? grp->r_prior : nullptr);
             bool last;
             { std::lock_guard<std::mutex> lk(sched_m); last = ++grp->done == grp->slots.size(); }
             if (last) finalize(*grp);
         }
     };
 
-    for (int gi = 0; gi < n_groups; ++gi) groups[gi].device_thread = std::thread(device_loop, std::ref(groups[gi]));
+    if (!engine_mode)
+        for (int gi = 0; gi < n_groups; ++gi) groups(gi).device_thread = std::thread(device_loop, std::ref(groups(gi)));
     {
         std::vector<std::thread> workers;
         const int n_workers = std::max(1, std::min(n_threads, n_slots));
@@ -591,7 +698,10 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     }
     {   // device threads still inside a call (deadline, error) come back first
         { std::lock_guard<std::mutex> lk(sched_m); quit = true; }
-        for (int gi = 0; gi < n_groups; ++gi) { groups[gi].cv.notify_all(); groups[gi].device_thread.join(); }
+        for (int gi = 0; gi < n_groups; ++gi) {
+            if (engine_mode) dg_engine_batch_release(groups(gi).lb);          // waits for a batch still in flight (deadline, error)
+            else { groups(gi).cv.notify_all(); groups(gi).device_thread.join(); }
+        }
     }
 
     if (trace_driver)
@@ -632,17 +742,25 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
 
 int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                         char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(predictor, nullptr, nullptr, ctx, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(predictor, nullptr, nullptr, ctx, nullptr, 0, false, config, stats, sgf_out, sgf_capacity);
 }
 
 int32_t dg_selfplay_run_raw(dg_predict_raw_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                             char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(nullptr, predictor, nullptr, ctx, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(nullptr, predictor, nullptr, ctx, nullptr, 0, false, config, stats, sgf_out, sgf_capacity);
 }
 
 int32_t dg_selfplay_run_prior(dg_predict_prior_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                               char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(nullptr, nullptr, predictor, ctx, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(nullptr, nullptr, predictor, ctx, nullptr, 0, false, config, stats, sgf_out, sgf_capacity);
+}
+
+int32_t dg_selfplay_run_engine(dg_engine* const* engines, int32_t n_engines, uint32_t flags, const dg_selfplay_config* config,
+                               dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity) {
+    if (!engines || n_engines <= 0) return DG_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < n_engines; ++i) if (!engines[i]) return DG_ERR_INVALID_ARGUMENT;
+    return selfplay_impl(nullptr, nullptr, nullptr, nullptr, engines, n_engines, (flags & DG_SELFPLAY_DEVICE_PRIORS) != 0, config, stats,
+                         sgf_out, sgf_capacity);
 }
 
 int32_t dg_engine_predict_prior(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy, uint8_t* legal,

@@ -62,7 +62,10 @@ ABI = {
     "dg_tree_total_count": (_I, [_P]), "dg_tree_to_move": (_I, [_P]), "dg_tree_initial_value": (C.c_float, [_P]),
     "dg_tree_children": (None, [_P, _P, _P, _P]), "dg_tree_num_nodes": (C.c_int64, [_P]),
     "dg_selfplay_run": (_I, [PREDICT_FN, _P, C.POINTER(_SelfPlayConfig), C.POINTER(_SelfPlayStats), _P, C.c_int64]),
+    "dg_selfplay_run_engine": (_I, [C.POINTER(C.c_void_p), _I, C.c_uint32, C.POINTER(_SelfPlayConfig), C.POINTER(_SelfPlayStats), _P,
+                                    C.c_int64]),
 }
+SELFPLAY_DEVICE_PRIORS = 0x1
 _ready = False
 
 
@@ -122,6 +125,17 @@ class EnginePriorPredictor:
         self.network = network
         self.fn = C.cast(lib().dg_engine_predict_prior, PREDICT_PRIOR_FN)
         self.ctx = network._handle
+
+
+class EngineQueue:
+    """The product path of self-play: one or several engines (one per device) driven through their leaf-batch queues by
+    `dg_selfplay_run_engine` -- no blocking predictor call.  `device_priors`: build the leaves' priors on the device
+    (None = when fewer than 8 host threads per engine are available, where the host is the scarce side)."""
+    engines = True
+
+    def __init__(self, networks, device_priors=None):
+        self.networks = list(networks) if isinstance(networks, (list, tuple)) else [networks]
+        self.device_priors = device_priors
 
 
 class RandomPredictor:
@@ -234,14 +248,25 @@ def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout:
               dirichlet_noise: float = 0.25, temperature: float = 0.8, seed: int = 1, max_seconds: float = 0.0,
               cache_capacity: int = 0, num_groups: int = 0, sgf_capacity: int = 1 << 24):
     """`dg_mcts::self_play`: returns (stats dict, list of SGF records)."""
-    fn, ctx = _fn_ctx(predictor)
     cfg = _SelfPlayConfig(num_games, num_parallel, num_rollout, probes_per_round, max_plies, num_threads, int(ex_it),
                           num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds, cache_capacity, num_groups)
     stats = _SelfPlayStats()
     buf = C.create_string_buffer(sgf_capacity)
-    kind = getattr(predictor, "raw", False)
-    run = lib().dg_selfplay_run_prior if kind == "prior" else lib().dg_selfplay_run_raw if kind else lib().dg_selfplay_run
-    rc = run(fn, ctx, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
+    if isinstance(predictor, EngineQueue):
+        import os
+        nets = predictor.networks
+        handles = (C.c_void_p * len(nets))(*[n._handle for n in nets])
+        priors = predictor.device_priors
+        if priors is None:
+            threads = num_threads if num_threads > 0 else (os.cpu_count() or 1)
+            priors = threads < 8 * len(nets)
+        rc = lib().dg_selfplay_run_engine(handles, len(nets), SELFPLAY_DEVICE_PRIORS if priors else 0, C.byref(cfg), C.byref(stats),
+                                          buf, sgf_capacity)
+    else:
+        fn, ctx = _fn_ctx(predictor)
+        kind = getattr(predictor, "raw", False)
+        run = lib().dg_selfplay_run_prior if kind == "prior" else lib().dg_selfplay_run_raw if kind else lib().dg_selfplay_run
+        rc = run(fn, ctx, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
     if rc:
         raise nn.Error(rc, "self-play failed")
     out = {name: getattr(stats, name) for name, _ in _SelfPlayStats._fields_}

@@ -33,6 +33,8 @@ FLAG_NO_PDL = 0x2
 FLAG_LAYERWISE = 0x4
 FLAG_NO_ROTATE = 0x8
 FLAG_BLOCKING_SYNC = 0x10
+FLAG_NO_GRAPH = 0x20
+LEAF_PRIOR = 0x1
 
 
 class Error(Exception):
@@ -79,9 +81,20 @@ ABI = {
     "dg_engine_forward_raw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dg_engine_forward_raw_prior": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dg_engine_features_raw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
-    "dg_engine_queue_push": (C.c_int64, [C.c_void_p, C.c_void_p]),
-    "dg_engine_queue_flush": (C.c_int32, [C.c_void_p]),
-    "dg_engine_queue_wait": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dg_engine_batch_acquire": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dg_engine_batch_release": (None, [C.c_void_p]),
+    "dg_leaf_batch_capacity": (C.c_int32, [C.c_void_p]),
+    "dg_leaf_batch_push": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "dg_leaf_batch_submit": (C.c_int32, [C.c_void_p, C.c_uint32]),
+    "dg_leaf_batch_ready": (C.c_int32, [C.c_void_p]),
+    "dg_leaf_batch_wait": (C.c_int32, [C.c_void_p]),
+    "dg_leaf_batch_size": (C.c_int32, [C.c_void_p]),
+    "dg_leaf_batch_slots": (C.c_void_p, [C.c_void_p]),
+    "dg_leaf_batch_value": (C.c_void_p, [C.c_void_p]),
+    "dg_leaf_batch_policy": (C.c_void_p, [C.c_void_p]),
+    "dg_leaf_batch_legal": (C.c_void_p, [C.c_void_p]),
+    "dg_leaf_batch_prior": (C.c_void_p, [C.c_void_p]),
+    "dg_leaf_batch_reset": (None, [C.c_void_p]),
     "dg_weights_file_probe": (C.c_int32, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_float),
                                           C.POINTER(C.c_uint64)]),
     "dg_engine_synchronize": (C.c_int32, [C.c_void_p]),
@@ -90,6 +103,7 @@ ABI = {
     "dg_engine_last_error": (C.c_char_p, [C.c_void_p]),
     "dg_engine_num_blocks": (C.c_int32, [C.c_void_p]),
     "dg_engine_max_batch": (C.c_int32, [C.c_void_p]),
+    "dg_engine_num_workspaces": (C.c_int32, [C.c_void_p]),
     "dg_engine_time_resident": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "dg_engine_time_e2e": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
@@ -262,21 +276,11 @@ class Network:
         self._check(lib().dg_engine_features_raw(self._handle, pos.ctypes.data, n, planes.ctypes.data, legal.ctypes.data))
         return planes, legal
 
-    def queue_push(self, position: np.ndarray) -> int:
-        pos = np.ascontiguousarray(position, dtype=PACKED_DTYPE).reshape(1)
-        ticket = int(lib().dg_engine_queue_push(self._handle, pos.ctypes.data))
-        if ticket < 0:
-            raise Error(ticket, self._last_error())
-        return ticket
-
-    def queue_flush(self) -> None:
-        self._check(lib().dg_engine_queue_flush(self._handle))
-
-    def queue_wait(self, ticket: int) -> Tuple[np.float16, np.ndarray]:
-        value = np.empty((1,), np.float16)
-        policy = np.empty((POLICY_SIZE,), np.float16)
-        self._check(lib().dg_engine_queue_wait(self._handle, ticket, value.ctypes.data, policy.ctypes.data))
-        return value[0], policy
+    def leaf_batch(self) -> "LeafBatch":
+        """One of the engine's in-flight evaluations as a leaf batch (the replacement of `pool::Batcher`)."""
+        h = C.c_void_p()
+        self._check(lib().dg_engine_batch_acquire(self._handle, C.byref(h)))
+        return LeafBatch(self, h)
 
     def time_resident(self, batch: int, iters: int, tower: bool = True, flush_l2: bool = True) -> Tuple[float, float, int]:
         """(ms for `iters` resident forwards, ms for the residual-conv launches of `iters` forwards, launches/forward)"""
@@ -367,3 +371,61 @@ def forward(workspace: Workspace, features: np.ndarray) -> OutputMap:
     policy = np.empty((batch * POLICY_SIZE,), np.float16)
     workspace.network.forward_into(feats, value, policy)
     return OutputMap(value, policy)
+
+
+def _view(ptr: int, shape, dtype) -> np.ndarray:
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    return np.frombuffer((C.c_uint8 * n).from_address(ptr), dtype=dtype).reshape(shape)
+
+
+class LeafBatch:
+    """`dg_leaf_batch`: lock-free pushes of raw positions from any thread, one graph launch per submit, completion read
+    from pinned host memory.  Mirrors `Batcher::{push, get_batch}` + `Batch::forward` (pool/batch.rs:61-124)."""
+
+    def __init__(self, network: "Network", handle):
+        self.network, self._h = network, handle
+
+    def close(self) -> None:
+        if self._h:
+            lib().dg_engine_batch_release(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    @property
+    def capacity(self) -> int:
+        return lib().dg_leaf_batch_capacity(self._h)
+
+    def push(self, positions: np.ndarray) -> int:
+        """Returns the index of the first pushed position, or -1 if they do not fit / the batch is sealed."""
+        pos = np.ascontiguousarray(positions, dtype=RAW_DTYPE).reshape(-1)
+        return int(lib().dg_leaf_batch_push(self._h, pos.ctypes.data, pos.shape[0]))
+
+    def submit(self, prior: bool = False) -> None:
+        self.network._check(lib().dg_leaf_batch_submit(self._h, LEAF_PRIOR if prior else 0))
+
+    def ready(self) -> bool:
+        return lib().dg_leaf_batch_ready(self._h) == 1
+
+    def wait(self) -> None:
+        self.network._check(lib().dg_leaf_batch_wait(self._h))
+
+    def reset(self) -> None:
+        lib().dg_leaf_batch_reset(self._h)
+
+    def results(self, prior: bool = False):
+        """Copies of (value [n], policy [n, 362], legal [n, 361][, prior [n, 368]]) of the last submit."""
+        n = lib().dg_leaf_batch_size(self._h)
+        out = [_view(lib().dg_leaf_batch_value(self._h), (n,), np.float16).copy(),
+               _view(lib().dg_leaf_batch_policy(self._h), (n, POLICY_SIZE), np.float16).copy(),
+               _view(lib().dg_leaf_batch_legal(self._h), (n, 361), np.uint8).copy()]
+        if prior:
+            out.append(_view(lib().dg_leaf_batch_prior(self._h), (n, 368), np.float32).copy())
+        return tuple(out)

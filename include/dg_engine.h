@@ -45,6 +45,7 @@ extern "C" {
 #define DG_FLAG_NO_PDL             0x2u  /* debug: launch the layers without programmatic dependent launch */
 #define DG_FLAG_LAYERWISE          0x4u  /* debug: one launch per convolution instead of the persistent tower kernel */
 #define DG_FLAG_NO_ROTATE          0x8u  /* debug: do not rotate the unit -> CTA-pair assignment between layers */
+#define DG_FLAG_NO_GRAPH          0x20u  /* debug: leaf batches are enqueued call by call instead of as one captured graph */
 #define DG_FLAG_BLOCKING_SYNC     0x10u  /* blocking calls poll the stream between 20 us naps instead of spinning in the driver
                                             (self-play: every core is busy searching and a spinning waiter steals one) */
 
@@ -161,14 +162,41 @@ int32_t dg_engine_features_raw(dg_engine* engine, const dg_raw_position* positio
 
 /* ---- leaf-batch queue (replaces pool::Batcher, src/libdg_mcts/pool/batch.rs:61-124) ---------- */
 
-/* Lock-free multi-producer enqueue of one leaf.  Returns a ticket (>= 0) or a negative status
- * when the ring is full (caller should dg_engine_queue_flush and retry). */
-int64_t dg_engine_queue_push(dg_engine* engine, const dg_packed_position* position);
-/* Evaluates every leaf pushed so far (in batches of <= max_batch).  Any thread may call it;
- * concurrent flushes take disjoint ticket ranges. */
-int32_t dg_engine_queue_flush(dg_engine* engine);
-/* Blocks until `ticket` has been evaluated, then copies its outputs (1 + 362 fp16). */
-int32_t dg_engine_queue_wait(dg_engine* engine, int64_t ticket, uint16_t* value_out, uint16_t* policy_out);
+/* The reference gathers leaves under a mutex (23 KB memcpy each), cuts batches of <= --batch-size with at most
+ * 2 x devices alive (batch.rs:98-123, predictors/nn.rs:64-67) and the worker that cut a batch blocks in
+ * `batch.forward(predictor)` (pool/worker_thread.rs:88-99).  Here a leaf batch is one of the engine's `num_workspaces`
+ * in-flight evaluations: any number of producer threads claim slots of its pinned input array lock-free (one
+ * compare-and-swap, 384 bytes per leaf), ONE CUDA-graph launch evaluates them -- host-to-device copy, feature planes and
+ * legal moves from the raw stones, tower, heads, optionally the ready-to-insert priors, device-to-host copies, all
+ * captured once per batch size bucket -- and completion is a word of pinned host memory written by the last kernel of
+ * the launch, so waiting costs no driver call and any thread can notice it.  Results stay valid until the batch is reset.
+ * Outputs are bit-identical to dg_engine_forward_raw(_prior) on the same positions. */
+typedef struct dg_leaf_batch dg_leaf_batch;
+#define DG_LEAF_PRIOR 0x1u           /* dg_leaf_batch_submit: also compute the priors (dg_engine_forward_raw_prior) */
+
+/* Takes one of the engine's workspaces (blocks while all are taken) / gives it back (waits for a submit in flight). */
+int32_t dg_engine_batch_acquire(dg_engine* engine, dg_leaf_batch** out);
+void    dg_engine_batch_release(dg_leaf_batch* batch);
+int32_t dg_leaf_batch_capacity(const dg_leaf_batch* batch);              /* = the engine's max_batch */
+/* Lock-free multi-producer: appends `n` positions, returns the index of the first one, or -1 when they do not fit or the
+ * batch is sealed (submitted and not yet reset) -- `Batcher::push` (batch.rs:87-91). */
+int32_t dg_leaf_batch_push(dg_leaf_batch* batch, const dg_raw_position* positions, int32_t n);
+/* Seals the batch and launches its evaluation; returns at once -- `Batcher::get_batch` + `Batch::forward` without the
+ * blocking (batch.rs:98-123).  Any thread may call it, once per fill. */
+int32_t dg_leaf_batch_submit(dg_leaf_batch* batch, uint32_t outputs);
+/* 1 when the results of the last submit are in the output arrays (a plain memory read), 0 while it runs. */
+int32_t dg_leaf_batch_ready(dg_leaf_batch* batch);
+/* Blocks until ready (spinning on the flag, or in 20 us naps under DG_FLAG_BLOCKING_SYNC); DG_ERR_CUDA if the launch failed. */
+int32_t dg_leaf_batch_wait(dg_leaf_batch* batch);
+int32_t dg_leaf_batch_size(const dg_leaf_batch* batch);                  /* leaves of the last submit */
+dg_raw_position* dg_leaf_batch_slots(dg_leaf_batch* batch);              /* the pinned input array (single-producer use) */
+/* Pinned output arrays of the last submit, in push order: [n] fp16, [n][362] fp16, [n][361], [n][368] floats. */
+const uint16_t* dg_leaf_batch_value(const dg_leaf_batch* batch);
+const uint16_t* dg_leaf_batch_policy(const dg_leaf_batch* batch);
+const uint8_t*  dg_leaf_batch_legal(const dg_leaf_batch* batch);
+const float*    dg_leaf_batch_prior(const dg_leaf_batch* batch);         /* only after DG_LEAF_PRIOR */
+/* Empties the batch for the next fill (after the results have been consumed). */
+void    dg_leaf_batch_reset(dg_leaf_batch* batch);
 
 /* ---- weight file (device-independent; usable without an engine) ------------------------------ */
 
@@ -189,8 +217,9 @@ void    dg_engine_free_host(dg_engine* engine, void* ptr);
 const char* dg_engine_last_error(dg_engine* engine);
 /* Network shape discovered from the weights (graph.rs:76-96). */
 int32_t dg_engine_num_blocks(dg_engine* engine);
-/* The max_batch the engine was created with. */
+/* The max_batch / num_workspaces (= leaf batches that can be held at once) the engine was created with. */
 int32_t dg_engine_max_batch(dg_engine* engine);
+int32_t dg_engine_num_workspaces(dg_engine* engine);
 /* Library/ABI version, for the FFI shim to assert on. */
 int32_t dg_engine_abi_version(void);
 

@@ -131,6 +131,17 @@ int32_t  dg_selfplay_run_raw(dg_predict_raw_fn predictor, void* ctx, const dg_se
 int32_t  dg_selfplay_run_prior(dg_predict_prior_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                                char* sgf_out, int64_t sgf_capacity);
 
+/* The product path: self-play on `n_engines` engines of ONE process (one per device, as `Device::all()` + the round-robin
+ * of predictors/nn.rs:84-92), the host threads shared by all of them.  Every group of games owns a leaf batch of its
+ * engine (dg_engine.h): the worker that advances the group's last game pushes the leaves and submits them (one graph
+ * launch), any worker notices the completion flag and goes on with the group's games -- no thread blocks in a predictor
+ * call (pool/worker_thread.rs:88-99 does).  Each engine needs num_workspaces >= its number of groups (config->num_groups
+ * per engine, 2..8) and max_batch >= games per group x max(8, probes_per_round).  Same games as the three calls above for the
+ * same seed.  flags: DG_SELFPLAY_DEVICE_PRIORS = the leaves' priors are built on the device (dg_engine_forward_raw_prior). */
+#define DG_SELFPLAY_DEVICE_PRIORS 0x1u
+int32_t  dg_selfplay_run_engine(dg_engine* const* engines, int32_t n_engines, uint32_t flags, const dg_selfplay_config* config,
+                                dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity);
+
 #ifdef __cplusplus
 }
 #endif

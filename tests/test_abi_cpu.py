@@ -164,5 +164,9 @@ def test_engine_entry_points_reject_null_engine():
     L = nn.lib()
     assert L.dg_engine_forward_f16(None, None, 1, None, None) == -5
     assert L.dg_engine_forward_raw(None, None, 1, None, None, None) == -5
-    assert L.dg_engine_queue_push(None, None) == -5
-    assert L.dg_engine_max_batch(None) == 0
+    assert L.dg_engine_batch_acquire(None, None) == -5
+    assert L.dg_leaf_batch_push(None, None, 1) == -5 and L.dg_leaf_batch_submit(None, 0) == -5
+    assert L.dg_leaf_batch_ready(None) == -5 and L.dg_leaf_batch_wait(None) == -5 and L.dg_leaf_batch_size(None) == 0
+    assert L.dg_engine_max_batch(None) == 0 and L.dg_engine_num_workspaces(None) == 0
+    from dream_go_b200 import mcts
+    assert mcts.lib().dg_selfplay_run_engine(None, 0, 0, None, None, None, 0) == -5

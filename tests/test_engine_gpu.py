@@ -167,31 +167,73 @@ def test_deterministic_and_packed_path_bit_exact(small_engine):
     assert np.array_equal(out.policy.reshape(-1), p1)
 
 
-def test_leaf_queue_matches_forward(small_engine):
-    feats = weights.bernoulli_features(150, seed=6)       # > max_batch: several flush batches
-    feats[:, :, 0] = 0
-    feats[:, :, 1] = np.float16(0.5)
-    packed = nn.pack_positions(feats)
-    tickets = [None] * 150
+def _raw_positions(n, game=4, start=20):
+    """n raw positions (consecutive plies of a fixture game, cycling through the symmetries and both search options)."""
+    from dream_go_b200 import go as pgo
+    from oracle import go as ogo
+    colors, moves, komi = ogo.load_games()[game]
+    board = pgo.Board(komi)
+    out = []
+    for ply, (c, m) in enumerate(zip(colors, moves)):
+        if ply >= start and len(out) < n:
+            out.append(board.raw_position(int(c), (ply % 8) | ((ply // 8 % 2) << 4)))
+        if m < 361:
+            board.place_index(int(c), int(m))
+    assert len(out) == n
+    return np.concatenate(out)
 
-    def producer(lo, hi):
-        for i in range(lo, hi):
-            tickets[i] = small_engine.queue_push(packed[i])
 
-    threads = [threading.Thread(target=producer, args=(i * 50, (i + 1) * 50)) for i in range(3)]
-    [t.start() for t in threads]
-    [t.join() for t in threads]
-    assert sorted(tickets) == list(range(min(tickets), min(tickets) + 150))
-    small_engine.queue_flush()
-    want_v, want_p = [], []
-    for lo in range(0, 150, 50):
-        o = small_engine.forward_packed(packed[lo:lo + 50])
-        want_v.append(o.value)
-        want_p.append(o.policy)
-    want_v, want_p = np.concatenate(want_v), np.concatenate(want_p)
-    for i in range(150):
-        v, p = small_engine.queue_wait(tickets[i])
-        assert v == want_v[i] and np.array_equal(p, want_p[i])
+@pytest.mark.parametrize("flags", [0, nn.FLAG_NO_GRAPH])
+def test_leaf_batch_queue_matches_blocking_forward(small_net, flags):
+    """The leaf-batch queue (lock-free pushes from several threads, one captured graph launch per submit, completion flag in
+    pinned memory) returns bit for bit what dg_engine_forward_raw_prior returns -- first submit (eager), replays of a captured
+    bucket, a second bucket, a batch that fills the workspace, and with the capture switched off."""
+    net = nn.Network.from_tensors(small_net, max_batch=64, num_workspaces=2, flags=flags)
+    try:
+        raw = _raw_positions(150)
+        want, want_legal, want_prior = net.forward_raw_prior(raw[:64])
+        with net.leaf_batch() as lb, net.leaf_batch() as lb2:
+            assert lb.capacity == 64
+            for rnd, (lo, hi, prior) in enumerate([(0, 37, True), (0, 37, True), (3, 40, True), (0, 64, True), (10, 15, False), (0, 64, False)]):
+                order = [None] * (hi - lo)
+
+                def producer(k, lo=lo, hi=hi, order=order):
+                    for i in range(lo + k, hi, 3):
+                        order[i - lo] = lb.push(raw[i:i + 1])
+
+                threads = [threading.Thread(target=producer, args=(k,)) for k in range(3)]
+                [t.start() for t in threads]
+                [t.join() for t in threads]
+                assert sorted(order) == list(range(hi - lo))
+                if hi - lo == 64:
+                    assert lb.push(raw[:1]) == -1              # full
+                lb.submit(prior=prior)
+                assert lb.push(raw[:1]) == -1                  # sealed until reset
+                lb.wait()
+                assert lb.ready()
+                res = lb.results(prior=prior)
+                slot = np.array(order)
+                idx = np.arange(lo, hi)
+                assert (res[0][slot].view(np.uint16) == want.value[idx].view(np.uint16)).all(), rnd
+                assert (res[1][slot].view(np.uint16) == want.policy.reshape(-1, 362)[idx].view(np.uint16)).all(), rnd
+                assert (res[2][slot] == want_legal[idx]).all(), rnd
+                if prior:
+                    assert (res[3][slot].view(np.uint32) == want_prior[idx].view(np.uint32)).all(), rnd
+                lb.reset()
+            # two batches in flight at once, as the reference allows per device (predictors/nn.rs:64-67)
+            assert lb.push(raw[64:100]) == 0 and lb2.push(raw[100:150]) == 0
+            lb.submit(prior=True)
+            lb2.submit(prior=True)
+            lb2.wait()
+            lb.wait()
+            got = np.concatenate([lb.results(True)[3], lb2.results(True)[3]])
+            a, _, pa = net.forward_raw_prior(raw[64:128])
+            b, _, pb = net.forward_raw_prior(raw[128:150])
+            assert (got.view(np.uint32) == np.concatenate([pa, pb]).view(np.uint32)).all()
+            with pytest.raises(nn.Error):
+                lb.submit()                                    # already submitted, not reset
+    finally:
+        net.close()
 
 
 def test_concurrent_forwards(small_engine, small_net):

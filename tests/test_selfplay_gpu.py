@@ -93,6 +93,25 @@ def test_device_features_give_the_same_search_and_games(engine):
     assert a["evals"] == b["evals"] == c["evals"]
 
 
+@pytest.mark.parametrize("flags", [0, nn.FLAG_NO_GRAPH | nn.FLAG_BLOCKING_SYNC])
+def test_leaf_batch_queue_driver_plays_the_same_games(small_net, flags):
+    """The product path (dg_selfplay_run_engine: leaf-batch queue, graph launches, completion flags, no device threads)
+    plays the games of the blocking-call drivers, with host or device priors, for any number of workers and groups."""
+    net = nn.Network.from_tensors(small_net, max_batch=128, num_workspaces=4, flags=flags)
+    try:
+        kw = dict(num_games=6, num_parallel=5, num_rollout=40, probes_per_round=4, max_plies=20, seed=11)
+        ref, sgf_ref = pm.self_play(pm.EnginePredictor(net), num_threads=2, **kw)
+        for priors, threads, groups in ((False, 1, 0), (True, 4, 2), (False, 3, 4), (True, 2, 3)):
+            got, sgf = pm.self_play(pm.EngineQueue(net, device_priors=priors), num_threads=threads, num_groups=groups, **kw)
+            assert got["digest"] == ref["digest"] and sorted(sgf) == sorted(sgf_ref), (priors, threads, groups)
+            assert got["evals"] == ref["evals"] and got["games_finished"] == 6 and got["moves"] == ref["moves"]
+        # a deadline in the middle of the run: the batches in flight are dropped, nothing hangs
+        cut, _ = pm.self_play(pm.EngineQueue(net), num_threads=2, max_seconds=0.3, **{**kw, "num_games": 1000, "max_plies": 722})
+        assert 0 < cut["evals"] and cut["seconds"] < 5.0
+    finally:
+        net.close()
+
+
 def test_whole_game_on_engine_matches_oracle_game(engine):
     """A self-play game on the engine, move for move against the oracle's self_play_one fed by the same engine."""
     import re

@@ -22,10 +22,14 @@ sys.path.insert(0, ROOT)
 
 
 def sample(net, *, games: int, parallel: int, rollouts: int, probes: int, seconds: float, threads: int, seed: int,
-           ex_it: bool = False, device_features: bool = True, cache_capacity: int = 0, ex_it_rollouts: int = 0):
-    """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics."""
+           ex_it: bool = False, device_features="queue", cache_capacity: int = 0, ex_it_rollouts: int = 0, device_priors=None):
+    """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics.
+    device_features: "queue" = the product path (leaf-batch queue, dg_selfplay_run_engine; device_priors None = chosen from
+    the host threads per GPU), "prior" / True / False = the blocking predictor calls (priors on the device / planes on the
+    device / planes on the host)."""
     from dream_go_b200 import mcts
-    predictor = (mcts.EnginePriorPredictor(net) if device_features == "prior" else mcts.EngineRawPredictor(net) if device_features
+    predictor = (mcts.EngineQueue(net, device_priors=device_priors) if device_features == "queue"
+                 else mcts.EnginePriorPredictor(net) if device_features == "prior" else mcts.EngineRawPredictor(net) if device_features
                  else mcts.EnginePredictor(net))
     st, sgf = mcts.self_play(predictor, num_games=games, num_parallel=parallel, num_rollout=rollouts,
                              probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=ex_it_rollouts or rollouts, seed=seed,
@@ -52,6 +56,11 @@ def main():
                     help="engine calls spin in the driver while they wait (default: they nap, DG_FLAG_BLOCKING_SYNC, and leave the cores to the search)")
     ap.add_argument("--blocking-sync", action="store_true", help="(the default now; kept for old command lines)")
     ap.add_argument("--device-priors", action="store_true", help="also build the priors on the device (dg_engine_forward_raw_prior)")
+    ap.add_argument("--host-priors", action="store_true", help="build the priors on the host even with few host threads per GPU")
+    ap.add_argument("--blocking-calls", action="store_true",
+                    help="drive the engine through the blocking predictor calls + one device thread per group (the round-1 driver) "
+                         "instead of the leaf-batch queue")
+    ap.add_argument("--no-graph", action="store_true", help="leaf batches are enqueued call by call (DG_FLAG_NO_GRAPH)")
     ap.add_argument("--host-features", action="store_true",
                     help="compute the feature planes on the host (compact positions) instead of on the device (raw positions)")
     args = ap.parse_args()
@@ -76,7 +85,10 @@ def main():
                        "sample": (f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-stone cap)"
                                   if args.seconds > 0 else "all games played to the end"),
                        "probes_per_round": args.probes, "feature_planes": "host" if args.host_features else "device (csrc/features.cu)",
-                       "priors": "device" if args.device_priors else "host", "host_threads_per_gpu": threads, "host_cores": cores,
+                       "priors": "device" if args.device_priors or (not args.host_priors and not args.blocking_calls and threads < 8) else "host",
+                       "driver": "blocking predictor calls, one device thread per group" if args.blocking_calls or args.host_features
+                                 else "leaf-batch queue (dg_selfplay_run_engine): one graph launch per batch, completion flag in pinned memory",
+                       "host_threads_per_gpu": threads, "host_cores": cores,
                        "weights": f"{args.blocks} blocks x 128 filters, seeded random init", "data": "synthetic"},
             "host_only": {"evals_per_s": host["evals"] / host["seconds"], "moves_per_s": host["moves"] / host["seconds"],
                           "mean_batch": host["mean_batch"], "predictor": "RandomPredictor (no device)"}}
@@ -85,13 +97,15 @@ def main():
         shards = shard.Shards(backend="nccl")
         tensors = weights.synthetic_network(seed=20261017, num_blocks=args.blocks)
         net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=512, num_workspaces=8,
-                                      flags=0 if args.spin_sync else nn.FLAG_BLOCKING_SYNC)
+                                      flags=(0 if args.spin_sync else nn.FLAG_BLOCKING_SYNC) | (nn.FLAG_NO_GRAPH if args.no_graph else 0))
         shards.barrier()
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
                          seconds=args.seconds, threads=threads, seed=shards.seed(20261017), ex_it=args.ex_it,
-                         device_features="prior" if args.device_priors else not args.host_features, cache_capacity=args.cache,
-                         ex_it_rollouts=args.ex_it_rollouts)
+                         device_features=("queue" if not (args.blocking_calls or args.host_features) else
+                                          "prior" if args.device_priors else not args.host_features),
+                         device_priors=True if args.device_priors else False if args.host_priors else None,
+                         cache_capacity=args.cache, ex_it_rollouts=args.ex_it_rollouts)
         wall = time.perf_counter() - t0
         tot = shards.selfplay_totals(st)
         shards.close()
