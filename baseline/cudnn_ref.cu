@@ -13,9 +13,11 @@
 #include <cuda_runtime.h>
 #include <cudnn.h>
 
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -266,6 +268,97 @@ int dgref_read_tower(void* h, uint16_t* out) {
     const __half* a = (r.blocks % 2 == 0) ? r.a : r.t;
     CK(cudaMemcpy(out, a, static_cast<size_t>(r.batch) * 361 * 128 * 2, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// ---- the reference's predictor under the reference's batching rules ------------------------------------------------
+// `NnPredictor::predict` (src/libdg_mcts/predictors/nn.rs:84-107) as the pool drives it: a batch holds at most
+// `--batch-size` leaves (default 16, config.rs:137; batch.rs:113 splits off the last max_batch_size events), at most
+// `max_num_threads() = 2 x devices` batches are alive at a time (nn.rs:64-67, batch.rs:98-105), the thread that cut a batch
+// blocks in `batch.forward` (worker_thread.rs:88-99), the features are plain fp16 NHWC tensors in pageable host memory
+// (23,104 bytes per leaf, batch.rs:87-91) and `nn::forward` copies them in and the outputs out with blocking copies.
+// Signature == dg_predict_fn (include/dg_mcts.h), so the product's self-play loop can run on it: the loop is then the
+// product's restatement of self_play.rs / tree.rs, the evaluation path is the reference's.
+struct Packed { uint32_t planes[361]; uint16_t k_bits, reserved; };   // == dg_packed_position
+
+struct RefPredictor {
+    int batch_size = 16, lanes = 2, device = 0;
+    std::vector<Ref*> refs;
+    std::vector<std::vector<uint16_t>> feats, value, policy;
+    std::vector<char> busy;
+    std::mutex m;
+    std::condition_variable cv;
+    long long calls = 0, leaves = 0;
+};
+
+int dgref_predictor_create(int device, int batch_size, int lanes, const View* views, int count, float temperature, void** out) {
+    if (batch_size < 8) batch_size = 8;             // the root evaluation is one call of 8 positions (lib.rs:97-111)
+    RefPredictor* p = new RefPredictor();
+    *out = p;
+    p->batch_size = batch_size;
+    p->lanes = lanes;
+    p->device = device;
+    for (int i = 0; i < lanes; i++) {
+        void* r = nullptr;
+        if (int rc = dgref_create(device, batch_size, views, count, temperature, &r)) return rc;
+        p->refs.push_back(static_cast<Ref*>(r));
+        p->feats.emplace_back(static_cast<size_t>(batch_size) * 361 * 32, 0);
+        p->value.emplace_back(batch_size);
+        p->policy.emplace_back(static_cast<size_t>(batch_size) * 362);
+        p->busy.push_back(0);
+    }
+    return 0;
+}
+
+int dgref_predict(void* ctx, const Packed* positions, int n, uint16_t* value, uint16_t* policy) {
+    RefPredictor& p = *static_cast<RefPredictor*>(ctx);
+    for (int at = 0; at < n; at += p.batch_size) {
+        const int m = n - at < p.batch_size ? n - at : p.batch_size;
+        int lane = -1;
+        {
+            std::unique_lock<std::mutex> lk(p.m);
+            p.cv.wait(lk, [&] { for (int i = 0; i < p.lanes; i++) if (!p.busy[i]) return true; return false; });
+            for (int i = 0; i < p.lanes; i++) if (!p.busy[i]) { lane = i; break; }
+            p.busy[lane] = 1;
+            p.calls++;
+            p.leaves += m;
+        }
+        uint16_t* f = p.feats[lane].data();
+        for (int i = 0; i < p.batch_size; i++) {        // a short batch is padded with its last position (cuDNN time is flat in the batch size here)
+            const Packed& q = positions[at + (i < m ? i : m - 1)];
+            uint16_t* o = f + static_cast<size_t>(i) * 361 * 32;
+            for (int pt = 0; pt < 361; pt++) {
+                const uint32_t mask = q.planes[pt];
+                o[pt * 32 + 0] = (mask & 1u) ? q.k_bits : 0;
+                o[pt * 32 + 1] = (mask & 2u) ? q.k_bits : 0;
+                for (int c = 2; c < 32; c++) o[pt * 32 + c] = ((mask >> c) & 1u) ? 0x3c00 : 0;
+            }
+        }
+        int rc = cudaSetDevice(p.device) == cudaSuccess ? 0 : -1;
+        if (rc == 0) rc = dgref_forward(p.refs[lane], f, p.value[lane].data(), p.policy[lane].data());
+        if (rc == 0) {
+            memcpy(value + at, p.value[lane].data(), static_cast<size_t>(m) * 2);
+            memcpy(policy + static_cast<size_t>(at) * 362, p.policy[lane].data(), static_cast<size_t>(m) * 362 * 2);
+        }
+        { std::lock_guard<std::mutex> lk(p.m); p.busy[lane] = 0; }
+        p.cv.notify_one();
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+void dgref_predictor_stats(void* ctx, long long* calls, long long* leaves) {
+    RefPredictor& p = *static_cast<RefPredictor*>(ctx);
+    std::lock_guard<std::mutex> lk(p.m);
+    *calls = p.calls;
+    *leaves = p.leaves;
+}
+
+void dgref_destroy(void* h);
+void dgref_predictor_destroy(void* ctx) {
+    if (!ctx) return;
+    RefPredictor* p = static_cast<RefPredictor*>(ctx);
+    for (Ref* r : p->refs) dgref_destroy(r);
+    delete p;
 }
 
 void dgref_destroy(void* h) {

@@ -14,7 +14,13 @@ JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 * roofline   : dominant kernel = tower_kernel (ONE persistent launch per step that runs the up-sampling
                layer and all 18 residual 3x3 128->128 convolutions); tensor bound.  `achieved` is timed
                live on the 18 residual convolutions alone (a second pass of tower-only launches).
-* cpu_baseline / --impl reference : the CPU oracle port of dg_nn::forward on the host cores.
+* sustained  : the same resident step repeated for >= 2 s of device time (the power-capped regime), against
+               MEASURED_PEAKS.json:bf16_tflops_sustained.
+* self_play  : the metric's other half -- moves/s and evals/s of `--self-play --num-rollout 800` for configs[2] (32
+               concurrent games), configs[3]'s shape (64 per GPU) and 128 per GPU, and at N = 1 the same loop on the
+               reference's cuDNN evaluation path under the reference's batching rules (`cudnn_reference`).
+* cudnn_baseline / vs_cudnn : the reference's 25-call cuDNN forward restated on this box's cuDNN -- the GPU-vs-GPU ratio.
+* cpu_baseline / --impl reference : the CPU oracle port of dg_nn::forward on the host cores (a GPU-vs-CPU figure).
 """
 from __future__ import annotations
 
@@ -32,7 +38,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH = 256
-SELF_PLAY_GAMES = 128
 NUM_BLOCKS = 9
 METRIC = "nn_evals_per_s"
 UNIT = "evals/s"
@@ -203,6 +208,59 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def self_play_samples(args, tensors, shards, rank: int, world: int, local_rank: int):
+    """Fixed-duration samples of `--self-play --num-rollout 800` from the empty board (random-init weights: games run to
+    the 722-ply cap) through the product path -- leaf-batch queue, planes / legal moves (/ priors) on the device:
+    configs[2] (32 concurrent games on one GPU), configs[3]'s shape (64 concurrent games per GPU) and 128 per GPU; at
+    N = 1 also the SAME self-play loop on the reference's evaluation path -- cuDNN restatement of dg_nn::forward under the
+    reference's batching rules (<= --batch-size leaves per batch, <= 2 batches in flight per GPU, one leaf per probe,
+    fp16 feature tensors from the host; pool/batch.rs:98-123, predictors/nn.rs:64-67) -- and the host half alone."""
+    from dream_go_b200 import mcts, nn
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_selfplay
+    threads = max(1, (os.cpu_count() or 1) // world)
+    secs = args.self_play_seconds
+    # its own engine, one workspace per group of games; waits nap instead of spinning on a core
+    sp_net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=2 * BATCH, num_workspaces=4, flags=nn.FLAG_BLOCKING_SYNC)
+    out = {"unit": "moves/s, evals/s", "rollouts": 800, "probes_per_round": 8, "host_threads_per_gpu": threads, "host_cores": os.cpu_count(),
+           "driver": "dg_selfplay_run_engine (leaf-batch queue, graph launch per batch, device planes)",
+           "priors": "device" if threads < 8 else "host", "sample_seconds": secs}
+    for key, games in (("configs2", 32), ("configs3_shape", 64), ("games128", 128)):
+        shards.barrier()
+        st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=games, rollouts=800, probes=8, seconds=secs, threads=threads,
+                                      seed=20261017 + rank)
+        tot = shards.selfplay_totals(st)
+        out[key] = {"concurrent_games_per_gpu": games, "moves_per_s": tot["moves_per_s"], "nn_evals_per_s": tot["nn_evals_per_s"],
+                    "mean_device_batch": tot["mean_device_batch"], "device_busy_frac": tot["predictor_seconds"] / (tot["seconds"] * world)}
+    sp_net.close()
+    if rank == 0 and world == 1:
+        # the reference's evaluation path behind the same loop
+        ref = {}
+        try:
+            from baseline import cudnn_ref
+            for bs in (16, 32):
+                pred = cudnn_ref.ReferencePredictor(tensors, batch_size=bs, lanes=2, device=local_rank)
+                # 2 groups of 16 games, bs / 16 leaves per game and round: every group round is one full batch, two in flight
+                st, _ = mcts.self_play(pred, num_games=100000, num_parallel=32, num_rollout=800, probes_per_round=max(1, bs // 16),
+                                       num_threads=threads, seed=20261017, max_seconds=min(secs, 8.0), num_groups=2)
+                ps = pred.stats()
+                pred.close()
+                ref[f"batch{bs}"] = {"moves_per_s": st["moves"] / st["seconds"], "nn_evals_per_s": st["evals"] / st["seconds"],
+                                     "mean_cudnn_batch": ps["mean_batch"], "concurrent_games": 32}
+            ref["rules"] = "cuDNN 9.10.2 forward, <= batch-size leaves per batch, <= 2 batches in flight, 1 leaf per probe, fp16 features from pageable host memory"
+        except Exception as exc:   # noqa: BLE001
+            ref = {"unavailable": repr(exc)[:200]}
+        out["cudnn_reference"] = ref
+        if "batch16" in ref:
+            out["configs2_vs_cudnn_reference"] = {"batch16": out["configs2"]["moves_per_s"] / ref["batch16"]["moves_per_s"],
+                                                  "batch32": out["configs2"]["moves_per_s"] / ref["batch32"]["moves_per_s"]}
+        # the host half alone: same search and feature code, RandomPredictor instead of the device
+        ho, _ = mcts.self_play(mcts.RandomPredictor(), num_games=100000, num_parallel=128, num_rollout=800,
+                               probes_per_round=8, num_threads=threads, seed=20261017, max_seconds=4.0)
+        out["host_only"] = {"nn_evals_per_s": ho["evals"] / ho["seconds"], "moves_per_s": ho["moves"] / ho["seconds"], "threads": threads}
+    return out
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     from dream_go_b200 import nn, shard, weights
 
@@ -258,32 +316,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     e2e_packed_s = max_over_ranks(time.perf_counter() - t0)
     clocks.__exit__()
 
+    # ---- sustained: the same resident step for >= 2 s of device time (power-capped clocks), L2 flushed between steps -------
+    sustained = None
+    if args.sustained_seconds > 0:
+        steps_sus = max(args.steps, int(args.sustained_seconds / (ms_per_step * 1e-3)) + 1)
+        barrier()
+        ms_sus, tower_ms_sus, _ = net.time_resident(BATCH, steps_sus, tower=True, flush_l2=True)
+        ms_sus = max_over_ranks(ms_sus)
+        sustained = {"steps": steps_sus, "timed_seconds": ms_sus * 1e-3, "value": world * BATCH * steps_sus / (ms_sus * 1e-3), "unit": UNIT,
+                     "tower_us_per_launch": tower_ms_sus * 1e3 / steps_sus}
+
     # ---- the metric's other half: self-play moves/s through the whole hot path (BASELINE.json configs[2]/[3]) -----
     self_play = None
     if args.self_play_seconds > 0:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import bench_selfplay
-        threads = max(1, (os.cpu_count() or 1) // world)
-        # its own engine, one workspace per group of games; its calls nap while they wait instead of spinning on a core
-        sp_net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=2 * BATCH, num_workspaces=4, flags=nn.FLAG_BLOCKING_SYNC)
-        barrier()
-        st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=SELF_PLAY_GAMES, rollouts=800, probes=8,
-                                      seconds=args.self_play_seconds, threads=threads, seed=20261017 + rank)
-        tot = shards.selfplay_totals(st)
-        sp_net.close()
-        host_only = None
-        if rank == 0:      # the host half alone: same search and feature code, RandomPredictor instead of the device
-            from dream_go_b200 import mcts
-            ho, _ = mcts.self_play(mcts.RandomPredictor(), num_games=100000, num_parallel=SELF_PLAY_GAMES, num_rollout=800,
-                                   probes_per_round=8, num_threads=threads, seed=20261017, max_seconds=4.0)
-            host_only = {"nn_evals_per_s": ho["evals"] / ho["seconds"], "moves_per_s": ho["moves"] / ho["seconds"],
-                         "threads": threads, "predictor": "dg_random_predict (no device; feature planes on the host)"}
-        self_play = {"moves_per_s": tot["moves_per_s"], "nn_evals_per_s": tot["nn_evals_per_s"], "unit": "moves/s, evals/s",
-                     "mean_device_batch": tot["mean_device_batch"],
-                     "predictor_time_frac": tot["predictor_seconds"] / (tot["seconds"] * world),   # the groups' device calls overlap, so this can exceed 1
-                     "workload": f"--self-play, --num-rollout 800, {SELF_PLAY_GAMES} concurrent games per GPU in 4 groups (host and device stages overlap), engine calls napping while they wait, real positions: "
-                                 f"feature planes + legal moves derived on the device from raw stones (ladder planes on the host), random-init weights; fixed-duration sample of {args.self_play_seconds:.0f} s",
-                     "host_threads_per_gpu": threads, "host_cores": os.cpu_count(), "host_only": host_only}
+        self_play = self_play_samples(args, tensors, shards, rank, world, local_rank)
 
     shards.close()
     if rank != 0:
@@ -296,10 +342,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get("tower_kernel_dram_bytes_per_launch")
+    peak_sus = None
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        with open(ppath) as fh:
+            peak_sus = json.load(fh).get("bf16_tflops_sustained")
     line = {
         "metric": METRIC, "value": value_evals, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
+    }
+    if self_play is not None:          # the metric's other half, next to the headline
+        line["self_play"] = self_play
+    line.update({
         "config": {**workload_config(world), "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)"},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_evals, "unit": UNIT, "h2d_bytes_per_step": BATCH * 11552 * 2, "d2h_bytes_per_step": BATCH * 363 * 2,
@@ -315,11 +370,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
                      "us_per_launch": tower_launch_s * 1e6, "us_per_conv_layer": tower_launch_s * 1e6 / (2 * NUM_BLOCKS),
                      "whole_net_frac": (value_evals / world) * FLOP_PER_EVAL / (peak_tf * 1e12)},
-    }
-    if self_play is not None:
-        line["self_play"] = self_play
+    })
+    if sustained is not None:
+        tf = 2 * NUM_BLOCKS * BATCH * TOWER_CONV_FLOP_PER_POS / (sustained["tower_us_per_launch"] * 1e-6) / 1e12
+        sustained["tower_tflops"] = tf
+        if peak_sus:
+            sustained["tower_frac_of_sustained_peak"] = tf / float(peak_sus)
+            sustained["sustained_peak"] = float(peak_sus)
+        line["sustained"] = sustained
     if world == 1 and not os.environ.get("DG_BENCH_SKIP_CPU"):      # skipped only under the profiler
         line["cudnn_baseline"] = cudnn_baseline(tensors, feats, args.steps)
+        if "value" in line["cudnn_baseline"]:      # the ratio the north star asks for: this engine vs the reference's cuDNN path, same box
+            line["vs_cudnn"] = {"resident": value_evals / line["cudnn_baseline"]["value"], "e2e": e2e_evals / line["cudnn_baseline"]["e2e"]}
         rate, info = oracle_rate(seconds_target=15.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
         line["host_features"] = host_feature_rates()
@@ -332,8 +394,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--self-play-seconds", type=float, default=0.0 if os.environ.get("DG_BENCH_SKIP_CPU") else 12.0,
-                    help="length of the self-play sample appended to the line (0 = skip)")
+    ap.add_argument("--self-play-seconds", type=float, default=0.0 if os.environ.get("DG_BENCH_SKIP_CPU") else 10.0,
+                    help="length of each self-play sample appended to the line (0 = skip)")
+    ap.add_argument("--sustained-seconds", type=float, default=0.0 if os.environ.get("DG_BENCH_SKIP_CPU") else 2.0,
+                    help="device time of the sustained resident measurement (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -210,7 +210,7 @@ class Tree:
 
 
 def _fn_ctx(predictor):
-    if isinstance(predictor, (EnginePredictor, EngineRawPredictor, EnginePriorPredictor, RandomPredictor)):
+    if hasattr(predictor, "fn") and hasattr(predictor, "ctx"):      # a native predictor: function pointer + context
         return predictor.fn, predictor.ctx
     return predictor, None
 

@@ -79,7 +79,8 @@ def test_full_network_batch_256_matches_oracle(full_engine, full_net, inputs):
     else:
         from oracle import go as ogo
         games = ogo.load_games()
-        feats = np.concatenate([ogo.replay(c[:160], m[:160], k, features=True)["features"][96:160] for c, m, k in games[3:7]])[:batch]
+        long_games = [g for g in games if len(g[1]) >= 160][:4]
+        feats = np.concatenate([ogo.replay(c[:160], m[:160], k, features=True)["features"][96:160] for c, m, k in long_games])[:batch]
         assert feats.shape == (batch, 361, 32)
     with full_engine.get_workspace(batch) as ws:
         value, policy = nn.forward(ws, np.ascontiguousarray(feats)).unwrap()
