@@ -305,6 +305,8 @@ int dgref_predictor_create(int device, int batch_size, int lanes, const View* vi
         p->value.emplace_back(batch_size);
         p->policy.emplace_back(static_cast<size_t>(batch_size) * 362);
         p->busy.push_back(0);
+        // first use loads cuDNN's kernels (seconds): not part of any timed sample
+        if (int rc = dgref_forward(p->refs.back(), p->feats.back().data(), p->value.back().data(), p->policy.back().data())) return rc;
     }
     return 0;
 }

@@ -193,7 +193,9 @@ def test_leaf_batch_queue_matches_blocking_forward(small_net, flags):
     try:
         raw = _raw_positions(150)
         want, want_legal, want_prior = net.forward_raw_prior(raw[:64])
-        with net.leaf_batch() as lb, net.leaf_batch() as lb2:
+        _, _, pa = net.forward_raw_prior(raw[64:128])
+        _, _, pb = net.forward_raw_prior(raw[128:150])
+        with net.leaf_batch() as lb, net.leaf_batch() as lb2:        # both workspaces of the engine: a blocking forward would wait now
             assert lb.capacity == 64
             for rnd, (lo, hi, prior) in enumerate([(0, 37, True), (0, 37, True), (3, 40, True), (0, 64, True), (10, 15, False), (0, 64, False)]):
                 order = [None] * (hi - lo)
@@ -228,8 +230,6 @@ def test_leaf_batch_queue_matches_blocking_forward(small_net, flags):
             lb2.wait()
             lb.wait()
             got = np.concatenate([lb.results(True)[3], lb2.results(True)[3]])
-            a, _, pa = net.forward_raw_prior(raw[64:128])
-            b, _, pb = net.forward_raw_prior(raw[128:150])
             assert (got.view(np.uint32) == np.concatenate([pa, pb]).view(np.uint32)).all()
             with pytest.raises(nn.Error):
                 lb.submit()                                    # already submitted, not reset
