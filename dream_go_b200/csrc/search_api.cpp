@@ -96,7 +96,8 @@ struct Game {
     bool allow_pass = false;
     Rng rng;
     SearchTask task;
-    std::unique_ptr<PredictionCache> cache;
+    std::unique_ptr<PredictionCache> cache;                      // this game's own table (cache_shared == 0)
+    long cache_hits_before = 0;
     std::string sgf;
     std::vector<uint16_t> moves;
     std::vector<dg_packed_position> batch;                       // this round's leaves (host feature planes) ...
@@ -132,6 +133,7 @@ struct Driver {
     std::string sgf_all;
     uint64_t digest = 0;
     int64_t total_moves = 0, total_evals = 0, total_searches = 0, total_cache_hits = 0;
+    PredictionCache* shared_cache = nullptr;                     // one table for every game (cfg.cache_shared), as predictors/nn.rs:48-50
 
     void start_game(Game& g) {
         g.clear_trees();
@@ -147,7 +149,7 @@ struct Driver {
         g.mode = Game::IDLE;
         g.sgf.clear();
         g.moves.clear();
-        g.cache.reset(cfg.cache_capacity > 0 ? new PredictionCache((size_t)cfg.cache_capacity) : nullptr);
+        g.cache.reset(cfg.cache_capacity > 0 && !shared_cache ? new PredictionCache((size_t)cfg.cache_capacity) : nullptr);
     }
 
     void finish_game(Game& g) {                                  // game_result.rs:23-93 (Ended)
@@ -176,7 +178,7 @@ struct Driver {
         total_moves += g.n_moves;
         total_evals += g.evals;
         total_searches += g.searches;
-        if (g.cache) { total_cache_hits += g.cache->hits; g.cache.reset(); }
+        if (g.cache) { total_cache_hits += g.cache->hits.load(); g.cache.reset(); }
         g.n_moves = g.evals = g.searches = 0;
         g.active = false;
         g.clear_trees();
@@ -193,7 +195,7 @@ struct Driver {
         opt.temperature = cfg.temperature;
         opt.num_rollout = ex_it ? cfg.num_ex_it_rollout : p.num_rollout(cfg.num_rollout);
         opt.policy_only = !ex_it && opt.num_rollout <= 1;
-        opt.cache = g.cache.get();
+        opt.cache = shared_cache ? shared_cache : g.cache.get();
         Node* tree = p.root;
         p.root = nullptr;
         if (tree && !g.allow_pass) tree->disqualify(PASS);
@@ -267,6 +269,24 @@ int32_t dg_random_predict(void* ctx, const dg_packed_position* positions, int32_
     return DG_OK;
 }
 
+// A peaked stand-in for a trained network (host only, measurement): policy = softmax(sharpness * u) with u uniform per
+// point and position, so a handful of moves carry the mass and searches go deep instead of wide.  ctx = float* sharpness
+// (NULL: 12).
+int32_t dg_peaked_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy) {
+    const float sharp = ctx ? *static_cast<const float*>(ctx) : 12.0f;
+    for (int i = 0; i < n; ++i) {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (int p = 0; p < N_POINTS; ++p) { h ^= positions[i].planes[p]; h *= 0x100000001b3ull; }
+        Rng rng(h ^ positions[i].k_bits);
+        value[i] = f32_to_f16_bits((float)(0.6 * rng.uniform() - 0.3));
+        float x[362], total = 0.0f;
+        for (int k = 0; k < 362; ++k) { x[k] = std::exp(sharp * ((float)rng.uniform() - 1.0f)); total += x[k]; }
+        float recip = 1.0f / total;
+        for (int k = 0; k < 362; ++k) policy[(size_t)i * 362 + k] = f32_to_f16_bits(x[k] * recip);
+    }
+    return DG_OK;
+}
+
 int32_t dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
                         const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                         int64_t* evals_out) {
@@ -295,11 +315,14 @@ int32_t dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_opti
 }
 
 dg_cache* dg_cache_new(int32_t capacity) { return reinterpret_cast<dg_cache*>(new PredictionCache(capacity > 0 ? (size_t)capacity : 0)); }
+dg_cache* dg_cache_new_shared(int32_t capacity, int32_t stripes) {
+    return reinterpret_cast<dg_cache*>(new PredictionCache(capacity > 0 ? (size_t)capacity : 0, stripes > 0 ? stripes : 64));
+}
 void dg_cache_free(dg_cache* cache) { delete reinterpret_cast<PredictionCache*>(cache); }
 void dg_cache_stats(const dg_cache* cache, int64_t* hits, int64_t* misses, int64_t* size) {
     const PredictionCache* c = reinterpret_cast<const PredictionCache*>(cache);
-    if (hits) *hits = c->hits;
-    if (misses) *misses = c->misses;
+    if (hits) *hits = c->hits.load();
+    if (misses) *misses = c->misses.load();
     if (size) *size = (int64_t)c->size();
 }
 
@@ -339,6 +362,11 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     const bool prior_mode = prior_predictor != nullptr || (engine_mode && engine_priors);
     Driver d;
     d.cfg = *config;
+    std::unique_ptr<PredictionCache> process_table;
+    if (config->cache_capacity > 0 && config->cache_shared) {
+        process_table.reset(new PredictionCache((size_t)config->cache_capacity, config->cache_shared));
+        d.shared_cache = process_table.get();
+    }
     if (d.cfg.max_plies <= 0 || d.cfg.max_plies > 722) d.cfg.max_plies = 722;
     int hw = (int)std::thread::hardware_concurrency();
     int n_threads = d.cfg.num_threads > 0 ? d.cfg.num_threads : (hw > 0 ? hw : 1);
@@ -529,14 +557,13 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         int32_t push_rc = DG_OK;
         for (int s : grp.slots) {
             Game& g = d.games[s];
-            if (g.n_emitted == -1) {
+            while (g.n_emitted == -1) {                          // (a game answered entirely by the transposition table ends at once)
                 g.n_emitted = 0;
                 g.active = true;
                 d.finish_game(g);
                 if (d.started < d.cfg.num_games && !out_of_time()) {
                     d.start_game(g);
                     advance(g, nullptr, nullptr, nullptr, nullptr);
-                    if (g.n_emitted == -1) { g.n_emitted = 0; g.active = false; }
                 }
             }
             if (g.active && g.n_emitted > 0) {
@@ -718,8 +745,9 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     // account for the games that were cut off by max_seconds
     for (Game& g : d.games) {
         d.total_moves += g.n_moves; d.total_evals += g.evals; d.total_searches += g.searches;
-        if (g.cache) d.total_cache_hits += g.cache->hits;
+        if (g.cache) d.total_cache_hits += g.cache->hits.load();
     }
+    if (d.shared_cache) d.total_cache_hits += d.shared_cache->hits.load();
     if (stats) {
         stats->games_finished = d.finished;
         stats->moves = d.total_moves;

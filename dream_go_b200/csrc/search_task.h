@@ -12,6 +12,8 @@
 #include <immintrin.h>
 
 #include <atomic>
+#include <memory>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -27,7 +29,11 @@ inline float f16_to_f32(uint16_t h) { return _cvtsh_ss(h); }     // exact (F16C)
 // (`cache` stores with_transform(response, symmetry.inverse()), `fetch` returns with_transform(entry, symmetry),
 // predictor.rs:30-44), so one evaluation answers the position under every symmetry.  `get` makes the entry the most
 // recent one, `insert` of an existing key does nothing, the least recent entry is dropped beyond `capacity`.
-// One table per game (the reference shares one behind a mutex; per-game tables keep the games reproducible).
+// The reference keeps ONE table of 200,000 entries for the whole process behind one mutex (nn.rs:48-50).  Here a table
+// has `stripes` independent LRU lists, each behind its own lock (a key lives in the stripe its hash selects): one stripe
+// is exactly the reference's table; many stripes are the process-wide table that all games and worker threads share
+// without queueing on one lock (eviction is then least-recent within a stripe).  A per-game single-stripe table keeps the
+// games a function of the seed; a shared one, like the reference's, makes them depend on the other games' timing.
 class PredictionCache {
   public:
     struct Entry {
@@ -37,40 +43,57 @@ class PredictionCache {
         uint16_t policy[362];
         int32_t prev, next;
     };
-    explicit PredictionCache(size_t capacity) : capacity_(capacity) {}
-    size_t size() const { return map_.size(); }
-    long hits = 0, misses = 0;
+    explicit PredictionCache(size_t capacity, int stripes = 1) {
+        size_t n = (size_t)(stripes < 1 ? 1 : stripes);
+        if (capacity > 0 && capacity < n) n = capacity;
+        for (size_t i = 0; i < n; ++i) {
+            stripes_.emplace_back(new Stripe());
+            stripes_.back()->capacity = capacity / n;
+        }
+    }
+    size_t size() const {
+        size_t n = 0;
+        for (const auto& st : stripes_) { std::lock_guard<std::mutex> g(st->m); n += st->map.size(); }
+        return n;
+    }
+    std::atomic<long> hits{0}, misses{0};
 
-    const Entry* get(uint64_t hash, int to_move) {
-        auto it = map_.find(Key{hash, (uint8_t)to_move});
-        if (it == map_.end()) { ++misses; return nullptr; }
-        ++hits;
-        detach(it->second);
-        attach(it->second);
-        return &pool_[it->second];
+    // Copies the entry out (the table may drop it the moment the lock is released); true on a hit.
+    bool get(uint64_t hash, int to_move, Entry* out) {
+        Stripe& st = stripe(hash);
+        std::lock_guard<std::mutex> g(st.m);
+        auto it = st.map.find(Key{hash, (uint8_t)to_move});
+        if (it == st.map.end()) { misses.fetch_add(1, std::memory_order_relaxed); return false; }
+        hits.fetch_add(1, std::memory_order_relaxed);
+        st.detach(it->second);
+        st.attach(it->second);
+        *out = st.pool[it->second];
+        return true;
     }
     // `policy` is in orientation `symmetry`; it is stored un-transformed
     void insert(uint64_t hash, int to_move, int symmetry, uint16_t value, const uint16_t* policy) {
-        if (capacity_ == 0) return;
+        Stripe& st = stripe(hash);
+        if (st.capacity == 0) return;
         Key key{hash, (uint8_t)to_move};
-        if (map_.count(key)) return;
+        std::lock_guard<std::mutex> g(st.m);
+        if (st.map.count(key)) return;
         int32_t idx;
-        if (!free_.empty()) { idx = free_.back(); free_.pop_back(); }
-        else { idx = (int32_t)pool_.size(); pool_.emplace_back(); }
-        Entry& e = pool_[idx];
+        if (!st.free.empty()) { idx = st.free.back(); st.free.pop_back(); }
+        else { idx = (int32_t)st.pool.size(); st.pool.emplace_back(); }
+        Entry& e = st.pool[idx];
         e.hash = hash;
         e.to_move = (uint8_t)to_move;
         e.value = value;
         const uint16_t* inv = tables().sym[tables().sym_inverse[symmetry]];
         for (int i = 0; i < N_POINTS; ++i) e.policy[inv[i]] = policy[i];     // with_transform(response, symmetry.inverse())
         e.policy[PASS] = policy[PASS];
-        attach(idx);
-        map_.emplace(key, idx);
-        if (map_.size() > capacity_) {
-            int32_t t = tail_;
-            detach(t);
-            map_.erase(Key{pool_[t].hash, pool_[t].to_move});
-            free_.push_back(t);
+        st.attach(idx);
+        st.map.emplace(key, idx);
+        if (st.map.size() > st.capacity) {
+            int32_t t = st.tail;
+            st.detach(t);
+            st.map.erase(Key{st.pool[t].hash, st.pool[t].to_move});
+            st.free.push_back(t);
         }
     }
 
@@ -81,25 +104,32 @@ class PredictionCache {
         bool operator==(const Key& o) const { return hash == o.hash && to_move == o.to_move; }
     };
     struct KeyHash { size_t operator()(const Key& k) const { return (size_t)(k.hash * 0x9e3779b97f4a7c15ull) ^ k.to_move; } };
-    void attach(int32_t i) {
-        pool_[i].prev = -1;
-        pool_[i].next = head_;
-        if (head_ >= 0) pool_[head_].prev = i;
-        head_ = i;
-        if (tail_ < 0) tail_ = i;
+    struct Stripe {
+        mutable std::mutex m;
+        size_t capacity = 0;
+        std::vector<Entry> pool;
+        std::vector<int32_t> free;
+        std::unordered_map<Key, int32_t, KeyHash> map;
+        int32_t head = -1, tail = -1;
+        void attach(int32_t i) {
+            pool[i].prev = -1;
+            pool[i].next = head;
+            if (head >= 0) pool[head].prev = i;
+            head = i;
+            if (tail < 0) tail = i;
+        }
+        void detach(int32_t i) {
+            Entry& e = pool[i];
+            if (e.prev >= 0) pool[e.prev].next = e.next;
+            if (e.next >= 0) pool[e.next].prev = e.prev;
+            if (head == i) head = e.next;
+            if (tail == i) tail = e.prev;
+        }
+    };
+    Stripe& stripe(uint64_t hash) {
+        return stripes_.size() == 1 ? *stripes_[0] : *stripes_[(size_t)((hash * 0xd6e8feb86659fd93ull) >> 32) % stripes_.size()];
     }
-    void detach(int32_t i) {
-        Entry& e = pool_[i];
-        if (e.prev >= 0) pool_[e.prev].next = e.next;
-        if (e.next >= 0) pool_[e.next].prev = e.prev;
-        if (head_ == i) head_ = e.next;
-        if (tail_ == i) tail_ = e.prev;
-    }
-    size_t capacity_;
-    std::vector<Entry> pool_;
-    std::vector<int32_t> free_;
-    std::unordered_map<Key, int32_t, KeyHash> map_;
-    int32_t head_ = -1, tail_ = -1;
+    std::vector<std::unique_ptr<Stripe>> stripes_;
 };
 
 // What create_initial_policy (pool/policy_helper.rs:28-75) derives from the board alone; computed when the leaf is
@@ -256,7 +286,8 @@ class SearchTask {
         if (phase_ == DONE) return 0;
         if (phase_ == ROOT && opt_.cache) {
             // full_forward (lib.rs:97-111): a cached evaluation answers all 8 symmetries without the network
-            const PredictionCache::Entry* hit = opt_.cache->get(board_.hash, color_);
+            PredictionCache::Entry entry;
+            const PredictionCache::Entry* hit = opt_.cache->get(board_.hash, color_, &entry) ? &entry : nullptr;
             if (hit) opt_.cache->hits += 7; else opt_.cache->misses += 7;      // the reference asks once per symmetry
             if (hit) {
                 uint8_t legal[N_POINTS];
@@ -311,7 +342,8 @@ class SearchTask {
             p.to_move = opposite(p.trace.back().node->to_move);
             p.symmetry = next_leaf_symmetry();
             if (opt_.cache) {                                // Event::predict (pool/event.rs:50-52): fetch before extracting
-                if (const PredictionCache::Entry* hit = opt_.cache->get(p.board.hash, p.to_move)) {
+                PredictionCache::Entry entry;
+                if (const PredictionCache::Entry* hit = opt_.cache->get(p.board.hash, p.to_move, &entry) ? &entry : nullptr) {
                     uint8_t legal[N_POINTS];
                     for (int q = 0; q < N_POINTS; ++q) legal[q] = (uint8_t)p.board.is_valid(p.to_move, q);
                     p.plan.build(p.board, p.to_move, opt_.search_kind, legal);

@@ -32,7 +32,7 @@ class _SelfPlayConfig(C.Structure):
                 ("probes_per_round", C.c_int32), ("max_plies", C.c_int32), ("num_threads", C.c_int32),
                 ("ex_it", C.c_int32), ("num_ex_it_rollout", C.c_int32), ("dirichlet_noise", C.c_float),
                 ("temperature", C.c_float), ("seed", C.c_uint64), ("max_seconds", C.c_double),
-                ("cache_capacity", C.c_int32), ("num_groups", C.c_int32)]
+                ("cache_capacity", C.c_int32), ("num_groups", C.c_int32), ("cache_shared", C.c_int32)]
 
 
 class _SelfPlayStats(C.Structure):
@@ -46,6 +46,7 @@ _P, _I = C.c_void_p, C.c_int32
 ABI = {
     "dg_engine_predict": (_I, [_P, _P, _I, _P, _P]),
     "dg_random_predict": (_I, [_P, _P, _I, _P, _P]),
+    "dg_peaked_predict": (_I, [_P, _P, _I, _P, _P]),
     "dg_engine_predict_raw": (_I, [_P, _P, _I, _P, _P, _P]),
     "dg_engine_predict_prior": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "dg_mcts_predict_prior": (_I, [PREDICT_PRIOR_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
@@ -56,7 +57,7 @@ ABI = {
     "dg_selfplay_run_raw": (_I, [PREDICT_RAW_FN, _P, C.POINTER(_SelfPlayConfig), C.POINTER(_SelfPlayStats), _P, C.c_int64]),
     "dg_mcts_predict": (_I, [PREDICT_FN, _P, C.POINTER(_SearchOptions), _P, _P, _I, C.POINTER(C.c_float),
                              C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
-    "dg_cache_new": (_P, [_I]), "dg_cache_free": (None, [_P]),
+    "dg_cache_new": (_P, [_I]), "dg_cache_new_shared": (_P, [_I, _I]), "dg_cache_free": (None, [_P]),
     "dg_cache_stats": (None, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dg_tree_free": (None, [_P]), "dg_tree_forward": (_P, [_P, _I]), "dg_tree_disqualify": (None, [_P, _I]),
     "dg_tree_total_count": (_I, [_P]), "dg_tree_to_move": (_I, [_P]), "dg_tree_initial_value": (C.c_float, [_P]),
@@ -146,11 +147,21 @@ class RandomPredictor:
         self.ctx = None
 
 
+class PeakedPredictor:
+    """A peaked stand-in for a trained network (host only): searches go deep instead of wide."""
+
+    def __init__(self, sharpness: float = 12.0):
+        self._sharp = C.c_float(sharpness)
+        self.fn = C.cast(lib().dg_peaked_predict, PREDICT_FN)
+        self.ctx = C.cast(C.pointer(self._sharp), C.c_void_p)
+
+
 class Cache:
     """Transposition table of evaluations (`NnPredictor`'s `LruCache`, predictors/nn.rs:29-82)."""
 
-    def __init__(self, capacity: int = 200_000):
-        self._h = lib().dg_cache_new(capacity)
+    def __init__(self, capacity: int = 200_000, stripes: int = 0):
+        """stripes = 0: one LRU list behind one lock (the reference's table); n > 0: n lock stripes (shared by many searches)."""
+        self._h = lib().dg_cache_new_shared(capacity, stripes) if stripes > 0 else lib().dg_cache_new(capacity)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -246,10 +257,10 @@ def predict(predictor, board: "go.Board", color: int, *, search: int = go.STANDA
 def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout: int = 800, probes_per_round: int = 8,
               max_plies: int = 722, num_threads: int = 0, ex_it: bool = False, num_ex_it_rollout: int = 800,
               dirichlet_noise: float = 0.25, temperature: float = 0.8, seed: int = 1, max_seconds: float = 0.0,
-              cache_capacity: int = 0, num_groups: int = 0, sgf_capacity: int = 1 << 24):
+              cache_capacity: int = 0, num_groups: int = 0, sgf_capacity: int = 1 << 24, cache_shared: int = 0):
     """`dg_mcts::self_play`: returns (stats dict, list of SGF records)."""
     cfg = _SelfPlayConfig(num_games, num_parallel, num_rollout, probes_per_round, max_plies, num_threads, int(ex_it),
-                          num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds, cache_capacity, num_groups)
+                          num_ex_it_rollout, dirichlet_noise, temperature, seed, max_seconds, cache_capacity, num_groups, cache_shared)
     stats = _SelfPlayStats()
     buf = C.create_string_buffer(sgf_capacity)
     if isinstance(predictor, EngineQueue):

@@ -45,6 +45,9 @@ int32_t dg_engine_predict_prior(void* engine, const dg_raw_position* positions, 
 /* `RandomPredictor` (predictors/random.rs:30-59) as a deterministic function of the position; ctx = NULL or a
  * uint64_t* salt.  No device involved: it measures the host half of self-play alone. */
 int32_t dg_random_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
+/* The same with a PEAKED policy (softmax(sharpness * u), ctx = float* sharpness or NULL for 12): a stand-in for a trained
+ * network's narrow, deep searches when measuring the host side (transposition-table hit rates, tree depth). */
+int32_t dg_peaked_predict(void* ctx, const dg_packed_position* positions, int32_t n, uint16_t* value, uint16_t* policy);
 
 struct dg_cache;
 typedef struct dg_search_options {
@@ -65,7 +68,10 @@ typedef struct dg_search_options {
 /* Transposition table `LruCache<(zobrist hash, to_move), Prediction>` (src/libdg_mcts/predictors/nn.rs:29-82,
  * lru_cache.rs): entries are kept in identity orientation and answer every symmetry (predictor.rs:30-44). */
 typedef struct dg_cache dg_cache;
-dg_cache* dg_cache_new(int32_t capacity);                 /* the reference: 200,000, one table for the process */
+dg_cache* dg_cache_new(int32_t capacity);                 /* one LRU list behind one lock: the reference's table (200,000 entries) */
+/* The same table split into `stripes` LRU lists with a lock each (<= 0: 64): many searches on many threads share it without
+ * queueing on one mutex; eviction is least-recent within a stripe.  Every dg_cache is safe to use from several threads. */
+dg_cache* dg_cache_new_shared(int32_t capacity, int32_t stripes);
 void      dg_cache_free(dg_cache* cache);
 void      dg_cache_stats(const dg_cache* cache, int64_t* hits, int64_t* misses, int64_t* size);
 
@@ -109,6 +115,9 @@ typedef struct dg_selfplay_config {
     double   max_seconds;         /* stop starting new rounds after this much wall time (<= 0: no limit)                */
     int32_t  cache_capacity;      /* entries of each game's transposition table (0 = none); see dg_cache                */
     int32_t  num_groups;          /* groups of games, each either on the host or on the device (1..8); 0 = chosen from num_parallel * probes_per_round */
+    int32_t  cache_shared;        /* 0: one table of cache_capacity entries per game (games stay a function of the seed);
+                                     n > 0: ONE table of cache_capacity entries in n lock stripes shared by all games, as the
+                                     reference's process-wide LRU (predictors/nn.rs:48-50) -- games then depend on each other's timing */
 } dg_selfplay_config;
 
 typedef struct dg_selfplay_stats {

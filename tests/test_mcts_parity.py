@@ -273,6 +273,55 @@ def test_self_play_with_tables_is_reproducible_and_saves_evaluations():
     assert a["evals"] < c["evals"] and c["cache_hits"] == 0
 
 
+def test_striped_table_keeps_the_reference_semantics_per_stripe_and_survives_many_threads():
+    """dg_cache_new_shared: a one-stripe table searches exactly like dg_cache_new (the reference's single LRU); a striped one
+    shared by concurrent searches on several threads stays consistent (size <= capacity, hits + misses = lookups) and a
+    second pass over the same positions is answered from it."""
+    import threading
+    plays, komi = corpus_position(30, 50)
+    po, oo = boards(plays, komi)
+    color = po.to_move()
+    stub = hash_predictor(1.2)
+    kw = dict(deterministic=True, num_rollout=110, probes_per_round=3, leaf_symmetries=[0, 4, 7, 2, 5])
+    one, ref = pm.Cache(48, stripes=1), pm.Cache(48)
+    _, i1, t1, e1 = pm.predict(pm.python_predictor(stub), po, color, cache=one, **kw)
+    _, i2, t2, e2 = pm.predict(pm.python_predictor(stub), po, color, cache=ref, **kw)
+    assert (t1.children()[0] == t2.children()[0]).all() and i1 == i2 and e1 == e2 and one.stats() == ref.stats()
+    # many searches at once on one striped table (RandomPredictor: native, releases the GIL inside the search)
+    shared = pm.Cache(20000, stripes=16)
+    positions = []
+    for game in (3, 8, 12, 30):
+        pl, km = corpus_position(game, 40)
+        positions.append(boards(pl, km)[0])
+    evals = [[0, 0] for _ in positions]
+
+    def worker(k, rnd):
+        b = positions[k]
+        _, _, _, ev = pm.predict(pm.RandomPredictor(), b, b.to_move(), deterministic=True, num_rollout=300, probes_per_round=4,
+                                 leaf_symmetries=[k, 1, 5], cache=shared)
+        evals[k][rnd] = ev
+
+    for rnd in range(2):
+        threads = [threading.Thread(target=worker, args=(k, rnd)) for k in range(len(positions))]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+    st = shared.stats()
+    assert 0 < st["size"] <= 20000 and st["hits"] > 0
+    assert all(second < first for first, second in evals), evals      # the second pass finds the first one's evaluations
+
+
+def test_self_play_with_one_shared_table():
+    """cache_shared: one process-wide table for every game (predictors/nn.rs:48-50) instead of one per game."""
+    kw = dict(num_games=12, num_parallel=2, num_rollout=24, probes_per_round=2, max_plies=8, seed=3, num_threads=2)
+    own, _ = pm.self_play(pm.RandomPredictor(), cache_capacity=4096, **kw)
+    shared, games = pm.self_play(pm.RandomPredictor(), cache_capacity=200000, cache_shared=16, **kw)
+    none, _ = pm.self_play(pm.RandomPredictor(), cache_capacity=0, **kw)
+    assert shared["games_finished"] == 12 and len(games) == 12 and shared["moves"] == none["moves"] == 96
+    # every game opens on the same empty board: only a shared table lets the later games reuse the earlier games' opening
+    # evaluations (the root's 8 symmetries and the first plies of the tree)
+    assert shared["cache_hits"] > own["cache_hits"] > 0 and shared["evals"] < own["evals"] < none["evals"]
+
+
 # ---- self-play records (self_play.rs:187-214, game_result.rs:23-43) --------------------------------------------------
 
 def parse_record(sgf: str):
