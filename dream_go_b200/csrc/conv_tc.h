@@ -73,6 +73,7 @@ struct TowerParams {
     uint32_t gen;                           // flag base of this launch: done[tile] = gen + layers completed
     uint32_t* done;                         // [ntiles rounded up to even] progress flags
     long long* trace;
+    int late_a;                             // debug (DG_FLAG_TOWER_LATE_A): request a layer's first windows after its filter slabs
 };
 
 cudaError_t launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream);

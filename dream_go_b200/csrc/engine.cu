@@ -500,7 +500,7 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
         }
         if (nl > 0) {
             tp.nlayers = nl;
-            tp.ntiles = dg_num_tiles(batch);
+            tp.ntiles = 3 * batch;                    // position-aligned tiles (conv_tc2.cu: tower_tile_base)
             tp.valid_rows = batch * DG_POS_ROWS;
             const int nunits = (tp.ntiles + 1) / 2;
             const int pairs = std::min(e->num_sms / 2, nunits);
@@ -518,6 +518,7 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
             }
             tp.done = w.done;
             tp.trace = e->trace_buf;
+            tp.late_a = (e->cfg.flags & DG_FLAG_TOWER_LATE_A) ? 1 : 0;
             DG_CUDA(e, dg::launch_tower(tp, e->num_sms, w.stream));
         }
     } else {

@@ -213,6 +213,194 @@ __device__ void plan_candidates(PlanScratch* S, const uint8_t* col, const uint16
     }
 }
 
+
+// ---- ladder reading on the device (utils/ladder.rs:53-179) ------------------------------------------------------------------
+// The two ladder planes (features.rs:223-231) are a search: play the atari, extend the chain, count its liberties, recurse
+// while it has exactly two.  One WARP per reading.  A board is two registers per lane -- lane y holds the 19-bit row masks
+// of the black and of the white stones of board line y (lanes 19..31 hold zeros) -- so a board copy is two moves, a chain is
+// a flood fill over rows (occluded Kogge-Stone fill along the row, one shuffle up and one down per sweep), liberties are a
+// dilation, captures are "flood the neighbouring chain, no liberty -> clear it".  Nothing is kept incrementally: every
+// answer is derived from the two masks, which is what makes the per-step board copies of the reference free here.
+// Branches (both liberties of the extended chain are tried, ladder.rs:112-118) go on a per-lane stack in local memory; the
+// answer is "any branch captures", so the order in which they are read does not matter.  Neighbour order E, S, W, N
+// (iter/adjacent_iter.rs:42-43) decides which chain is extended first, as in the reference.
+namespace lad {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t ROW = 0x7ffffu;
+constexpr int CAP = 128;      // pending branches: one per step of the line being read; a 19 x 19 board cannot hold a ladder this long
+
+struct B2 { uint32_t s[2]; };                                    // [0] black rows, [1] white rows
+
+__device__ __forceinline__ uint32_t up(uint32_t v, int lane) { const uint32_t r = __shfl_up_sync(FULL, v, 1); return lane ? r : 0u; }
+__device__ __forceinline__ uint32_t down(uint32_t v) { return __shfl_down_sync(FULL, v, 1); }     // lane 31 reads its own 0
+__device__ __forceinline__ uint32_t dilate(uint32_t v, int lane, uint32_t rm) { return ((v << 1) | (v >> 1) | up(v, lane) | down(v)) & rm; }
+__device__ __forceinline__ uint32_t pt(int p, int lane) { return lane == p / 19 ? 1u << (p % 19) : 0u; }
+__device__ __forceinline__ int count(uint32_t v) { return static_cast<int>(__reduce_add_sync(FULL, static_cast<unsigned>(__popc(v)))); }
+__device__ __forceinline__ bool any(uint32_t v) { return __any_sync(FULL, v != 0); }
+__device__ __forceinline__ int first_point(uint32_t v) {          // lowest point of a non-empty set (warp-uniform)
+    const int y = __ffs(__ballot_sync(FULL, v != 0)) - 1;
+    return y * 19 + __ffs(__shfl_sync(FULL, v, y)) - 1;
+}
+
+// connected component of `mask` that contains `seed`
+__device__ uint32_t flood(uint32_t seed, uint32_t mask, int lane) {
+    uint32_t cur = seed & mask;
+    for (;;) {
+        uint32_t g = cur, p = mask;
+        g |= p & (g << 1); p &= p << 1;
+        g |= p & (g << 2); p &= p << 2;
+        g |= p & (g << 4); p &= p << 4;
+        g |= p & (g << 8); p &= p << 8;
+        g |= p & (g << 16);
+        uint32_t h = cur;
+        p = mask;
+        h |= p & (h >> 1); p &= p >> 1;
+        h |= p & (h >> 2); p &= p >> 2;
+        h |= p & (h >> 4); p &= p >> 4;
+        h |= p & (h >> 8); p &= p >> 8;
+        h |= p & (h >> 16);
+        const uint32_t x = g | h;
+        const uint32_t nxt = x | ((up(x, lane) | down(x)) & mask);
+        const bool changed = __any_sync(FULL, nxt != cur);
+        cur = nxt;
+        if (!changed) return cur;
+    }
+}
+
+// BoardFast::place (board_fast.rs:441-474) without the hash: plays colour index ci at p, removes the enemy chains that lose
+// their last liberty, returns the liberties of the chain the stone belongs to (0 = the move was suicide).
+__device__ int place(B2& b, int ci, int p, int lane, uint32_t rm) {
+    const uint32_t stone = pt(p, lane);
+    const uint32_t own = b.s[ci] | stone;
+    uint32_t opp = b.s[ci ^ 1];
+    uint32_t nb = dilate(stone, lane, rm) & opp;
+    while (any(nb)) {
+        const uint32_t f = flood(pt(first_point(nb), lane), opp, lane);
+        if (!any(dilate(f, lane, rm) & ~(own | opp))) opp &= ~f;
+        nb &= ~f;
+    }
+    b.s[ci] = own;
+    b.s[ci ^ 1] = opp;
+    return count(dilate(flood(stone, own, lane), lane, rm) & ~(own | opp));
+}
+
+// `_can_escape_with_capture` (ladder.rs:33-41): some enemy chain next to the chain `f` (colour index ci) is in atari
+__device__ bool chain_can_capture(const B2& b, int ci, uint32_t f, int lane, uint32_t rm) {
+    const uint32_t enemy = b.s[ci ^ 1], occupied = b.s[0] | b.s[1];
+    uint32_t a = dilate(f, lane, rm) & enemy;
+    while (any(a)) {
+        const uint32_t g = flood(pt(first_point(a), lane), enemy, lane);
+        if (count(dilate(g, lane, rm) & ~occupied) < 2) return true;
+        a &= ~g;
+    }
+    return false;
+}
+
+// `_is_ladder_capture` (ladder.rs:53-119) once the attacker (colour index ci) has played p on `start`
+__device__ bool capture_search(const B2& start, int ci, int p0, int lane, uint32_t rm, uint32_t* st0, uint32_t* st1, int16_t* stp) {
+    const int oi = ci ^ 1;
+    int top = 1;
+    st0[0] = start.s[0];
+    st1[0] = start.s[1];
+    stp[0] = static_cast<int16_t>(p0);
+    while (top > 0) {
+        --top;
+        B2 b;
+        b.s[0] = st0[top];
+        b.s[1] = st1[top];
+        const int p = stp[top];
+        const int px = p % 19, py = p / 19;
+        // the first neighbouring enemy chain that is in atari, cannot capture its way out and may extend into its liberty
+        int run = -1, nl = 0;
+        B2 t = b;
+#pragma unroll 1
+        for (int k = 0; k < 4 && run < 0; k++) {
+            const int qx = px + (k == 0) - (k == 2), qy = py - (k == 1) + (k == 3);
+            if (qx < 0 || qx > 18 || qy < 0 || qy > 18) continue;
+            if (!((__shfl_sync(FULL, b.s[oi], qy) >> qx) & 1u)) continue;
+            const uint32_t f = flood(pt(qy * 19 + qx, lane), b.s[oi], lane);
+            const uint32_t libs = dilate(f, lane, rm) & ~(b.s[0] | b.s[1]);
+            if (count(libs) != 1) continue;                                   // not in atari
+            if (chain_can_capture(b, oi, f, lane, rm)) continue;
+            const int lib = first_point(libs);
+            t = b;
+            nl = place(t, oi, lib, lane, rm);                                 // 0: the extension is not a legal move
+            if (nl > 0) run = lib;
+        }
+        if (run < 0) continue;                                                // this line of play captures nothing
+        if (nl < 2) return true;                                              // still in atari after extending: captured
+        if (nl >= 3) continue;                                                // escaped
+        b = t;
+        const int rx = run % 19, ry = run / 19;
+        // the extension put one of the attacker's chains into atari: no ladder (ladder.rs:97-103)
+        bool atari = false;
+        uint32_t seen = 0;
+#pragma unroll 1
+        for (int k = 0; k < 4 && !atari; k++) {
+            const int qx = rx + (k == 0) - (k == 2), qy = ry - (k == 1) + (k == 3);
+            if (qx < 0 || qx > 18 || qy < 0 || qy > 18) continue;
+            const uint32_t q = pt(qy * 19 + qx, lane);
+            if (!any(q & b.s[ci]) || any(q & seen)) continue;
+            const uint32_t f = flood(q, b.s[ci], lane);
+            seen |= f;
+            atari = count(dilate(f, lane, rm) & ~(b.s[0] | b.s[1])) < 2;
+        }
+        if (atari) continue;
+        // every legal attacker move next to the extension is a branch (ladder.rs:109-118)
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            const int qx = rx + (k == 0) - (k == 2), qy = ry - (k == 1) + (k == 3);
+            if (qx < 0 || qx > 18 || qy < 0 || qy > 18) continue;
+            const int q = qy * 19 + qx;
+            if (any(pt(q, lane) & (b.s[0] | b.s[1]))) continue;
+            B2 c = b;
+            if (place(c, ci, q, lane, rm) == 0) continue;                     // suicide
+            if (top < CAP) {
+                st0[top] = c.s[0];
+                st1[top] = c.s[1];
+                stp[top] = static_cast<int16_t>(q);
+                ++top;
+            }
+        }
+    }
+    return false;
+}
+
+// Ladder::is_ladder_capture (ladder.rs:131-135); p is a legal move of colour index ci
+__device__ bool is_capture(const B2& b, int ci, int p, int lane, uint32_t rm, uint32_t* st0, uint32_t* st1, int16_t* stp) {
+    B2 c = b;
+    place(c, ci, p, lane, rm);
+    return capture_search(c, ci, p, lane, rm, st0, st1, stp);
+}
+
+// Ladder::is_ladder_escape (ladder.rs:144-178); p is a legal move of colour index ci next to an own chain in atari
+__device__ bool is_escape(const B2& b, int ci, int p, int lane, uint32_t rm, uint32_t* st0, uint32_t* st1, int16_t* stp) {
+    B2 c = b;
+    if (place(c, ci, p, lane, rm) != 2) return false;
+    const int px = p % 19, py = p / 19;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const int qx = px + (k == 0) - (k == 2), qy = py - (k == 1) + (k == 3);
+        if (qx < 0 || qx > 18 || qy < 0 || qy > 18) continue;
+        const int q = qy * 19 + qx;
+        if (any(pt(q, lane) & (c.s[0] | c.s[1]))) continue;
+        B2 d = c;
+        if (place(d, ci ^ 1, q, lane, rm) == 0) continue;                     // not a legal move of the attacker
+        if (capture_search(d, ci ^ 1, q, lane, rm, st0, st1, stp)) return false;
+    }
+    return true;
+}
+
+// row y of a 361-bit point mask (bit p = point p = 19 y + x)
+__device__ __forceinline__ uint32_t row_of(const uint32_t* m, int y) {
+    const int at = 19 * y, w = at >> 5, sh = at & 31;
+    const uint32_t lo = m[w], hi = w + 1 < 12 ? m[w + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh) & ROW;
+}
+
+}  // namespace lad
+
 // Block n < batch handles position n and also expands its planes into the tower's input rows (what pack_compact_kernel
 // does for host-made planes: 400 rows x 64 fp16 channels, halo rows and channels 32..63 zero); block `batch` zeroes the
 // rows between the last position and the end of the last 128-row tile (stale after a larger batch).
@@ -288,6 +476,8 @@ __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPositi
 
     // 3. plane bits of this point
     const int tm = r.to_move, opp = 3 - tm;
+    const bool device_ladders = (r.symmetry & 8) != 0;     // the host did not read the ladders (DG_RAW_DEVICE_LADDERS)
+    int ladder_kinds = 0;                                  // 1: a ladder capture can start here, 2: a ladder escape
     uint32_t m = 0;
     bool legal = false;
     if (on && c) {
@@ -376,8 +566,21 @@ __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPositi
         if (counts[1] >= 0) m |= ((1u << min(counts[1], 6)) - 1u) << 23;
         if (ko) { m |= 1u << 29; any_ko = 1; }
         if (counts[0] >= 0) {
-            if (bit(r.ladder_capture, t)) m |= 1u << 30;
-            if (bit(r.ladder_escape, t)) m |= 1u << 31;
+            if (device_ladders) {
+                // a ladder can start here if the move puts a neighbouring enemy chain in atari (it has two liberties now)
+                // or extends an own chain that is in atari
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int q = nb[k];
+                    if (q < 0 || !col[q]) continue;
+                    const int n = nlib[lab[q]];
+                    if (col[q] == opp && n == 2) ladder_kinds |= 1;
+                    if (col[q] == tm && n == 1) ladder_kinds |= 2;
+                }
+            } else {
+                if (bit(r.ladder_capture, t)) m |= 1u << 30;
+                if (bit(r.ladder_escape, t)) m |= 1u << 31;
+            }
         }
         legal = counts[0] >= 0 && !ko;
     }
@@ -386,6 +589,42 @@ __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPositi
         if (r.last_move[1] == t) m |= 1u << 4;
     }
     __syncthreads();
+    if (device_ladders) {
+        // 3b. the ladder planes: a work list of (point, kind) in the liberty-set storage (free now), one warp per reading
+        uint32_t* scratch = &lib[0][0];
+        uint32_t* result = scratch;                                   // [361] bits 30 / 31
+        uint16_t* work = reinterpret_cast<uint16_t*>(scratch + 384);  // [722]
+        int* counters = reinterpret_cast<int*>(scratch + 384 + 384);  // [0] items, [1] next
+        if (on) result[t] = 0;
+        if (t < 2) counters[t] = 0;
+        __syncthreads();
+        if (ladder_kinds & 1) work[atomicAdd(&counters[0], 1)] = static_cast<uint16_t>(t);
+        if (ladder_kinds & 2) work[atomicAdd(&counters[0], 1)] = static_cast<uint16_t>(t | 512);
+        __syncthreads();
+        const int items = counters[0];
+        if (items > 0) {
+            const int lane = t & 31;
+            const uint32_t rm = lane < 19 ? lad::ROW : 0u;
+            lad::B2 board;
+            board.s[0] = lane < 19 ? lad::row_of(r.black, lane) : 0u;
+            board.s[1] = lane < 19 ? lad::row_of(r.white, lane) : 0u;
+            uint32_t st0[lad::CAP], st1[lad::CAP];
+            int16_t stp[lad::CAP];
+            for (;;) {
+                int i = 0;
+                if (lane == 0) i = atomicAdd(&counters[1], 1);
+                i = __shfl_sync(lad::FULL, i, 0);
+                if (i >= items) break;
+                const int item = work[i], p = item & 511;
+                const bool yes = (item & 512) ? lad::is_escape(board, tm - 1, p, lane, rm, st0, st1, stp)
+                                              : lad::is_capture(board, tm - 1, p, lane, rm, st0, st1, stp);
+                if (yes && lane == 0) atomicOr(&result[p], (item & 512) ? 1u << 31 : 1u << 30);
+            }
+        }
+        __syncthreads();
+        if (on) m |= result[t];
+        __syncthreads();
+    }
     // 4. output
     if (on) {
         const uint32_t global = (tm == 1 ? 1u : 2u) | (any_ko ? 4u : 0u);

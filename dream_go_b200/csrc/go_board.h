@@ -843,7 +843,8 @@ inline void features_v1(const Board& b, int to_move, int symmetry, uint32_t plan
 
 // ---- raw position for the device feature kernel (csrc/features.cu) ----------------------------------------------------
 // Everything the device needs to rebuild the planes: stones, visited bits, hashes, last moves -- plus the two ladder
-// planes, which are read here (sequential search) for the points that can start a ladder and are legal.
+// planes, which are read here (sequential search) for the points that can start a ladder and are legal, unless bit 3 of
+// `symmetry` (DG_RAW_DEVICE_LADDERS) leaves them to the device's own reader (csrc/features.cu: namespace lad).
 template <class Raw>
 inline void raw_position(const Board& b, int to_move, int symmetry, Raw* out) {
     static_assert(sizeof(Bits) == 48, "Bits is 12 x u32");
@@ -852,7 +853,8 @@ inline void raw_position(const Board& b, int to_move, int symmetry, Raw* out) {
     memcpy(out->visited, b.visited.w, 48);
     Bits capture_at, escape_at, capture, escape;
     capture.clear(); escape.clear();
-    ladder_starts(b, to_move, capture_at, escape_at);
+    capture_at.clear(); escape_at.clear();
+    if (!(symmetry & 8)) ladder_starts(b, to_move, capture_at, escape_at);       // bit 3 (DG_RAW_DEVICE_LADDERS): the device reads them
     Bits todo = capture_at | escape_at;
     while (todo.any()) {
         int p = todo.first();

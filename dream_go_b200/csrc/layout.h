@@ -18,7 +18,7 @@
 #define DG_POS_ROWS 400
 #define DG_HALO_ROWS 21          /* |20*dy + dx| <= 21 */
 #define DG_GUARD_ROWS 32
-#define DG_TAIL_ROWS 64
+#define DG_TAIL_ROWS 192
 #define DG_TILE_M 128            /* rows per MMA tile (UMMA M) */
 #define DG_WINDOW_ROWS (DG_TILE_M + 2 * DG_HALO_ROWS)   /* 170 rows staged per tile */
 

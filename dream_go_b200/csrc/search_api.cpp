@@ -39,6 +39,7 @@ static SearchOptions convert(const dg_search_options* o) {
     s.n_leaf_symmetries = o->n_leaf_symmetries;
     s.choose_at = o->choose_at;
     s.cache = reinterpret_cast<PredictionCache*>(o->cache);
+    s.device_ladders = o->device_ladders != 0;
     return s;
 }
 
@@ -134,6 +135,7 @@ struct Driver {
     uint64_t digest = 0;
     int64_t total_moves = 0, total_evals = 0, total_searches = 0, total_cache_hits = 0;
     PredictionCache* shared_cache = nullptr;                     // one table for every game (cfg.cache_shared), as predictors/nn.rs:48-50
+    bool device_ladders = false;                                 // DG_SELFPLAY_DEVICE_LADDERS
 
     void start_game(Game& g) {
         g.clear_trees();
@@ -196,6 +198,7 @@ struct Driver {
         opt.num_rollout = ex_it ? cfg.num_ex_it_rollout : p.num_rollout(cfg.num_rollout);
         opt.policy_only = !ex_it && opt.num_rollout <= 1;
         opt.cache = shared_cache ? shared_cache : g.cache.get();
+        opt.device_ladders = device_ladders;
         Node* tree = p.root;
         p.root = nullptr;
         if (tree && !g.allow_pass) tree->disqualify(PASS);
@@ -352,16 +355,17 @@ int64_t dg_tree_num_nodes(const dg_tree* tree) { return tree ? count_nodes(N(tre
 // group's last game pushes the leaves and submits them with one graph launch, and whichever worker looks for work next
 // notices the completion flag -- no device thread, no blocking call, no condition variable on that path.
 static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_predictor, dg_predict_prior_fn prior_predictor, void* ctx,
-                             dg_engine* const* engines, int32_t n_engines, bool engine_priors,
+                             dg_engine* const* engines, int32_t n_engines, uint32_t engine_flags,
                              const dg_selfplay_config* config, dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity) {
     const bool engine_mode = engines != nullptr;
     if ((!predictor && !raw_predictor && !prior_predictor && !engine_mode) || (engine_mode && n_engines <= 0) || !config ||
         config->num_games <= 0 || config->num_parallel <= 0)
         return DG_ERR_INVALID_ARGUMENT;
     const bool raw_mode = raw_predictor != nullptr || prior_predictor != nullptr || engine_mode;
-    const bool prior_mode = prior_predictor != nullptr || (engine_mode && engine_priors);
+    const bool prior_mode = prior_predictor != nullptr || (engine_mode && (engine_flags & DG_SELFPLAY_DEVICE_PRIORS));
     Driver d;
     d.cfg = *config;
+    d.device_ladders = engine_mode && (engine_flags & DG_SELFPLAY_DEVICE_LADDERS);
     std::unique_ptr<PredictionCache> process_table;
     if (config->cache_capacity > 0 && config->cache_shared) {
         process_table.reset(new PredictionCache((size_t)config->cache_capacity, config->cache_shared));
@@ -770,25 +774,24 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
 
 int32_t dg_selfplay_run(dg_predict_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                         char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(predictor, nullptr, nullptr, ctx, nullptr, 0, false, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(predictor, nullptr, nullptr, ctx, nullptr, 0, 0u, config, stats, sgf_out, sgf_capacity);
 }
 
 int32_t dg_selfplay_run_raw(dg_predict_raw_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                             char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(nullptr, predictor, nullptr, ctx, nullptr, 0, false, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(nullptr, predictor, nullptr, ctx, nullptr, 0, 0u, config, stats, sgf_out, sgf_capacity);
 }
 
 int32_t dg_selfplay_run_prior(dg_predict_prior_fn predictor, void* ctx, const dg_selfplay_config* config, dg_selfplay_stats* stats,
                               char* sgf_out, int64_t sgf_capacity) {
-    return selfplay_impl(nullptr, nullptr, predictor, ctx, nullptr, 0, false, config, stats, sgf_out, sgf_capacity);
+    return selfplay_impl(nullptr, nullptr, predictor, ctx, nullptr, 0, 0u, config, stats, sgf_out, sgf_capacity);
 }
 
 int32_t dg_selfplay_run_engine(dg_engine* const* engines, int32_t n_engines, uint32_t flags, const dg_selfplay_config* config,
                                dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity) {
     if (!engines || n_engines <= 0) return DG_ERR_INVALID_ARGUMENT;
     for (int i = 0; i < n_engines; ++i) if (!engines[i]) return DG_ERR_INVALID_ARGUMENT;
-    return selfplay_impl(nullptr, nullptr, nullptr, nullptr, engines, n_engines, (flags & DG_SELFPLAY_DEVICE_PRIORS) != 0, config, stats,
-                         sgf_out, sgf_capacity);
+    return selfplay_impl(nullptr, nullptr, nullptr, nullptr, engines, n_engines, flags, config, stats, sgf_out, sgf_capacity);
 }
 
 int32_t dg_engine_predict_prior(void* engine, const dg_raw_position* positions, int32_t n, uint16_t* value, uint16_t* policy, uint8_t* legal,

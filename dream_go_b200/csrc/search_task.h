@@ -239,6 +239,7 @@ struct SearchOptions {
     double choose_at = -1.0;                   // injected uniform number for the stochastic move choice
     bool policy_only = false;                  // no tree: play from the averaged policy (self_play.rs:360-396)
     PredictionCache* cache = nullptr;          // transposition table (predictors/nn.rs:29-82); null = none
+    bool device_ladders = false;               // raw positions: the device reads the ladders (DG_RAW_DEVICE_LADDERS)
 };
 
 class SearchTask {
@@ -311,8 +312,9 @@ class SearchTask {
             if (raw) {
                 size_t at = raw->size();
                 raw->resize(at + 8);
-                raw_position(board_, color_, opt_.search_kind << 4, &(*raw)[at]);
-                for (int t = 1; t < 8; ++t) { (*raw)[at + t] = (*raw)[at]; (*raw)[at + t].symmetry = (uint8_t)(t | (opt_.search_kind << 4)); }
+                const int extra = (opt_.search_kind << 4) | (opt_.device_ladders ? 8 : 0);
+                raw_position(board_, color_, extra, &(*raw)[at]);
+                for (int t = 1; t < 8; ++t) { (*raw)[at + t] = (*raw)[at]; (*raw)[at + t].symmetry = (uint8_t)(t | extra); }
             } else {
                 uint8_t legal[N_POINTS];
                 size_t at = packed->size();
@@ -357,7 +359,7 @@ class SearchTask {
             }
             if (raw) {
                 raw->emplace_back();
-                raw_position(p.board, p.to_move, p.symmetry | (opt_.search_kind << 4), &raw->back());
+                raw_position(p.board, p.to_move, p.symmetry | (opt_.search_kind << 4) | (opt_.device_ladders ? 8 : 0), &raw->back());
             } else {
                 uint8_t legal[N_POINTS];
                 packed->emplace_back();

@@ -24,7 +24,7 @@ class _SearchOptions(C.Structure):
     _fields_ = [("search", C.c_int32), ("deterministic", C.c_int32), ("num_rollout", C.c_int32),
                 ("probes_per_round", C.c_int32), ("dirichlet_noise", C.c_float), ("temperature", C.c_float),
                 ("seed", C.c_uint64), ("noise", C.c_void_p), ("leaf_symmetries", C.c_void_p),
-                ("n_leaf_symmetries", C.c_int32), ("choose_at", C.c_double), ("cache", C.c_void_p)]
+                ("n_leaf_symmetries", C.c_int32), ("choose_at", C.c_double), ("cache", C.c_void_p), ("device_ladders", C.c_int32)]
 
 
 class _SelfPlayConfig(C.Structure):
@@ -67,6 +67,7 @@ ABI = {
                                     C.c_int64]),
 }
 SELFPLAY_DEVICE_PRIORS = 0x1
+SELFPLAY_DEVICE_LADDERS = 0x2
 _ready = False
 
 
@@ -131,12 +132,14 @@ class EnginePriorPredictor:
 class EngineQueue:
     """The product path of self-play: one or several engines (one per device) driven through their leaf-batch queues by
     `dg_selfplay_run_engine` -- no blocking predictor call.  `device_priors`: build the leaves' priors on the device
-    (None = when fewer than 8 host threads per engine are available, where the host is the scarce side)."""
+    (None = when fewer than 4 host threads per engine are available, where the host is the scarce side); `device_ladders`: the
+    ladder planes are read on the device as well (None = below 3 host threads per engine)."""
     engines = True
 
-    def __init__(self, networks, device_priors=None):
+    def __init__(self, networks, device_priors=None, device_ladders=None):
         self.networks = list(networks) if isinstance(networks, (list, tuple)) else [networks]
         self.device_priors = device_priors
+        self.device_ladders = device_ladders
 
 
 class RandomPredictor:
@@ -229,11 +232,11 @@ def _fn_ctx(predictor):
 def predict(predictor, board: "go.Board", color: int, *, search: int = go.STANDARD_SEARCH, deterministic: bool = False,
             num_rollout: int = 800, probes_per_round: int = 1, starting_tree: Optional[Tree] = None, seed: int = 1,
             noise: Optional[np.ndarray] = None, dirichlet_noise: float = 0.25, temperature: float = 0.8,
-            leaf_symmetries=None, choose_at: float = -1.0, cache: Optional["Cache"] = None):
+            leaf_symmetries=None, choose_at: float = -1.0, cache: Optional["Cache"] = None, device_ladders: bool = False):
     """`dg_mcts::predict`.  Returns (value, index, Tree, evals)."""
     fn, ctx = _fn_ctx(predictor)
     opt = _SearchOptions(search, int(deterministic), num_rollout, probes_per_round, dirichlet_noise, temperature, seed,
-                         None, None, 0, choose_at, cache._h if cache is not None else None)
+                         None, None, 0, choose_at, cache._h if cache is not None else None, int(device_ladders))
     keep = []
     if noise is not None:
         eta = np.ascontiguousarray(noise, np.float32)
@@ -267,12 +270,16 @@ def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout:
         import os
         nets = predictor.networks
         handles = (C.c_void_p * len(nets))(*[n._handle for n in nets])
-        priors = predictor.device_priors
+        # what else moves to the device is a question of which side is scarce: with 4 or more host threads per engine the
+        # device is the limit even with the priors and the ladders on the host (measured), below that the host is
+        threads = num_threads if num_threads > 0 else (os.cpu_count() or 1)
+        priors, ladders = predictor.device_priors, predictor.device_ladders
         if priors is None:
-            threads = num_threads if num_threads > 0 else (os.cpu_count() or 1)
-            priors = threads < 8 * len(nets)
-        rc = lib().dg_selfplay_run_engine(handles, len(nets), SELFPLAY_DEVICE_PRIORS if priors else 0, C.byref(cfg), C.byref(stats),
-                                          buf, sgf_capacity)
+            priors = threads < 4 * len(nets)
+        if ladders is None:
+            ladders = threads < 3 * len(nets)
+        flags = (SELFPLAY_DEVICE_PRIORS if priors else 0) | (SELFPLAY_DEVICE_LADDERS if ladders else 0)
+        rc = lib().dg_selfplay_run_engine(handles, len(nets), flags, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
     else:
         fn, ctx = _fn_ctx(predictor)
         kind = getattr(predictor, "raw", False)

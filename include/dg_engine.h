@@ -45,6 +45,7 @@ extern "C" {
 #define DG_FLAG_NO_PDL             0x2u  /* debug: launch the layers without programmatic dependent launch */
 #define DG_FLAG_LAYERWISE          0x4u  /* debug: one launch per convolution instead of the persistent tower kernel */
 #define DG_FLAG_NO_ROTATE          0x8u  /* debug: do not rotate the unit -> CTA-pair assignment between layers */
+#define DG_FLAG_TOWER_LATE_A      0x40u  /* debug (A/B): the tower kernel requests a layer's first activation windows after its filter slabs */
 #define DG_FLAG_NO_GRAPH          0x20u  /* debug: leaf batches are enqueued call by call instead of as one captured graph */
 #define DG_FLAG_BLOCKING_SYNC     0x10u  /* blocking calls poll the stream between 20 us naps instead of spinning in the driver
                                             (self-play: every core is busy searching and a spinning waiter steals one) */
@@ -86,8 +87,8 @@ typedef struct dg_packed_position {
 /* The smallest description of a position from which the DEVICE computes the V1 feature planes and the legal moves
  * (csrc/features.cu): stones, which points have ever held a stone (the super-ko rule only looks at those,
  * board.rs:135), the zobrist hash of the position and of the last 16 positions (board.rs:132-141; the keys are the
- * engine's own, csrc/go_board.h), the last two moves (361 = none) and -- computed on the host, a ladder is a sequential
- * search -- the two ladder planes.  Bit p of a mask = point p = 19*y + x.  `dg_board_raw_position` (dg_go.h) fills it. */
+ * engine's own, csrc/go_board.h), the last two moves (361 = none) and the two ladder planes -- read on the host (a ladder is
+ * a sequential search) or, with DG_RAW_DEVICE_LADDERS, left to the device.  Bit p of a mask = point p = 19*y + x.  `dg_board_raw_position` (dg_go.h) fills it. */
 typedef struct dg_raw_position {
     uint32_t black[12], white[12], visited[12], ladder_capture[12], ladder_escape[12];
     uint64_t hash;
@@ -96,8 +97,11 @@ typedef struct dg_raw_position {
     uint16_t k_bits;               /* fp16 bits of k (features.rs:236) */
     uint8_t  to_move;              /* 1 black, 2 white */
     uint8_t  symmetry;             /* bits 0-2: orientation the planes are produced in (symmetry::ALL order);
+                                      bit 3: DG_RAW_DEVICE_LADDERS -- the two ladder masks above are not filled in, the device
+                                      reads the ladders itself (one warp per reading, utils/ladder.rs:53-179);
                                       bits 4-7: search options of the position (DG_STANDARD_SEARCH / DG_SCORING_SEARCH) */
 } dg_raw_position;                 /* 384 bytes */
+#define DG_RAW_DEVICE_LADDERS 0x08
 
 /* ---- devices ------------------------------------------------------------------------------- */
 

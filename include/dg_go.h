@@ -74,7 +74,8 @@ void      dg_board_features_packed(const dg_board* board, int32_t to_move, int32
                                    dg_packed_position* out, uint8_t* legal);
 /* The raw form for dg_engine_forward_raw: stones, visited bits, hashes, last moves and the two ladder planes; the
  * device derives the other 30 planes and the legal moves from it (csrc/features.cu).  `symmetry` may carry the search
- * options of the position in bits 4.. (DG_SCORING_SEARCH << 4) for dg_engine_forward_raw_prior. */
+ * options of the position in bits 4.. (DG_SCORING_SEARCH << 4) for dg_engine_forward_raw_prior, and DG_RAW_DEVICE_LADDERS
+ * (0x08): the ladders are not read here, the device reads them. */
 void      dg_board_raw_position(const dg_board* board, int32_t to_move, int32_t symmetry, dg_raw_position* out);
 /* Bit-identical to `get_features::<HWC, f16>`: 11,552 fp16, index 32*(19y+x)+c. */
 void      dg_board_features_f16(const dg_board* board, int32_t to_move, int32_t symmetry, uint16_t* out);

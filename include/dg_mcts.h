@@ -63,6 +63,7 @@ typedef struct dg_search_options {
     int32_t  n_leaf_symmetries;
     double   choose_at;           /* optional: the uniform number of the stochastic move choice; < 0 = draw it          */
     struct dg_cache* cache;       /* optional: transposition table of evaluations (NnPredictor::fetch / cache)          */
+    int32_t  device_ladders;      /* raw-position predictors: leave the ladder planes to the device (DG_RAW_DEVICE_LADDERS) */
 } dg_search_options;
 
 /* Transposition table `LruCache<(zobrist hash, to_move), Prediction>` (src/libdg_mcts/predictors/nn.rs:29-82,
@@ -147,7 +148,8 @@ int32_t  dg_selfplay_run_prior(dg_predict_prior_fn predictor, void* ctx, const d
  * call (pool/worker_thread.rs:88-99 does).  Each engine needs num_workspaces >= its number of groups (config->num_groups
  * per engine, 2..8) and max_batch >= games per group x max(8, probes_per_round).  Same games as the three calls above for the
  * same seed.  flags: DG_SELFPLAY_DEVICE_PRIORS = the leaves' priors are built on the device (dg_engine_forward_raw_prior). */
-#define DG_SELFPLAY_DEVICE_PRIORS 0x1u
+#define DG_SELFPLAY_DEVICE_PRIORS  0x1u
+#define DG_SELFPLAY_DEVICE_LADDERS 0x2u   /* the ladder planes are read on the device too: the host only walks the trees */
 int32_t  dg_selfplay_run_engine(dg_engine* const* engines, int32_t n_engines, uint32_t flags, const dg_selfplay_config* config,
                                 dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity);
 

@@ -19,13 +19,19 @@ def engine(small_net):
     net.close()
 
 
-def replay_raw(colors, moves, komi, symmetries=None):
-    """Raw positions, host planes and host legal masks for every ply of a game (to_move = the move's colour)."""
+DEVICE_LADDERS = 0x08      # DG_RAW_DEVICE_LADDERS
+
+
+def replay_raw(colors, moves, komi, symmetries=None, device_ladders=False):
+    """Raw positions, host planes and host legal masks for every ply of a game (to_move = the move's colour).
+    device_ladders: the raw positions carry no ladder masks, the device has to read the ladders itself."""
     board = pgo.Board(komi)
     raws, planes, legal = [], [], []
     for i, (c, m) in enumerate(zip(colors, moves)):
         s = 0 if symmetries is None else int(symmetries[i])
-        raws.append(board.raw_position(int(c), s)[0])
+        raws.append(board.raw_position(int(c), s | (DEVICE_LADDERS if device_ladders else 0))[0])
+        if device_ladders:
+            assert not raws[-1]["ladder_capture"].any() and not raws[-1]["ladder_escape"].any()
         p, lg = board.features_packed(int(c), s, legal=True)
         planes.append(p[0])
         legal.append(lg)
@@ -104,6 +110,92 @@ def test_long_random_game_bit_exact(engine):
     colors, moves = random_playout(5, 1500, pass_rate=0.0)
     raws, planes, legal = replay_raw(colors, moves, 7.5)
     check(engine, raws, planes, legal)
+
+
+# ---- ladder reading on the device (utils/ladder.rs:53-179; csrc/features.cu: namespace lad) -----------------------------------
+
+def test_device_ladder_reader_on_the_reference_ladder_positions(engine):
+    """The positions of the reference's own ladder tests (utils/ladder.rs:187-351): the device reads planes 30 / 31 itself
+    (one warp per reading) and they are the host's, which tests/test_go_parity.py pins to the oracle."""
+    from test_oracle_go import NOT_LADDER
+    boards = []
+    b = pgo.Board(7.5)                                   # ladder.rs: corner captures
+    for x, y in [(0, 0), (0, 18), (18, 0), (18, 18)]:
+        b.place(BLACK, x, y)
+    boards.append((b, WHITE, {"capture": 8}))
+    b = pgo.Board(7.5)                                   # a working ladder for black at (3, 4)
+    b.place(WHITE, 3, 3)
+    for x, y in [(2, 3), (3, 2), (4, 2)]:
+        b.place(BLACK, x, y)
+    boards.append((b, BLACK, {"capture": 1}))
+    b = pgo.Board(7.5)                                   # ... and the escape at (4, 3) once a breaker stands at (15, 15)
+    b.place(WHITE, 3, 3)
+    b.place(WHITE, 15, 15)
+    for x, y in [(2, 3), (3, 2), (4, 2), (3, 4)]:
+        b.place(BLACK, x, y)
+    boards.append((b, WHITE, {"escape": 1}))
+    b = pgo.Board(7.5)                                   # real-game position: (4, 13) escapes
+    for c, x, y in NOT_LADDER:
+        b.place(c, x, y)
+    boards.append((b, WHITE, {"escape_at": (4, 13)}))
+    for first in [(1, 2), (3, 4)]:                       # not a ladder because of self-atari
+        b = pgo.Board(7.5)
+        for c, (x, y) in [(BLACK, first), (WHITE, (2, 4)), (BLACK, (2, 3)), (WHITE, (1, 5)), (BLACK, (1, 4))]:
+            b.place(c, x, y)
+        boards.append((b, WHITE, {"no_capture_at": (1, 3)}))
+    for b, tm, expect in boards:
+        for sym in (0, 5):
+            raw = b.raw_position(tm, sym | DEVICE_LADDERS)
+            want, want_legal = b.features_packed(tm, sym, legal=True)
+            got, got_legal = engine.features_raw(raw)
+            assert (got["planes"] == want["planes"]).all() and (got_legal[0] == want_legal).all()
+        ident = b.features_packed(tm, 0)["planes"][0]
+        if "capture" in expect:
+            assert int(((ident >> 30) & 1).sum()) == expect["capture"]
+        if "escape" in expect:
+            assert int(((ident >> 31) & 1).sum()) == expect["escape"]
+        if "escape_at" in expect:
+            x, y = expect["escape_at"]
+            assert (ident[19 * y + x] >> 31) & 1
+        if "no_capture_at" in expect:
+            x, y = expect["no_capture_at"]
+            assert not (ident[19 * y + x] >> 30) & 1
+
+
+def test_device_ladder_reader_on_games_and_playouts(engine):
+    """Every ply of fixture games and of capture-heavy random playouts, random symmetries: the device's own ladder planes
+    are the host reader's, and so is everything else in the planes."""
+    from test_go_parity import random_playout
+    games = ogo.load_games()
+    n_ladders = 0
+    for k, (colors, moves, komi) in enumerate(games[1::6]):
+        rng = np.random.default_rng(k)
+        raws, planes, legal = replay_raw(colors, moves, komi, symmetries=rng.integers(0, 8, size=len(moves)), device_ladders=True)
+        check(engine, raws, planes, legal)
+        n_ladders += int(((planes["planes"] >> 30) != 0).sum())
+    assert n_ladders > 200                               # the games do contain ladders
+    for seed in range(3):
+        colors, moves = random_playout(4242 + seed, 500, komi=7.5)
+        raws, planes, legal = replay_raw(colors, moves, 7.5, device_ladders=True)
+        check(engine, raws, planes, legal)
+
+
+def test_long_ladder_across_the_board(engine):
+    """A ladder that runs from one corner region across the whole board (30+ steps), with and without a breaker."""
+    for breaker in (None, (15, 15), (14, 15), (16, 14)):
+        b = pgo.Board(7.5)
+        b.place(WHITE, 2, 2)
+        for x, y in [(1, 2), (2, 1), (3, 1)]:
+            b.place(BLACK, x, y)
+        if breaker:
+            b.place(WHITE, *breaker)
+        for tm in (BLACK, WHITE):
+            raw = b.raw_position(tm, DEVICE_LADDERS)
+            want = b.features_packed(tm, 0)
+            got, _ = engine.features_raw(raw)
+            assert (got["planes"] == want["planes"]).all(), (breaker, tm)
+        if breaker is None:
+            assert (b.features_packed(BLACK, 0)["planes"][0][19 * 3 + 2] >> 30) & 1     # black (2, 3) starts the ladder
 
 
 # ---- prior construction on the device (pool/policy_helper.rs) ------------------------------------------------------------

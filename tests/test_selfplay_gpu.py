@@ -101,9 +101,10 @@ def test_leaf_batch_queue_driver_plays_the_same_games(small_net, flags):
     try:
         kw = dict(num_games=6, num_parallel=5, num_rollout=40, probes_per_round=4, max_plies=20, seed=11)
         ref, sgf_ref = pm.self_play(pm.EnginePredictor(net), num_threads=2, **kw)
-        for priors, threads, groups in ((False, 1, 0), (True, 4, 2), (False, 3, 4), (True, 2, 3)):
-            got, sgf = pm.self_play(pm.EngineQueue(net, device_priors=priors), num_threads=threads, num_groups=groups, **kw)
-            assert got["digest"] == ref["digest"] and sorted(sgf) == sorted(sgf_ref), (priors, threads, groups)
+        for priors, ladders, threads, groups in ((False, False, 1, 0), (True, False, 4, 2), (False, True, 3, 4), (True, True, 2, 3)):
+            got, sgf = pm.self_play(pm.EngineQueue(net, device_priors=priors, device_ladders=ladders), num_threads=threads,
+                                    num_groups=groups, **kw)
+            assert got["digest"] == ref["digest"] and sorted(sgf) == sorted(sgf_ref), (priors, ladders, threads, groups)
             assert got["evals"] == ref["evals"] and got["games_finished"] == 6 and got["moves"] == ref["moves"]
         # a deadline in the middle of the run: the batches in flight are dropped, nothing hangs
         cut, _ = pm.self_play(pm.EngineQueue(net), num_threads=2, max_seconds=0.3, **{**kw, "num_games": 1000, "max_plies": 722})
