@@ -412,12 +412,16 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                     const int tile = 2 * u + rank;
                     DG_TRACE(0);
                     if (l > 0) {        // rows tile*128-21 .. +149 of layer l-1 must be complete and visible
+                        // the three flags are read together (one L2 round trip, not three dependent ones), then one fence
+                        // turns the observation into an acquire
                         const uint32_t want = p.gen + l;
-                        for (int t = tile - 1; t <= tile + 1; t++) {
-                            if (t < 0 || t >= ntiles_even) continue;
-                            while (static_cast<int32_t>(ld_acquire_gpu(p.done + t) - want) < 0) {
-                            }
+                        const uint32_t* f0 = p.done + (tile > 0 ? tile - 1 : tile);
+                        const uint32_t* f2 = p.done + (tile + 1 < ntiles_even ? tile + 1 : tile);
+                        for (;;) {
+                            const uint32_t a = ld_relaxed_gpu(f0), b = ld_relaxed_gpu(p.done + tile), c = ld_relaxed_gpu(f2);
+                            if (static_cast<int32_t>(a - want) >= 0 && static_cast<int32_t>(b - want) >= 0 && static_cast<int32_t>(c - want) >= 0) break;
                         }
+                        fence_acq_rel_gpu();
                         fence_proxy_async_global();
                     }
                     for (int h = 0; h < nh; h++) {

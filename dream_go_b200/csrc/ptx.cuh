@@ -261,6 +261,13 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* ptr) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
     return v;
 }
+// relaxed loads may be in flight together; a fence_acq_rel_gpu() after the values have been seen makes it an acquire
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* ptr) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release_gpu(uint32_t* ptr, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }

@@ -22,7 +22,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdg_engine.so")
+LIB_PATH = os.environ.get("DG_ENGINE_LIB") or os.path.join(_HERE, "libdg_engine.so")     # (the override is for A/B runs of two builds)
 
 FEATURE_SIZE = 11552
 POLICY_SIZE = 362
@@ -123,6 +123,8 @@ def lib() -> C.CDLL:
                                "(make -C dream_go_b200/csrc); the engine has no CPU or library fallback")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in ABI.items():
+            if os.environ.get("DG_ENGINE_LIB") and not hasattr(handle, name):
+                continue                    # an older build in an A/B run: it lacks the newer entry points
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
         _lib = handle
