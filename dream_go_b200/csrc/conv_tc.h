@@ -60,6 +60,8 @@ struct TowerLayer {
     const float* bias;          // [128] fp32
     __half* out;                // output board-row buffer (row 0 = guard start)
     const __half* skip;         // residual input buffer or nullptr
+    int wrows;                  // output channels of the layer: 128, or 16 = the head convolution (8 policy + 2 value samples)
+    __half* out2;               // head convolution only: value samples [row][2] (`out` = policy samples [row][8])
 };
 
 struct TowerParams {

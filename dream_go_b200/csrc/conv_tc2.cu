@@ -50,15 +50,16 @@ constexpr uint32_t kIdesc = umma_idesc_f16(256, 128);
 }  // namespace t2
 
 template <int NH, int H, int I>
-__device__ __forceinline__ void issue_one(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
+__device__ __forceinline__ void issue_one(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo, uint32_t idesc) {
     constexpr int tap = I / 4, k = I % 4;
     constexpr int row_off = DG_HALO_ROWS + (tap / 3 - 1) * DG_LINE_STRIDE + (tap % 3 - 1);
     umma_f16_ss_pair<((row_off * 128 + k * 32) >> 4), (((tap * NH + H) * t2::kSlab + k * 32) >> 4)>(
-        d_tmem, a_lo, w_lo, kUmmaDescHiSw128, t2::kIdesc, (H | I) != 0);
+        d_tmem, a_lo, w_lo, kUmmaDescHiSw128, idesc, (H | I) != 0);
 }
 template <int NH, int H, int... I>
-__device__ __forceinline__ void issue_half(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo, std::integer_sequence<int, I...>) {
-    (issue_one<NH, H, I>(d_tmem, a_lo, w_lo), ...);
+__device__ __forceinline__ void issue_half(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo, std::integer_sequence<int, I...>,
+                                           uint32_t idesc = t2::kIdesc) {
+    (issue_one<NH, H, I>(d_tmem, a_lo, w_lo, idesc), ...);
 }
 
 // NH = number of 64-channel k-halves of the input: 2 for the tower (128 channels), 1 for the
@@ -395,12 +396,16 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                 const CUtensorMap* tm_a = &p.act[p.layer[l].in_map];
                 // slab by slab, in the order the MMAs consume them: a slab of layer l is fetched as soon as the last unit
                 // of layer l-1 is done with it, so the reload spreads over a whole unit time instead of two bursts
+                // a layer's filter bank: per tap `wrows` output channels (128; 16 for the head convolution), half of them
+                // in each CTA -- a slab is [wrows / 2 out][64 in] at the start of its 8 KiB slot
+                const int wrows = p.layer[l].wrows, wbytes = wrows * 64;
                 auto load_weights = [&](int h) {
                     for (int tap = 0; tap < 9; tap++) {
                         const int s = tap * 2 + h;
                         if (l > 0) mbar_wait(&w_free[s], (l - 1) & 1);      // layer l-1 no longer reads this slab
-                        if (rank == 0) mbar_expect_tx(&w_full[s], 2 * kSlab);
-                        tma_load_2d_pair(w_s + s * kSlab, tm_w, mapa_shared(smem_u32(&w_full[s]), 0), h * 64, tap * 128 + rank * 64);
+                        if (rank == 0) mbar_expect_tx(&w_full[s], 2 * wbytes);
+                        tma_load_2d_pair(w_s + s * kSlab, tm_w, mapa_shared(smem_u32(&w_full[s]), 0), h * 64,
+                                         tap * wrows + rank * (wrows >> 1));
                     }
                 };
                 // The first unit's activation windows do not depend on the filter bank: they are requested BEFORE the
@@ -445,6 +450,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
             const uint32_t w_lo = umma_desc_lo(smem_u32(w_s));
             for (int l = 0; l < p.nlayers; l++) {
                 const int nh = p.layer[l].nh;
+                const uint32_t idesc = umma_idesc_f16(256, p.layer[l].wrows);      // N = 128, or 16 for the head convolution
                 const int u0 = first_unit(l);
                 for (int u = u0; u < nunits; u += npairs) {
                     const bool last = (u + npairs >= nunits);
@@ -460,7 +466,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
     do {                                                                                                      \
         if (first) { mbar_wait(&w_full[(T) * 2 + (H)], wfull_phase[H]); tc_fence_after(); }                    \
         if (elect_one()) {                                                                                    \
-            issue_half<2, H>(d_tmem, a_lo, w_lo, std::integer_sequence<int, (T) * 4, (T) * 4 + 1, (T) * 4 + 2, (T) * 4 + 3>{}); \
+            issue_half<2, H>(d_tmem, a_lo, w_lo, std::integer_sequence<int, (T) * 4, (T) * 4 + 1, (T) * 4 + 2, (T) * 4 + 3>{}, idesc); \
             if (last) umma_commit_pair(&w_free[(T) * 2 + (H)], 3);                                             \
         }                                                                                                     \
         __syncwarp();                                                                                         \
@@ -476,7 +482,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                             DG_TAPS(0);
                             if (first) wfull_phase[0] ^= 1;
                         } else if (elect_one()) {
-                            issue_half<2, 0>(d_tmem, a_lo, w_lo, std::make_integer_sequence<int, 36>{});
+                            issue_half<2, 0>(d_tmem, a_lo, w_lo, std::make_integer_sequence<int, 36>{}, idesc);
                         }
                         __syncwarp();
                         if (elect_one()) {
@@ -498,7 +504,7 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                             DG_TAPS(1);
                             if (first) wfull_phase[1] ^= 1;
                         } else if (elect_one()) {
-                            issue_half<2, 1>(d_tmem, a_lo, w_lo, std::make_integer_sequence<int, 36>{});
+                            issue_half<2, 1>(d_tmem, a_lo, w_lo, std::make_integer_sequence<int, 36>{}, idesc);
                         }
                         __syncwarp();
                         if (elect_one()) {
@@ -612,6 +618,39 @@ tower_kernel(const __grid_constant__ TowerParams p) {
                 st_global_256(out + off + part * 32, &packed[0]);
                 st_global_256(out + off + part * 32 + 16, &packed[8]);
             };
+            if (L.wrows == 16) {
+                // the head convolution (policy_head.rs:49-52, value_head.rs:45-49): 8 policy + 2 value samples (+ 6 zero channels)
+                // per board row -> pbuf[row][8] (the A operand of the policy FC) and vbuf[row][2]
+                uint32_t acc[16];
+                tmem_ld_32x32b_x16(taddr, acc);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty0);
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float v0 = fmaf(alpha, __uint_as_float(acc[2 * j]), bias_l[2 * j]);
+                    float v1 = fmaf(alpha, __uint_as_float(acc[2 * j + 1]), bias_l[2 * j + 1]);
+                    v0 = (v0 > 0.f && !halo) ? v0 : 0.f;     // NaN-non-propagating ReLU; halo rows stay zero
+                    v1 = (v1 > 0.f && !halo) ? v1 : 0.f;
+                    const __half2 hv = __floats2half2_rn(v0, v1);
+                    packed[j] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+                const size_t grow = off >> 7;
+                *reinterpret_cast<uint4*>(out + grow * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint32_t*>(L.out2 + grow * 2) = packed[4];
+                named_bar_sync(1 + g, 128);
+                if (leader) {
+                    __threadfence();
+                    st_release_gpu(p.done + 2 * u + rank, p.gen + l + 1);
+                }
+                if (tracer) DG_TRACE(2);
+                next_item(l, u);
+                if (l < p.nlayers) next_item(l, u);
+                if (l < p.nlayers) prefetch_skip(l, u);
+                continue;
+            }
             uint32_t acc0[32], acc1[32];
             tmem_ld_32x32b_x32(taddr, acc0);
             tmem_ld_wait();

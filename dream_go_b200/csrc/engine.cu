@@ -89,6 +89,7 @@ struct DeviceNet {
     std::vector<ConvWeights> c1, c2;
     std::vector<float> gate;
     ConvWeights heads;
+    CUtensorMap tm_heads_pair;        // heads.w as [8 out][64 in] boxes (one CTA's half) for the tower kernel's last layer
     __half* w_pfc = nullptr;          // [384 out][3200 = 400 board rows x 8 samples] (zero for halo rows / padding)
     CUtensorMap tm_pfc;
     float* b_pfc = nullptr;           // fp16(tau * b) as fp32
@@ -371,10 +372,13 @@ int32_t load_net(dg_engine* e, const dg::TensorMap& t) {
         std::vector<uint16_t> wl(9 * kHeadChan * 128, 0);
         relayout_conv(reinterpret_cast<const uint16_t*>(pw->bytes.data()), 8, 128, kHeadChan, 128, 0, wl);
         relayout_conv(reinterpret_cast<const uint16_t*>(vw->bytes.data()), 2, 128, kHeadChan, 128, 8, wl);
-        std::vector<float> bl(kHeadChan, 0.f);
+        std::vector<float> bl(kChan, 0.f);       // (128 entries: the tower kernel stages a layer's bias as one 128-float vector)
         for (int i = 0; i < 8; i++) bl[i] = h2f(reinterpret_cast<const uint16_t*>(pb->bytes.data())[i]);
         for (int i = 0; i < 2; i++) bl[8 + i] = h2f(reinterpret_cast<const uint16_t*>(vb->bytes.data())[i]);
         if ((rc = build_conv(e, n, n.heads, wl, bl, kHeadChan, 128, kHeadChan))) return cleanup(rc);
+        // the same filter bank as the last layer of the persistent tower kernel: each CTA of a pair holds 8 of the 16 channels
+        if (!make_tmap(e, &n.tm_heads_pair, n.heads.w, 128, 9ull * kHeadChan, kHeadChan / 2))
+            return cleanup(fail(e, DG_ERR_CUDA, "cuTensorMapEncodeTiled failed for the head filter"));
 
         const float temperature = e->cfg.softmax_temperature > 0.f ? e->cfg.softmax_temperature : 0.709888f;
         n.tau = 1.0f / temperature;                                  // policy_head.rs:46
@@ -482,6 +486,7 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
     }
     const int nb = (blocks < 0 || blocks > n.num_blocks) ? n.num_blocks : blocks;
     const bool layerwise = (e->cfg.flags & (DG_FLAG_DEBUG_DIRECT_CONV | DG_FLAG_LAYERWISE)) != 0;
+    const bool heads_in_tower = !layerwise && blocks < 0 && stage != 2 && !(e->cfg.flags & DG_FLAG_SEPARATE_HEAD_CONV);
     if (!layerwise) {
         // the whole tower in one persistent launch (tower_kernel)
         dg::TowerParams tp;
@@ -489,7 +494,7 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
         int nl = 0;
         auto add = [&](int in_map, int nh, const ConvWeights& cw, __half* out, const __half* skip, float alpha, float beta) {
             tp.w[nl] = cw.tm;
-            tp.layer[nl] = dg::TowerLayer{in_map, nh, skip != nullptr, alpha, beta, cw.bias, out, skip};
+            tp.layer[nl] = dg::TowerLayer{in_map, nh, skip != nullptr, alpha, beta, cw.bias, out, skip, kChan, nullptr};
             nl++;
         };
         if (stage != 2) add(0, 1, n.up, w.x, nullptr, 1.f, 0.f);
@@ -497,6 +502,11 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
             const float g = n.gate[i];
             add(1, 2, n.c1[i], w.y, nullptr, 1.f, 0.f);
             add(2, 2, n.c2[i], w.x, w.x, g, 1.0f - g);
+        }
+        if (heads_in_tower) {      // the head convolution (policy + value samples) as the last layer of the same launch
+            tp.w[nl] = n.tm_heads_pair;
+            tp.layer[nl] = dg::TowerLayer{1, 2, 0, 1.f, 0.f, n.heads.bias, w.pbuf, nullptr, kHeadChan, w.vbuf};
+            nl++;
         }
         if (nl > 0) {
             tp.nlayers = nl;
@@ -534,7 +544,7 @@ int32_t enqueue_network(dg_engine* e, Workspace& w, int batch, int blocks, int s
     if (e->cfg.flags & DG_FLAG_DEBUG_DIRECT_CONV) {
         if ((rc = run_conv(e, w, ConvTcShape::kHeads, w.tm_x, w.x, kChan, n.heads, kHeadChan, w.h, kHeadChan, nullptr, 1.f, 0.f, batch))) return rc;
         DG_CUDA(e, dg::launch_split_heads(w.h, w.pbuf, w.vbuf, batch, w.stream));
-    } else {
+    } else if (!heads_in_tower) {
         if ((rc = run_conv(e, w, ConvTcShape::kHeads, w.tm_x, w.x, kChan, n.heads, kHeadChan, w.pbuf, 8, nullptr, 1.f, 0.f, batch, w.vbuf))) return rc;
     }
     DG_CUDA(e, dg::launch_policy_fc(w.tm_pa, n.tm_pfc, w.part, batch, w.stream));
@@ -1054,7 +1064,8 @@ int32_t dg_engine_time_resident(dg_engine* e, int32_t batch, int32_t iters, int3
     float ms = 0.f;
     rc = timed_pass(0, &ms);
     if (rc == DG_OK && ms_total) *ms_total = ms;
-    if (launches) *launches = (e->cfg.flags & (DG_FLAG_DEBUG_DIRECT_CONV | DG_FLAG_LAYERWISE)) ? 5 + 2 * e->net.num_blocks : 5;   // pack, tower, head conv, policy FC, finish
+    if (launches) *launches = (e->cfg.flags & (DG_FLAG_DEBUG_DIRECT_CONV | DG_FLAG_LAYERWISE)) ? 5 + 2 * e->net.num_blocks
+                            : (e->cfg.flags & DG_FLAG_SEPARATE_HEAD_CONV) ? 5 : 4;   // pack, tower (+ head conv), policy FC, finish
     if (rc == DG_OK && tower_ms) {
         rc = timed_pass(2, tower_ms);
         // leave the workspace holding a complete forward again

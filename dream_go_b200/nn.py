@@ -35,6 +35,7 @@ FLAG_NO_ROTATE = 0x8
 FLAG_BLOCKING_SYNC = 0x10
 FLAG_NO_GRAPH = 0x20
 FLAG_TOWER_LATE_A = 0x40
+FLAG_SEPARATE_HEAD_CONV = 0x80
 LEAF_PRIOR = 0x1
 
 

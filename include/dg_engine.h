@@ -46,6 +46,7 @@ extern "C" {
 #define DG_FLAG_LAYERWISE          0x4u  /* debug: one launch per convolution instead of the persistent tower kernel */
 #define DG_FLAG_NO_ROTATE          0x8u  /* debug: do not rotate the unit -> CTA-pair assignment between layers */
 #define DG_FLAG_TOWER_LATE_A      0x40u  /* debug (A/B): the tower kernel requests a layer's first activation windows after its filter slabs */
+#define DG_FLAG_SEPARATE_HEAD_CONV 0x80u /* debug (A/B): the head convolution runs as its own launch instead of as the tower kernel's last layer */
 #define DG_FLAG_NO_GRAPH          0x20u  /* debug: leaf batches are enqueued call by call instead of as one captured graph */
 #define DG_FLAG_BLOCKING_SYNC     0x10u  /* blocking calls poll the stream between 20 us naps instead of spinning in the driver
                                             (self-play: every core is busy searching and a spinning waiter steals one) */
