@@ -569,14 +569,21 @@ __global__ void __launch_bounds__(384) planes_from_stones_kernel(const RawPositi
             if (device_ladders) {
                 // a ladder can start here if the move puts a neighbouring enemy chain in atari (it has two liberties now)
                 // or extends an own chain that is in atari
+                bool captures = false;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int q = nb[k];
                     if (q < 0 || !col[q]) continue;
                     const int n = nlib[lab[q]];
                     if (col[q] == opp && n == 2) ladder_kinds |= 1;
+                    if (col[q] == opp && n == 1) captures = true;
                     if (col[q] == tm && n == 1) ladder_kinds |= 2;
                 }
+                // decided without reading anything (csrc/go_board.h: ladder_capture_first_step, is_ladder_escape): an attacker
+                // stone that neither captures nor has two liberties is captured itself; an extension that does not end up
+                // with exactly two liberties is no ladder escape
+                if (!captures && counts[0] < 2) ladder_kinds &= ~1;
+                if (counts[0] != 2) ladder_kinds &= ~2;
             } else {
                 if (bit(r.ladder_capture, t)) m |= 1u << 30;
                 if (bit(r.ladder_escape, t)) m |= 1u << 31;
