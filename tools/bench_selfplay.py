@@ -22,18 +22,19 @@ sys.path.insert(0, ROOT)
 
 
 def sample(net, *, games: int, parallel: int, rollouts: int, probes: int, seconds: float, threads: int, seed: int,
-           ex_it: bool = False, device_features="queue", cache_capacity: int = 0, ex_it_rollouts: int = 0, device_priors=None):
+           ex_it: bool = False, device_features="queue", cache_capacity: int = 0, ex_it_rollouts: int = 0, device_priors=None,
+           device_ladders=None, cache_shared: int = 0):
     """Runs a fixed-duration self-play sample on an existing engine; returns the driver's statistics.
     device_features: "queue" = the product path (leaf-batch queue, dg_selfplay_run_engine; device_priors None = chosen from
     the host threads per GPU), "prior" / True / False = the blocking predictor calls (priors on the device / planes on the
     device / planes on the host)."""
     from dream_go_b200 import mcts
-    predictor = (mcts.EngineQueue(net, device_priors=device_priors) if device_features == "queue"
+    predictor = (mcts.EngineQueue(net, device_priors=device_priors, device_ladders=device_ladders) if device_features == "queue"
                  else mcts.EnginePriorPredictor(net) if device_features == "prior" else mcts.EngineRawPredictor(net) if device_features
                  else mcts.EnginePredictor(net))
     st, sgf = mcts.self_play(predictor, num_games=games, num_parallel=parallel, num_rollout=rollouts,
                              probes_per_round=probes, num_threads=threads, ex_it=ex_it, num_ex_it_rollout=ex_it_rollouts or rollouts, seed=seed,
-                             max_seconds=seconds, cache_capacity=cache_capacity)
+                             max_seconds=seconds, cache_capacity=cache_capacity, cache_shared=cache_shared)
     return st, sgf
 
 
@@ -57,6 +58,9 @@ def main():
     ap.add_argument("--blocking-sync", action="store_true", help="(the default now; kept for old command lines)")
     ap.add_argument("--device-priors", action="store_true", help="also build the priors on the device (dg_engine_forward_raw_prior)")
     ap.add_argument("--host-priors", action="store_true", help="build the priors on the host even with few host threads per GPU")
+    ap.add_argument("--device-ladders", action="store_true", help="read the ladder planes on the device too (DG_RAW_DEVICE_LADDERS)")
+    ap.add_argument("--host-ladders", action="store_true", help="read the ladder planes on the host even with very few host threads per GPU")
+    ap.add_argument("--shared-cache", type=int, default=0, help="lock stripes of ONE transposition table of --cache entries shared by all games (0 = one table per game)")
     ap.add_argument("--blocking-calls", action="store_true",
                     help="drive the engine through the blocking predictor calls + one device thread per group (the round-1 driver) "
                          "instead of the leaf-batch queue")
@@ -85,7 +89,8 @@ def main():
                        "sample": (f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-stone cap)"
                                   if args.seconds > 0 else "all games played to the end"),
                        "probes_per_round": args.probes, "feature_planes": "host" if args.host_features else "device (csrc/features.cu)",
-                       "priors": "device" if args.device_priors or (not args.host_priors and not args.blocking_calls and threads < 8) else "host",
+                       "priors": "device" if args.device_priors or (not args.host_priors and not args.blocking_calls and threads < 4) else "host",
+                       "ladders": "device" if args.device_ladders or (not args.host_ladders and not args.blocking_calls and threads < 3) else "host",
                        "driver": "blocking predictor calls, one device thread per group" if args.blocking_calls or args.host_features
                                  else "leaf-batch queue (dg_selfplay_run_engine): one graph launch per batch, completion flag in pinned memory",
                        "host_threads_per_gpu": threads, "host_cores": cores,
@@ -105,7 +110,8 @@ def main():
                          device_features=("queue" if not (args.blocking_calls or args.host_features) else
                                           "prior" if args.device_priors else not args.host_features),
                          device_priors=True if args.device_priors else False if args.host_priors else None,
-                         cache_capacity=args.cache, ex_it_rollouts=args.ex_it_rollouts)
+                         device_ladders=True if args.device_ladders else False if args.host_ladders else None,
+                         cache_capacity=args.cache, cache_shared=args.shared_cache, ex_it_rollouts=args.ex_it_rollouts)
         wall = time.perf_counter() - t0
         tot = shards.selfplay_totals(st)
         shards.close()
