@@ -224,7 +224,7 @@ def self_play_samples(args, tensors, shards, rank: int, world: int, local_rank: 
     sp_net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=2 * BATCH, num_workspaces=4, flags=nn.FLAG_BLOCKING_SYNC)
     out = {"unit": "moves/s, evals/s", "rollouts": 800, "probes_per_round": 8, "host_threads_per_gpu": threads, "host_cores": os.cpu_count(),
            "driver": "dg_selfplay_run_engine (leaf-batch queue, graph launch per batch, device planes)",
-           "priors": "device" if threads < 4 else "host", "ladders": "device" if threads < 3 else "host", "sample_seconds": secs}
+           "priors": "device" if threads < 4 else "host", "ladders": "device" if threads < 2 else "host", "sample_seconds": secs}
     for key, games in (("configs2", 32), ("configs3_shape", 64), ("games128", 128)):
         shards.barrier()
         st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=games, rollouts=800, probes=8, seconds=secs, threads=threads,
@@ -232,6 +232,15 @@ def self_play_samples(args, tensors, shards, rank: int, world: int, local_rank: 
         tot = shards.selfplay_totals(st)
         out[key] = {"concurrent_games_per_gpu": games, "moves_per_s": tot["moves_per_s"], "nn_evals_per_s": tot["nn_evals_per_s"],
                     "mean_device_batch": tot["mean_device_batch"], "device_busy_frac": tot["predictor_seconds"] / (tot["seconds"] * world)}
+    # the reference keeps ONE 200,000-entry transposition table for the whole process (predictors/nn.rs:29-82): the same here
+    # (games then depend on each other's timing, as the reference's do); evaluations answered by the table are not counted
+    shards.barrier()
+    st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=128, rollouts=800, probes=8, seconds=secs, threads=threads,
+                                  seed=20261017 + rank, cache_capacity=200000, cache_shared=64)
+    tot = shards.selfplay_totals(st)
+    out["games128_shared_table"] = {"concurrent_games_per_gpu": 128, "moves_per_s": tot["moves_per_s"], "nn_evals_per_s": tot["nn_evals_per_s"],
+                                    "table": "one table of 200,000 entries in 64 lock stripes per process (cache_shared)",
+                                    "table_hits_rank0": st.get("cache_hits", 0), "evals_rank0": st.get("evals", 0)}
     sp_net.close()
     if rank == 0 and world == 1:
         # the reference's evaluation path behind the same loop

@@ -133,7 +133,7 @@ class EngineQueue:
     """The product path of self-play: one or several engines (one per device) driven through their leaf-batch queues by
     `dg_selfplay_run_engine` -- no blocking predictor call.  `device_priors`: build the leaves' priors on the device
     (None = when fewer than 4 host threads per engine are available, where the host is the scarce side); `device_ladders`: the
-    ladder planes are read on the device as well (None = below 3 host threads per engine)."""
+    ladder planes are read on the device as well (None = with a single host thread per engine)."""
     engines = True
 
     def __init__(self, networks, device_priors=None, device_ladders=None):
@@ -277,7 +277,7 @@ def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout:
         if priors is None:
             priors = threads < 4 * len(nets)
         if ladders is None:
-            ladders = threads < 3 * len(nets)
+            ladders = threads < 2 * len(nets)        # (measured: even with 2 host threads per engine the host reader wins)
         flags = (SELFPLAY_DEVICE_PRIORS if priors else 0) | (SELFPLAY_DEVICE_LADDERS if ladders else 0)
         rc = lib().dg_selfplay_run_engine(handles, len(nets), flags, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
     else:
