@@ -113,6 +113,27 @@ def test_leaf_batch_queue_driver_plays_the_same_games(small_net, flags):
         net.close()
 
 
+def test_self_play_on_two_engines_of_one_process(small_net):
+    """`NnPredictor` drives every GPU from one process, round-robin (predictors/nn.rs:84-92): dg_selfplay_run_engine with two
+    engines on two devices (groups dealt round-robin, host threads shared) plays the games one engine plays."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nets = [nn.Network.from_tensors(small_net, device=d, max_batch=128, num_workspaces=4) for d in (0, 1)]
+    try:
+        kw = dict(num_games=8, num_parallel=6, num_rollout=40, probes_per_round=4, max_plies=20, seed=13, num_threads=4)
+        one, sgf_one = pm.self_play(pm.EngineQueue(nets[0], device_priors=False), **kw)
+        for priors in (False, True):
+            two, sgf_two = pm.self_play(pm.EngineQueue(nets, device_priors=priors), **kw)
+            assert two["digest"] == one["digest"] and sorted(sgf_two) == sorted(sgf_one) and two["evals"] == one["evals"]
+        # and both devices really worked: a deadline run with many games keeps both engines' batches in flight
+        big, _ = pm.self_play(pm.EngineQueue(nets), max_seconds=1.0, **{**kw, "num_games": 10000, "num_parallel": 64, "max_plies": 722})
+        assert big["evals"] > 0 and big["rounds"] > 4
+    finally:
+        for net in nets:
+            net.close()
+
+
 def test_whole_game_on_engine_matches_oracle_game(engine):
     """A self-play game on the engine, move for move against the oracle's self_play_one fed by the same engine."""
     import re
