@@ -12,12 +12,14 @@ sys.path.insert(0, %r)
 import numpy as np
 from dream_go_b200 import nn, weights
 t = weights.synthetic_network(seed=20261017, num_blocks=9)
-net = nn.Network.from_tensors(t, max_batch=256, num_workspaces=1)
-f = net.pinned((256, 361, 32), np.float16); f[...] = weights.bernoulli_features(256, seed=3)
-v, p = net.pinned((256,), np.float16), net.pinned((256, 362), np.float16)
+B = int(os.environ.get("DG_AB_BATCH", "256"))
+net = nn.Network.from_tensors(t, max_batch=B, num_workspaces=1)
+f = net.pinned((B, 361, 32), np.float16); f[...] = weights.bernoulli_features(B, seed=3)
+v, p = net.pinned((B,), np.float16), net.pinned((B, 362), np.float16)
 for _ in range(5): net.forward_into(f, v, p)
-ms, tms, _ = net.time_resident(256, 2500, tower=True, flush_l2=True)
-print(json.dumps({"ms_forward": ms / 2500, "us_tower": 1e3 * tms / 2500, "checksum": float(p.astype(np.float64).sum())}))
+iters = 2500 if B >= 256 else 4000
+ms, tms, _ = net.time_resident(B, iters, tower=True, flush_l2=True)
+print(json.dumps({"batch": B, "ms_forward": ms / iters, "us_tower": 1e3 * tms / iters, "checksum": float(p.astype(np.float64).sum())}))
 ''' % ROOT
 out = []
 for rnd in range(2):
