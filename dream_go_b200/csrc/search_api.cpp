@@ -362,7 +362,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         config->num_games <= 0 || config->num_parallel <= 0)
         return DG_ERR_INVALID_ARGUMENT;
     const bool raw_mode = raw_predictor != nullptr || prior_predictor != nullptr || engine_mode;
-    const bool prior_mode = prior_predictor != nullptr || (engine_mode && (engine_flags & DG_SELFPLAY_DEVICE_PRIORS));
+    const bool prior_mode = prior_predictor != nullptr || (engine_mode && (engine_flags & DG_SELFPLAY_DEVICE_PRIORS));   // (the start value under DG_SELFPLAY_AUTO_PRIORS)
     Driver d;
     d.cfg = *config;
     d.device_ladders = engine_mode && (engine_flags & DG_SELFPLAY_DEVICE_LADDERS);
@@ -375,6 +375,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     int hw = (int)std::thread::hardware_concurrency();
     int n_threads = d.cfg.num_threads > 0 ? d.cfg.num_threads : (hw > 0 ? hw : 1);
     int n_slots = std::min(config->num_parallel, config->num_games);
+    const int n_workers_total = std::max(1, std::min(n_threads, n_slots));
     d.games = std::vector<Game>(n_slots);
     for (Game& g : d.games) d.start_game(g);
 
@@ -420,6 +421,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         const uint8_t* r_legal = nullptr;
         const float* r_prior = nullptr;
         dg_leaf_batch* lb = nullptr;                              // engine mode
+        bool with_prior = false;                                  // this round's batch also carries the leaves' priors
         int64_t t_submit = 0;
         enum State { HOST, SUBMITTED, RETIRED } state = HOST;     // guarded by sched_m
         size_t next = 0, done = 0;                                // games handed out / advanced in this round (sched_m)
@@ -535,8 +537,20 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     std::atomic<int64_t> ns_worker_idle{0}, ns_worker_busy{0}, ns_worker_cpu{0}, ns_device_cpu{0};
     auto thread_cpu_ns = [] { timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return (int64_t)ts.tv_sec * 1000000000 + ts.tv_nsec; };
     int64_t ns_serial = 0;                    // guarded by gather_m
-    int calls_in_flight = 0;                  // trace: wall time during which no predictor call was in flight (sched_m)
+    int calls_in_flight = 0;                  // wall time during which no predictor call was in flight (sched_m)
     int64_t idle_since = 0, ns_idle = 0;
+    // DG_SELFPLAY_AUTO_PRIORS: where the leaves' priors are built follows which side is scarce.  The signal is how busy the
+    // worker threads are (time inside advance() / finalize() over threads x wall time, per window of 64 batches): above 85 %
+    // the host is the limit and the priors move to the device (that takes a fifth of the host's work per leaf away); below
+    // 60 % they move back, because on the device they only lengthen the batches; a decision stands for at least four
+    // windows.  (Whether the device runs out of work is NOT the signal: with two groups of games it does so 10 % of the time
+    // for structural reasons, and device priors then cost 4 %.)  The priors are bit-identical either way, so the games do not
+    // depend on the switch.
+    const bool auto_priors = engine_mode && (engine_flags & DG_SELFPLAY_AUTO_PRIORS) != 0;
+    bool priors_on_device = prior_mode;
+    std::atomic<int64_t> busy_ns{0};
+    int64_t win_start = 0, win_idle = 0, win_busy = 0, prior_switches = 0, prior_batches = 0;
+    int win_batches = 0, win_hold = 0;
 
     std::mutex sched_m;                       // group states, task cursors, rc, stop
     std::condition_variable sched_cv;         // workers: "a group came back from the device" / "stop"
@@ -598,15 +612,36 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         gl.unlock();
         if (!empty && grp.lb) {
             // one graph launch: H2D, planes + legal moves, tower, heads, (priors), D2H, completion flag
-            int32_t r = push_rc ? push_rc : dg_leaf_batch_submit(grp.lb, prior_mode ? DG_LEAF_PRIOR : 0u);
+            bool with_prior;
+            { std::lock_guard<std::mutex> lk(sched_m); with_prior = priors_on_device; }
+            int32_t r = push_rc ? push_rc : dg_leaf_batch_submit(grp.lb, with_prior ? DG_LEAF_PRIOR : 0u);
             std::lock_guard<std::mutex> lk(sched_m);
             if (r != DG_OK) {
                 if (rc == DG_OK) rc = r;
                 retire(grp);
                 stop = true;
             } else {
+                grp.with_prior = with_prior;
                 grp.t_submit = now_ns();
-                if (trace_driver && calls_in_flight++ == 0 && idle_since) ns_idle += grp.t_submit - idle_since;
+                if (with_prior) ++prior_batches;
+                if (calls_in_flight++ == 0 && idle_since) {
+                    ns_idle += grp.t_submit - idle_since;
+                    win_idle += grp.t_submit - idle_since;
+                }
+                if (auto_priors) {
+                    if (win_start == 0) win_start = grp.t_submit;
+                    if (++win_batches >= 64) {
+                        const int64_t busy = busy_ns.load(std::memory_order_relaxed);
+                        const double load = (double)(busy - win_busy) / ((double)n_workers_total * (double)std::max<int64_t>(1, grp.t_submit - win_start));
+                        const bool want = load > 0.85 ? true : load < 0.60 ? false : priors_on_device;
+                        if (win_hold > 0) --win_hold;
+                        else if (want != priors_on_device) { priors_on_device = want; ++prior_switches; win_hold = 4; }
+                        win_start = grp.t_submit;
+                        win_busy = busy;
+                        win_idle = 0;
+                        win_batches = 0;
+                    }
+                }
                 grp.state = Group::SUBMITTED;
             }
             if (r != DG_OK) sched_cv.notify_all();
@@ -623,7 +658,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
     auto complete = [&](Group& grp, int32_t ready) {
         const int64_t t = now_ns();
         eval_ns += t - grp.t_submit;
-        if (trace_driver && --calls_in_flight == 0) idle_since = t;
+        if (--calls_in_flight == 0) idle_since = t;
         if (ready < 0) {
             if (rc == DG_OK) rc = ready;
             retire(grp);
@@ -707,10 +742,13 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 }
             }
             const bool absorb = grp->absorb;
+            const int64_t t_work = auto_priors ? now_ns() : 0;
             advance(d.games[grp->slots[i]], absorb ? grp->r_value : nullptr, absorb ? grp->r_policy : nullptr,
-                    absorb && raw_mode ? grp->r_legal : nullptr, absorb && prior_mode ? grp->r_prior : nullptr);
+                    absorb && raw_mode ? grp->r_legal : nullptr,
+                    absorb && (engine_mode ? grp->with_prior : prior_mode) ? grp->r_prior : nullptr);
             bool last;
             { std::lock_guard<std::mutex> lk(sched_m); last = ++grp->done == grp->slots.size(); }
+            if (auto_priors) busy_ns.fetch_add(now_ns() - t_work, std::memory_order_relaxed);
             if (last) finalize(*grp);
         }
     };
@@ -719,7 +757,7 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
         for (int gi = 0; gi < n_groups; ++gi) groups(gi).device_thread = std::thread(device_loop, std::ref(groups(gi)));
     {
         std::vector<std::thread> workers;
-        const int n_workers = std::max(1, std::min(n_threads, n_slots));
+        const int n_workers = n_workers_total;
         for (int i = 1; i < n_workers; ++i) workers.emplace_back(worker_loop);
         const int64_t cpu_before = trace_driver ? thread_cpu_ns() : 0;   // the calling thread has a history
         worker_loop();
@@ -740,6 +778,9 @@ static int32_t selfplay_impl(dg_predict_fn predictor, dg_predict_raw_fn raw_pred
                 "predictor calls %.3f s (sum over device threads), no call in flight %.3f s, CPU time: workers %.3f s, device threads %.3f s, wall %.3f s\n",
                 n_groups, n_threads, (long long)rounds, ns_worker_busy.load() * 1e-9, ns_worker_idle.load() * 1e-9, ns_serial * 1e-9,
                 (double)eval_ns.load() * 1e-9, ns_idle * 1e-9, ns_worker_cpu.load() * 1e-9, ns_device_cpu.load() * 1e-9, seconds());
+    if (trace_driver && engine_mode)
+        fprintf(stderr, "[dg_selfplay] priors on the device for %lld of %lld batches, %lld switches%s\n", (long long)prior_batches, (long long)rounds,
+                (long long)prior_switches, auto_priors ? " (auto)" : "");
     if (trace_driver) {
         PhaseClock& c = phase_clock();
         const double n = (double)std::max<uint64_t>(1, c.leaves.load());

@@ -68,6 +68,7 @@ ABI = {
 }
 SELFPLAY_DEVICE_PRIORS = 0x1
 SELFPLAY_DEVICE_LADDERS = 0x2
+SELFPLAY_AUTO_PRIORS = 0x4
 _ready = False
 
 
@@ -132,7 +133,7 @@ class EnginePriorPredictor:
 class EngineQueue:
     """The product path of self-play: one or several engines (one per device) driven through their leaf-batch queues by
     `dg_selfplay_run_engine` -- no blocking predictor call.  `device_priors`: build the leaves' priors on the device
-    (None = when fewer than 4 host threads per engine are available, where the host is the scarce side); `device_ladders`: the
+    (None = the driver decides batch by batch from whether the device runs out of work, DG_SELFPLAY_AUTO_PRIORS); `device_ladders`: the
     ladder planes are read on the device as well (None = with a single host thread per engine)."""
     engines = True
 
@@ -270,15 +271,20 @@ def self_play(predictor, *, num_games: int, num_parallel: int = 32, num_rollout:
         import os
         nets = predictor.networks
         handles = (C.c_void_p * len(nets))(*[n._handle for n in nets])
-        # what else moves to the device is a question of which side is scarce: with 4 or more host threads per engine the
-        # device is the limit even with the priors and the ladders on the host (measured), below that the host is
+        # what else moves to the device is a question of which side is scarce, and that changes during a run (a leaf of the
+        # middle game costs the host twice what a leaf of the opening costs): by default the driver decides batch by batch
+        # (DG_SELFPLAY_AUTO_PRIORS), starting on the device when host threads are few
         threads = num_threads if num_threads > 0 else (os.cpu_count() or 1)
         priors, ladders = predictor.device_priors, predictor.device_ladders
+        flags = 0
         if priors is None:
-            priors = threads < 4 * len(nets)
+            flags |= SELFPLAY_AUTO_PRIORS | (SELFPLAY_DEVICE_PRIORS if threads < 8 * len(nets) else 0)
+        elif priors:
+            flags |= SELFPLAY_DEVICE_PRIORS
         if ladders is None:
             ladders = threads < 2 * len(nets)        # (measured: even with 2 host threads per engine the host reader wins)
-        flags = (SELFPLAY_DEVICE_PRIORS if priors else 0) | (SELFPLAY_DEVICE_LADDERS if ladders else 0)
+        if ladders:
+            flags |= SELFPLAY_DEVICE_LADDERS
         rc = lib().dg_selfplay_run_engine(handles, len(nets), flags, C.byref(cfg), C.byref(stats), buf, sgf_capacity)
     else:
         fn, ctx = _fn_ctx(predictor)

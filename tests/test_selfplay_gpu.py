@@ -101,7 +101,9 @@ def test_leaf_batch_queue_driver_plays_the_same_games(small_net, flags):
     try:
         kw = dict(num_games=6, num_parallel=5, num_rollout=40, probes_per_round=4, max_plies=20, seed=11)
         ref, sgf_ref = pm.self_play(pm.EnginePredictor(net), num_threads=2, **kw)
-        for priors, ladders, threads, groups in ((False, False, 1, 0), (True, False, 4, 2), (False, True, 3, 4), (True, True, 2, 3)):
+        # (None = DG_SELFPLAY_AUTO_PRIORS: the driver moves the prior construction between host and device as it sees fit)
+        for priors, ladders, threads, groups in ((False, False, 1, 0), (True, False, 4, 2), (False, True, 3, 4), (True, True, 2, 3),
+                                                 (None, False, 2, 4), (None, None, 8, 2)):
             got, sgf = pm.self_play(pm.EngineQueue(net, device_priors=priors, device_ladders=ladders), num_threads=threads,
                                     num_groups=groups, **kw)
             assert got["digest"] == ref["digest"] and sorted(sgf) == sorted(sgf_ref), (priors, ladders, threads, groups)
