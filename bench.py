@@ -224,7 +224,8 @@ def self_play_samples(args, tensors, shards, rank: int, world: int, local_rank: 
     sp_net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=2 * BATCH, num_workspaces=4, flags=nn.FLAG_BLOCKING_SYNC)
     out = {"unit": "moves/s, evals/s", "rollouts": 800, "probes_per_round": 8, "host_threads_per_gpu": threads, "host_cores": os.cpu_count(),
            "driver": "dg_selfplay_run_engine (leaf-batch queue, graph launch per batch, device planes)",
-           "priors": "device" if threads < 4 else "host", "ladders": "device" if threads < 2 else "host", "sample_seconds": secs}
+           "priors": "host or device, decided batch by batch from the worker threads' load (DG_SELFPLAY_AUTO_PRIORS)",
+           "ladders": "device" if threads < 2 else "host", "sample_seconds": secs}
     for key, games in (("configs2", 32), ("configs3_shape", 64), ("games128", 128)):
         shards.barrier()
         st, _ = bench_selfplay.sample(sp_net, games=100000, parallel=games, rollouts=800, probes=8, seconds=secs, threads=threads,

@@ -89,7 +89,8 @@ def main():
                        "sample": (f"fixed-duration sample: the first {args.seconds:.0f} s of the run (games with random-init weights reach the 722-stone cap)"
                                   if args.seconds > 0 else "all games played to the end"),
                        "probes_per_round": args.probes, "feature_planes": "host" if args.host_features else "device (csrc/features.cu)",
-                       "priors": "device" if args.device_priors or (not args.host_priors and not args.blocking_calls and threads < 4) else "host",
+                       "priors": "device" if args.device_priors else "host" if args.host_priors or args.blocking_calls or args.host_features
+                                 else "auto: host or device batch by batch, from the worker threads' load (DG_SELFPLAY_AUTO_PRIORS)",
                        "ladders": "device" if args.device_ladders or (not args.host_ladders and not args.blocking_calls and threads < 2) else "host",
                        "driver": "blocking predictor calls, one device thread per group" if args.blocking_calls or args.host_features
                                  else "leaf-batch queue (dg_selfplay_run_engine): one graph launch per batch, completion flag in pinned memory",
