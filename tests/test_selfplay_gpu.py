@@ -158,3 +158,28 @@ def test_whole_game_on_engine_matches_oracle_game(engine):
     game_rng = Rng((seed * 0x9e3779b97f4a7c15 + 1) & ((1 << 64) - 1))
     want_komi, want_moves = om.self_play_one(engine_on_features, game_rng, num_rollout=rollouts, probes_per_round=2, max_plies=plies)
     assert komi == want_komi and moves == want_moves
+
+
+def test_self_play_on_engine_with_one_shared_table(small_net):
+    """The process-wide transposition table (`cache_shared`, predictors/nn.rs:29-82) on the engine path: every game is played
+    to the end with legal moves, later games reuse the evaluations of earlier ones (all start from the empty board), fewer
+    positions reach the device than without a table."""
+    import re
+    net = nn.Network.from_tensors(small_net, max_batch=128, num_workspaces=4)
+    try:
+        kw = dict(num_games=8, num_parallel=2, num_rollout=24, probes_per_round=2, max_plies=8, seed=3, num_threads=2)
+        plain, _ = pm.self_play(pm.EngineQueue(net, device_priors=False), **kw)
+        shared, games = pm.self_play(pm.EngineQueue(net, device_priors=False), cache_capacity=200000, cache_shared=16, **kw)
+        assert shared["games_finished"] == 8 and len(games) == 8 and shared["moves"] == plain["moves"] == 64
+        assert shared["cache_hits"] > 0 and shared["evals"] < plain["evals"]
+        for sgf in games:
+            komi = float(re.search(r"KM\[([-0-9.]+)\]", sgf).group(1))
+            board = ogo.Board(komi)
+            for m in re.finditer(r";([BW])\[([a-s]{0,2})\]", sgf):
+                color = 1 if m.group(1) == "B" else 2
+                if m.group(2):
+                    x, y = ord(m.group(2)[0]) - 97, ord(m.group(2)[1]) - 97
+                    assert board.is_valid(color, x, y)
+                    board.place(color, x, y)
+    finally:
+        net.close()
