@@ -208,6 +208,24 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def self_play_summary(self_play: dict) -> dict:
+    """The metric's other half in a form that survives the driver's parsing (sub-keys of `e2e` are kept; unknown top-level keys
+    are not) and its 1,500-character tail of stdout (the last key of the line): [moves/s, NN evals/s] per sample."""
+    pair = lambda d: [round(d["moves_per_s"], 1), round(d["nn_evals_per_s"])]
+    out = {"unit": "[moves/s, NN evals/s], --self-play --num-rollout 800, whole job", "host_threads_per_gpu": self_play["host_threads_per_gpu"],
+           "configs2_32_games_per_gpu": pair(self_play["configs2"]), "configs3_shape_64_games_per_gpu": pair(self_play["configs3_shape"]),
+           "games128_per_gpu": pair(self_play["games128"])}
+    if "games128_shared_table" in self_play:
+        out["games128_shared_table"] = pair(self_play["games128_shared_table"])
+    ref = self_play.get("cudnn_reference") or {}
+    for bs in (16, 32):
+        if f"batch{bs}" in ref:
+            out[f"cudnn_reference_32_games_batch{bs}"] = pair(ref[f"batch{bs}"])
+    if "batch16" in ref and ref["batch16"]["moves_per_s"] > 0:
+        out["configs2_vs_cudnn_reference_batch16"] = round(self_play["configs2"]["moves_per_s"] / ref["batch16"]["moves_per_s"], 2)
+    return out
+
+
 def self_play_samples(args, tensors, shards, rank: int, world: int, local_rank: int):
     """Fixed-duration samples of `--self-play --num-rollout 800` from the empty board (random-init weights: games run to
     the 722-ply cap) through the product path -- leaf-batch queue, planes / legal moves (/ priors) on the device:
@@ -392,6 +410,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             sustained["tower_frac_of_sustained_peak"] = tf / float(peak_sus)
             sustained["sustained_peak"] = float(peak_sus)
         line["sustained"] = sustained
+    sp_summary = self_play_summary(self_play) if self_play is not None else None
+    if sp_summary is not None:
+        line["e2e"]["self_play"] = sp_summary
     if world == 1 and not os.environ.get("DG_BENCH_SKIP_CPU"):      # skipped only under the profiler
         line["cudnn_baseline"] = cudnn_baseline(tensors, feats, args.steps)
         if "value" in line["cudnn_baseline"]:      # the ratio the north star asks for: this engine vs the reference's cuDNN path, same box
@@ -399,6 +420,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         rate, info = oracle_rate(seconds_target=15.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
         line["host_features"] = host_feature_rates()
+    if sp_summary is not None:
+        line["self_play_summary"] = sp_summary          # last: the tail of stdout is what the driver's record keeps verbatim
     print(json.dumps(line), flush=True)
 
 

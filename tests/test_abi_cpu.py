@@ -170,3 +170,19 @@ def test_engine_entry_points_reject_null_engine():
     assert L.dg_engine_max_batch(None) == 0 and L.dg_engine_num_workspaces(None) == 0
     from dream_go_b200 import mcts
     assert mcts.lib().dg_selfplay_run_engine(None, 0, 0, None, None, None, 0) == -5
+
+
+def test_bench_self_play_summary_on_recorded_lines():
+    """bench.py's compact self-play summary (the part of the line the driver's record keeps) on the lines recorded in profiles/."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, has_ref in (("r02_bench_n1.json", True), ("r02_bench_n8.json", False)):
+        line = json.load(open(os.path.join(ROOT, "profiles", name)))
+        out = bench.self_play_summary(line["self_play"])
+        assert out["configs2_32_games_per_gpu"][0] > 0 and out["games128_per_gpu"][1] > out["configs2_32_games_per_gpu"][1]
+        assert ("cudnn_reference_32_games_batch16" in out) == has_ref
+        if has_ref:
+            assert out["configs2_vs_cudnn_reference_batch16"] > 5
+        assert len(json.dumps(out)) < 900
