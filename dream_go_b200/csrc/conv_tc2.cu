@@ -302,13 +302,16 @@ cudaError_t launch_conv_pair(int k_halves, const CUtensorMap& tm_act, const CUte
 }
 
 // =============================================================================================
-// The whole tower (up-sampling layer + every residual-block convolution) as ONE persistent launch.
+// The whole tower (up-sampling layer + every residual-block convolution + the head convolution) as ONE
+// persistent launch.
 //
 // Same CTA-pair machinery as conv3x3_pair_kernel, plus:
 //   * no global barrier between layers: a 256-row unit of layer l only needs units u-1, u, u+1 of
-//     layer l-1, published through per-tile progress flags (st.release by the epilogue, ld.acquire
-//     + fence.proxy.async by the TMA producer).  The same RAW chain also covers every WAR hazard of
-//     the x/y ping-pong buffers;
+//     layer l-1, published through per-tile progress flags (st.release by the epilogue; the TMA producer
+//     reads a unit's three flags together with relaxed loads, then fence.acq_rel + fence.proxy.async).
+//     The same RAW chain also covers every WAR hazard of the x/y ping-pong buffers;
+//   * the last layer may be the head convolution (wrows = 16: 8 policy + 2 value samples + 6 zero channels,
+//     N = 16 MMAs, 1 KiB slabs at the start of the slab slots) whose epilogue writes pbuf / vbuf;
 //   * the filter bank of layer l+1 replaces layer l's in shared memory slab by slab (one 8 KiB slab per
 //     (tap, k-half), in the order the MMAs consume them): in the last unit of a layer every tap commits
 //     its own w_free barrier when its MMAs retire, the producer re-fetches that slab immediately, and in
