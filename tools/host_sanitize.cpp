@@ -1,6 +1,7 @@
 // AddressSanitizer / UBSan (and ThreadSanitizer: -fsanitize=thread) run of the host half (go_api.cpp + search_api.cpp) with the
 // RandomPredictor: self-play with per-game transposition tables, with --ex-it, policy-only play, with ONE striped table shared
-// by all games and threads, and a 600-ply game through the board API.
+// by all games and threads, the queue-driven driver (dg_selfplay_run_engine) on a CPU stand-in for the leaf-batch queue, and a
+// 600-ply game through the board API.
 //   g++ -O1 -g -fsanitize=address,undefined -march=x86-64-v3 -ffp-contract=off -std=c++17 -Idream_go_b200/csrc \
 //       tools/host_sanitize.cpp dream_go_b200/csrc/search_api.cpp dream_go_b200/csrc/go_api.cpp -o /tmp/host_sanitize -lpthread && /tmp/host_sanitize
 #include <cstdio>
@@ -9,17 +10,121 @@
 extern "C" int32_t dg_engine_forward_packed(dg_engine*, const dg_packed_position*, int32_t, uint16_t*, uint16_t*) { return -1; }
 extern "C" int32_t dg_engine_forward_raw(dg_engine*, const dg_raw_position*, int32_t, uint16_t*, uint16_t*, uint8_t*) { return -1; }
 extern "C" int32_t dg_engine_forward_raw_prior(dg_engine*, const dg_raw_position*, int32_t, uint16_t*, uint16_t*, uint8_t*, float*) { return -1; }
-extern "C" int32_t dg_engine_max_batch(dg_engine*) { return 0; }
-extern "C" int32_t dg_engine_num_workspaces(dg_engine*) { return 0; }
-extern "C" int32_t dg_engine_batch_acquire(dg_engine*, dg_leaf_batch**) { return -1; }
-extern "C" void dg_engine_batch_release(dg_leaf_batch*) {}
-extern "C" int32_t dg_leaf_batch_push(dg_leaf_batch*, const dg_raw_position*, int32_t) { return -1; }
-extern "C" int32_t dg_leaf_batch_submit(dg_leaf_batch*, uint32_t) { return -1; }
-extern "C" int32_t dg_leaf_batch_ready(dg_leaf_batch*) { return -1; }
-extern "C" void dg_leaf_batch_reset(dg_leaf_batch*) {}
-extern "C" const uint16_t* dg_leaf_batch_value(const dg_leaf_batch*) { return nullptr; }
-extern "C" const uint16_t* dg_leaf_batch_policy(const dg_leaf_batch*) { return nullptr; }
-extern "C" const uint8_t* dg_leaf_batch_legal(const dg_leaf_batch*) { return nullptr; }
+// ---- a functional CPU stand-in for the engine's leaf-batch queue (include/dg_engine.h), so that the queue-driven driver
+// (dg_selfplay_run_engine: polling scheduler, round-robin over engines, deadline handling) runs under the sanitizers without a
+// device.  A "device" thread per batch evaluates the raw positions: legal moves from the stones and hashes alone (chains by
+// flood fill, captures, super-ko through the zobrist table -- what csrc/features.cu does), value / policy = a hash of the stones.
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include "../dream_go_b200/csrc/go_board.h"
+#include "../dream_go_b200/csrc/search.h"
+struct dg_engine { int max_batch = 256, workspaces = 4; std::atomic<int> taken{0}; };
+struct dg_leaf_batch {
+    dg_engine* e;
+    std::vector<dg_raw_position> slots;
+    std::vector<uint16_t> value, policy;
+    std::vector<uint8_t> legal;
+    std::atomic<int> fill{0}, committed{0}, ready{1};
+    int submitted = 0;
+    std::thread worker;
+    ~dg_leaf_batch() { if (worker.joinable()) worker.join(); }
+};
+static void mock_legal(const dg_raw_position& r, uint8_t* legal) {
+    using namespace dg;
+    const Tables& T = tables();
+    auto bit = [](const uint32_t* m, int i) { return (m[i >> 5] >> (i & 31)) & 1u; };
+    int col[361], lab[361], nlib[361];
+    for (int p = 0; p < 361; ++p) { col[p] = bit(r.black, p) ? 1 : bit(r.white, p) ? 2 : 0; lab[p] = -1; }
+    std::vector<std::vector<int>> chains;
+    for (int p = 0; p < 361; ++p) {
+        if (!col[p] || lab[p] >= 0) continue;
+        std::vector<int> st{p}, ch;
+        lab[p] = (int)chains.size();
+        while (!st.empty()) {
+            int s = st.back(); st.pop_back(); ch.push_back(s);
+            for (int k = 0; k < T.n_nbr[s]; ++k) { int q = T.nbr_list[s][k]; if (col[q] == col[p] && lab[q] < 0) { lab[q] = lab[p]; st.push_back(q); } }
+        }
+        bool seen[361] = {false}; int n = 0;
+        for (int s : ch) for (int k = 0; k < T.n_nbr[s]; ++k) { int q = T.nbr_list[s][k]; if (!col[q] && !seen[q]) { seen[q] = true; ++n; } }
+        nlib[chains.size()] = n;
+        chains.push_back(ch);
+    }
+    const int c = r.to_move, opp = 3 - c;
+    for (int p = 0; p < 361; ++p) {
+        legal[p] = 0;
+        if (col[p]) continue;
+        bool ok = false;
+        uint64_t h = r.hash ^ T.zobrist[c][p];
+        int cap[4], nc = 0;
+        for (int k = 0; k < T.n_nbr[p]; ++k) {
+            int q = T.nbr_list[p][k];
+            if (!col[q]) { ok = true; continue; }
+            const int n = nlib[lab[q]];
+            if ((col[q] == c) == (n >= 2)) ok = true;
+            if (col[q] == opp && n < 2) {
+                bool dup = false;
+                for (int j = 0; j < nc; ++j) dup |= cap[j] == lab[q];
+                if (!dup) { cap[nc++] = lab[q]; for (int s : chains[lab[q]]) h ^= T.zobrist[opp][s]; }
+            }
+        }
+        if (!ok) continue;
+        bool ko = false;
+        if (bit(r.visited, p)) for (int i = 0; i < 16; ++i) ko |= r.hash_history[i] == h;
+        legal[p] = !ko;
+    }
+}
+static void mock_evaluate(dg_leaf_batch* b) {
+    for (int i = 0; i < b->submitted; ++i) {
+        const dg_raw_position& r = b->slots[i];
+        mock_legal(r, &b->legal[(size_t)i * 361]);
+        uint64_t h = 0xcbf29ce484222325ull ^ r.to_move ^ ((uint64_t)(r.symmetry & 7) << 8);
+        for (int w = 0; w < 12; ++w) { h ^= r.black[w]; h *= 0x100000001b3ull; h ^= r.white[w]; h *= 0x100000001b3ull; }
+        dg::Rng rng(h);
+        b->value[i] = dg::f32_to_f16_bits((float)(2.0 * rng.uniform() - 1.0));
+        float x[362], total = 0.f;
+        for (int k = 0; k < 362; ++k) { x[k] = (float)rng.uniform(); total += x[k]; }
+        for (int k = 0; k < 362; ++k) b->policy[(size_t)i * 362 + k] = dg::f32_to_f16_bits(x[k] / total);
+    }
+    b->ready.store(1, std::memory_order_release);
+}
+extern "C" int32_t dg_engine_max_batch(dg_engine* e) { return e ? e->max_batch : 0; }
+extern "C" int32_t dg_engine_num_workspaces(dg_engine* e) { return e ? e->workspaces : 0; }
+extern "C" int32_t dg_engine_batch_acquire(dg_engine* e, dg_leaf_batch** out) {
+    if (!e || !out) return -5;
+    dg_leaf_batch* b = new dg_leaf_batch();
+    b->e = e;
+    b->slots.resize(e->max_batch); b->value.resize(e->max_batch); b->policy.resize((size_t)e->max_batch * 362); b->legal.resize((size_t)e->max_batch * 361);
+    e->taken++;
+    *out = b;
+    return 0;
+}
+extern "C" void dg_engine_batch_release(dg_leaf_batch* b) { if (b) { b->e->taken--; delete b; } }
+extern "C" int32_t dg_leaf_batch_push(dg_leaf_batch* b, const dg_raw_position* pos, int32_t n) {
+    int at = b->fill.load();
+    do { if (at < 0 || at + n > b->e->max_batch) return -1; } while (!b->fill.compare_exchange_weak(at, at + n));
+    memcpy(&b->slots[at], pos, sizeof(dg_raw_position) * (size_t)n);
+    b->committed.fetch_add(n, std::memory_order_release);
+    return at;
+}
+extern "C" int32_t dg_leaf_batch_submit(dg_leaf_batch* b, uint32_t outputs) {
+    if (outputs) return -5;                                       // the stand-in has no prior construction
+    const int n = b->fill.exchange(INT32_MIN);
+    if (n <= 0) return -5;
+    while (b->committed.load(std::memory_order_acquire) < n) {}
+    if (b->worker.joinable()) b->worker.join();
+    b->submitted = n;
+    b->ready.store(0, std::memory_order_release);
+    b->worker = std::thread(mock_evaluate, b);
+    return 0;
+}
+extern "C" int32_t dg_leaf_batch_ready(dg_leaf_batch* b) { return b->ready.load(std::memory_order_acquire); }
+extern "C" void dg_leaf_batch_reset(dg_leaf_batch* b) { b->committed.store(0); b->fill.store(0, std::memory_order_release); }
+extern "C" const uint16_t* dg_leaf_batch_value(const dg_leaf_batch* b) { return b->value.data(); }
+extern "C" const uint16_t* dg_leaf_batch_policy(const dg_leaf_batch* b) { return b->policy.data(); }
+extern "C" const uint8_t* dg_leaf_batch_legal(const dg_leaf_batch* b) { return b->legal.data(); }
 extern "C" const float* dg_leaf_batch_prior(const dg_leaf_batch*) { return nullptr; }
 int main(){
   for (int variant = 0; variant < 4; ++variant) {
@@ -30,6 +135,30 @@ int main(){
     int rc=dg_selfplay_run(dg_random_predict,nullptr,&c,&s,sgf.data(),sgf.size());
     printf("variant %d rc %d games %ld moves %ld evals %ld hits %ld\n",variant,rc,(long)s.games_finished,(long)s.moves,(long)s.evals,(long)s.cache_hits);
   }
+  // the queue-driven driver on two stand-in engines: same games whatever the number of workers, groups and engines
+  {
+    uint64_t digests[4];
+    for (int variant = 0; variant < 4; ++variant) {
+      dg_engine e0, e1;
+      dg_engine* engines[2] = {&e0, &e1};
+      dg_selfplay_config c{}; c.num_games=7; c.num_parallel=5; c.num_rollout=50; c.probes_per_round=4; c.max_plies=24; c.dirichlet_noise=0.25f; c.temperature=0.8f; c.seed=11;
+      c.num_threads = variant == 0 ? 1 : 4; c.num_groups = variant == 2 ? 1 : 2;
+      dg_selfplay_stats s{};
+      std::vector<char> sgf(1<<20);
+      int rc = dg_selfplay_run_engine(engines, variant == 3 ? 1 : 2, 0u, &c, &s, sgf.data(), sgf.size());
+      digests[variant] = s.digest;
+      printf("queue variant %d rc %d games %ld moves %ld evals %ld batches %ld leaf batches still held %d\n", variant, rc, (long)s.games_finished,
+             (long)s.moves, (long)s.evals, (long)s.rounds, e0.taken.load() + e1.taken.load());
+      if (rc || s.games_finished != 7 || digests[variant] != digests[0]) { printf("FAILED\n"); return 1; }
+    }
+    dg_engine e0; dg_engine* engines[1] = {&e0};                   // a deadline in the middle of the run
+    dg_selfplay_config c{}; c.num_games=100000; c.num_parallel=16; c.num_rollout=200; c.probes_per_round=8; c.num_threads=4; c.seed=5; c.max_seconds=0.5;
+    c.dirichlet_noise=0.25f; c.temperature=0.8f;
+    dg_selfplay_stats s{};
+    int rc = dg_selfplay_run_engine(engines, 1, 0u, &c, &s, nullptr, 0);
+    printf("queue deadline run rc %d evals %ld seconds %.2f held %d\n", rc, (long)s.evals, s.seconds, e0.taken.load());
+    if (rc || s.evals <= 0 || e0.taken.load() != 0) { printf("FAILED\n"); return 1; }
+  }
   // board API: a game with captures, features, priors
   dg_board* b = dg_board_new(7.5f);
   int color = 1; unsigned long long rng = 12345;
@@ -37,6 +166,7 @@ int main(){
     uint8_t legal[361]; dg_packed_position pos; dg_raw_position raw;
     dg_board_features_packed(b, color, ply % 8, &pos, legal);
     dg_board_raw_position(b, color, ply % 8, &raw);
+    { uint8_t again[361]; mock_legal(raw, again); if (memcmp(again, legal, 361)) { printf("stand-in legal mask differs at ply %d\n", ply); return 1; } }
     std::vector<int> cand; for (int p = 0; p < 361; ++p) if (legal[p]) cand.push_back(p);
     if (cand.empty()) break;
     rng = rng * 6364136223846793005ull + 1442695040888963407ull;
