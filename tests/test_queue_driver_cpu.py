@@ -1,7 +1,7 @@
 """The queue-driven self-play driver (dg_selfplay_run_engine: polling scheduler, round-robin over engines, deadline handling)
 without a device: tools/host_sanitize.cpp links the host half of the path against a functional CPU stand-in for the engine's
 leaf-batch queue (legal moves from raw stones and hashes, evaluated by a "device" thread per batch) and checks that the games do
-not depend on workers, groups or engines, that a deadline drops the batches in flight cleanly, and that the stand-in's legal
+not depend on workers, groups, engines or on where the priors are built, that a deadline drops the batches in flight cleanly, and that the stand-in's legal
 masks are the board's over a 600-ply game.  (The same program is what runs under ASan / UBSan / TSan:
 profiles/r02_host_asan_ubsan.log, r02_host_tsan.log.)"""
 import os
@@ -21,5 +21,5 @@ def test_queue_driver_on_the_cpu_stand_in(tmp_path):
     lines = out.stdout.strip().splitlines()
     assert lines[-1] == "board api ok" and "FAILED" not in out.stdout
     queue = [l for l in lines if l.startswith("queue variant")]
-    assert len(queue) == 4 and all("games 7 moves 168" in l and "still held 0" in l for l in queue)
+    assert len(queue) == 6 and all("games 7 moves 168" in l and "still held 0" in l for l in queue)
     assert len({l.split("evals")[1].split()[0] for l in queue}) == 1          # the same evaluations whatever the schedule

@@ -27,8 +27,10 @@ struct dg_leaf_batch {
     std::vector<dg_raw_position> slots;
     std::vector<uint16_t> value, policy;
     std::vector<uint8_t> legal;
+    std::vector<float> prior;
     std::atomic<int> fill{0}, committed{0}, ready{1};
     int submitted = 0;
+    bool want_prior = false;
     std::thread worker;
     ~dg_leaf_batch() { if (worker.joinable()) worker.join(); }
 };
@@ -87,6 +89,17 @@ static void mock_evaluate(dg_leaf_batch* b) {
         float x[362], total = 0.f;
         for (int k = 0; k < 362; ++k) { x[k] = (float)rng.uniform(); total += x[k]; }
         for (int k = 0; k < 362; ++k) b->policy[(size_t)i * 362 + k] = dg::f32_to_f16_bits(x[k] / total);
+        if (b->want_prior) {
+            // the priors the device would return (dg_engine_forward_raw_prior): the stones put back on a board (black first, then
+            // white: no chain of a legal position ever runs out of liberties on the way), then the host's own prior construction
+            dg_board* board = dg_board_new(7.5f);
+            for (int c = 1; c <= 2; ++c)
+                for (int p = 0; p < 361; ++p)
+                    if (((c == 1 ? r.black : r.white)[p >> 5] >> (p & 31)) & 1u) dg_board_place(board, c, p);
+            dg_board_prior(board, r.to_move, r.symmetry >> 4, &b->legal[(size_t)i * 361], &b->policy[(size_t)i * 362], r.symmetry & 7, 1.0f,
+                           &b->prior[(size_t)i * 368]);
+            dg_board_free(board);
+        }
     }
     b->ready.store(1, std::memory_order_release);
 }
@@ -97,6 +110,7 @@ extern "C" int32_t dg_engine_batch_acquire(dg_engine* e, dg_leaf_batch** out) {
     dg_leaf_batch* b = new dg_leaf_batch();
     b->e = e;
     b->slots.resize(e->max_batch); b->value.resize(e->max_batch); b->policy.resize((size_t)e->max_batch * 362); b->legal.resize((size_t)e->max_batch * 361);
+    b->prior.resize((size_t)e->max_batch * 368);
     e->taken++;
     *out = b;
     return 0;
@@ -110,12 +124,12 @@ extern "C" int32_t dg_leaf_batch_push(dg_leaf_batch* b, const dg_raw_position* p
     return at;
 }
 extern "C" int32_t dg_leaf_batch_submit(dg_leaf_batch* b, uint32_t outputs) {
-    if (outputs) return -5;                                       // the stand-in has no prior construction
     const int n = b->fill.exchange(INT32_MIN);
     if (n <= 0) return -5;
     while (b->committed.load(std::memory_order_acquire) < n) {}
     if (b->worker.joinable()) b->worker.join();
     b->submitted = n;
+    b->want_prior = (outputs & DG_LEAF_PRIOR) != 0;
     b->ready.store(0, std::memory_order_release);
     b->worker = std::thread(mock_evaluate, b);
     return 0;
@@ -125,7 +139,7 @@ extern "C" void dg_leaf_batch_reset(dg_leaf_batch* b) { b->committed.store(0); b
 extern "C" const uint16_t* dg_leaf_batch_value(const dg_leaf_batch* b) { return b->value.data(); }
 extern "C" const uint16_t* dg_leaf_batch_policy(const dg_leaf_batch* b) { return b->policy.data(); }
 extern "C" const uint8_t* dg_leaf_batch_legal(const dg_leaf_batch* b) { return b->legal.data(); }
-extern "C" const float* dg_leaf_batch_prior(const dg_leaf_batch*) { return nullptr; }
+extern "C" const float* dg_leaf_batch_prior(const dg_leaf_batch* b) { return b->prior.data(); }
 int main(){
   for (int variant = 0; variant < 4; ++variant) {
     dg_selfplay_config c{}; c.num_games=5; c.num_parallel=3; c.num_rollout= variant==2 ? 1 : 60; c.probes_per_round=4; c.max_plies=30; c.num_threads=3; c.dirichlet_noise=0.25f; c.temperature=0.8f; c.seed=3+variant;
@@ -137,15 +151,17 @@ int main(){
   }
   // the queue-driven driver on two stand-in engines: same games whatever the number of workers, groups and engines
   {
-    uint64_t digests[4];
-    for (int variant = 0; variant < 4; ++variant) {
+    uint64_t digests[6];
+    for (int variant = 0; variant < 6; ++variant) {
       dg_engine e0, e1;
       dg_engine* engines[2] = {&e0, &e1};
       dg_selfplay_config c{}; c.num_games=7; c.num_parallel=5; c.num_rollout=50; c.probes_per_round=4; c.max_plies=24; c.dirichlet_noise=0.25f; c.temperature=0.8f; c.seed=11;
       c.num_threads = variant == 0 ? 1 : 4; c.num_groups = variant == 2 ? 1 : 2;
       dg_selfplay_stats s{};
       std::vector<char> sgf(1<<20);
-      int rc = dg_selfplay_run_engine(engines, variant == 3 ? 1 : 2, 0u, &c, &s, sgf.data(), sgf.size());
+      // variants 4, 5: the priors from the "device" (always / placed by the driver from the workers' load)
+      const uint32_t flags = variant == 4 ? DG_SELFPLAY_DEVICE_PRIORS : variant == 5 ? DG_SELFPLAY_AUTO_PRIORS | DG_SELFPLAY_DEVICE_PRIORS : 0u;
+      int rc = dg_selfplay_run_engine(engines, variant == 3 ? 1 : 2, flags, &c, &s, sgf.data(), sgf.size());
       digests[variant] = s.digest;
       printf("queue variant %d rc %d games %ld moves %ld evals %ld batches %ld leaf batches still held %d\n", variant, rc, (long)s.games_finished,
              (long)s.moves, (long)s.evals, (long)s.rounds, e0.taken.load() + e1.taken.load());
