@@ -23,3 +23,5 @@ def test_queue_driver_on_the_cpu_stand_in(tmp_path):
     queue = [l for l in lines if l.startswith("queue variant")]
     assert len(queue) == 6 and all("games 7 moves 168" in l and "still held 0" in l for l in queue)
     assert len({l.split("evals")[1].split()[0] for l in queue}) == 1          # the same evaluations whatever the schedule
+    table = [l for l in lines if l.startswith("queue shared-table")]            # one process-wide table under the queue-driven driver
+    assert len(table) == 2 and all("games 8 moves 64" in l and "held 0" in l for l in table)

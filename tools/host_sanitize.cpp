@@ -167,6 +167,24 @@ int main(){
              (long)s.moves, (long)s.evals, (long)s.rounds, e0.taken.load() + e1.taken.load());
       if (rc || s.games_finished != 7 || digests[variant] != digests[0]) { printf("FAILED\n"); return 1; }
     }
+    // the process-wide transposition table under the queue-driven driver (the parameters of
+    // tests/test_selfplay_gpu.py::test_self_play_on_engine_with_one_shared_table): every game ends, later games reuse earlier evaluations
+    {
+      long evals[2], moves[2], hits[2];
+      for (int shared = 0; shared < 2; ++shared) {
+        dg_engine e; dg_engine* one[1] = {&e};
+        dg_selfplay_config c{}; c.num_games=8; c.num_parallel=2; c.num_rollout=24; c.probes_per_round=2; c.max_plies=8; c.num_threads=2; c.seed=3;
+        c.dirichlet_noise=0.25f; c.temperature=0.8f; c.cache_capacity = shared ? 200000 : 0; c.cache_shared = shared ? 16 : 0;
+        dg_selfplay_stats s{};
+        std::vector<char> sgf(1<<20);
+        int rc = dg_selfplay_run_engine(one, 1, 0u, &c, &s, sgf.data(), sgf.size());
+        evals[shared] = (long)s.evals; moves[shared] = (long)s.moves; hits[shared] = (long)s.cache_hits;
+        printf("queue shared-table %d rc %d games %ld moves %ld evals %ld hits %ld held %d\n", shared, rc, (long)s.games_finished, moves[shared], evals[shared],
+               hits[shared], e.taken.load());
+        if (rc || s.games_finished != 8 || e.taken.load() != 0) { printf("FAILED\n"); return 1; }
+      }
+      if (moves[0] != 64 || moves[1] != 64 || hits[1] <= 0 || evals[1] >= evals[0]) { printf("FAILED\n"); return 1; }
+    }
     dg_engine e0; dg_engine* engines[1] = {&e0};                   // a deadline in the middle of the run
     dg_selfplay_config c{}; c.num_games=100000; c.num_parallel=16; c.num_rollout=200; c.probes_per_round=8; c.num_threads=4; c.seed=5; c.max_seconds=0.5;
     c.dirichlet_noise=0.25f; c.temperature=0.8f;
