@@ -410,7 +410,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             sustained["tower_frac_of_sustained_peak"] = tf / float(peak_sus)
             sustained["sustained_peak"] = float(peak_sus)
         line["sustained"] = sustained
-    sp_summary = self_play_summary(self_play) if self_play is not None else None
+    sp_summary = None
+    if self_play is not None:
+        try:
+            sp_summary = self_play_summary(self_play)
+        except Exception as exc:   # noqa: BLE001  (a summary must never cost the line)
+            sp_summary = {"unavailable": repr(exc)[:200]}
     if sp_summary is not None:
         line["e2e"]["self_play"] = sp_summary
     if world == 1 and not os.environ.get("DG_BENCH_SKIP_CPU"):      # skipped only under the profiler
