@@ -140,7 +140,21 @@ extern "C" const uint16_t* dg_leaf_batch_value(const dg_leaf_batch* b) { return 
 extern "C" const uint16_t* dg_leaf_batch_policy(const dg_leaf_batch* b) { return b->policy.data(); }
 extern "C" const uint8_t* dg_leaf_batch_legal(const dg_leaf_batch* b) { return b->legal.data(); }
 extern "C" const float* dg_leaf_batch_prior(const dg_leaf_batch* b) { return b->prior.data(); }
-int main(){
+// `host_sanitize bench [seconds] [games] [threads] [flags]`: the queue-driven driver on the stand-in for a fixed time, with
+// DG_SELFPLAY_TRACE=1 the worker threads' cycles per leaf by phase (games run from the opening into the middle game)
+static int bench(int argc, char** argv) {
+    dg_engine e; dg_engine* one[1] = {&e};
+    dg_selfplay_config c{}; c.num_games = 100000; c.num_rollout = 800; c.probes_per_round = 8; c.seed = 20261017; c.dirichlet_noise = 0.25f; c.temperature = 0.8f;
+    c.max_seconds = argc > 2 ? atof(argv[2]) : 10.0; c.num_parallel = argc > 3 ? atoi(argv[3]) : 16; c.num_threads = argc > 4 ? atoi(argv[4]) : 1;
+    const uint32_t flags = argc > 5 ? (uint32_t)atoi(argv[5]) : 0u;
+    dg_selfplay_stats s{};
+    int rc = dg_selfplay_run_engine(one, 1, flags, &c, &s, nullptr, 0);
+    printf("bench rc %d games %ld moves %ld evals %ld seconds %.2f evals/s %.0f moves/s %.1f\n", rc, (long)s.games_finished, (long)s.moves, (long)s.evals, s.seconds,
+           s.evals / s.seconds, s.moves / s.seconds);
+    return rc;
+}
+int main(int argc, char** argv){
+  if (argc > 1 && !strcmp(argv[1], "bench")) return bench(argc, argv);
   for (int variant = 0; variant < 4; ++variant) {
     dg_selfplay_config c{}; c.num_games=5; c.num_parallel=3; c.num_rollout= variant==2 ? 1 : 60; c.probes_per_round=4; c.max_plies=30; c.num_threads=3; c.dirichlet_noise=0.25f; c.temperature=0.8f; c.seed=3+variant;
     c.ex_it = variant==1; c.num_ex_it_rollout=80; c.cache_capacity = variant==0 ? 64 : variant==3 ? 20000 : 0; c.cache_shared = variant==3 ? 8 : 0; c.num_groups = variant % 3 + 1;
