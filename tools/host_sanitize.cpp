@@ -93,9 +93,8 @@ static void mock_evaluate(dg_leaf_batch* b) {
             // the priors the device would return (dg_engine_forward_raw_prior): the stones put back on a board (black first, then
             // white: no chain of a legal position ever runs out of liberties on the way), then the host's own prior construction
             dg_board* board = dg_board_new(7.5f);
-            for (int c = 1; c <= 2; ++c)
-                for (int p = 0; p < 361; ++p)
-                    if (((c == 1 ? r.black : r.white)[p >> 5] >> (p & 31)) & 1u) dg_board_place(board, c, p);
+            for (int p = 0; p < 361; ++p) if ((r.black[p >> 5] >> (p & 31)) & 1u) dg_board_place(board, dg::BLACK, p);
+            for (int p = 0; p < 361; ++p) if ((r.white[p >> 5] >> (p & 31)) & 1u) dg_board_place(board, dg::WHITE, p);
             dg_board_prior(board, r.to_move, r.symmetry >> 4, &b->legal[(size_t)i * 361], &b->policy[(size_t)i * 362], r.symmetry & 7, 1.0f,
                            &b->prior[(size_t)i * 368]);
             dg_board_free(board);
