@@ -257,6 +257,16 @@ def best(node: Node, temperature: float, at: float):   # tree.rs:1232-1263
     return node.value[i], i
 
 
+def softmax(node: Node) -> np.ndarray:                  # tree.rs:1293-1306: the visit distribution the record's P[] holds
+    out = np.zeros(362, F)
+    total = F(0.0)
+    for i in node.nonzero():
+        total = F(total + F(node.count[i]))
+    for i in node.nonzero():
+        out[i] = F(F(node.count[i]) / total)
+    return out
+
+
 def forward(node: Node, index: int) -> Optional[Node]:  # tree.rs:1198-1225
     nxt = node.ptr[index]
     if nxt is None:
@@ -487,14 +497,32 @@ def get_random_komi(rng) -> float:                     # lib.rs:210-224
 
 
 def self_play_one(predictor: Predictor, game_rng, *, num_rollout: int = 800, probes_per_round: int = 1, max_plies: int = 722,
-                  dirichlet_noise: float = 0.25, temperature: float = 0.8, cache: Optional[Cache] = None):
-    """`self_play_one` (self_play.rs:423-459) without ex-it: returns (komi, [(color, index)])."""
+                  dirichlet_noise: float = 0.25, temperature: float = 0.8, cache: Optional[Cache] = None,
+                  ex_it: bool = False, num_ex_it_rollout: int = 800, recorded: Optional[list] = None):
+    """`self_play_one` (self_play.rs:423-459): returns (komi, [(color, index)]).  With `ex_it` (`--ex-it`, self_play.rs:287-319,
+    341-346, 384-389) a move whose value lies in [-0.8, 0.8] is, with probability 0.05, searched a second time from scratch with
+    `num_ex_it_rollout` rollouts and the RECORD takes its statistics from that tree while the game goes on with the first
+    search's move, value and sub-tree.  `recorded` (optional list) receives per move the rollouts of the recorded tree
+    (the record's TV[] property; None where the record has none) and its visit distribution."""
     from .rng import Rng
     komi = get_random_komi(game_rng)
     board = go.Board(komi)
     players = [Player(go.BLACK), Player(go.WHITE)]
     pass_count = 0
     played = []
+
+    def is_good_candidate(value) -> bool:              # self_play.rs:312-316 (one uniform f32 draw, only when the value qualifies)
+        return bool(ex_it and F(value) >= F(-0.80) and F(value) <= F(0.80) and F(game_rng.uniform()) < F(0.05))
+
+    def expert_iteration(allow_pass):                  # Player::ex_it (self_play.rs:287-304): self.root is None here
+        v2, _, deep, _ = predict(predictor, board, players[0].color, search=0 if allow_pass else 1, deterministic=not allow_pass,
+                                 num_rollout=num_ex_it_rollout, probes_per_round=probes_per_round, starting_tree=None,
+                                 dirichlet_noise=dirichlet_noise, temperature=temperature, cache=cache, rng=Rng(game_rng.next()))
+        return deep
+
+    def note(tree):
+        if recorded is not None:
+            recorded.append(None if tree is None else (int(tree.total_count), softmax(tree)))
     while board.count() < max_plies:
         me = players[0]
         allow_pass = board.is_scorable()
@@ -510,7 +538,9 @@ def self_play_one(predictor: Predictor, game_rng, *, num_rollout: int = 800, pro
                                             dirichlet_noise=dirichlet_noise, temperature=temperature, cache=cache, rng=search_rng)
             if not np.isfinite(value):
                 index, tree = 361, None
+                note(None)
             else:
+                note(expert_iteration(allow_pass) if is_good_candidate(value) else tree)
                 me.update(value)
                 tree = forward(tree, index)
             me.root = tree
@@ -520,6 +550,7 @@ def self_play_one(predictor: Predictor, game_rng, *, num_rollout: int = 800, pro
                 policy[361] = NEG_INF
             pick = choose([float(x) for x in policy[:362]], 0.5, 1.0 / float(F(temperature)), search_rng.uniform())
             index = 361 if pick is None else pick
+            note(expert_iteration(allow_pass) if is_good_candidate(value) else None)
             me.update(value)
             me.root = forward(tree, index) if tree is not None else None
         played.append((me.color, index))

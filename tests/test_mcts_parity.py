@@ -415,6 +415,37 @@ def test_whole_game_matches_the_oracle_game(probes, rollouts, cache):
     assert [(c, i) for c, i, _ in moves] == want_moves
 
 
+@pytest.mark.parametrize("rollouts,probes,plies", [(24, 2, 60), (1, 2, 120)])
+def test_whole_game_with_ex_it_matches_the_oracle_game(rollouts, probes, plies):
+    """`--ex-it` (BASELINE configs[4]; rollouts = 1 is its policy-only play): which moves get the second, deeper search (one f32
+    draw per eligible move), the seed it runs under, and what the record then holds -- TV[] = the rollouts of the recorded tree
+    and P[] = its visit distribution -- while the game goes on with the first search's move (self_play.rs:287-319, 341-346,
+    384-389).  Move for move against the oracle's self_play_one on the same random stream."""
+    from oracle import oracle as onn
+    from oracle.rng import Rng
+    stub = hash_predictor()
+    seed = 9
+    st, games = pm.self_play(pm.python_predictor(stub), num_games=1, num_parallel=1, num_rollout=rollouts, probes_per_round=probes,
+                             max_plies=plies, seed=seed, num_threads=1, ex_it=True, num_ex_it_rollout=40)
+    komi, moves = parse_record(games[0])
+    recorded = []
+    want_komi, want_moves = om.self_play_one(stub, Rng((seed * 0x9e3779b97f4a7c15 + 1) & ((1 << 64) - 1)), num_rollout=rollouts,
+                                             probes_per_round=probes, max_plies=plies, ex_it=True, num_ex_it_rollout=40, recorded=recorded)
+    assert komi == want_komi
+    assert [(c, i) for c, i, _ in moves] == want_moves
+    expanded = 0
+    for (_, _, props), rec in zip(moves, recorded):
+        if rec is None or rec[0] <= 1:
+            assert "TV" not in props and "P" not in props
+            continue
+        assert int(props["TV"]) == rec[0]
+        dist = np.frombuffer(onn.b85_decode(props["P"].encode("ascii")), "<f2")[:362]
+        assert (dist.view(np.uint16) == rec[1].astype(np.float16).view(np.uint16)).all()
+        expanded += 1
+    assert st["searches"] > len(moves) if rollouts > 1 else st["searches"] > 0     # some positions were searched a second time
+    assert expanded >= (len(moves) if rollouts > 1 else 1)
+
+
 # ---- the games themselves, pinned (tests/golden/selfplay_digests.json, tools/make_selfplay_digests.py) ---------------
 
 def test_self_play_digests_match_the_golden_file():
