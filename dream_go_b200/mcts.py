@@ -133,7 +133,7 @@ class EnginePriorPredictor:
 class EngineQueue:
     """The product path of self-play: one or several engines (one per device) driven through their leaf-batch queues by
     `dg_selfplay_run_engine` -- no blocking predictor call.  `device_priors`: build the leaves' priors on the device
-    (None = the driver decides batch by batch from whether the device runs out of work, DG_SELFPLAY_AUTO_PRIORS); `device_ladders`: the
+    (None = the driver decides batch by batch from how busy its worker threads are, DG_SELFPLAY_AUTO_PRIORS); `device_ladders`: the
     ladder planes are read on the device as well (None = with a single host thread per engine)."""
     engines = True
 

@@ -150,9 +150,10 @@ int32_t  dg_selfplay_run_prior(dg_predict_prior_fn predictor, void* ctx, const d
  * same seed.  flags: DG_SELFPLAY_DEVICE_PRIORS = the leaves' priors are built on the device (dg_engine_forward_raw_prior). */
 #define DG_SELFPLAY_DEVICE_PRIORS  0x1u
 #define DG_SELFPLAY_DEVICE_LADDERS 0x2u   /* the ladder planes are read on the device too: the host only walks the trees */
-#define DG_SELFPLAY_AUTO_PRIORS    0x4u   /* the driver decides batch by batch: priors on the device while the device runs out of work
-                                             (the host is the limit), on the host while it never does; DG_SELFPLAY_DEVICE_PRIORS is then
-                                             only the start value.  Same games either way (the priors are bit-identical). */
+#define DG_SELFPLAY_AUTO_PRIORS    0x4u   /* the driver decides batch by batch from how busy its worker threads are (windows of 64
+                                             batches): above 85 % the host is the limit and the priors move to the device, below 60 % back
+                                             to the host; DG_SELFPLAY_DEVICE_PRIORS is then only the start value.  Same games either way
+                                             (the priors are bit-identical). */
 int32_t  dg_selfplay_run_engine(dg_engine* const* engines, int32_t n_engines, uint32_t flags, const dg_selfplay_config* config,
                                 dg_selfplay_stats* stats, char* sgf_out, int64_t sgf_capacity);
 

@@ -186,3 +186,85 @@ def test_bench_self_play_summary_on_recorded_lines():
         if has_ref:
             assert out["configs2_vs_cudnn_reference_batch16"] > 5
         assert len(json.dumps(out)) < 900
+
+
+# ---- struct layouts: the headers as gcc lays them out, the ctypes mirrors, and the `repr(C)` mirrors of INTEGRATION.md ---------
+
+RUST_TYPES = {"i32": (4, 4), "u32": (4, 4), "f32": (4, 4), "i64": (8, 8), "u64": (8, 8), "f64": (8, 8), "u16": (2, 2), "u8": (1, 1), "i16": (2, 2)}
+
+
+def rust_layout(struct_name: str):
+    """Field offsets and size of a `#[repr(C)] pub struct` of INTEGRATION.md under the C layout rules."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    body = re.search(r"pub struct " + struct_name + r"\s*\{(.*?)\}", text, re.S).group(1)
+    body = re.sub(r"//[^\n]*", "", body)
+    at, align_max, offsets = 0, 1, {}
+    for name, ty in re.findall(r"(\w+)\s*:\s*([^,]+?)\s*(?:,|$)", body.replace("\n", " ")):
+        m = re.fullmatch(r"\[(\w+);\s*(\d+)\]", ty)
+        if ty.startswith("*"):
+            size, align = 8, 8
+        elif m:
+            size, align = RUST_TYPES[m.group(1)][0] * int(m.group(2)), RUST_TYPES[m.group(1)][1]
+        else:
+            size, align = RUST_TYPES[ty]
+        at = (at + align - 1) // align * align
+        offsets[name] = at
+        at += size
+        align_max = max(align_max, align)
+    return offsets, (at + align_max - 1) // align_max * align_max
+
+
+def c_layouts(tmp_path):
+    """sizeof / offsetof of the ABI structs, printed by a C program compiled against include/*.h."""
+    structs = {
+        "dg_search_options": ["search", "deterministic", "num_rollout", "probes_per_round", "dirichlet_noise", "temperature", "seed", "noise",
+                              "leaf_symmetries", "n_leaf_symmetries", "choose_at", "cache", "device_ladders"],
+        "dg_selfplay_config": ["num_games", "num_parallel", "num_rollout", "probes_per_round", "max_plies", "num_threads", "ex_it",
+                               "num_ex_it_rollout", "dirichlet_noise", "temperature", "seed", "max_seconds", "cache_capacity", "num_groups",
+                               "cache_shared"],
+        "dg_selfplay_stats": ["games_finished", "moves", "evals", "rounds", "searches", "seconds", "eval_seconds", "mean_batch", "digest",
+                              "cache_hits"],
+        "dg_packed_position": ["planes", "k_bits", "reserved"],
+        "dg_raw_position": ["black", "white", "visited", "ladder_capture", "ladder_escape", "hash", "hash_history", "last_move", "k_bits",
+                            "to_move", "symmetry"],
+    }
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "dg_mcts.h"', "int main(void) {"]
+    for s, fields in structs.items():
+        src.append(f'  printf("{s} size %zu\\n", sizeof({s}));')
+        for f in fields:
+            src.append(f'  printf("{s} {f} %zu\\n", offsetof({s}, {f}));')
+    src += ["  return 0;", "}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    out = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        s, f, v = line.split()
+        out.setdefault(s, {})[f] = int(v)
+    return out
+
+
+def test_struct_layouts_of_headers_ctypes_and_rust_mirrors_agree(tmp_path):
+    from dream_go_b200 import mcts
+    C = c_layouts(tmp_path)
+    for cname, ctype, rust in (("dg_search_options", mcts._SearchOptions, "DgSearchOptions"),
+                               ("dg_selfplay_config", mcts._SelfPlayConfig, "DgSelfPlayConfig"),
+                               ("dg_selfplay_stats", mcts._SelfPlayStats, "DgSelfPlayStats")):
+        want = dict(C[cname])
+        size = want.pop("size")
+        assert ctypes.sizeof(ctype) == size, cname
+        assert {n: getattr(ctype, n).offset for n, _ in ctype._fields_} == want, cname
+        offsets, rsize = rust_layout(rust)
+        assert offsets == want and rsize == size, (cname, offsets, want)
+    # the two position formats that cross the boundary by value
+    assert C["dg_packed_position"]["size"] == nn.PACKED_DTYPE.itemsize == 361 * 4 + 4
+    offsets, rsize = rust_layout("DgPackedPosition")
+    assert rsize == C["dg_packed_position"]["size"] and offsets["k_bits"] == C["dg_packed_position"]["k_bits"]
+    assert C["dg_raw_position"]["size"] == 384 and C["dg_raw_position"]["hash"] % 8 == 0
+    offsets, rsize = rust_layout("DgRawPosition")
+    want = dict(C["dg_raw_position"])
+    assert rsize == want.pop("size") and offsets == want
+    assert nn.RAW_DTYPE.itemsize == 384 and {n: nn.RAW_DTYPE.fields[n][1] for n in nn.RAW_DTYPE.names if n in want} == \
+        {n: want[n] for n in nn.RAW_DTYPE.names if n in want}
