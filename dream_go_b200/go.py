@@ -79,6 +79,14 @@ class Board:
     def clone(self) -> "Board":
         return Board(_handle=lib().dg_board_clone(self._h))
 
+    def copy_from(self, other: "Board") -> None:
+        """`*self = other.clone()` without an allocation (the searches copy a board per probe)."""
+        lib().dg_board_copy(self._h, other._h)
+
+    def set_komi(self, komi: float) -> None:
+        """`Board::set_komi` (board.rs:84-86)."""
+        lib().dg_board_set_komi(self._h, komi)
+
     def place(self, color: int, x: int, y: int) -> None:
         lib().dg_board_place(self._h, color, idx(x, y))
 

@@ -386,3 +386,29 @@ def test_out_of_range_arguments_are_rejected_at_the_boundary():
     assert b.zobrist_hash() == h and b.count() == 1 and b.to_move() == 2
     assert L.dg_symmetry_apply(8, 0) == -1 and L.dg_symmetry_apply(0, 362) == -1 and L.dg_symmetry_inverse(-1) == -1
     assert L.dg_symmetry_apply(3, 361) == 361
+
+
+def test_board_copy_and_komi_through_the_boundary():
+    """`dg_board_copy` / `dg_board_set_komi`: a copy is the same position (stones, hash, super-ko history, features) and is
+    independent of its source afterwards; the komi only moves the two colour planes' constant."""
+    colors, moves = random_playout(4, 120)
+    src = pgo.Board(7.5)
+    for c, m in zip(colors, moves):
+        if m < 361:
+            src.place_index(int(c), int(m))
+    dst = pgo.Board(0.5)
+    dst.copy_from(src)
+    to_move = src.to_move()
+    assert dst.zobrist_hash() == src.zobrist_hash() and dst.komi() == 7.5 and (dst.stones() == src.stones()).all()
+    assert (dst.legal_moves(to_move) == src.legal_moves(to_move)).all()            # super-ko history included
+    assert (dst.features(to_move).view(np.uint16) == src.features(to_move).view(np.uint16)).all()
+    free = int(np.flatnonzero(src.legal_moves(to_move))[0])
+    dst.place_index(to_move, free)
+    assert dst.zobrist_hash() != src.zobrist_hash() and src.at(free % 19, free // 19) == 0
+    src.set_komi(-3.5)
+    oo = ogo.Board(-3.5)
+    for c, m in zip(colors, moves):
+        if m < 361:
+            oo.place_index(int(c), int(m))
+    assert src.komi() == -3.5
+    assert (src.features(to_move).view(np.uint16) == oo.features(to_move).reshape(361, 32).view(np.uint16)).all()
