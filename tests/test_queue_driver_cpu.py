@@ -25,3 +25,7 @@ def test_queue_driver_on_the_cpu_stand_in(tmp_path):
     assert len({l.split("evals")[1].split()[0] for l in queue}) == 1          # the same evaluations whatever the schedule
     table = [l for l in lines if l.startswith("queue shared-table")]            # one process-wide table under the queue-driven driver
     assert len(table) == 2 and all("games 8 moves 64" in l and "held 0" in l for l in table)
+    # random configurations (games, rollouts, probes, threads, groups, one or two engines, where the priors are built, --ex-it,
+    # per-game tables): every run ends, gives its leaf batches back and plays the games of the plainest schedule
+    fuzz = subprocess.run([str(exe), "fuzz", "80", "3"], capture_output=True, text=True, timeout=600)
+    assert fuzz.returncode == 0 and "80 cases" in fuzz.stdout and " 0 failures" in fuzz.stdout, fuzz.stdout[-2000:]

@@ -152,8 +152,44 @@ static int bench(int argc, char** argv) {
            s.evals / s.seconds, s.moves / s.seconds);
     return rc;
 }
+// `host_sanitize fuzz [cases] [seed]`: random configurations of the queue-driven driver on one or two stand-in engines -- every
+// run ends, releases its leaf batches, and plays the games of the plainest schedule (one engine, one worker, host priors)
+static int fuzz(int argc, char** argv) {
+    const int cases = argc > 2 ? atoi(argv[2]) : 40;
+    dg::Rng rng(argc > 3 ? (uint64_t)atoll(argv[3]) : 1);
+    auto pick = [&](std::initializer_list<int> xs) { return *(xs.begin() + rng.below((int)xs.size())); };
+    int bad = 0, refused = 0;
+    for (int k = 0; k < cases; ++k) {
+        dg_selfplay_config c{};
+        c.num_games = pick({1, 2, 5, 9}); c.num_parallel = pick({1, 2, 5, 12, 40}); c.num_rollout = pick({1, 2, 20, 70}); c.probes_per_round = pick({1, 2, 4, 8, 12});
+        c.max_plies = pick({1, 6, 20, 50}); c.seed = 1 + (uint64_t)rng.below(1 << 30); c.dirichlet_noise = 0.25f; c.temperature = 0.8f;
+        c.ex_it = rng.below(4) == 0; c.num_ex_it_rollout = pick({5, 40}); c.cache_capacity = pick({0, 0, 9, 400});
+        dg_selfplay_stats want{}, got{};
+        dg_engine r0; dg_engine* plain[1] = {&r0};
+        dg_selfplay_config base = c; base.num_threads = 1; base.num_groups = 0;
+        const int rc0 = dg_selfplay_run_engine(plain, 1, 0u, &base, &want, nullptr, 0);
+        dg_engine e0, e1; dg_engine* two[2] = {&e0, &e1};
+        c.num_threads = pick({1, 2, 3, 6}); c.num_groups = pick({0, 1, 2, 3, 4});
+        const int n_engines = 1 + rng.below(2);
+        const uint32_t flags = (uint32_t)pick({0, 1, 4, 5});
+        const int rc = dg_selfplay_run_engine(two, n_engines, flags, &c, &got, nullptr, 0);
+        const bool same = rc == 0 && rc0 == 0 && got.digest == want.digest && got.moves == want.moves && got.games_finished == c.num_games;
+        const bool both_refused = rc == -5 || rc0 == -5;          // games per group x leaves per round beyond one leaf batch: DG_ERR_INVALID_ARGUMENT
+        refused += both_refused;
+        const int held = r0.taken.load() + e0.taken.load() + e1.taken.load();
+        if ((!same && !both_refused) || held != 0) {
+            ++bad;
+            printf("fuzz case %d FAILED: rc %d / %d games %ld of %d moves %ld / %ld digest %llx / %llx held %d (parallel %d rollout %d probes %d plies %d threads %d groups %d engines %d flags %u ex_it %d cache %d seed %llu)\n",
+                   k, rc, rc0, (long)got.games_finished, c.num_games, (long)got.moves, (long)want.moves, (unsigned long long)got.digest, (unsigned long long)want.digest, held,
+                   c.num_parallel, c.num_rollout, c.probes_per_round, c.max_plies, c.num_threads, c.num_groups, n_engines, flags, c.ex_it, c.cache_capacity, (unsigned long long)c.seed);
+        }
+    }
+    printf("fuzz: %d cases, %d refused (do not fit a leaf batch), %d failures\n", cases, refused, bad);
+    return bad ? 1 : 0;
+}
 int main(int argc, char** argv){
   if (argc > 1 && !strcmp(argv[1], "bench")) return bench(argc, argv);
+  if (argc > 1 && !strcmp(argv[1], "fuzz")) return fuzz(argc, argv);
   for (int variant = 0; variant < 4; ++variant) {
     dg_selfplay_config c{}; c.num_games=5; c.num_parallel=3; c.num_rollout= variant==2 ? 1 : 60; c.probes_per_round=4; c.max_plies=30; c.num_threads=3; c.dirichlet_noise=0.25f; c.temperature=0.8f; c.seed=3+variant;
     c.ex_it = variant==1; c.num_ex_it_rollout=80; c.cache_capacity = variant==0 ? 64 : variant==3 ? 20000 : 0; c.cache_shared = variant==3 ? 8 : 0; c.num_groups = variant % 3 + 1;
