@@ -105,6 +105,49 @@ def main():
                 n += 1
     say(f"unconditional life: {n} positions ({scorable} scorable): Benson sets, candidates of both search kinds, is_scorable, territory identical "
         f"({time.time() - t0:.0f} s)")
+    # 4. priors (create_initial_policy + add_valid_candidates + normalize_policy) through dg_board_prior, bit for bit: random and
+    #    symmetric positions (candidates folded onto orbit representatives), every symmetry of the network's policy, policies with
+    #    zeros, tiny entries and all zeros
+    t0 = time.time()
+    rng = np.random.default_rng(4)
+    n = folded = 0
+    for k in range(max(2, args.playouts // 10)):
+        po, oo = pgo.Board(7.5), ogo.Board(7.5)
+        if k % 3 == 0:
+            group = [[0, 1], [0, 2], [0, 3], [0, 4], [0, 6], [0, 1, 2, 6], [0, 3, 4, 6], list(range(8))][int(rng.integers(0, 8))]
+            taken = set()
+            for _ in range(int(rng.integers(0, 16))):
+                p0, c = int(rng.integers(0, 361)), int(rng.integers(1, 3))
+                orbit = sorted({ogo.symmetry_apply(t, p0) for t in group})
+                if not taken & set(orbit):
+                    taken |= set(orbit)
+                    for q in orbit:
+                        po.place_index(c, q)
+                        oo.place_index(c, q)
+        else:
+            colors, moves = T.random_playout(int(rng.integers(0, 1 << 20)), int(rng.integers(0, 300)), pass_rate=0.0)
+            for c, m in zip(colors, moves):
+                if m < 361:
+                    po.place_index(int(c), int(m))
+                    oo.place_index(int(c), int(m))
+        assert (po.stones() == oo.stones()).all()
+        folded += any(oo.is_symmetric(t) for t in range(1, 8))
+        for to_move in (BLACK, WHITE):
+            for symmetry in range(8):
+                logits = rng.normal(size=362).astype(np.float32) * float(rng.choice([0.5, 3.0, 12.0]))
+                policy = (np.exp(logits - logits.max()) / np.exp(logits - logits.max()).sum()).astype(np.float16)
+                kind = int(rng.integers(0, 4))
+                if kind == 1:
+                    policy[rng.random(362) < 0.5] = 0
+                elif kind == 2:
+                    policy[:] = 0
+                sum_to = float(rng.choice([1.0, 0.125]))
+                want = T.oracle_prior(oo, to_move, policy, symmetry, sum_to)
+                got = po.prior(to_move, policy, symmetry, sum_to)
+                f = np.isfinite(want)
+                assert (np.isfinite(got) == f).all() and (got[f].view(np.uint32) == want[f].view(np.uint32)).all(), (k, to_move, symmetry)
+                n += 1
+    say(f"priors: {n} priors on {max(2, args.playouts // 10)} positions ({folded} with a symmetry): candidates and values bit-identical ({time.time() - t0:.0f} s)")
     say("ALL IDENTICAL")
     if args.out:
         with open(args.out, "w") as fh:
