@@ -26,6 +26,13 @@ using namespace dg;
 static inline Node* N(dg_tree* t) { return reinterpret_cast<Node*>(t); }
 static inline const Node* N(const dg_tree* t) { return reinterpret_cast<const Node*>(t); }
 
+// What the reference's types make unrepresentable (`Color`, the `SearchOptions` implementations): a caller of the C ABI can
+// hand over any integer.
+static bool valid_search_call(const dg_search_options* o, const dg_board* board, int32_t color) {
+    return o && board && (color == BLACK || color == WHITE) && (o->search == STANDARD_SEARCH || o->search == SCORING_SEARCH) &&
+           (o->n_leaf_symmetries <= 0 || o->leaf_symmetries != nullptr);
+}
+
 static SearchOptions convert(const dg_search_options* o) {
     SearchOptions s;
     s.search_kind = o->search;
@@ -293,7 +300,7 @@ int32_t dg_peaked_predict(void* ctx, const dg_packed_position* positions, int32_
 int32_t dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
                         const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                         int64_t* evals_out) {
-    if (!predictor || !options || !board) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
+    if (!predictor || !valid_search_call(options, board, color)) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
     SearchTask task;
     task.start(*reinterpret_cast<const Board*>(board), color, convert(options), N(starting_tree), options->seed);
     std::vector<dg_packed_position> batch;
@@ -330,8 +337,12 @@ void dg_cache_stats(const dg_cache* cache, int64_t* hits, int64_t* misses, int64
 }
 
 void dg_tree_free(dg_tree* tree) { delete N(tree); }
-dg_tree* dg_tree_forward(dg_tree* tree, int32_t index) { return reinterpret_cast<dg_tree*>(forward(N(tree), index)); }
-void dg_tree_disqualify(dg_tree* tree, int32_t index) { N(tree)->disqualify(index); }
+dg_tree* dg_tree_forward(dg_tree* tree, int32_t index) {           // an index outside 0..361 has no sub-tree: the tree is consumed
+    if (!tree) return nullptr;
+    if (index < 0 || index > PASS) { delete N(tree); return nullptr; }
+    return reinterpret_cast<dg_tree*>(forward(N(tree), index));
+}
+void dg_tree_disqualify(dg_tree* tree, int32_t index) { if (tree && index >= 0 && index <= PASS) N(tree)->disqualify(index); }
 int32_t dg_tree_total_count(const dg_tree* tree) { return N(tree)->total_count; }
 int32_t dg_tree_to_move(const dg_tree* tree) { return N(tree)->to_move; }
 float dg_tree_initial_value(const dg_tree* tree) { return N(tree)->initial_value; }
@@ -852,7 +863,7 @@ int32_t dg_engine_predict_prior(void* engine, const dg_raw_position* positions, 
 int32_t dg_mcts_predict_prior(dg_predict_prior_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
                               const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                               int64_t* evals_out) {
-    if (!predictor || !options || !board) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
+    if (!predictor || !valid_search_call(options, board, color)) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
     SearchTask task;
     task.start(*reinterpret_cast<const Board*>(board), color, convert(options), N(starting_tree), options->seed);
     std::vector<dg_raw_position> batch;
@@ -895,7 +906,7 @@ int32_t dg_engine_predict_raw(void* engine, const dg_raw_position* positions, in
 int32_t dg_mcts_predict_raw(dg_predict_raw_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
                             const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                             int64_t* evals_out) {
-    if (!predictor || !options || !board) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
+    if (!predictor || !valid_search_call(options, board, color)) { delete N(starting_tree); return DG_ERR_INVALID_ARGUMENT; }
     SearchTask task;
     task.start(*reinterpret_cast<const Board*>(board), color, convert(options), N(starting_tree), options->seed);
     std::vector<dg_raw_position> batch;

@@ -455,7 +455,7 @@ class SearchTask {
     };
 
     int next_leaf_symmetry() {                               // pool/event.rs:47: one random symmetry per leaf
-        if (opt_.leaf_symmetries && opt_.n_leaf_symmetries > 0) return opt_.leaf_symmetries[leaf_counter_++ % opt_.n_leaf_symmetries];
+        if (opt_.leaf_symmetries && opt_.n_leaf_symmetries > 0) return opt_.leaf_symmetries[leaf_counter_++ % opt_.n_leaf_symmetries] & 7;
         ++leaf_counter_;
         return rng_.below(8);
     }

@@ -80,7 +80,8 @@ typedef struct dg_tree dg_tree;   /* `tree::Node` */
 
 /* `dg_mcts::predict`: searches `board` for `color`.  `starting_tree` (may be NULL) is consumed.  Outputs: the value
  * and index (0..361, 361 = pass) of the chosen move, and the searched tree (caller frees or forwards it).
- * evals_out (optional) = positions evaluated.  Returns 0, or the predictor's error. */
+ * evals_out (optional) = positions evaluated.  Returns 0, the predictor's error, or DG_ERR_INVALID_ARGUMENT for a null
+ * predictor / options / board, a colour other than 1 / 2 or an unknown search kind (the starting tree is consumed either way). */
 int32_t  dg_mcts_predict(dg_predict_fn predictor, void* ctx, const dg_search_options* options, dg_tree* starting_tree,
                          const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                          int64_t* evals_out);
@@ -92,8 +93,9 @@ int32_t  dg_mcts_predict_prior(dg_predict_prior_fn predictor, void* ctx, const d
                                const dg_board* board, int32_t color, float* value_out, int32_t* index_out, dg_tree** tree_out,
                                int64_t* evals_out);
 void     dg_tree_free(dg_tree* tree);
-dg_tree* dg_tree_forward(dg_tree* tree, int32_t index);            /* Node::forward (tree.rs:1198-1225); consumes `tree` */
-void     dg_tree_disqualify(dg_tree* tree, int32_t index);         /* Node::disqualify (tree.rs:1296-1301) */
+dg_tree* dg_tree_forward(dg_tree* tree, int32_t index);            /* Node::forward (tree.rs:1198-1225); consumes `tree`; NULL when there
+                                                                      is no sub-tree (or index is outside 0..361) */
+void     dg_tree_disqualify(dg_tree* tree, int32_t index);         /* Node::disqualify (tree.rs:1296-1301); indices outside 0..361 are ignored */
 int32_t  dg_tree_total_count(const dg_tree* tree);
 int32_t  dg_tree_to_move(const dg_tree* tree);
 float    dg_tree_initial_value(const dg_tree* tree);

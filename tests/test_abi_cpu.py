@@ -268,3 +268,53 @@ def test_struct_layouts_of_headers_ctypes_and_rust_mirrors_agree(tmp_path):
     assert rsize == want.pop("size") and offsets == want
     assert nn.RAW_DTYPE.itemsize == 384 and {n: nn.RAW_DTYPE.fields[n][1] for n in nn.RAW_DTYPE.names if n in want} == \
         {n: want[n] for n in nn.RAW_DTYPE.names if n in want}
+
+
+INVALID_ARGUMENT = -5                       # DG_ERR_INVALID_ARGUMENT (include/dg_engine.h)
+
+
+def test_search_entry_points_reject_what_the_reference_types_cannot_express():
+    """`Color`, `SearchOptions` and `Point` are types in the reference; at the C boundary they are integers and pointers."""
+    import ctypes as C
+    from dream_go_b200 import go as pgo, mcts as pm
+    L = pm.lib()
+    board = pgo.Board(7.5)
+    fn = C.cast(L.dg_random_predict, pm.PREDICT_FN)
+    v, i, t, e = C.c_float(), C.c_int32(), C.c_void_p(), C.c_int64()
+
+    def search(predictor=fn, options=None, board_handle=board._h, color=1, **fields):
+        opt = pm._SearchOptions(0, 1, 12, 2, 0.25, 0.8, 1, None, None, 0, -1.0, None, 0)
+        for name, value in fields.items():
+            setattr(opt, name, value)
+        t.value = None
+        rc = L.dg_mcts_predict(predictor, None, C.byref(opt) if options is None else options, None, board_handle, color,
+                               C.byref(v), C.byref(i), C.byref(t), C.byref(e))
+        if rc == 0:
+            L.dg_tree_free(t)
+        return rc
+
+    assert search() == 0 and 0 <= i.value <= 361
+    assert search(predictor=C.cast(None, pm.PREDICT_FN)) == INVALID_ARGUMENT
+    assert search(board_handle=None) == INVALID_ARGUMENT
+    for color in (0, 3, -1, 77):
+        assert search(color=color) == INVALID_ARGUMENT
+    assert search(search=2) == INVALID_ARGUMENT and search(search=-1) == INVALID_ARGUMENT
+    assert search(n_leaf_symmetries=3) == INVALID_ARGUMENT          # a count without the array
+    assert search(probes_per_round=0) == 0 and search(num_rollout=0) == 0 and search(probes_per_round=-4, num_rollout=-9) == 0
+    # trees: indices outside 0..361
+    _, _, tree, _ = pm.predict(pm.RandomPredictor(), board, 1, deterministic=True, num_rollout=20, seed=3)
+    before = tree.children()[0].copy()
+    for index in (-1, 362, 1 << 20):
+        L.dg_tree_disqualify(tree._h, index)
+    assert (tree.children()[0] == before).all()
+    assert L.dg_tree_forward(tree.release(), 4000) is None                      # consumed, no sub-tree
+    assert L.dg_tree_forward(None, 3) is None
+    # self-play configurations that cannot run
+    st = pm._SelfPlayStats()
+    for games, parallel in ((0, 1), (1, 0), (-3, 2)):
+        cfg = pm._SelfPlayConfig(games, parallel, 10, 1, 5, 1, 0, 10, 0.25, 0.8, 1, 0.0, 0, 0, 0)
+        assert L.dg_selfplay_run(fn, None, C.byref(cfg), C.byref(st), None, 0) == INVALID_ARGUMENT
+    cfg = pm._SelfPlayConfig(1, 1, 10, 1, 5, 1, 0, 10, 0.25, 0.8, 1, 0.0, 0, 0, 0)
+    assert L.dg_selfplay_run(C.cast(None, pm.PREDICT_FN), None, C.byref(cfg), C.byref(st), None, 0) == INVALID_ARGUMENT
+    assert L.dg_selfplay_run_engine(None, 1, 0, C.byref(cfg), C.byref(st), None, 0) == INVALID_ARGUMENT
+    assert L.dg_selfplay_run(fn, None, None, C.byref(st), None, 0) == INVALID_ARGUMENT
