@@ -37,6 +37,9 @@ extern "C" {
 static inline bool on_board(int32_t point) { return point >= 0 && point < dg::N_POINTS; }
 static inline bool is_color(int32_t color) { return color == dg::BLACK || color == dg::WHITE; }
 static inline bool is_transform(int32_t t) { return t >= 0 && t < 8; }
+static inline bool is_search(int32_t s) { return s == dg::STANDARD_SEARCH || s == dg::SCORING_SEARCH; }
+// Outputs of a call with arguments that are not a colour / transform / search kind: all zero (no plane set, no legal move,
+// no candidate), for the prior all -inf -- defined, and nothing is read or written out of bounds.
 
 void dg_go_set_zobrist(const uint64_t* table) {
     if (table) dg::mutable_tables().load_zobrist(table);
@@ -92,15 +95,22 @@ int32_t dg_symmetry_apply(int32_t transform, int32_t point) {
 int32_t dg_symmetry_inverse(int32_t transform) { return is_transform(transform) ? dg::tables().sym_inverse[transform] : -1; }
 
 void dg_board_features_packed(const dg_board* board, int32_t to_move, int32_t symmetry, dg_packed_position* out, uint8_t* legal) {
+    if (!is_color(to_move) || !is_transform(symmetry)) {
+        memset(out, 0, sizeof(*out));
+        if (legal) memset(legal, 0, dg::N_POINTS);
+        return;
+    }
     dg::features_v1(*B(board), to_move, symmetry, out->planes, &out->k_bits, legal);
     out->reserved = 0;
 }
 
 void dg_board_raw_position(const dg_board* board, int32_t to_move, int32_t symmetry, dg_raw_position* out) {
+    if (!is_color(to_move) || symmetry < 0 || symmetry > 0xff) { memset(out, 0, sizeof(*out)); return; }      // (the symmetry byte carries flags, dg_engine.h)
     dg::raw_position(*B(board), to_move, symmetry, out);
 }
 
 void dg_board_features_f16(const dg_board* board, int32_t to_move, int32_t symmetry, uint16_t* out) {
+    if (!is_color(to_move) || !is_transform(symmetry)) { memset(out, 0, sizeof(uint16_t) * 32 * dg::N_POINTS); return; }
     dg_packed_position pos;
     dg::features_v1(*B(board), to_move, symmetry, pos.planes, &pos.k_bits, nullptr);
     for (int p = 0; p < dg::N_POINTS; ++p) {
@@ -121,7 +131,7 @@ void dg_go_extract_batch(const dg_board* const* boards, const uint8_t* to_move, 
         for (;;) {
             int i = next.fetch_add(1);
             if (i >= count) break;
-            dg_board_features_packed(boards[i], to_move[i], symmetry ? symmetry[i] : 0, out + i, legal ? legal + (size_t)i * 361 : nullptr);
+            dg_board_features_packed(boards[i], to_move[i], symmetry ? symmetry[i] : 0, out + i, legal ? legal + (size_t)i * 361 : nullptr);   // (checks its arguments)
         }
     };
     if (threads <= 1 || count <= 1) { work(); return; }
@@ -138,6 +148,7 @@ int32_t dg_go_replay(float komi, const uint8_t* colors, const uint16_t* moves, i
     board.init(komi);
     for (int i = 0; i < n; ++i) {
         int c = colors[i];
+        if (!is_color(c)) return -(i + 1);                       // like an illegal move: the replay stops at this ply
         uint8_t* lg = legal ? legal + (size_t)i * 361 : nullptr;
         if (features) {
             dg::features_v1(board, c, 0, features[i].planes, &features[i].k_bits, lg);
@@ -159,12 +170,14 @@ int32_t dg_board_is_scorable(const dg_board* board) { return dg::is_scorable(*B(
 void dg_board_territory(const dg_board* board, uint8_t* out) { dg::territory_status(*B(board), out); }
 
 void dg_board_benson(const dg_board* board, int32_t color, uint8_t* out) {
+    if (!is_color(color)) { memset(out, 0, dg::N_POINTS); return; }
     dg::Bits alive, eyes;
     dg::benson(*B(board), color, alive, eyes);
     for (int p = 0; p < dg::N_POINTS; ++p) out[p] = alive.test(p) ? 1 : eyes.test(p) ? 2 : 0;
 }
 
 void dg_board_policy_candidates(const dg_board* board, int32_t to_move, int32_t search, const uint8_t* legal, uint8_t* out) {
+    if (!is_color(to_move) || !is_search(search)) { memset(out, 0, dg::N_POINTS + 1); return; }
     const Board* b = B(board);
     uint8_t local_legal[dg::N_POINTS];
     if (!legal) {
@@ -178,6 +191,7 @@ void dg_board_prior(const dg_board* board, int32_t to_move, int32_t search, cons
                     int32_t symmetry, float sum_to, float* prior) {
     const dg::Tables& T = dg::tables();
     const float NEG_INF = -std::numeric_limits<float>::infinity();
+    if (!is_color(to_move) || !is_search(search) || !is_transform(symmetry)) { for (int i = 0; i < 368; ++i) prior[i] = NEG_INF; return; }
     uint8_t candidates[dg::N_POINTS + 1];
     dg_board_policy_candidates(board, to_move, search, legal, candidates);
     // policy_helper.rs:36-47: candidates start at 0, everything else (and the padding) at -inf

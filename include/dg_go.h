@@ -26,9 +26,11 @@ extern "C" {
 
 typedef struct dg_board dg_board;
 
-/* Out-of-range arguments (point outside 0..360, colour outside 1..2, transform outside 0..7) are rejected at this
- * boundary: queries answer 0 / -1, dg_board_place does nothing -- in particular for 361, the pass index the search
- * hands out as a move (the reference does not call `place` for a pass, self_play.rs:442-451). */
+/* Out-of-range arguments (point outside 0..360, colour outside 1..2, transform outside 0..7, unknown search kind) are
+ * rejected at this boundary: queries answer 0 / -1, dg_board_place does nothing -- in particular for 361, the pass index
+ * the search hands out as a move (the reference does not call `place` for a pass, self_play.rs:442-451) --, functions
+ * that fill an array fill it with zeros (no plane, no legal move, no candidate; dg_board_prior: all -inf), dg_go_replay
+ * stops at the ply as at an illegal move.  Pointers must be valid (board handles, output arrays of the stated size). */
 
 /* The zobrist constants of the process, in the reference's layout `zobrist::TABLE: [[u64; 420]; 3]` (src/libdg_go/
  * zobrist.rs:18; index 20 * (y + 1) + (x + 1), board_fast.rs).  The shim passes `&dg_go::zobrist::TABLE` once at start-up

@@ -386,6 +386,50 @@ def test_out_of_range_arguments_are_rejected_at_the_boundary():
     assert b.zobrist_hash() == h and b.count() == 1 and b.to_move() == 2
     assert L.dg_symmetry_apply(8, 0) == -1 and L.dg_symmetry_apply(0, 362) == -1 and L.dg_symmetry_inverse(-1) == -1
     assert L.dg_symmetry_apply(3, 361) == 361
+    # array-filling entry points: zeros (priors: -inf) instead of reading tables out of bounds
+    import ctypes as C
+    from dream_go_b200 import nn
+    packed = np.ones(1, nn.PACKED_DTYPE)
+    legal = np.ones(361, np.uint8)
+    for to_move, symmetry in ((0, 0), (3, 0), (1, 8), (2, -1), (200, 200)):
+        packed["planes"][:] = 7
+        legal[:] = 1
+        L.dg_board_features_packed(b._h, to_move, symmetry, packed.ctypes.data, legal.ctypes.data)
+        assert not packed["planes"].any() and not legal.any()
+        f16 = np.ones((361, 32), np.float16)
+        L.dg_board_features_f16(b._h, to_move, symmetry, f16.ctypes.data)
+        assert not f16.any()
+        prior = np.zeros(368, np.float32)
+        policy = np.full(362, 1 / 362, np.float16)
+        L.dg_board_prior(b._h, to_move, 0, None, policy.ctypes.data, symmetry, C.c_float(1.0), prior.ctypes.data)
+        assert np.isneginf(prior).all()
+    raw = np.ones(1, nn.RAW_DTYPE)
+    raw["black"][:] = 5
+    L.dg_board_raw_position(b._h, 0, 0, raw.ctypes.data)
+    assert not raw["black"].any() and int(raw["to_move"][0]) == 0
+    out = np.ones(362, np.uint8)
+    for to_move, search in ((0, 0), (1, 2), (2, -1)):
+        out[:] = 1
+        L.dg_board_policy_candidates(b._h, to_move, search, None, out.ctypes.data)
+        assert not out.any()
+    prior = np.zeros(368, np.float32)
+    L.dg_board_prior(b._h, 1, 5, None, policy.ctypes.data, 0, C.c_float(1.0), prior.ctypes.data)
+    assert np.isneginf(prior).all()
+    alive = np.ones(361, np.uint8)
+    L.dg_board_benson(b._h, 0, alive.ctypes.data)
+    assert not alive.any()
+    # a replay stops at a ply whose colour is not a colour, as at an illegal move
+    colors = np.array([1, 2, 3, 1], np.uint8)
+    moves = np.array([0, 1, 2, 3], np.uint16)
+    assert L.dg_go_replay(C.c_float(7.5), colors.ctypes.data, moves.ctypes.data, 4, None, None, None) == -3
+    # a batch with one bad entry: that entry comes back empty, the others are computed
+    boards = (C.c_void_p * 2)(b._h, b._h)
+    tm = np.array([2, 9], np.uint8)
+    sym = np.array([0, 0], np.uint8)
+    two = np.zeros(2, nn.PACKED_DTYPE)
+    L.dg_go_extract_batch(boards, tm.ctypes.data, sym.ctypes.data, 2, two.ctypes.data, None, 1)
+    assert two["planes"][0].any() and not two["planes"][1].any()
+    assert b.zobrist_hash() == h and b.count() == 1
 
 
 def test_board_copy_and_komi_through_the_boundary():
