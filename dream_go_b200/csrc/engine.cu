@@ -766,6 +766,9 @@ static int32_t raw_impl(dg_engine* e, const dg_raw_position* positions, int32_t 
     if (batch < 1 || batch > e->cfg.max_batch) return fail(e, DG_ERR_INVALID_ARGUMENT, "batch %d outside 1..%d", batch, e->cfg.max_batch);
     const bool network = value_out && policy_out;
     if (network && !e->net.loaded) return fail(e, DG_ERR_MISSING_WEIGHTS, "no weights loaded");
+    // the colour to move selects tables on the device: anything but 1 / 2 stops here (every other field is masked or only compared)
+    for (int32_t i = 0; i < batch; i++)
+        if (positions[i].to_move != 1 && positions[i].to_move != 2) return fail(e, DG_ERR_INVALID_ARGUMENT, "position %d: to_move %d is not a colour", i, positions[i].to_move);
     DG_CUDA(e, cudaSetDevice(e->cfg.device));
     WsGuard guard(e);
     Workspace& w = *guard.w;
@@ -896,6 +899,8 @@ int32_t dg_leaf_batch_capacity(const dg_leaf_batch* b) { return b ? WSC(b).owner
 
 int32_t dg_leaf_batch_push(dg_leaf_batch* b, const dg_raw_position* positions, int32_t n) {
     if (!b || !positions || n < 1) return DG_ERR_INVALID_ARGUMENT;
+    for (int32_t i = 0; i < n; i++)                            // as dg_engine_forward_raw: the colour to move selects tables on the device
+        if (positions[i].to_move != 1 && positions[i].to_move != 2) return DG_ERR_INVALID_ARGUMENT;
     Workspace& w = WS(b);
     const int32_t cap = w.owner->cfg.max_batch;
     int32_t at = w.fill.load(std::memory_order_relaxed);
@@ -915,6 +920,10 @@ int32_t dg_leaf_batch_submit(dg_leaf_batch* b, uint32_t outputs) {
     const int32_t n = w.fill.exchange(kSealed, std::memory_order_acq_rel);      // later pushes fail until dg_leaf_batch_reset
     if (n <= 0) { w.fill.store(n < 0 ? kSealed : 0); return n == 0 ? fail(e, DG_ERR_INVALID_ARGUMENT, "empty leaf batch") : fail(e, DG_ERR_INVALID_ARGUMENT, "leaf batch already submitted"); }
     while (w.committed.load(std::memory_order_acquire) < n) {}               // producers that claimed a slot finish their 384-byte copy
+    for (int32_t i = 0; i < n; i++) {                                          // (slots written directly through dg_leaf_batch_slots come by here too)
+        const uint8_t tm = reinterpret_cast<const dg_raw_position*>(w.h_in)[i].to_move;
+        if (tm != 1 && tm != 2) return fail(e, DG_ERR_INVALID_ARGUMENT, "leaf %d: to_move %d is not a colour", i, tm);
+    }
     DG_CUDA(e, cudaSetDevice(e->cfg.device));
     const bool prior = (outputs & DG_LEAF_PRIOR) != 0;
     const int cap = e->cfg.max_batch;

@@ -96,7 +96,7 @@ typedef struct dg_raw_position {
     uint64_t hash_history[16];
     int16_t  last_move[2];
     uint16_t k_bits;               /* fp16 bits of k (features.rs:236) */
-    uint8_t  to_move;              /* 1 black, 2 white */
+    uint8_t  to_move;              /* 1 black, 2 white (anything else: DG_ERR_INVALID_ARGUMENT from the calls that take positions) */
     uint8_t  symmetry;             /* bits 0-2: orientation the planes are produced in (symmetry::ALL order);
                                       bit 3: DG_RAW_DEVICE_LADDERS -- the two ladder masks above are not filled in, the device
                                       reads the ladders itself (one warp per reading, utils/ladder.rs:53-179);
