@@ -184,7 +184,8 @@ int32_t dg_engine_batch_acquire(dg_engine* engine, dg_leaf_batch** out);
 void    dg_engine_batch_release(dg_leaf_batch* batch);
 int32_t dg_leaf_batch_capacity(const dg_leaf_batch* batch);              /* = the engine's max_batch */
 /* Lock-free multi-producer: appends `n` positions, returns the index of the first one, or -1 when they do not fit or the
- * batch is sealed (submitted and not yet reset) -- `Batcher::push` (batch.rs:87-91). */
+ * batch is sealed (submitted and not yet reset) -- `Batcher::push` (batch.rs:87-91); DG_ERR_INVALID_ARGUMENT for a position
+ * whose to_move is not a colour (nothing is appended). */
 int32_t dg_leaf_batch_push(dg_leaf_batch* batch, const dg_raw_position* positions, int32_t n);
 /* Seals the batch and launches its evaluation; returns at once -- `Batcher::get_batch` + `Batch::forward` without the
  * blocking (batch.rs:98-123).  Any thread may call it, once per fill. */
