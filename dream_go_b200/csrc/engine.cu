@@ -920,10 +920,6 @@ int32_t dg_leaf_batch_submit(dg_leaf_batch* b, uint32_t outputs) {
     const int32_t n = w.fill.exchange(kSealed, std::memory_order_acq_rel);      // later pushes fail until dg_leaf_batch_reset
     if (n <= 0) { w.fill.store(n < 0 ? kSealed : 0); return n == 0 ? fail(e, DG_ERR_INVALID_ARGUMENT, "empty leaf batch") : fail(e, DG_ERR_INVALID_ARGUMENT, "leaf batch already submitted"); }
     while (w.committed.load(std::memory_order_acquire) < n) {}               // producers that claimed a slot finish their 384-byte copy
-    for (int32_t i = 0; i < n; i++) {                                          // (slots written directly through dg_leaf_batch_slots come by here too)
-        const uint8_t tm = reinterpret_cast<const dg_raw_position*>(w.h_in)[i].to_move;
-        if (tm != 1 && tm != 2) return fail(e, DG_ERR_INVALID_ARGUMENT, "leaf %d: to_move %d is not a colour", i, tm);
-    }
     DG_CUDA(e, cudaSetDevice(e->cfg.device));
     const bool prior = (outputs & DG_LEAF_PRIOR) != 0;
     const int cap = e->cfg.max_batch;

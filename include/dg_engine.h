@@ -195,7 +195,8 @@ int32_t dg_leaf_batch_ready(dg_leaf_batch* batch);
 /* Blocks until ready (spinning on the flag, or in 20 us naps under DG_FLAG_BLOCKING_SYNC); DG_ERR_CUDA if the launch failed. */
 int32_t dg_leaf_batch_wait(dg_leaf_batch* batch);
 int32_t dg_leaf_batch_size(const dg_leaf_batch* batch);                  /* leaves of the last submit */
-dg_raw_position* dg_leaf_batch_slots(dg_leaf_batch* batch);              /* the pinned input array (single-producer use) */
+dg_raw_position* dg_leaf_batch_slots(dg_leaf_batch* batch);              /* the pinned input array (single-producer use; the writer
+                                                                            vouches for to_move = 1 / 2, dg_leaf_batch_push checks it) */
 /* Pinned output arrays of the last submit, in push order: [n] fp16, [n][362] fp16, [n][361], [n][368] floats. */
 const uint16_t* dg_leaf_batch_value(const dg_leaf_batch* batch);
 const uint16_t* dg_leaf_batch_policy(const dg_leaf_batch* batch);
