@@ -60,3 +60,20 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
     assert line["config"]["workload"].startswith("residual tower 9-block x 128-filter")
+
+
+def test_self_play_front_end_prints_one_record_per_game():
+    """tools/self_play.py (`dream_go --self-play N`): records on stdout, progress on stderr; host-only predictor here."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "self_play.py"), "--self-play", "3", "--num-games", "2", "--num-rollout", "12",
+                          "--ex-it", "--num-ex-it-rollout", "20", "--host-only", "--seed", "5", "--num-threads", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    records = out.stdout.strip().splitlines()
+    assert len(records) == 3 and all(r.startswith("(;GM[1]FF[4]SZ[19]RU[Chinese]KM[") and r.endswith(")") for r in records)
+    assert out.stderr.startswith("...") and "3 games" in out.stderr
+    # and without a device the engine path fails loudly instead of falling back
+    bad = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "self_play.py"), "--self-play", "1", "--random-weights"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    import torch
+    if not torch.cuda.is_available():
+        assert bad.returncode != 0 and "Cuda" in bad.stderr

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks", type=int, default=9)
+    ap.add_argument("--weights", default=None, help="a dream_go.json weight file (loader.rs format) instead of seeded random-init weights")
     ap.add_argument("--ex-it", action="store_true")
     ap.add_argument("--ex-it-rollouts", type=int, default=0, help="`--num-ex-it-rollout` (default: same as --rollouts)")
     ap.add_argument("--no-host-sample", action="store_true", help="skip the host-only (RandomPredictor) sample")
@@ -101,9 +102,14 @@ def main():
     if not args.host_only:
         from dream_go_b200 import shard
         shards = shard.Shards(backend="nccl")
-        tensors = weights.synthetic_network(seed=20261017, num_blocks=args.blocks)
-        net = nn.Network.from_tensors(tensors, device=local_rank, max_batch=512, num_workspaces=8,
-                                      flags=(0 if args.spin_sync else nn.FLAG_BLOCKING_SYNC) | (nn.FLAG_NO_GRAPH if args.no_graph else 0))
+        engine_kw = dict(device=local_rank, max_batch=512, num_workspaces=8,
+                         flags=(0 if args.spin_sync else nn.FLAG_BLOCKING_SYNC) | (nn.FLAG_NO_GRAPH if args.no_graph else 0))
+        if args.weights:
+            net = nn.Network(**engine_kw)
+            net.load_json(args.weights)
+            line["config"]["weights"] = f"{args.weights} ({net.num_blocks()} blocks)"
+        else:
+            net = nn.Network.from_tensors(weights.synthetic_network(seed=20261017, num_blocks=args.blocks), **engine_kw)
         shards.barrier()
         t0 = time.perf_counter()
         st, sgf = sample(net, games=args.games, parallel=args.parallel, rollouts=args.rollouts, probes=args.probes,
