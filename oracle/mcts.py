@@ -1,6 +1,6 @@
 """Single-threaded restatement of dream-go's tree search (`src/libdg_mcts`), SURVEY.md section 8c-3.
 
-TEST INFRASTRUCTURE ONLY (tests/ and bench.py's CPU-baseline leg) -- never imported by the product.
+TEST INFRASTRUCTURE ONLY (tests/, the soak / fuzz checkers under tools/ and bench.py's CPU-baseline leg) -- never imported by the product.
 
 Follows the reference function by function with its dense per-node tables (`BigChildrenImpl`, tree.rs:540-620):
 `Node::select` (tree.rs:1311-1385) incl. the blocked argmax of asm/argmax.rs:23-76, `probe` (:1421-1471),
