@@ -148,6 +148,32 @@ def main():
                 assert (np.isfinite(got) == f).all() and (got[f].view(np.uint32) == want[f].view(np.uint32)).all(), (k, to_move, symmetry)
                 n += 1
     say(f"priors: {n} priors on {max(2, args.playouts // 10)} positions ({folded} with a symmetry): candidates and values bit-identical ({time.time() - t0:.0f} s)")
+    # 5. exact liberty counts: `get_n_liberty` of every stone, `get_n_liberty_if` of both colours at every point where the move
+    #    is legal without the ko rule (the planes only pin the counts up to 6)
+    t0 = time.time()
+    n = q = 0
+    for seed in range(5000, 5000 + max(2, args.playouts // 20)):
+        colors, moves = T.random_playout(seed, 400, pass_rate=0.0)
+        po, oo = pgo.Board(7.5), ogo.Board(7.5)
+        for k, (c, m) in enumerate(zip(colors, moves)):
+            if m < 361:
+                po.place_index(int(c), int(m))
+                oo.place_index(int(c), int(m))
+            if k % 5:
+                continue
+            for y in range(19):
+                for x in range(19):
+                    if oo.at(x, y):
+                        assert po.get_n_liberty(x, y) == oo.get_n_liberty(x, y), (seed, k, x, y)
+                        q += 1
+                    else:
+                        for col in (BLACK, WHITE):
+                            if oo.is_valid_fast(col, x, y):
+                                assert po.get_n_liberty_if(col, x, y) == oo.get_n_liberty_if(col, x, y), (seed, k, x, y, col)
+                                q += 1
+            n += 1
+    say(f"liberties: {q} exact liberty counts (stones, and both colours' liberties-if-played at every playable point) on {n} positions identical "
+        f"({time.time() - t0:.0f} s)")
     say("ALL IDENTICAL")
     if args.out:
         with open(args.out, "w") as fh:
