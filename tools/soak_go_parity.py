@@ -103,6 +103,39 @@ def main():
                     assert (po.policy_candidates(color, 1) == oo.policy_candidates(color, 1)).all(), (seed, k)
                 assert (po.territory() == oo.territory()).all(), (seed, k)
                 n += 1
+    # fully settled boards: black fills the lines below a random border line, white the lines above, each side with a random number of
+    # one-point eyes (two or more: alive, everything is settled and the board is scorable; fewer: it is not)
+    rng = np.random.default_rng(9)
+    for k in range(max(4, args.playouts // 5)):
+        border = int(rng.integers(4, 15))
+        holes = {}
+        for color, lines in ((BLACK, range(0, border)), (WHITE, range(border, 19))):
+            want, pts = int(rng.integers(0, 5)), []
+            for _ in range(200):
+                if len(pts) == want:
+                    break
+                x, y = int(rng.integers(0, 19)), int(rng.choice(list(lines)))
+                if (color == BLACK and y == border - 1) or (color == WHITE and y == border):
+                    continue                                     # an eye on the border line would touch the other colour
+                if all(abs(x - a) + abs(y - b) > 1 for a, b in pts):
+                    pts.append((x, y))
+            holes[color] = pts
+        po, oo = pgo.Board(7.5), ogo.Board(7.5)
+        for y in range(19):
+            for x in range(19):
+                color = BLACK if y < border else WHITE
+                if (x, y) not in holes[color] and oo.is_valid(color, x, y):
+                    po.place(color, x, y)
+                    oo.place(color, x, y)
+        assert (po.stones() == oo.stones()).all()
+        for color in (BLACK, WHITE):
+            assert (po.benson(color) == oo.benson(color)).all(), k
+            for kind in (0, 1):
+                assert (po.policy_candidates(color, kind) == oo.policy_candidates(color, kind)).all(), k
+        assert po.is_scorable() == oo.is_scorable(), k
+        assert (po.territory() == oo.territory()).all(), k
+        scorable += int(oo.is_scorable())
+        n += 1
     say(f"unconditional life: {n} positions ({scorable} scorable): Benson sets, candidates of both search kinds, is_scorable, territory identical "
         f"({time.time() - t0:.0f} s)")
     # 4. priors (create_initial_policy + add_valid_candidates + normalize_policy) through dg_board_prior, bit for bit: random and
