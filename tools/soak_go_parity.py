@@ -109,12 +109,12 @@ def main():
     for k in range(max(4, args.playouts // 5)):
         border = int(rng.integers(4, 15))
         holes = {}
-        for color, lines in ((BLACK, range(0, border)), (WHITE, range(border, 19))):
+        for color, rows in ((BLACK, range(0, border)), (WHITE, range(border, 19))):
             want, pts = int(rng.integers(0, 5)), []
             for _ in range(200):
                 if len(pts) == want:
                     break
-                x, y = int(rng.integers(0, 19)), int(rng.choice(list(lines)))
+                x, y = int(rng.integers(0, 19)), int(rng.choice(list(rows)))
                 if (color == BLACK and y == border - 1) or (color == WHITE and y == border):
                     continue                                     # an eye on the border line would touch the other colour
                 if all(abs(x - a) + abs(y - b) > 1 for a, b in pts):
