@@ -47,10 +47,11 @@ WORKLOAD = "residual tower 9-block x 128-filter forward, batch=256 (BASELINE.jso
 
 
 def workload_config(world: int):
-    """The workload both arms run (BASELINE.json configs[1])."""
+    """The workload both arms run (BASELINE.json configs[1]); the same dictionary in both arms' lines."""
     return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "blocks": NUM_BLOCKS, "filters": 128,
             "inputs": "iid Bernoulli(0.2) fp16 features (dg_tests/benches/batch_sizes.rs:44-49), seeded He-init weights",
-            "parallelism": f"{world} independent engine shard(s), no collective"}
+            "parallelism": f"{world} independent engine shard(s), no collective",
+            "l2": "device arm: flushed between steps (256 MiB memset outside the per-step event pairs); CPU arm: not applicable"}
 
 
 def measured_peaks():
@@ -199,8 +200,9 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {**workload_config(args.gpus), "sample": info["sample"],
-                   "note": "CPU restatement of dg_nn::forward on the host cores of rank 0 (the Rust + cuDNN reference cannot be built here)"},
+        "config": workload_config(args.gpus),       # the same dictionary as the device arm's line (the CPU arm's sample is below)
+        "sample": info["sample"],
+        "note": "CPU restatement of dg_nn::forward on the host cores of rank 0 (the Rust + cuDNN reference cannot be built here)",
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -387,7 +389,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if self_play is not None:          # the metric's other half, next to the headline
         line["self_play"] = self_play
     line.update({
-        "config": {**workload_config(world), "l2": "flushed between steps (256 MiB memset outside the per-step event pairs)"},
+        "config": workload_config(world),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_evals, "unit": UNIT, "h2d_bytes_per_step": BATCH * 11552 * 2, "d2h_bytes_per_step": BATCH * 363 * 2,
                 "call": "dg_engine_forward_f16 (pinned host buffers, blocking), 2 concurrent callers per device as in predictors/nn.rs:64-67",

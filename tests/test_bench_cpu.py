@@ -60,6 +60,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
     assert line["config"]["workload"].startswith("residual tower 9-block x 128-filter")
+    import bench
+    assert line["config"] == bench.workload_config(1)            # both arms print the same config dictionary
 
 
 def test_self_play_front_end_prints_one_record_per_game():
