@@ -79,3 +79,93 @@ def test_self_play_front_end_prints_one_record_per_game():
     import torch
     if not torch.cuda.is_available():
         assert bad.returncode != 0 and "Cuda" in bad.stderr
+
+
+def test_line_assembly_of_the_device_arm_with_the_device_mocked(monkeypatch, capsys):
+    """bench.run_ours end to end with every device-facing piece replaced (engine, shards, clock sampler, cuDNN and oracle legs):
+    the line carries every key of the contract at N = 1 and N = 8, the self-play summary sits inside `e2e` and at the end."""
+    import types
+    import numpy as np
+    import bench
+    from dream_go_b200 import nn, shard
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_selfplay
+
+    class FakeNet:
+        def __init__(self, *a, **k):
+            self.max_batch = k.get("max_batch", 256)
+
+        @classmethod
+        def from_tensors(cls, tensors, **k):
+            return cls(**k)
+
+        def pinned(self, shape, dtype):
+            return np.zeros(shape, dtype)
+
+        def forward_into(self, feats, value, policy, packed=False):
+            policy[...] = np.float16(1.0 / 362)
+
+        def synchronize(self):
+            pass
+
+        def time_resident(self, batch, steps, tower=False, flush_l2=False):
+            return 0.4 * steps, 0.36 * steps, 4
+
+        def time_e2e(self, feats, steps, callers=2):
+            return 0.0004 * steps
+
+        def close(self):
+            pass
+
+    class FakeShards:
+        def __init__(self, backend="nccl"):
+            pass
+
+        def barrier(self):
+            pass
+
+        def max(self, x):
+            return x
+
+        def sum(self, x):
+            return x
+
+        def close(self):
+            pass
+
+        def selfplay_totals(self, st):
+            return {"moves_per_s": 500.0, "nn_evals_per_s": 400000.0, "mean_device_batch": 250.0, "predictor_seconds": 9.0, "seconds": 10.0}
+
+    class FakeClock:
+        def __init__(self, device):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def summary(self):
+            return {"sm_mhz": 1900.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 10}
+
+    monkeypatch.setattr(nn, "Network", FakeNet)
+    monkeypatch.setattr(nn, "pack_positions", lambda feats: np.zeros(feats.shape[0], nn.PACKED_DTYPE))
+    monkeypatch.setattr(shard, "Shards", FakeShards)
+    monkeypatch.setattr(bench_selfplay, "sample", lambda net, **k: ({"cache_hits": 5, "evals": 100, "moves": 10, "seconds": 10.0}, []))
+    monkeypatch.setattr(bench, "ClockSampler", FakeClock)
+    monkeypatch.setattr(bench, "cudnn_baseline", lambda tensors, feats, steps: {"value": 260000.0, "unit": bench.UNIT, "ms_per_step": 0.97, "e2e": 180000.0})
+    monkeypatch.setattr(bench, "oracle_rate", lambda seconds_target, steps=1, warmup=0: (140.0, {"cores": 16, "kind": "port", "seconds": 1.8, "sample": "mock"}))
+    monkeypatch.setattr(bench, "host_feature_rates", lambda positions=512: {"unit": "positions/s"})
+    args = types.SimpleNamespace(gpus=1, steps=20, warmup=3, self_play_seconds=0.5, sustained_seconds=0.5, impl="ours")
+    contract = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "clocks", "e2e", "gpu_launches", "roofline"}
+    for world in (1, 8):
+        bench.run_ours(args, 0, world, 0)
+        line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+        assert contract <= set(line) and line["n_gpus"] == world and line["config"] == bench.workload_config(world)
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"]) and 0 < line["roofline"]["frac"] < 1.2
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "self_play"} <= set(line["e2e"])
+        assert list(line)[-1] == "self_play_summary" and line["self_play_summary"] == line["e2e"]["self_play"]
+        assert ("cpu_baseline" in line) == (world == 1) and ("vs_cudnn" in line) == (world == 1)
+        assert line["gpu_launches"] == 4 * args.steps and line["vs_baseline"] is None
